@@ -1,0 +1,244 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's vectors.
+
+Bar: bit-exact for every integer output (clipped score, penalty, status, CIGAR bytes, counts);
+floating-point reduction outputs within 1e-9 relative (tolerance stated by north_star).
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import tdo
+from tests.util import make_pairs, mutate, rand_seq, to_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tdb():
+    import __graft_entry__ as entry
+    entry.build()
+    import trgt_denovo_b200 as m
+    assert m.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(tdb):
+    c = tdb.Context(device_id=0)
+    yield c
+    c.close()
+
+
+def test_reference_known_answers(tdb, golden_dir):
+    """src/aligner.rs tests B5,B6,B7,B9 through the WFAligner shim (B4 is single-piece affine: oracle only)."""
+    for x in json.load(open(os.path.join(golden_dir, "aligner_vectors.json"))):
+        if x["penalties"][3] < 0:
+            continue
+        heur = (1, 10, 50, 1) if x["heuristic"] == "default" else (0, 0, 0, 0)
+        c = tdb.Context(penalties=tuple(x["penalties"]), heuristic=heur)
+        a = tdb.WFAligner(c)
+        st = a.align_end_to_end(x["pattern"].encode(), x["text"].encode())
+        assert st == tdb.AlignmentStatus.StatusAlgCompleted, x["id"]
+        assert a.score() == x["score"], x["id"]
+        if "cigar" in x:
+            assert a.cigar() == x["cigar"], x["id"]
+        for clip, exp in (x.get("clipped") or {}).items():
+            assert a.cigar_score_clipped(int(clip)) == exp
+        for clip, exp in (x.get("clipped_cigar") or {}).items():
+            assert a.cigar(int(clip)) == exp
+        assert a.cigar_score() == x["score"]
+        c.close()
+
+
+def test_b9_default_heuristic_matches_oracle(tdb, golden_dir):
+    x = [v for v in json.load(open(os.path.join(golden_dir, "aligner_vectors.json"))) if v["id"] == "B9"][0]
+    a = tdb.create_aligner_with_scoring()
+    assert a.align_end_to_end(x["pattern"].encode(), x["text"].encode()) == 0
+    o = tdo.Aligner()
+    o.align_end_to_end(x["pattern"].encode(), x["text"].encode())
+    assert a.score() == o.score() == -1007
+    assert a.cigar_wfa() == o.cigar_ops()
+    assert a.cigar_score_clipped(50) == o.cigar_score_clipped(50) == -969
+
+
+def _check_batch(ctx, seqs, pp, pt, clip, heuristic=tdo.DEFAULT_HEURISTIC, cigars=True):
+    blob, off, ln = to_arrays(seqs)
+    ctx.set_clip_len(clip)
+    want, wst, wtot = tdo.align_batch(blob, off, ln, pp, pt, clip, heuristic=heuristic, n_threads=8)
+    got, st = ctx.align_batch(blob, off, ln, pp, pt)
+    cnt = ctx.counters()
+    assert (wst == 0).all()
+    assert (st == wst).all()
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, f"{len(bad)} score mismatches, first pair {bad[:5]}: gpu {got[bad[:5]]} oracle {want[bad[:5]]}"
+    # exact algorithmic work accounting agrees with the oracle (C, E, T)
+    assert (cnt.cells, cnt.ext16, cnt.columns) == (wtot.cells, wtot.ext16, wtot.columns)
+    if cigars:
+        g2, st2, pen2, cigs = ctx.align_batch_cigar(blob, off, ln, pp, pt)
+        assert (g2 == want).all() and (st2 == 0).all()
+        o = tdo.Aligner(heuristic=heuristic)
+        for i in range(0, len(pp), max(1, len(pp) // 300)):
+            o.align_end_to_end(seqs[pp[i]], seqs[pt[i]])
+            assert pen2[i] == -o.score()
+            assert cigs[i] == o.cigar_ops(), f"pair {i}"
+    return cnt
+
+
+@pytest.mark.parametrize("clip", [50, 0])
+def test_str_pairs_bit_exact(ctx, clip):
+    rng = random.Random(100 + clip)
+    seqs, pp, pt = make_pairs(rng, n_targets=300, reads_per_target=12)
+    cnt = _check_batch(ctx, seqs, pp, pt, clip)
+    assert cnt.tier_pairs[0] > 0.8 * len(pp)  # the shared-memory tier carries the bulk
+
+
+def test_random_divergent_pairs(ctx):
+    """Unrelated / highly divergent pairs: wide wavefronts, heuristic active, global-scratch tier."""
+    rng = random.Random(5)
+    seqs, pp, pt = [], [], []
+    for _ in range(150):
+        L = rng.randint(1, 700)
+        t = rand_seq(rng, L)
+        p = mutate(rng, t, rng.choice([0.0, 0.02, 0.1, 0.3, 0.6]))
+        pt.append(len(seqs)); seqs.append(t.encode())
+        pp.append(len(seqs)); seqs.append(p.encode())
+    cnt = _check_batch(ctx, seqs, np.array(pp, np.uint32), np.array(pt, np.uint32), 50)
+    assert cnt.tier_pairs[1] > 0
+
+
+def test_heuristic_none(tdb):
+    rng = random.Random(9)
+    seqs, pp, pt = make_pairs(rng, n_targets=60, reads_per_target=6, err=0.05)
+    c = tdb.Context(heuristic=(0, 0, 0, 0))
+    _check_batch(c, seqs, pp, pt, 50, heuristic=tdo.NO_HEURISTIC)
+    c.close()
+
+
+def test_non_acgt_bytes_take_byte_path(ctx):
+    """Raw byte equality: N==N matches, lower case differs from upper case (SURVEY.md hard parts)."""
+    rng = random.Random(21)
+    seqs, pp, pt = make_pairs(rng, n_targets=40, reads_per_target=6, alphabet="ACGTN")
+    seqs[0] = seqs[0].lower()
+    seqs[3] = seqs[3][:20] + b"nnRYK" + seqs[3][25:]
+    _check_batch(ctx, seqs, pp, pt, 50)
+
+
+def test_edge_cases(ctx):
+    seqs = [b"A", b"C", b"ACGT", b"ACGT", b"ACGTACGTACGTACGTA", b"ACGTACGTACGTACGT", b"G" * 300, b"G" * 299 + b"T",
+            b"T", b"ACGT" * 60, b"ACGT" * 40]
+    pairs = [(0, 1), (2, 3), (4, 5), (5, 4), (6, 7), (7, 6), (8, 6), (6, 8), (9, 10), (10, 9), (0, 0)]
+    pp = np.array([p for p, _ in pairs], np.uint32)
+    pt = np.array([t for _, t in pairs], np.uint32)
+    for clip in (0, 3, 50):
+        _check_batch(ctx, seqs, pp, pt, clip)
+
+
+def test_empty_batch(ctx):
+    z8, z4 = np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+    got, st = ctx.align_batch(np.zeros(0, np.uint8), z8, z4, z4, z4)
+    assert len(got) == 0 and len(st) == 0
+
+
+def test_long_expansion_pairs(ctx):
+    """Config-4 style: 300 bp allele reads vs kb-scale expansions (long wavefronts, second gap piece)."""
+    rng = random.Random(77)
+    seqs, pp, pt = [], [], []
+    for _ in range(12):
+        lf, rf, motif = rand_seq(rng, 50), rand_seq(rng, 50), rand_seq(rng, rng.randint(2, 6))
+        big = lf + motif * rng.randint(300, 900) + rf
+        small = lf + motif * rng.randint(20, 60) + rf
+        t = len(seqs); seqs.append(big.encode())
+        for src in (big, big, small):
+            pp.append(len(seqs)); pt.append(t); seqs.append(mutate(rng, src, 0.003).encode())
+    _check_batch(ctx, seqs, np.array(pp, np.uint32), np.array(pt, np.uint32), 50)
+
+
+def _random_loci(rng, n_loci, duo=False):
+    loci, flat = [], []
+    for _ in range(n_loci):
+        nc, nm = rng.randint(1, 2), rng.randint(1, 2)
+        nf = 0 if duo else rng.randint(1, 2)
+        loc = tdo.TrioLocus()
+        loc.n_child, loc.n_mother, loc.n_father = nc, nm, nf
+        for c in range(nc):
+            sizes = [rng.randint(0, 25), rng.randint(0, 25) if nm > 1 else 0,
+                     rng.randint(0, 25) if nf > 0 else 0, rng.randint(0, 25) if nf > 1 else 0, rng.randint(0, 30)]
+            if rng.random() < 0.7:
+                sizes[0] = max(sizes[0], 1)
+                if nf:
+                    sizes[2] = max(sizes[2], 1)
+            base = rng.choice([0, -6, -20, -60])
+            for j, sz in enumerate(sizes):
+                loc.list_off[c][j] = len(flat)
+                flat.extend(int(base + rng.choice([0, 0, 0, -2, -4, -6, -8, -12, -30, -100]) * rng.random()) for _ in range(sz))
+            loc.list_off[c][5] = len(flat)
+        for i in range(2):
+            loc.child_len[i], loc.mother_len[i], loc.father_len[i] = (rng.randint(100, 400) for _ in range(3))
+        loci.append(loc)
+    return loci, np.array(flat, dtype=np.int32)
+
+
+FIELDS_INT = ["denovo_coverage", "allele_origin", "denovo_status", "error"]
+FIELDS_F = ["mean_diff_father", "mean_diff_mother", "top_mother", "top_father", "child_median"]
+
+
+def _close(a, b, tol=1e-9):
+    if a == b:
+        return True
+    if np.isnan(a) and np.isnan(b):
+        return True
+    return abs(a - b) <= tol * max(abs(a), abs(b))
+
+
+@pytest.mark.parametrize("duo", [False, True])
+@pytest.mark.parametrize("q", [1.0, 0.9, 0.5, 0.0])
+def test_reduction_matches_oracle(tdb, ctx, duo, q):
+    rng = random.Random(1000 + int(q * 10) + duo)
+    loci, scores = _random_loci(rng, 400, duo=duo)
+    arr = (tdb.TrioLocus * len(loci))()
+    for i, l in enumerate(loci):
+        C = __import__("ctypes")
+        C.memmove(C.byref(arr[i]), C.byref(l), C.sizeof(l))
+    out, mask = ctx.reduce(arr, scores, q=q, duo=duo)
+    for i, l in enumerate(loci):
+        want, wmask = tdo.trio_assess(l, scores, q, duo=duo)
+        for c in range(l.n_child):
+            g, w = out[2 * i + c], want[c]
+            for f in FIELDS_INT:
+                assert getattr(g, f) == getattr(w, f), (i, c, f)
+            if w.error:
+                continue
+            for f in FIELDS_F:
+                assert _close(getattr(g, f), getattr(w, f)), (i, c, f, getattr(g, f), getattr(w, f))
+            assert list(g.mother_overlap) == list(w.mother_overlap)
+            assert list(g.father_overlap) == list(w.father_overlap)
+            for r in range(4):
+                assert _close(g.mean_col[r], w.mean_col[r]) or duo
+            o4, o5 = l.list_off[c][4], l.list_off[c][5]
+            assert (mask[o4:o5] == wmask[o4:o5]).all()
+
+
+def test_reduction_reference_vectors(tdb, ctx, golden_dir):
+    r = json.load(open(os.path.join(golden_dir, "reduction_vectors.json")))
+    import ctypes as C
+    for case in r["trio_get_denovo_coverage"]:
+        loc, scores = tdo.make_locus([case["mother"]], [case["father"]], [case["child"]])
+        arr = (tdb.TrioLocus * 1)()
+        C.memmove(C.byref(arr[0]), C.byref(loc), C.sizeof(loc))
+        out, mask = ctx.reduce(arr, scores, q=case["q"])
+        e = case["expect"]
+        assert out[0].denovo_coverage == e["denovo_coverage"]
+        assert out[0].mean_diff_father == e["mean_diff_father"] and out[0].mean_diff_mother == e["mean_diff_mother"]
+        o4 = loc.list_off[0][4]
+        assert list(mask[o4:o4 + 3]) == e["mask"]
+    m = np.array(r["parent_origin_matrix"]["matrix_rowmajor_4x2"]).reshape(4, 2)
+    mother = [[[int(m[0, c])], [int(m[1, c])]] for c in range(2)]
+    father = [[[int(m[2, c])], [int(m[3, c])]] for c in range(2)]
+    loc, scores = tdo.make_locus(mother, father, [[0], [0]])
+    arr = (tdb.TrioLocus * 1)()
+    C.memmove(C.byref(arr[0]), C.byref(loc), C.sizeof(loc))
+    out, _ = ctx.reduce(arr, scores, q=1.0)
+    assert [out[0].allele_origin, out[1].allele_origin] == r["parent_origin_matrix"]["expect_origin"]

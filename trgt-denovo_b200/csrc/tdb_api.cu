@@ -1,0 +1,686 @@
+// tdb_api.cu -- C ABI (include/trgt_denovo_b200.h) over the sm_100a kernels.  No CPU compute path:
+// every entry point that does arithmetic launches CUDA kernels or fails.
+#include "tdb_kernels.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace tdb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr, cap = 0;
+    }
+};
+
+struct TierCfg {
+    int wlog2, s_cap, ops_cap;
+    unsigned prov_cap;
+    int workers;
+};
+
+} // namespace
+
+struct tdb_ctx {
+    tdb_config cfg;
+    int dev = 0;
+    int sm_count = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // grow-only device buffers
+    DevBuf blob, seq_off, seq_len, woff, packed, seq_flag, pair_p, pair_t, score, status, penalty;
+    DevBuf todo_a, todo_b, ctrl, cub_tmp, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
+    DevBuf scratch[2];
+    int t0_ctas_per_sm = 0;
+    bool count_work = true;
+    tdb_counters counters;
+    // single-pair shim state
+    std::vector<uint8_t> last_cigar;
+    int last_penalty = INT32_MIN, last_status = TDB_STATUS_UNATTAINABLE;
+};
+
+namespace {
+
+int fail(tdb_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? TDB_E_OOM : TDB_E_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+    } while (0)
+
+int ensure(tdb_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return TDB_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr, b.cap = 0;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return TDB_OK;
+}
+#define ENSURE(buf, bytes)                          \
+    do {                                            \
+        int r_ = ensure(ctx, (buf), (bytes));       \
+        if (r_ != TDB_OK) return r_;                \
+    } while (0)
+
+// ctrl block layout (unsigned): [0] work counter, [1] next count A, [2] next count B, pad;
+// counters (unsigned long long) at byte 64: 4 per tier x 3 tiers
+constexpr size_t CTRL_BYTES = 64 + 3 * 4 * sizeof(unsigned long long);
+
+struct DevBatch {
+    const uint8_t *blob;
+    size_t blob_bytes;
+    const uint64_t *seq_off;
+    const uint32_t *seq_len;
+    size_t n_seqs;
+    const uint32_t *pp, *pt;
+    size_t n_pairs;
+    int32_t *score, *status, *penalty;
+    uint8_t *cigar_buf;
+    const uint64_t *cigar_off;
+    uint32_t *cigar_len;
+};
+
+int check_sizes(tdb_ctx *ctx, size_t blob_bytes, size_t n_seqs, size_t n_pairs) {
+    if (n_seqs >= 0xffffffffull || n_pairs >= 0xffffffffull)
+        return fail(ctx, TDB_E_UNSUPPORTED, "batch too large: n_seqs=%zu n_pairs=%zu (max 2^32-2 per call)", n_seqs,
+                    n_pairs);
+    if (blob_bytes / 16 + 2 * n_seqs + 2 >= 0xffffffffull)
+        return fail(ctx, TDB_E_UNSUPPORTED, "sequence blob too large for 32-bit word offsets: %zu bytes", blob_bytes);
+    return TDB_OK;
+}
+
+// Runs pack + alignment tiers on device-resident inputs.  Leaves results in b.score/status/penalty.
+int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n_seqs = (uint32_t)b.n_seqs, n_pairs = (uint32_t)b.n_pairs;
+    memset(&ctx->counters, 0, sizeof(ctx->counters));
+    ctx->counters.pairs = n_pairs;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    if (n_pairs == 0 || n_seqs == 0) {
+        CK(cudaEventRecord(ctx->ev[1], s));
+        CK(cudaEventRecord(ctx->ev[2], s));
+        CK(cudaStreamSynchronize(s));
+        return TDB_OK;
+    }
+    // ---- packed layout: exclusive scan of words per sequence -------------------------------------
+    ENSURE(ctx->woff, ((size_t)n_seqs + 1) * 4);
+    ENSURE(ctx->seq_flag, (size_t)n_seqs);
+    const size_t max_words = b.blob_bytes / 16 + 2 * (size_t)n_seqs + 2;
+    ENSURE(ctx->packed, max_words * 4);
+    {
+        NWordsOp op{b.seq_len};
+        auto it = thrust::make_transform_iterator(thrust::make_counting_iterator<uint32_t>(0), op);
+        size_t tmp = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, (uint32_t *)ctx->woff.p, (int)n_seqs, s));
+        ENSURE(ctx->cub_tmp, tmp);
+        CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, it, (uint32_t *)ctx->woff.p, (int)n_seqs, s));
+    }
+    {
+        const int threads = 256;
+        const unsigned warps_needed = n_seqs;
+        unsigned blocks = (unsigned)std::min<size_t>(((size_t)warps_needed * 32 + threads - 1) / threads,
+                                                     (size_t)ctx->sm_count * 32);
+        k_pack<<<blocks, threads, 0, s>>>(b.blob, b.blob_bytes, b.seq_off, b.seq_len, (const uint32_t *)ctx->woff.p,
+                                          n_seqs, (uint32_t *)ctx->packed.p, (uint8_t *)ctx->seq_flag.p);
+        CK(cudaGetLastError());
+        ctx->counters.kernel_launches += 2; // scan + pack
+    }
+    CK(cudaEventRecord(ctx->ev[1], s));
+    // ---- tiers -------------------------------------------------------------------------------------
+    ENSURE(ctx->ctrl, CTRL_BYTES);
+    CK(cudaMemsetAsync(ctx->ctrl.p, 0, CTRL_BYTES, s));
+    ENSURE(ctx->todo_a, (size_t)n_pairs * 4);
+    unsigned *ctrl = (unsigned *)ctx->ctrl.p;
+    unsigned long long *cnt64 = (unsigned long long *)((uint8_t *)ctx->ctrl.p + 64);
+    AlignParams p;
+    memset(&p, 0, sizeof(p));
+    p.pn = {ctx->cfg.penalties.mismatch, ctx->cfg.penalties.gap_opening1, ctx->cfg.penalties.gap_extension1,
+            ctx->cfg.penalties.gap_opening2, ctx->cfg.penalties.gap_extension2};
+    p.heur = {ctx->cfg.heuristic.kind, ctx->cfg.heuristic.min_wavefront_length,
+              ctx->cfg.heuristic.max_distance_threshold, ctx->cfg.heuristic.steps_between_cutoffs};
+    p.clip = ctx->cfg.clip_len;
+    p.packed = (const uint32_t *)ctx->packed.p, p.woff = (const uint32_t *)ctx->woff.p;
+    p.seq_flag = (const uint8_t *)ctx->seq_flag.p;
+    p.blob = b.blob, p.seq_off = b.seq_off, p.seq_len = b.seq_len, p.pair_p = b.pp, p.pair_t = b.pt;
+    p.out_score = b.score, p.out_status = b.status, p.out_penalty = b.penalty;
+    p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
+
+    unsigned pending = n_pairs;
+    const uint32_t *todo = nullptr;
+    if (!cigar_mode) {
+        p.todo = nullptr, p.n_items = n_pairs, p.n_items_ptr = nullptr;
+        p.work_counter = ctrl + 0, p.next_todo = (uint32_t *)ctx->todo_a.p, p.next_count = ctrl + 1;
+        p.counters = cnt64 + 0;
+        const size_t smem = sizeof(T0Smem) * T0_WARPS;
+        const unsigned grid = (unsigned)(ctx->sm_count * ctx->t0_ctas_per_sm);
+        k_align_tier0<<<grid, T0_WARPS * 32, smem, s>>>(p);
+        CK(cudaGetLastError());
+        ctx->counters.kernel_launches += 1;
+        CK(cudaMemcpyAsync(&pending, ctrl + 1, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        todo = (const uint32_t *)ctx->todo_a.p;
+        ctx->counters.tier_pairs[0] = n_pairs - pending;
+    }
+    // global tiers
+    const uint64_t cap = ctx->cfg.scratch_bytes ? ctx->cfg.scratch_bytes : (48ull << 30);
+    TierCfg tiers[2] = {
+        {10, 1 << 16, 1 << 17, 8u << 20, ctx->sm_count * 8},   // W=1024, S<65536, 8 MiB provenance
+        {15, 1 << 18, 1 << 19, 192u << 20, ctx->sm_count * 1}, // W=32768, S<262144, 192 MiB provenance
+    };
+    for (int t = 0; t < 2 && pending > 0; ++t) {
+        const TierCfg tc = tiers[t];
+        const size_t stride = global_tier_stride(tc.wlog2, tc.s_cap, tc.ops_cap, tc.prov_cap);
+        uint64_t workers = std::min<uint64_t>((uint64_t)tc.workers, std::max<uint64_t>(1, (cap / 2) / stride));
+        workers = std::min<uint64_t>(workers, pending);
+        workers = (workers + 3) & ~(uint64_t)3; // whole CTAs of 4 warps
+        ENSURE(ctx->scratch[t], stride * (size_t)workers);
+        CK(cudaMemsetAsync(ctrl + 0, 0, 4, s));
+        p.todo = todo, p.n_items = pending, p.n_items_ptr = nullptr;
+        p.work_counter = ctrl + 0;
+        p.next_todo = nullptr, p.next_count = ctrl + 2;
+        if (t == 0) { // the last tier has nowhere to defer to: it reports TDB_STATUS_OOM
+            ENSURE(ctx->todo_b, (size_t)pending * 4);
+            p.next_todo = (uint32_t *)ctx->todo_b.p;
+        }
+        p.counters = cnt64 + 4 * (t + 1);
+        p.scratch = (uint8_t *)ctx->scratch[t].p, p.scratch_stride = stride;
+        p.wlog2 = tc.wlog2, p.s_cap = tc.s_cap, p.ops_cap = tc.ops_cap, p.prov_cap = tc.prov_cap;
+        const unsigned grid = (unsigned)(workers / 4);
+        if (cigar_mode) k_align_global<true><<<grid, 128, 0, s>>>(p);
+        else k_align_global<false><<<grid, 128, 0, s>>>(p);
+        CK(cudaGetLastError());
+        ctx->counters.kernel_launches += 1;
+        unsigned next = 0;
+        if (t == 0) {
+            CK(cudaMemcpyAsync(&next, ctrl + 2, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        ctx->counters.tier_pairs[t + 1] = pending - next;
+        pending = next;
+        todo = (const uint32_t *)ctx->todo_b.p;
+    }
+    CK(cudaEventRecord(ctx->ev[2], s));
+    unsigned long long h[12];
+    CK(cudaMemcpyAsync(h, cnt64, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int t = 0; t < 3; ++t) {
+        ctx->counters.cells += h[4 * t + 0];
+        ctx->counters.ext16 += h[4 * t + 1];
+        ctx->counters.columns += h[4 * t + 2];
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->counters.ms_pack = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+    ctx->counters.ms_align = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
+    ctx->counters.ms_total_device = ms;
+    return TDB_OK;
+}
+
+int run_reduce_device(tdb_ctx *ctx, const tdb_trio_locus *dloci, size_t n_loci, const int32_t *dscores, double q,
+                      int is_duo, tdb_allele_out *dout, uint8_t *dmask) {
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[3], s));
+    if (n_loci) {
+        const unsigned threads = 128, blocks = (unsigned)((n_loci + threads - 1) / threads);
+        k_reduce<<<blocks, threads, 0, s>>>(dloci, (uint32_t)n_loci, dscores, q, is_duo, dout, dmask);
+        CK(cudaGetLastError());
+        ctx->counters.kernel_launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+    ctx->counters.ms_reduce = ms;
+    ctx->counters.ms_total_device += ms;
+    return TDB_OK;
+}
+
+int upload(tdb_ctx *ctx, DevBuf &buf, const void *src, size_t bytes, size_t pad = 0) {
+    ENSURE(buf, bytes + pad + 1);
+    if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (pad) CK(cudaMemsetAsync((uint8_t *)buf.p + bytes, 0, pad, ctx->stream));
+    return TDB_OK;
+}
+#define UPLOAD(buf, src, bytes, pad)                            \
+    do {                                                        \
+        int r_ = upload(ctx, (buf), (src), (bytes), (pad));     \
+        if (r_ != TDB_OK) return r_;                            \
+    } while (0)
+
+int validate_common(tdb_ctx *ctx, const void *blob, const void *off, const void *len, const void *pp, const void *pt,
+                    size_t n_seqs, size_t n_pairs, const void *out_score) {
+    if (!ctx) return TDB_E_INVALID;
+    ctx->err.clear();
+    if ((n_seqs && (!off || !len)) || (n_pairs && (!pp || !pt || !out_score)) || (n_pairs && !n_seqs))
+        return fail(ctx, TDB_E_INVALID, "null pointer argument");
+    (void)blob;
+    return TDB_OK;
+}
+
+int host_align_common(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
+                      const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern, const uint32_t *pair_text,
+                      size_t n_pairs, DevBatch &b) {
+    int r = check_sizes(ctx, blob_bytes, n_seqs, n_pairs);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->dev));
+    UPLOAD(ctx->blob, seq_blob, blob_bytes, 32);
+    UPLOAD(ctx->seq_off, seq_off, n_seqs * 8, 0);
+    UPLOAD(ctx->seq_len, seq_len, n_seqs * 4, 0);
+    UPLOAD(ctx->pair_p, pair_pattern, n_pairs * 4, 0);
+    UPLOAD(ctx->pair_t, pair_text, n_pairs * 4, 0);
+    ENSURE(ctx->score, n_pairs * 4 + 4);
+    ENSURE(ctx->status, n_pairs * 4 + 4);
+    ENSURE(ctx->penalty, n_pairs * 4 + 4);
+    memset(&b, 0, sizeof(b));
+    b.blob = (const uint8_t *)ctx->blob.p, b.blob_bytes = blob_bytes;
+    b.seq_off = (const uint64_t *)ctx->seq_off.p, b.seq_len = (const uint32_t *)ctx->seq_len.p, b.n_seqs = n_seqs;
+    b.pp = (const uint32_t *)ctx->pair_p.p, b.pt = (const uint32_t *)ctx->pair_t.p, b.n_pairs = n_pairs;
+    b.score = (int32_t *)ctx->score.p, b.status = (int32_t *)ctx->status.p, b.penalty = (int32_t *)ctx->penalty.p;
+    return TDB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void tdb_default_config(tdb_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->penalties = {8, 4, 2, 24, 1};
+    cfg->heuristic = {TDB_HEURISTIC_WFADAPTIVE, 10, 50, 1};
+    cfg->clip_len = 50;
+}
+
+int tdb_abi_version(void) { return TDB_ABI_VERSION; }
+
+int tdb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int check_config(tdb_ctx *ctx, const tdb_penalties &pn, const tdb_heuristic &h, int clip) {
+    if (pn.mismatch < 1 || pn.gap_opening1 < 0 || pn.gap_extension1 < 1 || pn.gap_opening2 < 0 ||
+        pn.gap_extension2 < 1)
+        return fail(ctx, TDB_E_INVALID, "penalties must be positive");
+    const int scope = std::max(pn.mismatch, std::max(pn.gap_opening1 + pn.gap_extension1,
+                                                     pn.gap_opening2 + pn.gap_extension2)) + 1;
+    if (scope > MS || pn.gap_extension1 + 1 > GS || pn.gap_extension2 + 1 > GS)
+        return fail(ctx, TDB_E_UNSUPPORTED,
+                    "penalties outside kernel ring sizes (need max(x,o1+e1,o2+e2) < %d and e1,e2 < %d)", MS, GS);
+    if (h.kind != TDB_HEURISTIC_NONE && h.kind != TDB_HEURISTIC_WFADAPTIVE)
+        return fail(ctx, TDB_E_UNSUPPORTED, "only Heuristic::None and Heuristic::WFadaptive are implemented");
+    if (h.kind == TDB_HEURISTIC_WFADAPTIVE && (h.min_wavefront_length < 1 || h.steps_between_cutoffs < 1))
+        return fail(ctx, TDB_E_INVALID, "bad wf-adaptive parameters");
+    if (clip < 0) return fail(ctx, TDB_E_INVALID, "clip_len must be >= 0");
+    return TDB_OK;
+}
+
+int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
+    tdb_ctx *ctx = nullptr; // CK() reports into the thread-local slot while ctx is null
+    if (!cfg || !out) return fail(nullptr, TDB_E_INVALID, "null argument");
+    *out = nullptr;
+    int r = check_config(nullptr, cfg->penalties, cfg->heuristic, cfg->clip_len);
+    if (r) return r;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, TDB_E_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    if (cfg->device_id < 0 || cfg->device_id >= ndev)
+        return fail(nullptr, TDB_E_INVALID, "device_id %d out of range (%d devices)", cfg->device_id, ndev);
+    CK(cudaSetDevice(cfg->device_id));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device_id));
+    if (prop.major != 10)
+        return fail(nullptr, TDB_E_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", cfg->device_id,
+                    prop.major, prop.minor);
+    tdb_ctx *c = new tdb_ctx();
+    c->cfg = *cfg;
+    c->dev = cfg->device_id;
+    c->sm_count = prop.multiProcessorCount;
+    memset(&c->counters, 0, sizeof(c->counters));
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    const size_t smem = sizeof(T0Smem) * T0_WARPS;
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_align_tier0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_align_tier0, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int occ = 0;
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_align_tier0, T0_WARPS * 32, smem);
+    if (e != cudaSuccess || occ < 1) {
+        int code = fail(nullptr, TDB_E_CUDA, "context setup failed: %s (occupancy %d)", cudaGetErrorString(e), occ);
+        tdb_destroy(c);
+        return code;
+    }
+    c->t0_ctas_per_sm = occ;
+    *out = c;
+    return TDB_OK;
+}
+
+void tdb_destroy(tdb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->woff, &c->packed, &c->seq_flag, &c->pair_p, &c->pair_t,
+                      &c->score, &c->status, &c->penalty, &c->todo_a, &c->todo_b, &c->ctrl, &c->cub_tmp, &c->loci,
+                      &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
+                      &c->scratch[1]};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 6; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *tdb_last_error(const tdb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tdb_set_clip_len(tdb_ctx *ctx, int32_t clip_len) {
+    if (!ctx) return TDB_E_INVALID;
+    if (clip_len < 0) return fail(ctx, TDB_E_INVALID, "clip_len must be >= 0");
+    ctx->cfg.clip_len = clip_len;
+    return TDB_OK;
+}
+
+int tdb_set_heuristic(tdb_ctx *ctx, const tdb_heuristic *h) {
+    if (!ctx || !h) return TDB_E_INVALID;
+    int r = check_config(ctx, ctx->cfg.penalties, *h, ctx->cfg.clip_len);
+    if (r) return r;
+    ctx->cfg.heuristic = *h;
+    return TDB_OK;
+}
+
+int tdb_set_count_work(tdb_ctx *ctx, int32_t on) {
+    if (!ctx) return TDB_E_INVALID;
+    ctx->count_work = on != 0;
+    return TDB_OK;
+}
+
+int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out) {
+    if (!ctx || !out) return TDB_E_INVALID;
+    *out = ctx->counters;
+    return TDB_OK;
+}
+
+int tdb_align_batch(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
+                    const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern, const uint32_t *pair_text,
+                    size_t n_pairs, int32_t *out_score, int32_t *out_status) {
+    int r = validate_common(ctx, seq_blob, seq_off, seq_len, pair_pattern, pair_text, n_seqs, n_pairs, out_score);
+    if (r) return r;
+    DevBatch b;
+    r = host_align_common(ctx, seq_blob, blob_bytes, seq_off, seq_len, n_seqs, pair_pattern, pair_text, n_pairs, b);
+    if (r) return r;
+    r = run_align_device(ctx, b, false);
+    if (r) return r;
+    if (n_pairs) {
+        CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_status) CK(cudaMemcpyAsync(out_status, b.status, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return TDB_OK;
+}
+
+int tdb_align_batch_device(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
+                           const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern,
+                           const uint32_t *pair_text, size_t n_pairs, int32_t *out_score, int32_t *out_status) {
+    int r = validate_common(ctx, seq_blob, seq_off, seq_len, pair_pattern, pair_text, n_seqs, n_pairs, out_score);
+    if (r) return r;
+    r = check_sizes(ctx, blob_bytes, n_seqs, n_pairs);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->dev));
+    DevBatch b;
+    memset(&b, 0, sizeof(b));
+    b.blob = seq_blob, b.blob_bytes = blob_bytes, b.seq_off = seq_off, b.seq_len = seq_len, b.n_seqs = n_seqs;
+    b.pp = pair_pattern, b.pt = pair_text, b.n_pairs = n_pairs;
+    b.score = out_score, b.status = out_status, b.penalty = nullptr;
+    return run_align_device(ctx, b, false);
+}
+
+int tdb_align_batch_cigar(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
+                          const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern,
+                          const uint32_t *pair_text, size_t n_pairs, int32_t *out_score, int32_t *out_status,
+                          int32_t *out_penalty, uint8_t *cigar_buf, const uint64_t *cigar_off, uint32_t *cigar_len) {
+    int r = validate_common(ctx, seq_blob, seq_off, seq_len, pair_pattern, pair_text, n_seqs, n_pairs, out_score);
+    if (r) return r;
+    if (n_pairs && (!cigar_buf || !cigar_off || !cigar_len)) return fail(ctx, TDB_E_INVALID, "null cigar argument");
+    DevBatch b;
+    r = host_align_common(ctx, seq_blob, blob_bytes, seq_off, seq_len, n_seqs, pair_pattern, pair_text, n_pairs, b);
+    if (r) return r;
+    // size of the cigar area = max(cigar_off[j] + plen + tlen)
+    size_t total = 0;
+    for (size_t j = 0; j < n_pairs; ++j) {
+        if (pair_pattern[j] >= n_seqs || pair_text[j] >= n_seqs) return fail(ctx, TDB_E_INVALID, "pair index out of range");
+        total = std::max<size_t>(total, cigar_off[j] + seq_len[pair_pattern[j]] + seq_len[pair_text[j]]);
+    }
+    ENSURE(ctx->cigar, total + 16);
+    UPLOAD(ctx->cigar_off, cigar_off, n_pairs * 8, 0);
+    ENSURE(ctx->cigar_len, n_pairs * 4 + 4);
+    b.cigar_buf = (uint8_t *)ctx->cigar.p, b.cigar_off = (const uint64_t *)ctx->cigar_off.p;
+    b.cigar_len = (uint32_t *)ctx->cigar_len.p;
+    r = run_align_device(ctx, b, true);
+    if (r) return r;
+    if (n_pairs) {
+        CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_status) CK(cudaMemcpyAsync(out_status, b.status, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_penalty) CK(cudaMemcpyAsync(out_penalty, b.penalty, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(cigar_buf, b.cigar_buf, total, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(cigar_len, b.cigar_len, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return TDB_OK;
+}
+
+static int reduce_host(tdb_ctx *ctx, int is_duo, const tdb_trio_locus *loci, size_t n_loci, const int32_t *scores,
+                       size_t n_scores, double q, tdb_allele_out *out, uint8_t *denovo_mask) {
+    if (!ctx) return TDB_E_INVALID;
+    ctx->err.clear();
+    if (n_loci && (!loci || !out || (n_scores && !scores))) return fail(ctx, TDB_E_INVALID, "null pointer argument");
+    if (n_loci >= 0xffffffffull) return fail(ctx, TDB_E_UNSUPPORTED, "too many loci");
+    CK(cudaSetDevice(ctx->dev));
+    UPLOAD(ctx->loci, loci, n_loci * sizeof(tdb_trio_locus), 0);
+    UPLOAD(ctx->scores_in, scores, n_scores * 4, 0);
+    ENSURE(ctx->aout, n_loci * 2 * sizeof(tdb_allele_out) + 16);
+    ENSURE(ctx->mask, n_scores + 16);
+    CK(cudaMemsetAsync(ctx->aout.p, 0, n_loci * 2 * sizeof(tdb_allele_out), ctx->stream));
+    CK(cudaMemsetAsync(ctx->mask.p, 0, n_scores + 16, ctx->stream));
+    memset(&ctx->counters, 0, sizeof(ctx->counters));
+    int r = run_reduce_device(ctx, (const tdb_trio_locus *)ctx->loci.p, n_loci, (const int32_t *)ctx->scores_in.p, q,
+                              is_duo, (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p);
+    if (r) return r;
+    if (n_loci) CK(cudaMemcpyAsync(out, ctx->aout.p, n_loci * 2 * sizeof(tdb_allele_out), cudaMemcpyDeviceToHost, ctx->stream));
+    if (denovo_mask && n_scores) CK(cudaMemcpyAsync(denovo_mask, ctx->mask.p, n_scores, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDB_OK;
+}
+
+int tdb_trio_reduce(tdb_ctx *ctx, const tdb_trio_locus *loci, size_t n_loci, const int32_t *scores, size_t n_scores,
+                    double parent_quantile, tdb_allele_out *out, uint8_t *denovo_mask) {
+    return reduce_host(ctx, 0, loci, n_loci, scores, n_scores, parent_quantile, out, denovo_mask);
+}
+int tdb_duo_reduce(tdb_ctx *ctx, const tdb_trio_locus *loci, size_t n_loci, const int32_t *scores, size_t n_scores,
+                   double parent_quantile, tdb_allele_out *out, uint8_t *denovo_mask) {
+    return reduce_host(ctx, 1, loci, n_loci, scores, n_scores, parent_quantile, out, denovo_mask);
+}
+
+static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
+                       const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern, const uint32_t *pair_text,
+                       size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci, double q, tdb_allele_out *out,
+                       int32_t *out_score, uint8_t *denovo_mask) {
+    int32_t dummy = 0;
+    int r = validate_common(ctx, seq_blob, seq_off, seq_len, pair_pattern, pair_text, n_seqs, n_pairs, &dummy);
+    if (r) return r;
+    if (n_loci && (!loci || !out)) return fail(ctx, TDB_E_INVALID, "null pointer argument");
+    if (n_loci >= 0xffffffffull) return fail(ctx, TDB_E_UNSUPPORTED, "too many loci");
+    DevBatch b;
+    r = host_align_common(ctx, seq_blob, blob_bytes, seq_off, seq_len, n_seqs, pair_pattern, pair_text, n_pairs, b);
+    if (r) return r;
+    UPLOAD(ctx->loci, loci, n_loci * sizeof(tdb_trio_locus), 0);
+    ENSURE(ctx->aout, n_loci * 2 * sizeof(tdb_allele_out) + 16);
+    ENSURE(ctx->mask, n_pairs + 16);
+    CK(cudaMemsetAsync(ctx->aout.p, 0, n_loci * 2 * sizeof(tdb_allele_out), ctx->stream));
+    CK(cudaMemsetAsync(ctx->mask.p, 0, n_pairs + 16, ctx->stream));
+    r = run_align_device(ctx, b, false);
+    if (r) return r;
+    r = run_reduce_device(ctx, (const tdb_trio_locus *)ctx->loci.p, n_loci, b.score, q, is_duo,
+                          (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p);
+    if (r) return r;
+    if (n_loci) CK(cudaMemcpyAsync(out, ctx->aout.p, n_loci * 2 * sizeof(tdb_allele_out), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_score && n_pairs) CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (denovo_mask && n_pairs) CK(cudaMemcpyAsync(denovo_mask, ctx->mask.p, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDB_OK;
+}
+
+int tdb_trio_batch(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
+                   const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern, const uint32_t *pair_text,
+                   size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci, double parent_quantile,
+                   tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
+    return assess_host(ctx, 0, seq_blob, blob_bytes, seq_off, seq_len, n_seqs, pair_pattern, pair_text, n_pairs, loci,
+                       n_loci, parent_quantile, out, out_score, denovo_mask);
+}
+int tdb_duo_batch(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
+                  const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern, const uint32_t *pair_text,
+                  size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci, double parent_quantile,
+                  tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
+    return assess_host(ctx, 1, seq_blob, blob_bytes, seq_off, seq_len, n_seqs, pair_pattern, pair_text, n_pairs, loci,
+                       n_loci, parent_quantile, out, out_score, denovo_mask);
+}
+
+int tdb_assess_batch_device(tdb_ctx *ctx, int32_t is_duo, const uint8_t *seq_blob, size_t blob_bytes,
+                            const uint64_t *seq_off, const uint32_t *seq_len, size_t n_seqs,
+                            const uint32_t *pair_pattern, const uint32_t *pair_text, size_t n_pairs,
+                            const tdb_trio_locus *loci, size_t n_loci, double parent_quantile, tdb_allele_out *out,
+                            int32_t *out_score, uint8_t *denovo_mask) {
+    int32_t dummy = 0;
+    int r = validate_common(ctx, seq_blob, seq_off, seq_len, pair_pattern, pair_text, n_seqs, n_pairs, &dummy);
+    if (r) return r;
+    if (n_loci && (!loci || !out)) return fail(ctx, TDB_E_INVALID, "null pointer argument");
+    r = check_sizes(ctx, blob_bytes, n_seqs, n_pairs);
+    if (r) return r;
+    CK(cudaSetDevice(ctx->dev));
+    int32_t *dscore = out_score;
+    if (!dscore) {
+        ENSURE(ctx->score, n_pairs * 4 + 4);
+        dscore = (int32_t *)ctx->score.p;
+    }
+    DevBatch b;
+    memset(&b, 0, sizeof(b));
+    b.blob = seq_blob, b.blob_bytes = blob_bytes, b.seq_off = seq_off, b.seq_len = seq_len, b.n_seqs = n_seqs;
+    b.pp = pair_pattern, b.pt = pair_text, b.n_pairs = n_pairs;
+    b.score = dscore, b.status = nullptr, b.penalty = nullptr;
+    r = run_align_device(ctx, b, false);
+    if (r) return r;
+    return run_reduce_device(ctx, loci, n_loci, dscore, parent_quantile, is_duo, out, denovo_mask);
+}
+
+int tdb_align_end_to_end(tdb_ctx *ctx, const uint8_t *pattern, int32_t pattern_len, const uint8_t *text,
+                         int32_t text_len) {
+    if (!ctx) return TDB_E_INVALID;
+    ctx->err.clear();
+    if (pattern_len < 0 || text_len < 0 || (pattern_len && !pattern) || (text_len && !text))
+        return fail(ctx, TDB_E_INVALID, "bad sequence argument");
+    std::vector<uint8_t> blob((size_t)pattern_len + (size_t)text_len);
+    if (pattern_len) memcpy(blob.data(), pattern, (size_t)pattern_len);
+    if (text_len) memcpy(blob.data() + pattern_len, text, (size_t)text_len);
+    const uint64_t off[2] = {0, (uint64_t)pattern_len};
+    const uint32_t len[2] = {(uint32_t)pattern_len, (uint32_t)text_len};
+    const uint32_t pp = 0, pt = 1;
+    const uint64_t coff = 0;
+    int32_t score = 0, status = TDB_STATUS_UNATTAINABLE, pen = INT32_MIN;
+    uint32_t clen = 0;
+    ctx->last_cigar.assign(blob.size() + 1, 0);
+    const int saved_clip = ctx->cfg.clip_len;
+    int r = tdb_align_batch_cigar(ctx, blob.data(), blob.size(), off, len, 2, &pp, &pt, 1, &score, &status, &pen,
+                                  ctx->last_cigar.data(), &coff, &clen);
+    ctx->cfg.clip_len = saved_clip;
+    if (r) {
+        ctx->last_status = TDB_STATUS_UNATTAINABLE, ctx->last_penalty = INT32_MIN, ctx->last_cigar.clear();
+        return r;
+    }
+    ctx->last_cigar.resize(status == 0 ? clen : 0);
+    ctx->last_status = status;
+    ctx->last_penalty = pen;
+    return status;
+}
+
+int32_t tdb_score(const tdb_ctx *ctx) {
+    if (!ctx || ctx->last_status != 0) return INT32_MIN;
+    return -ctx->last_penalty;
+}
+
+const uint8_t *tdb_cigar_ops(const tdb_ctx *ctx, int32_t *len) {
+    if (len) *len = ctx ? (int32_t)ctx->last_cigar.size() : 0;
+    return ctx ? ctx->last_cigar.data() : nullptr;
+}
+
+// src/aligner.rs:320-357: pure re-scoring of the CIGAR the device produced (host string scan, as the
+// Rust side of the reference does over wfa2's cigar_t buffer).
+int32_t tdb_cigar_score_clipped(const tdb_ctx *ctx, int32_t flank_len) {
+    if (!ctx) return 0;
+    const tdb_penalties &pn = ctx->cfg.penalties;
+    const long begin = flank_len, end = (long)ctx->last_cigar.size() - flank_len;
+    int score = 0, oplen = 0;
+    uint8_t last = 0;
+    auto cost = [&](uint8_t op, int len) {
+        if (op == 'M') return 0;
+        if (op == 'X') return len * pn.mismatch;
+        return std::min(pn.gap_opening1 + pn.gap_extension1 * len, pn.gap_opening2 + pn.gap_extension2 * len);
+    };
+    for (long i = begin; i < end; ++i) {
+        const uint8_t cur = ctx->last_cigar[(size_t)i];
+        if (last && cur != last) score -= cost(last, oplen), oplen = 0;
+        last = cur, ++oplen;
+    }
+    if (last) score -= cost(last, oplen);
+    return score;
+}
+
+void *tdb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void tdb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+} // extern "C"

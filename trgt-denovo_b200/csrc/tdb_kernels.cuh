@@ -1,0 +1,454 @@
+// tdb_kernels.cuh -- kernels of the hot path: sequence packing, tiered WFA alignment, fused reduction.
+#pragma once
+#include "tdb_wfa.cuh"
+
+#include "../../include/trgt_denovo_b200.h"
+
+namespace tdb {
+
+// ------------------------------------------------------------------------------------------------
+// Packing: raw ASCII -> 2-bit words (the role north_star gives locus.rs/read.rs, done at HBM speed).
+// One warp per sequence, lane j builds word j (16 bases).  A sequence containing any byte outside
+// {A,C,G,T} is flagged; pairs touching a flagged sequence take the byte-compare path so that raw byte
+// equality (N==N, case-sensitive) is preserved exactly as WFA2 sees it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nwords_of(uint32_t len) { return (len + 15u) / 16u + 1u; }
+
+struct NWordsOp {
+    const uint32_t *len;
+    __host__ __device__ uint32_t operator()(uint32_t i) const { return (len[i] + 15u) / 16u + 1u; }
+};
+
+__device__ __forceinline__ uint32_t pack4(uint32_t w) { // 4 ASCII bytes -> 8 bits
+    const uint32_t c = (w >> 1) & 0x03030303u;
+    return (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu;
+}
+__device__ __forceinline__ uint32_t acgt_mask4(uint32_t w) { // 0xff per byte that is one of ACGT
+    return __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) |
+           __vcmpeq4(w, 0x54545454u);
+}
+
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, size_t blob_bytes,
+                                              const uint64_t *__restrict__ seq_off,
+                                              const uint32_t *__restrict__ seq_len,
+                                              const uint32_t *__restrict__ woff, uint32_t n_seqs,
+                                              uint32_t *__restrict__ packed, uint8_t *__restrict__ seq_flag) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp0; i < n_seqs; i += nwarps) {
+        const uint32_t len = seq_len[i];
+        const uint64_t off = seq_off[i];
+        const uint32_t nw = nwords_of(len);
+        uint32_t *dst = packed + woff[i];
+        bool bad = false;
+        for (uint32_t j = lane; j < nw; j += 32) {
+            const uint32_t base = j * 16u;
+            uint32_t word = 0;
+            if (base < len) {
+                const uint32_t cnt = min(16u, len - base);
+                const uint8_t *src = blob + off + base;
+                uint32_t q[4];
+                if (off + base + 20 <= blob_bytes) { // aligned word loads + byte funnel shift
+                    const uintptr_t a = (uintptr_t)src;
+                    const uint32_t *ap = (const uint32_t *)(a & ~(uintptr_t)3);
+                    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+                    uint32_t r[5];
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) r[t] = __ldg(ap + t);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) q[t] = __funnelshift_r(r[t], r[t + 1], sh);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        uint32_t w = 0;
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t bi = (uint32_t)(t * 4 + u);
+                            if (bi < cnt) w |= (uint32_t)src[bi] << (8 * u);
+                        }
+                        q[t] = w;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int rem = (int)cnt - 4 * t; // bytes of this quad that belong to the sequence
+                    const uint32_t need = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
+                    bad |= (~acgt_mask4(q[t]) & need) != 0;
+                    word |= pack4(q[t] & need) << (8 * t);
+                }
+            }
+            dst[j] = word;
+        }
+        const unsigned any_bad = __ballot_sync(TDB_FULL, bad);
+        if (lane == 0) seq_flag[i] = any_bad ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Alignment tiers.  Persistent warps pull pairs from a device-side counter (work per pair spans three
+// orders of magnitude, so static assignment would leave SMs idle).
+// ------------------------------------------------------------------------------------------------
+struct AlignParams {
+    Penalties pn;
+    Heur heur;
+    int clip;
+    const uint32_t *packed;
+    const uint32_t *woff;
+    const uint8_t *seq_flag;
+    const uint8_t *blob;
+    const uint64_t *seq_off;
+    const uint32_t *seq_len;
+    const uint32_t *pair_p;
+    const uint32_t *pair_t;
+    const uint32_t *todo;        // pair ids to process (nullptr: 0..n_items-1)
+    const unsigned *n_items_ptr; // device-side count (nullptr: n_items)
+    unsigned n_items;
+    unsigned *work_counter;
+    uint32_t *next_todo; // pairs this tier could not finish (nullptr on the last tier)
+    unsigned *next_count;
+    int32_t *out_score;
+    int32_t *out_status;
+    int32_t *out_penalty;
+    uint8_t *cigar_buf;
+    const uint64_t *cigar_off;
+    uint32_t *cigar_len;
+    unsigned long long *counters; // cells, ext16, columns, pairs finished by this launch
+    uint8_t *scratch;             // global tiers: per-warp slices
+    size_t scratch_stride;
+    int wlog2, s_cap, ops_cap;
+    unsigned prov_cap;
+};
+
+constexpr int T0_WLOG2 = 6;
+constexpr int T0_W = 1 << T0_WLOG2;
+constexpr int T0_SCAP = 128;
+constexpr int T0_PROV = 2048;
+constexpr int T0_WARPS = 4;
+constexpr int T0_MAXLEN = 8000; // int16 offsets
+constexpr int WORK_CHUNK = 8;
+
+struct __align__(16) T0Smem {
+    int16_t M[MS * T0_W];
+    int16_t G[4 * GS * T0_W];
+    int2 mmeta[MS];
+    int2 gmeta[4 * GS];
+    int16_t step_lo[T0_SCAP];
+    uint16_t step_base[T0_SCAP];
+    uint8_t prov[T0_PROV];
+};
+
+__device__ __forceinline__ void flush_counts(const AlignParams &p, const WorkCount &wc,
+                                             unsigned long long lane_ext16, unsigned long long done, int lane) {
+    for (int o = 16; o; o >>= 1) lane_ext16 += __shfl_xor_sync(TDB_FULL, lane_ext16, o);
+    if (lane == 0 && p.counters) {
+        atomicAdd(p.counters + 0, wc.cells);
+        atomicAdd(p.counters + 1, lane_ext16);
+        atomicAdd(p.counters + 2, wc.columns);
+        atomicAdd(p.counters + 3, done);
+    }
+}
+
+__device__ __forceinline__ void defer_pair(const AlignParams &p, uint32_t idx, int lane) {
+    if (lane == 0) {
+        if (p.next_todo) {
+            const unsigned j = atomicAdd(p.next_count, 1u);
+            p.next_todo[j] = idx;
+        } else {
+            p.out_score[idx] = 0;
+            if (p.out_status) p.out_status[idx] = TDB_STATUS_OOM;
+            if (p.out_penalty) p.out_penalty[idx] = INT32_MIN;
+            if (p.cigar_len) p.cigar_len[idx] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(T0_WARPS * 32) k_align_tier0(const AlignParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    T0Smem &sm = reinterpret_cast<T0Smem *>(smem_raw)[wid];
+    Storage<int16_t, int16_t, uint16_t> st;
+    st.M = sm.M, st.G = sm.G, st.mmeta = sm.mmeta, st.gmeta = sm.gmeta;
+    st.step_lo = sm.step_lo, st.step_base = sm.step_base, st.prov = sm.prov;
+    st.ops = reinterpret_cast<uint8_t *>(sm.M);
+    st.wlog2 = T0_WLOG2, st.s_cap = T0_SCAP, st.ops_cap = (int)sizeof(sm.M), st.prov_cap = T0_PROV;
+    const unsigned n_items = p.n_items_ptr ? *p.n_items_ptr : p.n_items;
+    WorkCount wc = {0, 0, 0};
+    unsigned long long lane_ext16 = 0, done = 0;
+    for (;;) {
+        unsigned b = 0;
+        if (lane == 0) b = atomicAdd(p.work_counter, (unsigned)WORK_CHUNK);
+        b = __shfl_sync(TDB_FULL, b, 0);
+        if (b >= n_items) break;
+        const unsigned e = min(b + WORK_CHUNK, n_items);
+        for (unsigned it = b; it < e; ++it) {
+            const uint32_t idx = p.todo ? p.todo[it] : it;
+            const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
+            const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
+            if ((p.seq_flag[ip] | p.seq_flag[jt]) || n > T0_MAXLEN || m > T0_MAXLEN) {
+                defer_pair(p, idx, lane);
+                continue;
+            }
+            SeqView P = {p.packed + p.woff[ip], nullptr, n}, T = {p.packed + p.woff[jt], nullptr, m};
+            int pen = 0, clipped = 0;
+            const int r = wfa_align_warp<int16_t, int16_t, uint16_t, false>(
+                P, T, p.pn, p.heur, p.clip, st, lane, pen, clipped, wc, lane_ext16, nullptr, nullptr);
+            __syncwarp();
+            if (r == WFA_OK) {
+                ++done;
+                if (lane == 0) {
+                    p.out_score[idx] = clipped;
+                    if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
+                    if (p.out_penalty) p.out_penalty[idx] = pen;
+                }
+            } else {
+                defer_pair(p, idx, lane);
+            }
+        }
+    }
+    flush_counts(p, wc, lane_ext16, done, lane);
+}
+
+// Global-scratch tier: int32 offsets, runtime ring width, optional CIGAR output.
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t global_tier_stride(int wlog2, int s_cap, int ops_cap, unsigned prov_cap) {
+    const size_t W = (size_t)1 << wlog2;
+    return align16(MS * W * 4) + align16(4 * GS * W * 4) + align16(MS * 8) + align16(4 * GS * 8) +
+           align16((size_t)s_cap * 4) * 2 + align16((size_t)ops_cap) + align16((size_t)prov_cap);
+}
+
+template <bool WANT_CIGAR>
+__global__ void __launch_bounds__(128) k_align_global(const AlignParams p) {
+    const int lane = threadIdx.x & 31;
+    const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint8_t *base = p.scratch + gw * p.scratch_stride;
+    const size_t W = (size_t)1 << p.wlog2;
+    Storage<int32_t, int32_t, uint32_t> st;
+    st.M = reinterpret_cast<int32_t *>(base), base += align16(MS * W * 4);
+    st.G = reinterpret_cast<int32_t *>(base), base += align16(4 * GS * W * 4);
+    st.mmeta = reinterpret_cast<int2 *>(base), base += align16(MS * 8);
+    st.gmeta = reinterpret_cast<int2 *>(base), base += align16(4 * GS * 8);
+    st.step_lo = reinterpret_cast<int32_t *>(base), base += align16((size_t)p.s_cap * 4);
+    st.step_base = reinterpret_cast<uint32_t *>(base), base += align16((size_t)p.s_cap * 4);
+    st.ops = base, base += align16((size_t)p.ops_cap);
+    st.prov = base;
+    st.wlog2 = p.wlog2, st.s_cap = p.s_cap, st.ops_cap = p.ops_cap, st.prov_cap = p.prov_cap;
+    const unsigned n_items = p.n_items_ptr ? *p.n_items_ptr : p.n_items;
+    WorkCount wc = {0, 0, 0};
+    unsigned long long lane_ext16 = 0, done = 0;
+    for (;;) {
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(p.work_counter, 1u);
+        it = __shfl_sync(TDB_FULL, it, 0);
+        if (it >= n_items) break;
+        const uint32_t idx = p.todo ? p.todo[it] : it;
+        const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
+        const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
+        const bool bytes = (p.seq_flag[ip] | p.seq_flag[jt]) != 0;
+        SeqView P, T;
+        P.len = n, T.len = m;
+        P.w = bytes ? nullptr : p.packed + p.woff[ip];
+        T.w = bytes ? nullptr : p.packed + p.woff[jt];
+        P.b = p.blob + p.seq_off[ip];
+        T.b = p.blob + p.seq_off[jt];
+        int pen = 0, clipped = 0;
+        uint8_t *cig = WANT_CIGAR ? p.cigar_buf + p.cigar_off[idx] : nullptr;
+        uint32_t *cl = WANT_CIGAR ? p.cigar_len + idx : nullptr;
+        const int r = wfa_align_warp<int32_t, int32_t, uint32_t, WANT_CIGAR>(P, T, p.pn, p.heur, p.clip, st, lane,
+                                                                             pen, clipped, wc, lane_ext16, cig, cl);
+        __syncwarp();
+        if (r == WFA_OK) {
+            ++done;
+            if (lane == 0) {
+                p.out_score[idx] = clipped;
+                if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
+                if (p.out_penalty) p.out_penalty[idx] = pen;
+            }
+        } else {
+            defer_pair(p, idx, lane);
+        }
+    }
+    flush_counts(p, wc, lane_ext16, done, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused per-locus reduction (src/trio/denovo.rs:83-186, src/duo/denovo.rs:46-119, src/denovo.rs:68-129,
+// src/math.rs:82-155).  One thread per locus: the lists are a few dozen scores, the arithmetic is
+// integer counting plus a handful of IEEE f64 operations that must round exactly as the Rust code
+// does (explicit _rn intrinsics: no FMA contraction).
+// ------------------------------------------------------------------------------------------------
+__device__ inline int kth_smallest(const int32_t *xs, int n, int k) {
+    for (int i = 0; i < n; ++i) {
+        const int x = xs[i];
+        int less = 0, eq = 0;
+        for (int j = 0; j < n; ++j) {
+            const int y = xs[j];
+            less += y < x;
+            eq += y == x;
+        }
+        if (less <= k && k < less + eq) return x;
+    }
+    return 0;
+}
+
+// math::quantile on one list (src/math.rs:82-98); n > 0.
+__device__ inline double list_quantile(const int32_t *xs, int n, double q) {
+    const double index = __dmul_rn(q, __dsub_rn((double)n, 1.0));
+    const double fl = floor(index);
+    const long long lower = fl <= 0.0 ? 0 : (fl >= 9.0e18 ? (long long)9.0e18 : (long long)fl);
+    const long long upper = lower + 1;
+    if (upper >= (long long)n) {
+        int mx = xs[0];
+        for (int i = 1; i < n; ++i) mx = max(mx, xs[i]);
+        return (double)mx;
+    }
+    const double fraction = __dsub_rn(index, (double)lower);
+    const double a = (double)kth_smallest(xs, n, (int)lower), b = (double)kth_smallest(xs, n, (int)upper);
+    return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), fraction));
+}
+
+// get_top_other_score over lists [first, first+n_lists) (src/denovo.rs:93-101)
+__device__ inline bool top_other(const int32_t *scores, const uint32_t *off, int first, int n_lists, double q,
+                                 double &out) {
+    bool have = false;
+    double best = 0.0;
+    for (int l = 0; l < n_lists; ++l) {
+        const int n = (int)(off[first + l + 1] - off[first + l]);
+        if (n <= 0) continue;
+        const double v = list_quantile(scores + off[first + l], n, q);
+        if (!have || v >= best) best = v, have = true;
+    }
+    out = best;
+    return have;
+}
+
+// get_score_count_diff (src/denovo.rs:117-129)
+__device__ inline void count_diff(double top, const int32_t *a, int n, int &count, float &mean_diff) {
+    int c = 0;
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double x = (double)a[i];
+        if (x > top) ++c, sum = __dadd_rn(sum, x);
+    }
+    count = c;
+    mean_diff = c > 0 ? (float)fabs(__dsub_rn(__ddiv_rn(sum, (double)c), top)) : 0.0f;
+}
+
+__device__ inline int overlap_cov(double thr, const int32_t *a, int n) {
+    int c = 0;
+    for (int i = 0; i < n; ++i) c += ((double)a[i] >= thr);
+    return c;
+}
+
+__device__ inline double list_mean(const int32_t *s, uint32_t b, uint32_t e) {
+    if (e <= b) return -INFINITY;
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += (uint32_t)s[i]; // i32 sum (wrapping)
+    return __ddiv_rn((double)(int32_t)sum, (double)(e - b));
+}
+
+__device__ inline double list_median(const int32_t *a, int n) {
+    if (n == 0) return 1.7976931348623157e308; // unwrap_or(f64::MAX)
+    if (n & 1) return (double)kth_smallest(a, n, n / 2);
+    const int x = kth_smallest(a, n, n / 2 - 1), y = kth_smallest(a, n, n / 2);
+    return __ddiv_rn((double)(int32_t)((uint32_t)x + (uint32_t)y), 2.0);
+}
+
+__constant__ int8_t c_combs2[8][2] = {{0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 0}, {3, 0}, {2, 1}, {3, 1}};
+
+__global__ void __launch_bounds__(128) k_reduce(const tdb_trio_locus *__restrict__ loci, uint32_t n_loci,
+                                                const int32_t *__restrict__ scores, double q, int is_duo,
+                                                tdb_allele_out *__restrict__ out, uint8_t *__restrict__ mask) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_loci) return;
+    const tdb_trio_locus loc = loci[li];
+    const double F64_MIN = -1.7976931348623157e308;
+    double matrix[4][2];
+    for (int i = 0; i < 4; ++i) matrix[i][0] = matrix[i][1] = F64_MIN;
+    bool any_err = false;
+    tdb_allele_out o[2];
+    for (int c = 0; c < loc.n_child && c < 2; ++c) {
+        const uint32_t *off = loc.list_off[c];
+        tdb_allele_out &r = o[c];
+        r.denovo_coverage = 0, r.mean_diff_father = 0.f, r.mean_diff_mother = 0.f;
+        r.mother_overlap[0] = r.mother_overlap[1] = r.father_overlap[0] = r.father_overlap[1] = 0;
+        r.allele_origin = is_duo ? 5 : 4, r.denovo_status = 0, r.error = 0;
+        r.top_mother = r.top_father = r.child_median = 0.0;
+        r.mean_col[0] = r.mean_col[1] = r.mean_col[2] = r.mean_col[3] = 0.0;
+        const int32_t *own = scores + off[4];
+        const int nown = (int)(off[5] - off[4]);
+        double top_m = 0.0, top_f = 0.0;
+        const bool hm = top_other(scores, off, 0, loc.n_mother, q, top_m);
+        const bool hf = is_duo ? true : top_other(scores, off, 2, loc.n_father, q, top_f);
+        if (!hm || !hf) {
+            r.error = 1, any_err = true;
+            continue;
+        }
+        r.top_mother = top_m, r.top_father = top_f;
+        const double thr = is_duo ? top_m : fmax(top_m, top_f);
+        if (mask)
+            for (int i = 0; i < nown; ++i) mask[off[4] + i] = ((double)own[i] > thr) ? 1 : 0;
+        int cm = 0, cf = 0;
+        count_diff(top_m, own, nown, cm, r.mean_diff_mother);
+        if (!is_duo) count_diff(top_f, own, nown, cf, r.mean_diff_father);
+        r.denovo_coverage = is_duo ? cm : (top_m >= top_f ? cm : cf);
+        const double med = list_median(own, nown);
+        r.child_median = med;
+        for (int a = 0; a < loc.n_mother && a < 2; ++a)
+            r.mother_overlap[a] = overlap_cov(med, scores + off[a], (int)(off[a + 1] - off[a]));
+        if (!is_duo) {
+            for (int a = 0; a < loc.n_father && a < 2; ++a)
+                r.father_overlap[a] = overlap_cov(med, scores + off[2 + a], (int)(off[3 + a] - off[2 + a]));
+            matrix[0][c] = list_mean(scores, off[0], off[1]);
+            matrix[1][c] = loc.n_mother > 1 ? list_mean(scores, off[1], off[2]) : F64_MIN;
+            matrix[2][c] = list_mean(scores, off[2], off[3]);
+            matrix[3][c] = loc.n_father > 1 ? list_mean(scores, off[3], off[4]) : F64_MIN;
+            for (int i = 0; i < 4; ++i) r.mean_col[i] = matrix[i][c];
+        } else {
+            r.denovo_status = cm == 0 ? 0 : 4;
+        }
+    }
+    if (!is_duo && !any_err) {
+        double cs[8];
+        int idx[8], ncomb;
+        if (loc.n_child > 1) {
+            ncomb = 8;
+            for (int i = 0; i < 8; ++i) {
+                const double s = __dadd_rn(__dadd_rn(0.0, matrix[c_combs2[i][0]][0]), matrix[c_combs2[i][1]][1]);
+                cs[i] = s, idx[i] = i;
+            }
+        } else {
+            ncomb = 4;
+            for (int i = 0; i < 4; ++i) cs[i] = matrix[i][0], idx[i] = i;
+        }
+        for (int i = 1; i < ncomb; ++i) { // stable insertion sort, descending (sort_unstable_by on <= 8 items)
+            const double v = cs[i];
+            const int vi = idx[i];
+            int j = i - 1;
+            while (j >= 0 && cs[j] < v) cs[j + 1] = cs[j], idx[j + 1] = idx[j], --j;
+            cs[j + 1] = v, idx[j + 1] = vi;
+        }
+        const double comb_diff = fabs(__dsub_rn(cs[0], cs[1]));
+        for (int c = 0; c < loc.n_child && c < 2; ++c) {
+            tdb_allele_out &r = o[c];
+            if (comb_diff < 1.0) r.allele_origin = 4;
+            else r.allele_origin = loc.n_child > 1 ? c_combs2[idx[0]][c] : idx[0];
+            if (r.denovo_coverage == 0) r.denovo_status = 0;
+            else {
+                int plen = -1;
+                switch (r.allele_origin) {
+                case 0: plen = loc.mother_len[0]; break;
+                case 1: plen = loc.mother_len[1]; break;
+                case 2: plen = loc.father_len[0]; break;
+                case 3: plen = loc.father_len[1]; break;
+                default: break;
+                }
+                r.denovo_status = plen < 0 ? 4 : (plen < loc.child_len[c] ? 1 : (plen > loc.child_len[c] ? 2 : 3));
+            }
+        }
+    }
+    for (int c = 0; c < 2; ++c) {
+        if (c < loc.n_child) out[2 * (size_t)li + c] = o[c];
+    }
+}
+
+} // namespace tdb
