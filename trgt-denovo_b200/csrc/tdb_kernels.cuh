@@ -190,11 +190,14 @@ __global__ void __launch_bounds__(T0_WARPS * 32) k_align_tier0(const AlignParams
             }
             SeqView P = {p.packed + p.woff[ip], nullptr, n}, T = {p.packed + p.woff[jt], nullptr, m};
             int pen = 0, clipped = 0;
+            WorkCount wc1 = {0, 0, 0}; // work of this attempt: only counted when the tier finishes the pair
+            unsigned long long ext1 = 0;
             const int r = wfa_align_warp<int16_t, int16_t, uint16_t, false>(
-                P, T, p.pn, p.heur, p.clip, st, lane, pen, clipped, wc, lane_ext16, nullptr, nullptr);
+                P, T, p.pn, p.heur, p.clip, st, lane, pen, clipped, wc1, ext1, nullptr, nullptr);
             __syncwarp();
             if (r == WFA_OK) {
                 ++done;
+                wc.cells += wc1.cells, wc.columns += wc1.columns, lane_ext16 += ext1;
                 if (lane == 0) {
                     p.out_score[idx] = clipped;
                     if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
@@ -253,11 +256,14 @@ __global__ void __launch_bounds__(128) k_align_global(const AlignParams p) {
         int pen = 0, clipped = 0;
         uint8_t *cig = WANT_CIGAR ? p.cigar_buf + p.cigar_off[idx] : nullptr;
         uint32_t *cl = WANT_CIGAR ? p.cigar_len + idx : nullptr;
+        WorkCount wc1 = {0, 0, 0};
+        unsigned long long ext1 = 0;
         const int r = wfa_align_warp<int32_t, int32_t, uint32_t, WANT_CIGAR>(P, T, p.pn, p.heur, p.clip, st, lane,
-                                                                             pen, clipped, wc, lane_ext16, cig, cl);
+                                                                             pen, clipped, wc1, ext1, cig, cl);
         __syncwarp();
         if (r == WFA_OK) {
             ++done;
+            wc.cells += wc1.cells, wc.columns += wc1.columns, lane_ext16 += ext1;
             if (lane == 0) {
                 p.out_score[idx] = clipped;
                 if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
