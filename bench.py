@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py -- trio loci/s of the read<->allele alignment hot path on B200 (BASELINE.json metric).
+
+A step = one pass of the hot path (2-bit packing, tiered WFA alignment with on-device backtrace and
+clipped scoring, fused per-locus reduction) over the whole synthetic genome-wide trio assigned to
+this rank (configs[1]: 937k-locus catalog at 30x).  Loci are sharded by
+the host with no collective (weak scaling: every rank runs its own 937k-locus shard of an
+N x 937k-locus catalog).
+
+  value     loci/s with the inputs already resident in HBM (tdb_assess_batch_device), timed with the
+            CUDA events the library records on its launching stream, max over ranks
+  e2e       the same pass through the host-buffer C-ABI call (tdb_trio_batch): pinned host inputs,
+            H2D + kernels + D2H of the per-allele results inside the timed region
+  roofline  the dominant kernel (k_align_tier0): algorithmic HBM bytes and lane-int-ops per launch
+            (ops = 24*C + 8*E + 4*T, counted exactly on the device and checked
+            against the oracle in tests/) over its CUDA-event duration
+  cpu_baseline / --impl reference
+            the CPU oracle (scalar C restatement of the reference path, "port": the reference's own
+            Rust+WFA2-lib binary cannot be built here) on all host cores, on a bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+INT_OPS_PER_CELL, INT_OPS_PER_EXT, INT_OPS_PER_COL = 24, 8, 4
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, f in self.rows:
+            if len(f) < 9 or not (t0 - 0.1 <= ts <= t1 + 0.3):
+                continue
+            try:
+                sm.append(float(f[1])), smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_pass(tdo, batch, n_loci, clip, q, duo, threads):
+    """align + reduce of loci [0, n_loci) of `batch` on the CPU oracle; returns seconds."""
+    n_pairs = int(batch.meta[n_loci - 1].pair_end)
+    t0 = time.perf_counter()
+    scores, status, _ = tdo.align_batch(batch.blob, batch.seq_off, batch.seq_len, batch.pair_pattern[:n_pairs],
+                                        batch.pair_text[:n_pairs], clip, n_threads=threads)
+    tdo.assess_batch(batch.loci_ptr, n_loci, scores, q, duo=duo, n_threads=threads)
+    return time.perf_counter() - t0, n_pairs
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on all host threads, rank 0 only."""
+    if rank != 0:
+        return 0
+    import __graft_entry__ as entry
+    entry.build()
+    from importlib import import_module
+    from oracle import tdo
+    S = import_module("trgt_denovo_b200.synth")
+    threads = os.cpu_count() or 1
+    sample = min(args.loci, args.cpu_sample_loci)
+    params = S.config("duo_genome" if args.duo else "trio_genome")
+    batch = S.generate(params, 0, sample, threads)
+    for _ in range(args.warmup):
+        oracle_pass(tdo, batch, min(sample, 2000), args.clip, args.quantile, args.duo, threads)
+    times, n_pairs = [], 0
+    for _ in range(args.steps):
+        dt, n_pairs = oracle_pass(tdo, batch, sample, args.clip, args.quantile, args.duo, threads)
+        times.append(dt)
+    tot = sum(times)
+    val = sample * args.steps / tot
+    line = {
+        "impl": "reference", "metric": "trio_loci_per_sec" if not args.duo else "duo_loci_per_sec", "value": val,
+        "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "loci_per_step": sample,
+                   "pairs_per_step": n_pairs, "clip_len": args.clip},
+        "alignments_per_sec": n_pairs * args.steps / tot,
+        "cpu_baseline": {"value": val, "unit": "loci/s", "cores": threads, "kind": "port",
+                         "sample": f"first {sample} loci of the workload per step, {threads} threads; scalar C "
+                                   "restatement of the reference path (not WFA2-lib, which cannot be built here)"},
+        "e2e": {"value": val, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(args):
+    kind = "duo" if args.duo else "trio"
+    return (f"genome-wide synthetic {kind}, {args.loci} loci per GPU at 30x (SURVEY.md 8d config "
+            f"{'3' if args.duo else '2'}, seed 20250002), inputs larger than L2")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--loci", type=int, default=int(os.environ.get("TDB_BENCH_LOCI", 937000)))
+    ap.add_argument("--duo", action="store_true")
+    ap.add_argument("--clip", type=int, default=50)
+    ap.add_argument("--quantile", type=float, default=1.0)
+    ap.add_argument("--cpu-sample-loci", type=int, default=int(os.environ.get("TDB_BENCH_CPU_LOCI", 150000)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from importlib import import_module
+    import trgt_denovo_b200 as tdb
+    S = import_module("trgt_denovo_b200.synth")
+    B = import_module("trgt_denovo_b200.binding")
+    if tdb.device_count() == 0:
+        raise SystemExit("no CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = tdb.lib()
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+
+    # ---- workload: this rank's shard -----------------------------------------------------------------
+    threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    params = S.config("duo_genome" if args.duo else "trio_genome", pinned=1)
+    t0 = time.time()
+    batch = S.generate(params, rank * args.loci, (rank + 1) * args.loci, threads)
+    log(f"[rank {rank}] generated {batch.n_loci} loci, {batch.n_pairs} pairs, {batch.blob.size / 1e9:.2f} GB "
+        f"of reads in {time.time() - t0:.1f}s")
+    n_loci, n_pairs, n_seqs = batch.n_loci, batch.n_pairs, batch.n_seqs
+    ctx = tdb.Context(device_id=local_rank, clip_len=args.clip)
+    h = ctx._h
+
+    # ---- device-resident copies (plumbing via torch) ----------------------------------------------
+    def dev_copy(arr, pad=0):
+        t = torch.empty(arr.nbytes + pad, dtype=torch.uint8, device=dev)
+        t[:arr.nbytes].copy_(torch.from_numpy(arr.view(np.uint8)), non_blocking=False)
+        if pad:
+            t[arr.nbytes:].zero_()
+        return t
+    loci_np = np.frombuffer((C.c_uint8 * (C.sizeof(B.TrioLocus) * n_loci)).from_address(batch.loci_ptr), dtype=np.uint8)
+    d_blob, d_off, d_len = dev_copy(batch.blob, 64), dev_copy(batch.seq_off), dev_copy(batch.seq_len)
+    d_pp, d_pt, d_loci = dev_copy(batch.pair_pattern), dev_copy(batch.pair_text), dev_copy(loci_np)
+    d_out = torch.zeros(n_loci * 2 * C.sizeof(B.AlleleOut), dtype=torch.uint8, device=dev)
+    d_score = torch.zeros(n_pairs, dtype=torch.int32, device=dev)
+    d_mask = torch.zeros(n_pairs, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        r = L.tdb_assess_batch_device(h, int(args.duo), d_blob.data_ptr(), batch.blob.size, d_off.data_ptr(),
+                                      d_len.data_ptr(), n_seqs, d_pp.data_ptr(), d_pt.data_ptr(), n_pairs,
+                                      d_loci.data_ptr(), n_loci, args.quantile, d_out.data_ptr(), d_score.data_ptr(),
+                                      d_mask.data_ptr())
+        if r != 0:
+            raise RuntimeError(L.tdb_last_error(h).decode())
+        return ctx.counters()
+
+    h_out = (B.AlleleOut * (2 * n_loci))()
+    h_mask = np.zeros(n_pairs, dtype=np.uint8)
+
+    def step_host():
+        r = L.tdb_trio_batch if not args.duo else L.tdb_duo_batch
+        rc = r(h, batch.blob.ctypes.data, batch.blob.size, batch.seq_off.ctypes.data, batch.seq_len.ctypes.data,
+               n_seqs, batch.pair_pattern.ctypes.data, batch.pair_text.ctypes.data, n_pairs, batch.loci_ptr, n_loci,
+               args.quantile, C.cast(h_out, C.c_void_p), None, h_mask.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(L.tdb_last_error(h).decode())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    w0 = time.time()
+    dev_ms, t0_ms, pack_ms, red_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
+    cnt = None
+    for _ in range(args.steps):
+        cnt = step_device()
+        dev_ms += cnt.ms_total_device
+        t0_ms += cnt.ms_tier[0]
+        pack_ms += cnt.ms_pack
+        red_ms += cnt.ms_reduce
+        launches += cnt.kernel_launches
+    barrier()
+    w1 = time.time()
+    clocks = sampler.stop(w0, w1)
+    wall_ms = 1e3 * (w1 - w0)
+
+    # ---- end-to-end through the host-buffer C ABI ------------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier()
+    e0 = time.time()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.time() - e0
+    h2d = batch.blob.size + batch.seq_off.nbytes + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
+        batch.pair_text.nbytes + loci_np.nbytes
+    d2h = C.sizeof(h_out) + h_mask.nbytes
+
+    # ---- quick self-check of the step's result against the oracle (outside the timed regions) --------
+    check = None
+    if rank == 0:
+        from oracle import tdo
+        ncheck = min(n_loci, 300)
+        npc = int(batch.meta[ncheck - 1].pair_end)
+        want, _, _ = tdo.align_batch(batch.blob, batch.seq_off, batch.seq_len, batch.pair_pattern[:npc],
+                                     batch.pair_text[:npc], args.clip, n_threads=threads)
+        got = d_score[:npc].cpu().numpy()
+        check = bool((got == want).all())
+        if not check:
+            raise SystemExit("bench self-check failed: GPU scores differ from the oracle")
+
+    # ---- reduce over ranks -------------------------------------------------------------------------------
+    vals = torch.tensor([dev_ms, wall_ms, 1e3 * e2e_s], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(n_loci), float(n_pairs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max, e2e_ms_max = [float(x) for x in vals.tolist()]
+    tot_loci, tot_pairs = [float(x) for x in sums.tolist()]
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import tdo
+        allthreads = os.cpu_count() or 1
+        sample = min(n_loci, args.cpu_sample_loci)
+        oracle_pass(tdo, batch, min(sample, 2000), args.clip, args.quantile, args.duo, allthreads)
+        dt, np_s = oracle_pass(tdo, batch, sample, args.clip, args.quantile, args.duo, allthreads)
+        dt1, np_1 = oracle_pass(tdo, batch, min(sample, 20000), args.clip, args.quantile, args.duo, 1)
+        cpu_baseline = {"value": sample / dt, "unit": "loci/s", "cores": allthreads, "kind": "port",
+                        "sample": f"first {sample} loci of the workload ({np_s} pairs), {allthreads} threads, "
+                                  f"{dt:.1f}s; scalar C restatement of the reference path, not WFA2-lib",
+                        "alignments_per_sec": np_s / dt,
+                        "single_thread_loci_per_sec": min(sample, 20000) / dt1}
+
+    if rank == 0:
+        # roofline of the dominant kernel (tier 0), per launch, rank 0's shard
+        ops = INT_OPS_PER_CELL * cnt.cells + INT_OPS_PER_EXT * cnt.ext16 + INT_OPS_PER_COL * cnt.columns
+        t0_s = (t0_ms / args.steps) * 1e-3
+        clk = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        int_peak = n_sm * 128 * clk
+        algo_bytes = float(np.sum((batch.seq_len[batch.pair_pattern].astype(np.int64) + 3) // 4 +
+                                  (batch.seq_len[batch.pair_text].astype(np.int64) + 3) // 4) + 16 * n_pairs)
+        frac_t0 = float(cnt.tier_pairs[0]) / max(1, n_pairs)
+        roofline = {
+            "bound": "hbm", "kernel": "k_align_tier0", "achieved": algo_bytes * frac_t0 / t0_s / 1e9,
+            "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes * frac_t0 / t0_s / 1e9 / hbm_peak, "traffic": None,
+            "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
+            "note": "HBM is not the binding roofline for this integer DP (SURVEY.md 8d); see int_issue",
+            "int_issue": {"bound": "int32_issue", "achieved": ops / t0_s, "peak": int_peak, "unit": "lane-int-ops/s",
+                          "frac": ops / t0_s / int_peak,
+                          "peak_source": f"{n_sm} SM x 128 lanes x {clk / 1e6:.0f} MHz (clock observed under load)",
+                          "accounting": "24*C + 8*E + 4*T, C/E/T counted exactly on device (all tiers), "
+                                        "divided by the tier-0 kernel time"},
+            "kernel_ms": t0_ms / args.steps, "step_share": t0_ms / max(dev_ms, 1e-9),
+        }
+        line = {
+            "metric": "trio_loci_per_sec" if not args.duo else "duo_loci_per_sec",
+            "value": tot_loci * args.steps / (dev_ms_max * 1e-3), "unit": "loci/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "loci_per_gpu": n_loci, "pairs_per_gpu": n_pairs,
+                       "clip_len": args.clip, "parent_quantile": args.quantile, "sharding": f"loci x{world}, no collective",
+                       "l2": "inputs larger than L2 (no flush needed)"},
+            "alignments_per_sec": tot_pairs * args.steps / (dev_ms_max * 1e-3),
+            "gcups": batch.sum_nm * args.steps / (dev_ms * 1e-3) / 1e9,
+            "wall_ms_per_step": wall_ms_max / args.steps,
+            "e2e": {"value": tot_loci * args.steps / (e2e_ms_max * 1e-3), "unit": "loci/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms_max / args.steps,
+                    "alignments_per_sec": tot_pairs * args.steps / (e2e_ms_max * 1e-3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "breakdown_ms_per_step": {"pack": pack_ms / args.steps, "align_tier0": t0_ms / args.steps,
+                                      "align_tier1": cnt.ms_tier[1], "align_tier2": cnt.ms_tier[2],
+                                      "reduce": red_ms / args.steps},
+            "tier_pairs": [int(x) for x in cnt.tier_pairs],
+            "work": {"cells": int(cnt.cells), "ext16": int(cnt.ext16), "columns": int(cnt.columns)},
+            "self_check_vs_oracle": check,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -218,6 +218,7 @@ typedef struct {
     uint64_t columns;       /* T: CIGAR columns replayed */
     uint64_t kernel_launches;
     float ms_pack, ms_align, ms_reduce, ms_total_device; /* CUDA-event times of the last call */
+    float ms_tier[4]; /* per alignment tier (events on the launching stream) */
 } tdb_counters;
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 /* Enables exact C/E/T work counting inside the kernels (off by default: it costs atomics). */

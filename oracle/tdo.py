@@ -94,6 +94,8 @@ def lib():
                                       C.c_void_p]
         L.tdo_duo_assess.restype = None
         L.tdo_duo_assess.argtypes = L.tdo_trio_assess.argtypes
+        L.tdo_assess_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -215,3 +217,14 @@ def trio_assess(loc, scores, q=1.0, duo=False):
     fn = lib().tdo_duo_assess if duo else lib().tdo_trio_assess
     fn(C.byref(loc), scores.ctypes.data, q, out, mask.ctypes.data)
     return [out[c] for c in range(loc.n_child)], mask
+
+
+def assess_batch(loci_ptr, n_loci, scores, q=1.0, duo=False, n_threads=1):
+    """loci_ptr: address of an array of TrioLocus (same layout as tdb_trio_locus).
+    -> (AlleleOut array [2*n_loci], mask uint8[n_scores])"""
+    scores = np.ascontiguousarray(scores, dtype=np.int32)
+    out = (AlleleOut * (2 * max(1, n_loci)))()
+    mask = np.zeros(max(1, len(scores)), dtype=np.uint8)
+    lib().tdo_assess_batch(loci_ptr, n_loci, scores.ctypes.data, q, int(duo), int(n_threads),
+                           C.cast(out, C.c_void_p), mask.ctypes.data)
+    return out, mask

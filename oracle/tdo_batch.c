@@ -90,3 +90,47 @@ int tdo_align_batch(const uint8_t *blob, const uint64_t *seq_off, const uint32_t
     free(th);
     return 0;
 }
+
+/* Per-locus reductions for a whole batch (trio or duo), threaded over loci: the CPU side of
+ * tdb_trio_batch's second half, used as checker and cpu_baseline. */
+typedef struct {
+    const tdo_trio_locus *loci;
+    size_t n_loci;
+    const int32_t *scores;
+    double q;
+    int duo;
+    tdo_allele_out *out;
+    uint8_t *mask;
+    size_t *next;
+} rjob_t;
+
+static void *rworker(void *arg) {
+    rjob_t *j = (rjob_t *)arg;
+    for (;;) {
+        size_t b = __atomic_fetch_add(j->next, (size_t)1024, __ATOMIC_RELAXED);
+        if (b >= j->n_loci) break;
+        size_t e = b + 1024 < j->n_loci ? b + 1024 : j->n_loci;
+        for (size_t i = b; i < e; ++i) {
+            tdo_allele_out o[2];
+            memset(o, 0, sizeof(o));
+            if (j->duo) tdo_duo_assess(&j->loci[i], j->scores, j->q, o, j->mask);
+            else tdo_trio_assess(&j->loci[i], j->scores, j->q, o, j->mask);
+            j->out[2 * i] = o[0];
+            j->out[2 * i + 1] = o[1];
+        }
+    }
+    return NULL;
+}
+
+int tdo_assess_batch(const tdo_trio_locus *loci, size_t n_loci, const int32_t *scores, double q, int duo,
+                     int n_threads, tdo_allele_out *out, uint8_t *mask) {
+    if (n_threads < 1) n_threads = 1;
+    size_t next = 0;
+    rjob_t job = {loci, n_loci, scores, q, duo, out, mask, &next};
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int i = 1; i < n_threads; ++i) pthread_create(&th[i], NULL, rworker, &job);
+    rworker(&job);
+    for (int i = 1; i < n_threads; ++i) pthread_join(th[i], NULL);
+    free(th);
+    return 0;
+}

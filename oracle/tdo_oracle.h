@@ -135,6 +135,10 @@ void tdo_trio_assess(const tdo_trio_locus *loc, const int32_t *scores, double q,
 void tdo_duo_assess(const tdo_trio_locus *loc, const int32_t *scores, double q, tdo_allele_out *out,
                     uint8_t *denovo_mask);
 
+/* Whole-batch reductions threaded over loci; out has 2 slots per locus. */
+int tdo_assess_batch(const tdo_trio_locus *loci, size_t n_loci, const int32_t *scores, double q, int duo,
+                     int n_threads, tdo_allele_out *out, uint8_t *mask);
+
 #ifdef __cplusplus
 }
 #endif

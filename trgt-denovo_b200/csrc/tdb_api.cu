@@ -42,7 +42,7 @@ struct tdb_ctx {
     int sm_count = 0;
     std::string err;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[12] = {};
     // grow-only device buffers
     DevBuf blob, seq_off, seq_len, woff, packed, seq_flag, pair_p, pair_t, score, status, penalty;
     DevBuf todo_a, todo_b, ctrl, cub_tmp, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
@@ -177,14 +177,18 @@ int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
 
     unsigned pending = n_pairs;
     const uint32_t *todo = nullptr;
+    bool tier_ran[3] = {false, false, false};
     if (!cigar_mode) {
         p.todo = nullptr, p.n_items = n_pairs, p.n_items_ptr = nullptr;
         p.work_counter = ctrl + 0, p.next_todo = (uint32_t *)ctx->todo_a.p, p.next_count = ctrl + 1;
         p.counters = cnt64 + 0;
         const size_t smem = sizeof(T0Smem) * T0_WARPS;
         const unsigned grid = (unsigned)(ctx->sm_count * ctx->t0_ctas_per_sm);
+        CK(cudaEventRecord(ctx->ev[6], s));
         k_align_tier0<<<grid, T0_WARPS * 32, smem, s>>>(p);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[7], s));
+        tier_ran[0] = true;
         ctx->counters.kernel_launches += 1;
         CK(cudaMemcpyAsync(&pending, ctrl + 1, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -216,9 +220,12 @@ int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         p.scratch = (uint8_t *)ctx->scratch[t].p, p.scratch_stride = stride;
         p.wlog2 = tc.wlog2, p.s_cap = tc.s_cap, p.ops_cap = tc.ops_cap, p.prov_cap = tc.prov_cap;
         const unsigned grid = (unsigned)(workers / 4);
+        CK(cudaEventRecord(ctx->ev[8 + 2 * t], s));
         if (cigar_mode) k_align_global<true><<<grid, 128, 0, s>>>(p);
         else k_align_global<false><<<grid, 128, 0, s>>>(p);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[9 + 2 * t], s));
+        tier_ran[t + 1] = true;
         ctx->counters.kernel_launches += 1;
         unsigned next = 0;
         if (t == 0) {
@@ -245,6 +252,11 @@ int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     ctx->counters.ms_align = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
     ctx->counters.ms_total_device = ms;
+    for (int t = 0; t < 3; ++t)
+        if (tier_ran[t]) {
+            cudaEventElapsedTime(&ms, ctx->ev[6 + 2 * t], ctx->ev[7 + 2 * t]);
+            ctx->counters.ms_tier[t] = ms;
+        }
     return TDB_OK;
 }
 
@@ -376,7 +388,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     memset(&c->counters, 0, sizeof(c->counters));
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 12 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     const size_t smem = sizeof(T0Smem) * T0_WARPS;
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_align_tier0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -403,7 +415,7 @@ void tdb_destroy(tdb_ctx *c) {
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 12; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
