@@ -92,7 +92,8 @@ def test_str_pairs_bit_exact(ctx, clip):
     rng = random.Random(100 + clip)
     seqs, pp, pt = make_pairs(rng, n_targets=300, reads_per_target=12)
     cnt = _check_batch(ctx, seqs, pp, pt, clip)
-    assert cnt.tier_pairs[0] > 0.8 * len(pp)  # the shared-memory tier carries the bulk
+    assert cnt.tier_pairs[0] + cnt.tier_pairs[1] > 0.8 * len(pp)  # the shared-memory tiers carry the bulk
+    assert cnt.tier_pairs[0] > 0 and cnt.tier_pairs[1] > 0
 
 
 def test_random_divergent_pairs(ctx):
@@ -106,7 +107,19 @@ def test_random_divergent_pairs(ctx):
         pt.append(len(seqs)); seqs.append(t.encode())
         pp.append(len(seqs)); seqs.append(p.encode())
     cnt = _check_batch(ctx, seqs, np.array(pp, np.uint32), np.array(pt, np.uint32), 50)
-    assert cnt.tier_pairs[1] > 0
+    assert cnt.tier_pairs[2] > 0
+
+
+def test_quad_tier_disabled_gives_same_scores(tdb, monkeypatch):
+    """The one-pair-per-warp tier must agree with the four-pairs-per-warp tier on the same batch."""
+    rng = random.Random(31)
+    seqs, pp, pt = make_pairs(rng, n_targets=120, reads_per_target=10, max_units=25)
+    monkeypatch.setenv("TDB_DISABLE_QUAD", "1")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_DISABLE_QUAD")
+    cnt = _check_batch(c, seqs, pp, pt, 50)
+    assert cnt.tier_pairs[0] == 0
+    c.close()
 
 
 def test_heuristic_none(tdb):

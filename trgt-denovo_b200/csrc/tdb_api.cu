@@ -1,6 +1,6 @@
 // tdb_api.cu -- C ABI (include/trgt_denovo_b200.h) over the sm_100a kernels.  No CPU compute path:
 // every entry point that does arithmetic launches CUDA kernels or fails.
-#include "tdb_kernels.cuh"
+#include "tdb_wfa_quad.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -42,12 +42,13 @@ struct tdb_ctx {
     int sm_count = 0;
     std::string err;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[12] = {};
+    cudaEvent_t ev[14] = {};
     // grow-only device buffers
     DevBuf blob, seq_off, seq_len, woff, packed, seq_flag, pair_p, pair_t, score, status, penalty;
     DevBuf todo_a, todo_b, ctrl, cub_tmp, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
-    int t0_ctas_per_sm = 0;
+    int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0;
+    bool disable_quad = false;
     bool count_work = true;
     tdb_counters counters;
     // single-pair shim state
@@ -94,7 +95,7 @@ int ensure(tdb_ctx *ctx, DevBuf &b, size_t bytes) {
 
 // ctrl block layout (unsigned): [0] work counter, [1] next count A, [2] next count B, pad;
 // counters (unsigned long long) at byte 64: 4 per tier x 3 tiers
-constexpr size_t CTRL_BYTES = 64 + 3 * 4 * sizeof(unsigned long long);
+constexpr size_t CTRL_BYTES = 64 + 4 * 4 * sizeof(unsigned long long);
 
 struct DevBatch {
     const uint8_t *blob;
@@ -157,15 +158,17 @@ int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     }
     CK(cudaEventRecord(ctx->ev[1], s));
     // ---- tiers -------------------------------------------------------------------------------------
+    // 0: four pairs per warp, shared memory (default penalties only)   1: one pair per warp, shared memory
+    // 2,3: one pair per warp, global scratch (long / wide alignments).  A tier that cannot finish a pair
+    // (ring, provenance or score capacity) appends it to the next tier's work list on the device.
     ENSURE(ctx->ctrl, CTRL_BYTES);
     CK(cudaMemsetAsync(ctx->ctrl.p, 0, CTRL_BYTES, s));
-    ENSURE(ctx->todo_a, (size_t)n_pairs * 4);
     unsigned *ctrl = (unsigned *)ctx->ctrl.p;
     unsigned long long *cnt64 = (unsigned long long *)((uint8_t *)ctx->ctrl.p + 64);
     AlignParams p;
     memset(&p, 0, sizeof(p));
-    p.pn = {ctx->cfg.penalties.mismatch, ctx->cfg.penalties.gap_opening1, ctx->cfg.penalties.gap_extension1,
-            ctx->cfg.penalties.gap_opening2, ctx->cfg.penalties.gap_extension2};
+    const tdb_penalties &cp = ctx->cfg.penalties;
+    p.pn = {cp.mismatch, cp.gap_opening1, cp.gap_extension1, cp.gap_opening2, cp.gap_extension2};
     p.heur = {ctx->cfg.heuristic.kind, ctx->cfg.heuristic.min_wavefront_length,
               ctx->cfg.heuristic.max_distance_threshold, ctx->cfg.heuristic.steps_between_cutoffs};
     p.clip = ctx->cfg.clip_len;
@@ -175,72 +178,70 @@ int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     p.out_score = b.score, p.out_status = b.status, p.out_penalty = b.penalty;
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
 
-    unsigned pending = n_pairs;
-    const uint32_t *todo = nullptr;
-    bool tier_ran[3] = {false, false, false};
-    if (!cigar_mode) {
-        p.todo = nullptr, p.n_items = n_pairs, p.n_items_ptr = nullptr;
-        p.work_counter = ctrl + 0, p.next_todo = (uint32_t *)ctx->todo_a.p, p.next_count = ctrl + 1;
-        p.counters = cnt64 + 0;
-        const size_t smem = sizeof(T0Smem) * T0_WARPS;
-        const unsigned grid = (unsigned)(ctx->sm_count * ctx->t0_ctas_per_sm);
-        CK(cudaEventRecord(ctx->ev[6], s));
-        k_align_tier0<<<grid, T0_WARPS * 32, smem, s>>>(p);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[7], s));
-        tier_ran[0] = true;
-        ctx->counters.kernel_launches += 1;
-        CK(cudaMemcpyAsync(&pending, ctrl + 1, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        todo = (const uint32_t *)ctx->todo_a.p;
-        ctx->counters.tier_pairs[0] = n_pairs - pending;
-    }
-    // global tiers
+    const bool default_pen = cp.mismatch == 8 && cp.gap_opening1 == 4 && cp.gap_extension1 == 2 &&
+                             cp.gap_opening2 == 24 && cp.gap_extension2 == 1;
     const uint64_t cap = ctx->cfg.scratch_bytes ? ctx->cfg.scratch_bytes : (48ull << 30);
-    TierCfg tiers[2] = {
+    const TierCfg gtiers[2] = {
         {10, 1 << 16, 1 << 17, 8u << 20, ctx->sm_count * 8},   // W=1024, S<65536, 8 MiB provenance
         {15, 1 << 18, 1 << 19, 192u << 20, ctx->sm_count * 1}, // W=32768, S<262144, 192 MiB provenance
     };
-    for (int t = 0; t < 2 && pending > 0; ++t) {
-        const TierCfg tc = tiers[t];
-        const size_t stride = global_tier_stride(tc.wlog2, tc.s_cap, tc.ops_cap, tc.prov_cap);
-        uint64_t workers = std::min<uint64_t>((uint64_t)tc.workers, std::max<uint64_t>(1, (cap / 2) / stride));
-        workers = std::min<uint64_t>(workers, pending);
-        workers = (workers + 3) & ~(uint64_t)3; // whole CTAs of 4 warps
-        ENSURE(ctx->scratch[t], stride * (size_t)workers);
+    unsigned pending = n_pairs;
+    const uint32_t *todo = nullptr; // nullptr: identity list 0..n_pairs-1
+    bool tier_ran[4] = {false, false, false, false};
+    DevBuf *lists[2] = {&ctx->todo_a, &ctx->todo_b};
+    int flip = 0;
+    for (int t = 0; t < 4 && pending > 0; ++t) {
+        if (cigar_mode && t < 2) continue;                 // CIGAR output lives in the general kernel
+        if (t == 0 && (!default_pen || ctx->disable_quad)) continue;
+        const bool last = t == 3;
         CK(cudaMemsetAsync(ctrl + 0, 0, 4, s));
-        p.todo = todo, p.n_items = pending, p.n_items_ptr = nullptr;
-        p.work_counter = ctrl + 0;
-        p.next_todo = nullptr, p.next_count = ctrl + 2;
-        if (t == 0) { // the last tier has nowhere to defer to: it reports TDB_STATUS_OOM
-            ENSURE(ctx->todo_b, (size_t)pending * 4);
-            p.next_todo = (uint32_t *)ctx->todo_b.p;
+        p.todo = todo, p.n_items = pending, p.n_items_ptr = nullptr, p.work_counter = ctrl + 0;
+        p.next_todo = nullptr, p.next_count = ctrl + 1 + t;
+        if (!last) {
+            ENSURE(*lists[flip], (size_t)pending * 4);
+            p.next_todo = (uint32_t *)lists[flip]->p;
         }
-        p.counters = cnt64 + 4 * (t + 1);
-        p.scratch = (uint8_t *)ctx->scratch[t].p, p.scratch_stride = stride;
-        p.wlog2 = tc.wlog2, p.s_cap = tc.s_cap, p.ops_cap = tc.ops_cap, p.prov_cap = tc.prov_cap;
-        const unsigned grid = (unsigned)(workers / 4);
-        CK(cudaEventRecord(ctx->ev[8 + 2 * t], s));
-        if (cigar_mode) k_align_global<true><<<grid, 128, 0, s>>>(p);
-        else k_align_global<false><<<grid, 128, 0, s>>>(p);
+        p.counters = cnt64 + 4 * t;
+        CK(cudaEventRecord(ctx->ev[6 + 2 * t], s));
+        if (t == 0) {
+            const size_t smem = sizeof(QPair) * (32 / QG) * Q_WARPS;
+            const unsigned grid = (unsigned)(ctx->sm_count * ctx->quad_ctas_per_sm);
+            k_align_quad<8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, s>>>(p);
+        } else if (t == 1) {
+            const size_t smem = sizeof(T0Smem) * T0_WARPS;
+            const unsigned grid = (unsigned)(ctx->sm_count * ctx->t0_ctas_per_sm);
+            k_align_tier0<<<grid, T0_WARPS * 32, smem, s>>>(p);
+        } else {
+            const TierCfg tc = gtiers[t - 2];
+            const size_t stride = global_tier_stride(tc.wlog2, tc.s_cap, tc.ops_cap, tc.prov_cap);
+            uint64_t workers = std::min<uint64_t>((uint64_t)tc.workers, std::max<uint64_t>(1, (cap / 2) / stride));
+            workers = std::min<uint64_t>(workers, pending);
+            workers = (workers + 3) & ~(uint64_t)3; // whole CTAs of 4 warps
+            ENSURE(ctx->scratch[t - 2], stride * (size_t)workers);
+            p.scratch = (uint8_t *)ctx->scratch[t - 2].p, p.scratch_stride = stride;
+            p.wlog2 = tc.wlog2, p.s_cap = tc.s_cap, p.ops_cap = tc.ops_cap, p.prov_cap = tc.prov_cap;
+            const unsigned grid = (unsigned)(workers / 4);
+            if (cigar_mode) k_align_global<true><<<grid, 128, 0, s>>>(p);
+            else k_align_global<false><<<grid, 128, 0, s>>>(p);
+        }
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[9 + 2 * t], s));
-        tier_ran[t + 1] = true;
+        CK(cudaEventRecord(ctx->ev[7 + 2 * t], s));
+        tier_ran[t] = true;
         ctx->counters.kernel_launches += 1;
         unsigned next = 0;
-        if (t == 0) {
-            CK(cudaMemcpyAsync(&next, ctrl + 2, 4, cudaMemcpyDeviceToHost, s));
+        if (!last) {
+            CK(cudaMemcpyAsync(&next, ctrl + 1 + t, 4, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
         }
-        ctx->counters.tier_pairs[t + 1] = pending - next;
+        ctx->counters.tier_pairs[t] = pending - next;
         pending = next;
-        todo = (const uint32_t *)ctx->todo_b.p;
+        if (!last) todo = (const uint32_t *)lists[flip]->p, flip ^= 1;
     }
     CK(cudaEventRecord(ctx->ev[2], s));
-    unsigned long long h[12];
+    unsigned long long h[16];
     CK(cudaMemcpyAsync(h, cnt64, sizeof(h), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    for (int t = 0; t < 3; ++t) {
+    for (int t = 0; t < 4; ++t) {
         ctx->counters.cells += h[4 * t + 0];
         ctx->counters.ext16 += h[4 * t + 1];
         ctx->counters.columns += h[4 * t + 2];
@@ -252,13 +253,14 @@ int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     ctx->counters.ms_align = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
     ctx->counters.ms_total_device = ms;
-    for (int t = 0; t < 3; ++t)
+    for (int t = 0; t < 4; ++t)
         if (tier_ran[t]) {
             cudaEventElapsedTime(&ms, ctx->ev[6 + 2 * t], ctx->ev[7 + 2 * t]);
             ctx->counters.ms_tier[t] = ms;
         }
     return TDB_OK;
 }
+
 
 int run_reduce_device(tdb_ctx *ctx, const tdb_trio_locus *dloci, size_t n_loci, const int32_t *dscores, double q,
                       int is_duo, tdb_allele_out *dout, uint8_t *dmask) {
@@ -388,7 +390,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     memset(&c->counters, 0, sizeof(c->counters));
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 12 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 14 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     const size_t smem = sizeof(T0Smem) * T0_WARPS;
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_align_tier0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -403,6 +405,21 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         return code;
     }
     c->t0_ctas_per_sm = occ;
+    {
+        const size_t qsmem = sizeof(QPair) * (32 / QG) * Q_WARPS;
+        auto kq = k_align_quad<8, 4, 2, 24, 1>;
+        e = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kq, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int qocc = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qocc, kq, Q_WARPS * 32, qsmem);
+        if (e != cudaSuccess || qocc < 1) {
+            int code = fail(nullptr, TDB_E_CUDA, "quad kernel setup failed: %s (occupancy %d)", cudaGetErrorString(e), qocc);
+            tdb_destroy(c);
+            return code;
+        }
+        c->quad_ctas_per_sm = qocc;
+        c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
+    }
     *out = c;
     return TDB_OK;
 }
@@ -415,7 +432,7 @@ void tdb_destroy(tdb_ctx *c) {
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
-    for (int i = 0; i < 12; ++i)
+    for (int i = 0; i < 14; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -1,0 +1,436 @@
+// tdb_wfa_quad.cuh -- tier 0 of the alignment path: FOUR pairs per warp, eight lanes per pair.
+//
+// Why: on the genome-wide trio the median pair has penalty 6 and wavefront width 3 (42 % are
+// identical), so a warp per pair leaves 27+ lanes idle and the kernel is bound by the instruction
+// issue of its warp-uniform bookkeeping (ncu r01: issue active 72 %, 3.5 k warp-instructions / pair).
+// Here a warp runs four consecutive pairs in lock-step -- consecutive pairs are reads of the same
+// parental allele against the same child allele, so their control flow is nearly identical -- and
+// every bookkeeping instruction serves four pairs.  Further:
+//   * existence of the last 26 M / gap wavefronts is tracked in register bit-masks, so the null
+//     score steps of the 2-piece-affine recurrence (most steps, penalties 8/6/25) touch no memory;
+//   * the M history lives in a FIFO arena (only non-null wavefronts occupy shared memory), which
+//     lets a pair with width <= 32 fit in 3 KB and keeps >= 17 warps resident per SM;
+//   * penalties are compile-time constants (the reference hard-wires 8,4,2,24,1:
+//     src/commands/shared.rs:39-51, src/model.rs:13-23), other penalties use the general tiers.
+// Semantics are exactly those of wfa_align_warp (tdb_wfa.cuh): SURVEY.md Appendix A.1-A.4.
+#pragma once
+#include "tdb_kernels.cuh"
+
+namespace tdb {
+
+constexpr int QG = 8;        // lanes per pair
+constexpr int QW = 32;       // widest wavefront handled here
+constexpr int Q_MAR = 512;   // M arena entries
+constexpr int Q_SCAP = 96;   // scores 0..95
+constexpr int Q_PROV = 736;  // provenance bytes
+constexpr int Q_MAXLEN = 8000;
+constexpr int Q_WARPS = 2;
+constexpr int Q_NULL = -16384;
+
+struct __align__(16) QPair {
+    int16_t marena[Q_MAR];        // FIFO arena of M wavefronts; reused as the op stream at backtrace
+    int16_t gap[12][QW];          // I1[4], D1[4], I2[2], D2[2] rings indexed by score
+    uint16_t m_off[32];           // arena index of diagonal m_lo (free-running, masked on access)
+    int16_t m_lo[32], m_hi[32];   // valid range of M[s], slot s & 31
+    int16_t g_lo[12], g_hi[12];
+    int16_t step_lo[Q_SCAP];      // computed lo of score s (provenance row origin)
+    uint16_t step_base[Q_SCAP];
+    uint8_t prov[Q_PROV];
+};
+static_assert(sizeof(QPair) % 16 == 0, "QPair must keep 16-byte alignment");
+
+struct QIn { // one input wavefront, group-uniform
+    const int16_t *p; // element for diagonal k at p[(base + k) & amask]
+    int base;         // arena: off - lo ; ring: 0 with k & (QW-1)
+    int lo;
+    unsigned span1;
+};
+
+__device__ __forceinline__ unsigned qballot(unsigned gmask, int gshift, bool pred) {
+    return (__ballot_sync(gmask, pred) >> gshift) & 0xffu;
+}
+
+// Eight lanes extend one diagonal: lane l compares bases [16l, 16l+16) per round.
+__device__ __forceinline__ int extend_group(const uint32_t *pw, const uint32_t *tw, int n, int m, int v, int h,
+                                            int gl, unsigned gmask, int gshift, int lane) {
+    const int room = min(n - v, m - h);
+    for (int base = 0; base < room; base += 16 * QG) {
+        const int off = base + gl * 16;
+        uint32_t x = 1u;
+        if (off < room) x = get16(pw, v + off) ^ get16(tw, h + off);
+        const unsigned bal = qballot(gmask, gshift, x != 0);
+        if (bal) {
+            const int l = __ffs(bal) - 1;
+            const uint32_t xl = __shfl_sync(gmask, x, (lane & ~(QG - 1)) + l);
+            return min(base + l * 16 + ((__ffs(xl) - 1) >> 1), room);
+        }
+    }
+    return room;
+}
+
+template <int X, int O1, int E1, int O2, int E2>
+__global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p) {
+    static_assert(X < 32 && O1 + E1 < 32 && O2 + E2 < 32 && E1 < 4 && E2 < 2, "ring sizes");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gl = lane & (QG - 1), gid = lane / QG, gshift = gid * QG;
+    const unsigned gmask = 0xffu << gshift;
+    QPair &sm = reinterpret_cast<QPair *>(smem_raw)[wid * (32 / QG) + gid];
+    const Penalties pn = {X, O1, E1, O2, E2};
+    const unsigned n_items = p.n_items_ptr ? *p.n_items_ptr : p.n_items;
+    constexpr int PER_FETCH = 32; // pairs per work-counter atomic (8 batches of 4)
+    unsigned long long acc_cells = 0, acc_cols = 0, acc_ext = 0, acc_done = 0; // acc_* valid on group lane 0
+
+    for (;;) {
+        unsigned fb = 0;
+        if (lane == 0) fb = atomicAdd(p.work_counter, (unsigned)PER_FETCH);
+        fb = __shfl_sync(TDB_FULL, fb, 0);
+        if (fb >= n_items) break;
+        for (unsigned bb = fb; bb < fb + PER_FETCH && bb < n_items; bb += 32 / QG) {
+            const unsigned it = bb + gid;
+            // ====================== one pair per group ======================
+            if (it < n_items) {
+                const uint32_t idx = p.todo ? p.todo[it] : it;
+                const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
+                const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
+                const int k_end = m - n;
+                bool overflow = (p.seq_flag[ip] | p.seq_flag[jt]) || n > Q_MAXLEN || m > Q_MAXLEN;
+                int penalty = 0, clipped = 0;
+                unsigned long long cells = 0, cols = 0, ext = 0;
+                if (!overflow) {
+                    const uint32_t *pw = p.packed + p.woff[ip], *tw = p.packed + p.woff[jt];
+                    const int m0 = extend_group(pw, tw, n, m, 0, 0, gl, gmask, gshift, lane);
+                    if (gl == 0) ext += (unsigned)(m0 >> 4) + 1;
+                    if (k_end == 0 && m0 >= m) {
+                        cols = (unsigned)m; // identical: penalty 0, clipped score 0
+                    } else {
+                        // ---------------- wavefront loop ----------------
+                        if (gl == 0) {
+                            sm.m_off[0] = 0, sm.m_lo[0] = 0, sm.m_hi[0] = 0;
+                            sm.marena[0] = (int16_t)m0;
+                            sm.step_lo[0] = 0, sm.step_base[0] = 0;
+                            sm.prov[0] = 0;
+                        }
+                        unsigned Mm = 1u, I1m = 0, I2m = 0, D1m = 0, D2m = 0; // bit j <-> score s-j exists
+                        unsigned mhead = 1, prov_used = 1;
+                        int steps_wait = p.heur.steps - (p.heur.kind == 1 ? 1 : 0);
+                        int s = 0;
+                        __syncwarp(gmask);
+                        for (;;) {
+                            // advance to the next score with a non-null input (register-only null steps)
+                            bool live;
+                            do {
+                                ++s;
+                                Mm <<= 1, I1m <<= 1, I2m <<= 1, D1m <<= 1, D2m <<= 1;
+                                live = (Mm & ((1u << X) | (1u << (O1 + E1)) | (1u << (O2 + E2)))) |
+                                       ((I1m | D1m) & (1u << E1)) | ((I2m | D2m) & (1u << E2));
+                            } while (!live && s < Q_SCAP);
+                            if (s >= Q_SCAP) {
+                                overflow = true;
+                                break;
+                            }
+                            // ---- inputs ----
+                            QIn mx, mo1, mo2, i1e, i2e, d1e, d2e;
+#define TDB_QM(w, lag)                                                              \
+    w.p = sm.marena, w.base = 0, w.lo = 1, w.span1 = 0;                             \
+    if (Mm & (1u << (lag))) {                                                       \
+        const int sl = (s - (lag)) & 31;                                            \
+        const int l_ = sm.m_lo[sl];                                                 \
+        w.lo = l_, w.span1 = (unsigned)(sm.m_hi[sl] - l_ + 1), w.base = (int)sm.m_off[sl] - l_; \
+    }
+                            TDB_QM(mx, X)
+                            TDB_QM(mo1, O1 + E1)
+                            TDB_QM(mo2, O2 + E2)
+#undef TDB_QM
+#define TDB_QG(w, msk, lag, row0, rmask)                                            \
+    w.p = sm.gap[0], w.base = 0, w.lo = 1, w.span1 = 0;                             \
+    if (msk & (1u << (lag))) {                                                      \
+        const int r_ = (row0) + ((s - (lag)) & (rmask));                            \
+        const int l_ = sm.g_lo[r_];                                                 \
+        w.p = sm.gap[r_], w.lo = l_, w.span1 = (unsigned)(sm.g_hi[r_] - l_ + 1);    \
+    }
+                            TDB_QG(i1e, I1m, E1, 0, 3)
+                            TDB_QG(d1e, D1m, E1, 4, 3)
+                            TDB_QG(i2e, I2m, E2, 8, 1)
+                            TDB_QG(d2e, D2m, E2, 10, 1)
+#undef TDB_QG
+                            int lo = INT32_MAX, hi = INT32_MIN;
+#define TDB_LIM(w, dl, dh)                                              \
+    if ((w).span1) {                                                    \
+        lo = min(lo, (w).lo + (dl));                                    \
+        hi = max(hi, (w).lo + (int)(w).span1 - 1 + (dh));               \
+    }
+                            TDB_LIM(mx, 0, 0)
+                            TDB_LIM(mo1, -1, 1)
+                            TDB_LIM(mo2, -1, 1)
+                            TDB_LIM(i1e, 1, 1)
+                            TDB_LIM(i2e, 1, 1)
+                            TDB_LIM(d1e, -1, -1)
+                            TDB_LIM(d2e, -1, -1)
+#undef TDB_LIM
+                            lo = max(lo, -n - 1), hi = min(hi, m + 1);
+                            const int width = hi - lo + 1;
+                            // arena room: everything from the oldest live M wavefront up to the new one
+                            const unsigned livem = Mm & 0x03fffffeu; // lags 1..25
+                            unsigned tail = mhead;
+                            if (livem) tail = sm.m_off[(s - (31 - __clz(livem))) & 31];
+                            if (width > QW || prov_used + (unsigned)width > Q_PROV ||
+                                ((mhead - tail) & 0xffffu) + (unsigned)width > Q_MAR) {
+                                overflow = true;
+                                break;
+                            }
+                            const bool has_i1 = mo1.span1 || i1e.span1, has_d1 = mo1.span1 || d1e.span1;
+                            const bool has_i2 = mo2.span1 || i2e.span1, has_d2 = mo2.span1 || d2e.span1;
+                            int16_t *I1o = sm.gap[0 + (s & 3)], *D1o = sm.gap[4 + (s & 3)];
+                            int16_t *I2o = sm.gap[8 + (s & 1)], *D2o = sm.gap[10 + (s & 1)];
+                            uint8_t *pv = sm.prov + prov_used;
+                            cells += (unsigned)width;
+                            int tl_m = INT32_MAX, th_m = INT32_MIN, tl_i1 = INT32_MAX, th_i1 = INT32_MIN,
+                                tl_i2 = INT32_MAX, th_i2 = INT32_MIN, tl_d1 = INT32_MAX, th_d1 = INT32_MIN,
+                                tl_d2 = INT32_MAX, th_d2 = INT32_MIN;
+                            int lane_min_d = 1 << 30;
+                            bool fin = false;
+                            for (int kb = lo; kb <= hi; kb += QG) {
+                                const int k = kb + gl;
+                                const bool act = k <= hi;
+                                int ins1 = Q_NULL, ins2 = Q_NULL, del1 = Q_NULL, del2 = Q_NULL, mv = Q_NULL;
+                                bool vm = false;
+                                if (act) {
+#define TDB_RDM(w, kk) (((unsigned)((kk) - (w).lo) < (w).span1) ? (int)sm.marena[((w).base + (kk)) & (Q_MAR - 1)] : Q_NULL)
+#define TDB_RDG(w, kk) (((unsigned)((kk) - (w).lo) < (w).span1) ? (int)(w).p[(kk) & (QW - 1)] : Q_NULL)
+                                    int b = 0, o, e;
+                                    o = TDB_RDM(mo1, k - 1), e = TDB_RDG(i1e, k - 1);
+                                    if (e >= o) ins1 = e, b |= PB_I1E; else ins1 = o;
+                                    ins1 += 1;
+                                    o = TDB_RDM(mo2, k - 1), e = TDB_RDG(i2e, k - 1);
+                                    if (e >= o) ins2 = e, b |= PB_I2E; else ins2 = o;
+                                    ins2 += 1;
+                                    o = TDB_RDM(mo1, k + 1), e = TDB_RDG(d1e, k + 1);
+                                    if (e >= o) del1 = e, b |= PB_D1E; else del1 = o;
+                                    o = TDB_RDM(mo2, k + 1), e = TDB_RDG(d2e, k + 1);
+                                    if (e >= o) del2 = e, b |= PB_D2E; else del2 = o;
+                                    const int mis = TDB_RDM(mx, k) + 1;
+#undef TDB_RDM
+#undef TDB_RDG
+                                    mv = max(max(max(ins1, ins2), max(del1, del2)), mis);
+                                    int src = PM_NONE; // later tests override: priority X > D2 > D1 > I2 > I1
+                                    if (mv == ins1) src = PM_I1;
+                                    if (mv == ins2) src = PM_I2;
+                                    if (mv == del1) src = PM_D1;
+                                    if (mv == del2) src = PM_D2;
+                                    if (mv == mis) src = PM_X;
+                                    pv[k - lo] = (uint8_t)(b | src);
+                                    if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = Q_NULL;
+                                    vm = mv >= 0;
+                                    if (vm) { // extend at once (trimming never changes offsets)
+                                        const int v = mv - k, room = min(n - v, m - mv);
+                                        int eq = 0;
+                                        while (eq < room) {
+                                            const uint32_t x = get16(pw, v + eq) ^ get16(tw, mv + eq);
+                                            if (x) {
+                                                eq += (__ffs(x) - 1) >> 1;
+                                                break;
+                                            }
+                                            eq += 16;
+                                        }
+                                        eq = min(eq, room);
+                                        ext += (unsigned)(eq >> 4) + 1;
+                                        mv += eq;
+                                        lane_min_d = min(lane_min_d, max(n - (mv - k), m - mv));
+                                        fin |= (k == k_end) && (mv >= m);
+                                    }
+                                    sm.marena[(mhead + (unsigned)(k - lo)) & (Q_MAR - 1)] = (int16_t)mv;
+                                    if (has_i1) I1o[k & (QW - 1)] = (int16_t)ins1;
+                                    if (has_i2) I2o[k & (QW - 1)] = (int16_t)ins2;
+                                    if (has_d1) D1o[k & (QW - 1)] = (int16_t)del1;
+                                    if (has_d2) D2o[k & (QW - 1)] = (int16_t)del2;
+                                }
+                                unsigned bal = qballot(gmask, gshift, vm);
+                                if (bal) tl_m = min(tl_m, kb + __ffs(bal) - 1), th_m = kb + 31 - __clz(bal);
+#define TDB_TRIM(has, val, tl, th)                                                                                     \
+    if (has) {                                                                                                         \
+        bal = qballot(gmask, gshift, act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n);     \
+        if (bal) tl = min(tl, kb + __ffs(bal) - 1), th = kb + 31 - __clz(bal);                                         \
+    }
+                                TDB_TRIM(has_i1, ins1, tl_i1, th_i1)
+                                TDB_TRIM(has_i2, ins2, tl_i2, th_i2)
+                                TDB_TRIM(has_d1, del1, tl_d1, th_d1)
+                                TDB_TRIM(has_d2, del2, tl_d2, th_d2)
+#undef TDB_TRIM
+                            }
+                            if (gl == 0) sm.step_lo[s] = (int16_t)lo, sm.step_base[s] = (uint16_t)prov_used;
+                            prov_used += (unsigned)width;
+                            __syncwarp(gmask);
+                            if (qballot(gmask, gshift, fin)) {
+                                penalty = s;
+                                break;
+                            }
+                            // ---- wf-adaptive cut-off + equate (A.3) ----
+                            int mlo = tl_m, mhi = th_m; // empty when mlo > mhi
+                            if (p.heur.kind == 1 && mlo <= mhi) {
+                                --steps_wait;
+                                if (steps_wait <= 0 && (mhi - mlo + 1) >= p.heur.min_len) {
+                                    int md = lane_min_d;
+                                    md = min(md, __shfl_xor_sync(gmask, md, 1));
+                                    md = min(md, __shfl_xor_sync(gmask, md, 2));
+                                    md = min(md, __shfl_xor_sync(gmask, md, 4));
+                                    const int min_d = min(max(n, m), md), thr = p.heur.max_dist;
+                                    const int abase = (int)mhead - lo;
+#define TDB_DIST_OK(kk, okv)                                                                  \
+    {                                                                                         \
+        const int off_ = (int)sm.marena[(abase + (kk)) & (Q_MAR - 1)];                        \
+        const int d_ = off_ >= 0 ? max(n - (off_ - (kk)), m - off_) : (1 << 30);              \
+        okv = d_ - min_d <= thr;                                                              \
+    }
+                                    const int top_limit = min(k_end, mhi);
+                                    int new_lo = mlo;
+                                    if (top_limit > mlo) {
+                                        int first_ok = INT32_MAX;
+                                        for (int kb = mlo; kb < top_limit && first_ok == INT32_MAX; kb += QG) {
+                                            const int k = kb + gl;
+                                            bool ok = false;
+                                            if (k < top_limit) TDB_DIST_OK(k, ok)
+                                            const unsigned bal = qballot(gmask, gshift, ok);
+                                            if (bal) first_ok = kb + __ffs(bal) - 1;
+                                        }
+                                        new_lo = min(first_ok, top_limit);
+                                    }
+                                    const int bot_limit = max(k_end, new_lo);
+                                    int new_hi = mhi;
+                                    if (bot_limit < mhi) {
+                                        int last_ok = INT32_MIN;
+                                        for (int kt = mhi; kt > bot_limit && last_ok == INT32_MIN; kt -= QG) {
+                                            const int k = kt - gl;
+                                            bool ok = false;
+                                            if (k > bot_limit) TDB_DIST_OK(k, ok)
+                                            const unsigned bal = qballot(gmask, gshift, ok);
+                                            if (bal) last_ok = kt - (__ffs(bal) - 1);
+                                        }
+                                        new_hi = max(last_ok, bot_limit);
+                                    }
+#undef TDB_DIST_OK
+                                    mlo = new_lo, mhi = new_hi;
+                                    steps_wait = p.heur.steps;
+                                }
+                                if (mlo <= mhi) { // equate
+                                    tl_i1 = max(tl_i1, mlo), th_i1 = min(th_i1, mhi);
+                                    tl_i2 = max(tl_i2, mlo), th_i2 = min(th_i2, mhi);
+                                    tl_d1 = max(tl_d1, mlo), th_d1 = min(th_d1, mhi);
+                                    tl_d2 = max(tl_d2, mlo), th_d2 = min(th_d2, mhi);
+                                }
+                            }
+                            // ---- publish metadata of score s ----
+                            if (mlo <= mhi) Mm |= 1u;
+                            if (tl_i1 <= th_i1) I1m |= 1u;
+                            if (tl_i2 <= th_i2) I2m |= 1u;
+                            if (tl_d1 <= th_d1) D1m |= 1u;
+                            if (tl_d2 <= th_d2) D2m |= 1u;
+                            if (gl == 0) {
+                                const int sl = s & 31;
+                                sm.m_lo[sl] = (int16_t)mlo, sm.m_hi[sl] = (int16_t)mhi;
+                                sm.m_off[sl] = (uint16_t)(mhead + (unsigned)(mlo - lo));
+                                sm.g_lo[0 + (s & 3)] = (int16_t)tl_i1, sm.g_hi[0 + (s & 3)] = (int16_t)th_i1;
+                                sm.g_lo[4 + (s & 3)] = (int16_t)tl_d1, sm.g_hi[4 + (s & 3)] = (int16_t)th_d1;
+                                sm.g_lo[8 + (s & 1)] = (int16_t)tl_i2, sm.g_hi[8 + (s & 1)] = (int16_t)th_i2;
+                                sm.g_lo[10 + (s & 1)] = (int16_t)tl_d2, sm.g_hi[10 + (s & 1)] = (int16_t)th_d2;
+                            }
+                            if (mlo <= mhi) mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
+                            __syncwarp(gmask);
+                        }
+                        // ---------------- backtrace + forward replay ----------------
+                        if (!overflow) {
+                            uint8_t *ops = reinterpret_cast<uint8_t *>(sm.marena); // arena is dead now
+                            int nops = 0, n_del = 0;
+                            {
+                                int comp = -1, cs = penalty, k = k_end;
+                                while (!(comp < 0 && cs == 0)) {
+                                    const int b = sm.prov[(unsigned)sm.step_base[cs] + (unsigned)(k - (int)sm.step_lo[cs])];
+                                    int op;
+                                    if (comp < 0) {
+                                        const int src = b & 7;
+                                        if (src == PM_X) op = OP_X, cs -= X;
+                                        else op = OP_CLOSE, comp = src - 1;
+                                    } else if (comp == CI1 || comp == CI2) {
+                                        op = OP_I;
+                                        const bool ex = b & (comp == CI1 ? PB_I1E : PB_I2E);
+                                        const int e = comp == CI1 ? E1 : E2, o = comp == CI1 ? O1 : O2;
+                                        if (ex) cs -= e; else cs -= o + e, comp = -1;
+                                        k -= 1;
+                                    } else {
+                                        op = OP_D;
+                                        ++n_del;
+                                        const bool ex = b & (comp == CD1 ? PB_D1E : PB_D2E);
+                                        const int e = comp == CD1 ? E1 : E2, o = comp == CD1 ? O1 : O2;
+                                        if (ex) cs -= e; else cs -= o + e, comp = -1;
+                                        k += 1;
+                                    }
+                                    if (gl == 0) ops[nops] = (uint8_t)op;
+                                    ++nops;
+                                }
+                            }
+                            __syncwarp(gmask);
+                            ClipAcc acc;
+                            acc.init(m + n_del, p.clip);
+                            int v = 0, h = 0;
+                            bool in_m = true;
+                            for (int i = nops - 1; i >= -1; --i) {
+                                if (in_m) {
+                                    const int eq = extend_group(pw, tw, n, m, v, h, gl, gmask, gshift, lane);
+                                    acc.emit('M', eq, pn);
+                                    v += eq, h += eq;
+                                }
+                                if (i < 0) break;
+                                const int op = ops[i];
+                                if (op == OP_CLOSE) {
+                                    in_m = true;
+                                    continue;
+                                }
+                                acc.emit(op == OP_X ? 'X' : (op == OP_I ? 'I' : 'D'), 1, pn);
+                                if (op == OP_X) ++v, ++h;
+                                else if (op == OP_I) ++h, in_m = false;
+                                else ++v, in_m = false;
+                            }
+                            clipped = acc.finish(pn);
+                            cols = (unsigned)acc.col;
+                            __syncwarp(gmask);
+                        }
+                    }
+                }
+                // ---- result ----
+                if (gl == 0) {
+                    if (!overflow) {
+                        p.out_score[idx] = clipped;
+                        if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
+                        if (p.out_penalty) p.out_penalty[idx] = penalty;
+                        acc_cells += cells, acc_cols += cols, acc_done += 1;
+                    } else if (p.next_todo) {
+                        const unsigned j = atomicAdd(p.next_count, 1u);
+                        p.next_todo[j] = idx;
+                    } else {
+                        p.out_score[idx] = 0;
+                        if (p.out_status) p.out_status[idx] = TDB_STATUS_OOM;
+                        if (p.out_penalty) p.out_penalty[idx] = INT32_MIN;
+                    }
+                }
+                if (!overflow) acc_ext += ext;
+            }
+            __syncwarp();
+        }
+    }
+    // per-warp totals: ext is per lane, the others live on each group's lane 0
+    unsigned long long c = (gl == 0) ? acc_cells : 0ull, t = (gl == 0) ? acc_cols : 0ull, d = (gl == 0) ? acc_done : 0ull;
+    for (int o = 16; o; o >>= 1) {
+        acc_ext += __shfl_xor_sync(TDB_FULL, acc_ext, o);
+        c += __shfl_xor_sync(TDB_FULL, c, o);
+        t += __shfl_xor_sync(TDB_FULL, t, o);
+        d += __shfl_xor_sync(TDB_FULL, d, o);
+    }
+    if (lane == 0 && p.counters) {
+        atomicAdd(p.counters + 0, c);
+        atomicAdd(p.counters + 1, acc_ext);
+        atomicAdd(p.counters + 2, t);
+        atomicAdd(p.counters + 3, d);
+    }
+}
+
+} // namespace tdb
