@@ -11,7 +11,7 @@ N x 937k-locus catalog).
             CUDA events the library records on its launching stream, max over ranks
   e2e       the same pass through the host-buffer C-ABI call (tdb_trio_batch): pinned host inputs,
             H2D + kernels + D2H of the per-allele results inside the timed region
-  roofline  the dominant kernel (k_align_tier0): algorithmic HBM bytes and lane-int-ops per launch
+  roofline  the dominant kernel (k_align_quad, tier 0): algorithmic HBM bytes and lane-int-ops per launch
             (ops = 24*C + 8*E + 4*T, counted exactly on the device and checked
             against the oracle in tests/) over its CUDA-event duration
   cpu_baseline / --impl reference
@@ -316,7 +316,7 @@ def main():
                                   (batch.seq_len[batch.pair_text].astype(np.int64) + 3) // 4) + 16 * n_pairs)
         frac_t0 = float(cnt.tier_pairs[0]) / max(1, n_pairs)
         roofline = {
-            "bound": "hbm", "kernel": "k_align_tier0", "achieved": algo_bytes * frac_t0 / t0_s / 1e9,
+            "bound": "hbm", "kernel": "k_align_quad", "achieved": algo_bytes * frac_t0 / t0_s / 1e9,
             "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes * frac_t0 / t0_s / 1e9 / hbm_peak, "traffic": None,
             "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
             "note": "HBM is not the binding roofline for this integer DP (SURVEY.md 8d); see int_issue",
