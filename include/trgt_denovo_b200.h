@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define TDB_ABI_VERSION 1
+#define TDB_ABI_VERSION 2
 
 /* return codes */
 #define TDB_OK 0
@@ -118,11 +118,20 @@ int tdb_set_heuristic(tdb_ctx *ctx, const tdb_heuristic *h);
 /*
  * Batched alignment.  Sequences are raw ASCII bytes exactly as the reference passes them
  * (`read.bases`, `allele.seq`; raw byte equality: 'N'=='N', case matters), concatenated in
- * `seq_blob`; sequence i is seq_blob[seq_off[i] .. seq_off[i]+seq_len[i]).  Pair j aligns
+ * `seq_blob`; sequence i is seq_blob[seq_off[i] .. seq_off[i]+seq_len[i]).  Layout contract (checked
+ * on the device, TDB_E_INVALID otherwise): sequences are stored in index order and do not overlap
+ * (seq_off[i] + seq_len[i] <= seq_off[i+1] <= blob_bytes) -- what appending reads and alleles locus
+ * by locus produces.  Pair j aligns
  * pattern = sequence pair_pattern[j] (the read) against text = sequence pair_text[j] (the target).
  * out_score[j]  = cigar_score_clipped(clip_len) (<= 0), written when out_status[j] == 0;
  * out_status[j] = WFA2 status.  out_status may be NULL.
- * All pointers are HOST pointers (pinned memory makes the copies faster but is not required).
+ * All pointers are HOST pointers (pinned memory -- tdb_host_alloc -- lets the copies overlap the
+ * kernels; pageable memory works but serialises them).  Large batches are cut into pair chunks
+ * whose uploads are pipelined against the alignment of the previous chunk; this needs the pair list
+ * to walk the sequence table roughly in order (locus by locus), otherwise the call still works but
+ * uploads everything first.
+ * Equal (pattern bytes, text bytes) pairs are aligned once and the result copied to the duplicates
+ * (the alignment is a pure function of the two byte strings).
  */
 int tdb_align_batch(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
                     const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern,
@@ -211,14 +220,21 @@ int32_t tdb_cigar_score_clipped(const tdb_ctx *ctx, int32_t flank_len);
 
 /* Counters of the last batch call (for roofline accounting and tier diagnostics). */
 typedef struct {
-    uint64_t pairs;         /* pairs aligned */
-    uint64_t tier_pairs[4]; /* pairs finished by tier 0 (shared-memory kernel), 1, 2 (global scratch), 3 unused */
-    uint64_t cells;         /* C: sum over computed score steps of wavefront width */
-    uint64_t ext16;         /* E: 16-base extension compares */
-    uint64_t columns;       /* T: CIGAR columns replayed */
+    uint64_t pairs;         /* pairs in the call */
+    uint64_t tier_pairs[4]; /* pairs ALIGNED by tier 0 (four pairs per warp, shared memory), 1 (one pair per
+                               warp, shared memory), 2 and 3 (one pair per warp, global scratch) */
+    uint64_t cells;         /* C: sum over computed score steps of wavefront width, ALGORITHMIC: */
+    uint64_t ext16;         /* E: 16-base extension compares         every pair counted, duplicates included */
+    uint64_t columns;       /* T: CIGAR columns replayed             (= what the CPU oracle counts) */
+    uint64_t exec_cells, exec_ext16, exec_columns; /* the same for the work the kernels actually executed */
+    uint64_t tier_cells[4], tier_ext16[4], tier_columns[4]; /* executed work per tier */
+    uint64_t pairs_identical; /* pattern bytes == text bytes: resolved without an alignment */
+    uint64_t pairs_duplicate; /* copies of an already aligned (pattern, text) content */
     uint64_t kernel_launches;
-    float ms_pack, ms_align, ms_reduce, ms_total_device; /* CUDA-event times of the last call */
-    float ms_tier[4]; /* per alignment tier (events on the launching stream) */
+    uint64_t chunks;        /* pipeline chunks the call was cut into */
+    float ms_pack, ms_dedup, ms_align, ms_scatter, ms_reduce, ms_total_device; /* CUDA-event times */
+    float ms_tier[4]; /* per alignment tier (events on the launching stream); [2] covers both global tiers.
+                         Stage times are recorded for single-chunk calls only (ms_total_device always). */
 } tdb_counters;
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 /* Enables exact C/E/T work counting inside the kernels (off by default: it costs atomics). */

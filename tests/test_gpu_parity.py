@@ -92,7 +92,9 @@ def test_str_pairs_bit_exact(ctx, clip):
     rng = random.Random(100 + clip)
     seqs, pp, pt = make_pairs(rng, n_targets=300, reads_per_target=12)
     cnt = _check_batch(ctx, seqs, pp, pt, clip)
-    assert cnt.tier_pairs[0] + cnt.tier_pairs[1] > 0.8 * len(pp)  # the shared-memory tiers carry the bulk
+    aligned = sum(cnt.tier_pairs)
+    assert aligned + cnt.pairs_identical + cnt.pairs_duplicate == len(pp)
+    assert cnt.tier_pairs[0] + cnt.tier_pairs[1] > 0.8 * aligned  # the shared-memory tiers carry the bulk
     assert cnt.tier_pairs[0] > 0 and cnt.tier_pairs[1] > 0
 
 
@@ -120,6 +122,58 @@ def test_quad_tier_disabled_gives_same_scores(tdb, monkeypatch):
     cnt = _check_batch(c, seqs, pp, pt, 50)
     assert cnt.tier_pairs[0] == 0
     c.close()
+
+
+def test_dedup_disabled_gives_same_scores(tdb, monkeypatch):
+    """Duplicate elimination must be invisible: every pair aligned on its own gives the same scores."""
+    rng = random.Random(32)
+    seqs, pp, pt = make_pairs(rng, n_targets=60, reads_per_target=10, max_units=25, err=0.001)
+    monkeypatch.setenv("TDB_DISABLE_DEDUP", "1")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_DISABLE_DEDUP")
+    cnt = _check_batch(c, seqs, pp, pt, 50)
+    assert cnt.pairs_duplicate == 0
+    c.close()
+
+
+def test_duplicate_heavy_batch_counts(ctx):
+    """Error-free reads repeat the allele sequence: most pairs are duplicates or identical, and the
+    algorithmic work counters still equal the oracle's (every pair counted)."""
+    rng = random.Random(33)
+    seqs, pp, pt = make_pairs(rng, n_targets=80, reads_per_target=15, max_units=20, err=0.0005)
+    cnt = _check_batch(ctx, seqs, pp, pt, 50)
+    assert cnt.pairs_duplicate + cnt.pairs_identical > 0.3 * len(pp) and cnt.pairs_duplicate > 0
+    assert cnt.exec_cells < cnt.cells and cnt.exec_columns < cnt.columns
+
+
+def test_chunked_host_pipeline(tdb, monkeypatch):
+    """Many small pipeline chunks (upload of chunk k+1 overlapping the alignment of chunk k)."""
+    rng = random.Random(34)
+    seqs, pp, pt = make_pairs(rng, n_targets=400, reads_per_target=12, max_units=20, err=0.002)
+    monkeypatch.setenv("TDB_CHUNK_PAIRS", "1024")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_CHUNK_PAIRS")
+    cnt = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    assert cnt.chunks >= 4
+    # a pair list that jumps around the sequence table falls back to one chunk, same scores
+    perm = np.array(random.Random(1).sample(range(len(pp)), len(pp)))
+    cnt = _check_batch(c, seqs, pp[perm], pt[perm], 50, cigars=False)
+    assert cnt.chunks == 1
+    c.close()
+
+
+def test_bad_layout_and_bad_pair_index_fail(tdb, ctx):
+    blob = np.frombuffer(b"ACGTACGTAC" * 4, dtype=np.uint8)
+    ln = np.array([10, 10], np.uint32)
+    pp, pt = np.array([0], np.uint32), np.array([1], np.uint32)
+    with pytest.raises(tdb.TdbError):  # overlapping sequences
+        ctx.align_batch(blob, np.array([0, 5], np.uint64), ln, pp, pt)
+    with pytest.raises(tdb.TdbError):  # outside the blob
+        ctx.align_batch(blob, np.array([0, 35], np.uint64), ln, pp, pt)
+    with pytest.raises(tdb.TdbError):  # pair index out of range
+        ctx.align_batch(blob, np.array([0, 10], np.uint64), ln, pp, np.array([2], np.uint32))
+    got, st = ctx.align_batch(blob, np.array([0, 10], np.uint64), ln, pp, pt)  # the ctx is still usable
+    assert st[0] == 0
 
 
 def test_heuristic_none(tdb):

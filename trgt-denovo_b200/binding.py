@@ -46,9 +46,13 @@ class AlleleOut(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("tier_pairs", C.c_uint64 * 4), ("cells", C.c_uint64),
-                ("ext16", C.c_uint64), ("columns", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_reduce", C.c_float),
-                ("ms_total_device", C.c_float), ("ms_tier", C.c_float * 4)]
+                ("ext16", C.c_uint64), ("columns", C.c_uint64), ("exec_cells", C.c_uint64),
+                ("exec_ext16", C.c_uint64), ("exec_columns", C.c_uint64), ("tier_cells", C.c_uint64 * 4),
+                ("tier_ext16", C.c_uint64 * 4), ("tier_columns", C.c_uint64 * 4), ("pairs_identical", C.c_uint64),
+                ("pairs_duplicate", C.c_uint64), ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64),
+                ("ms_pack", C.c_float), ("ms_dedup", C.c_float), ("ms_align", C.c_float),
+                ("ms_scatter", C.c_float), ("ms_reduce", C.c_float), ("ms_total_device", C.c_float),
+                ("ms_tier", C.c_float * 4)]
 
 
 # every symbol include/trgt_denovo_b200.h declares (checked by tests/test_abi.py)

@@ -2,15 +2,14 @@
 // every entry point that does arithmetic launches CUDA kernels or fails.
 #include "tdb_wfa_quad.cuh"
 
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace tdb;
@@ -34,6 +33,23 @@ struct TierCfg {
     int workers;
 };
 
+// Device control block (one per ctx).  "call" fields live for a whole batch call, "chunk" fields are
+// zeroed before every chunk.
+struct Ctrl {
+    unsigned err;      // ERR_* bits
+    unsigned gcount;   // pairs queued for the global-scratch tier (listB)
+    unsigned ccount;   // pairs the first global tier could not finish (listC)
+    unsigned wc_g[2];  // work counters of the two global tiers
+    unsigned pad0[3];
+    unsigned long long exec[4][4]; // executed cells, ext16, columns, pairs finished; per tier
+    unsigned long long algo[4];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self
+    // ---- per chunk ----
+    unsigned wc_quad, wc_warp, acount, pad1;
+    unsigned hist[N_HIST];
+    unsigned seg[4];
+};
+constexpr size_t CTRL_CHUNK_OFF = offsetof(Ctrl, wc_quad);
+
 } // namespace
 
 struct tdb_ctx {
@@ -41,14 +57,17 @@ struct tdb_ctx {
     int dev = 0;
     int sm_count = 0;
     std::string err;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[14] = {};
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[16] = {};
+    std::vector<cudaEvent_t> up_ev; // one per in-flight chunk upload
     // grow-only device buffers
-    DevBuf blob, seq_off, seq_len, woff, packed, seq_flag, pair_p, pair_t, score, status, penalty;
-    DevBuf todo_a, todo_b, ctrl, cub_tmp, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
+    DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, canon, pair_p, pair_t, score, status, penalty;
+    DevBuf rep, work, skey_in, skey_out, sval_in, sval_out, cub_tmp, seq_tab, pair_tab, list_a, list_b, list_c;
+    DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0;
-    bool disable_quad = false;
+    bool disable_quad = false, disable_dedup = false;
+    size_t chunk_pairs = 2u << 20;
     bool count_work = true;
     tdb_counters counters;
     // single-pair shim state
@@ -81,7 +100,10 @@ int ensure(tdb_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return TDB_OK;
     size_t want = std::max(bytes, b.cap + b.cap / 2);
     want = (want + 255) & ~(size_t)255;
-    if (b.p) CK(cudaFree(b.p));
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream)); // the old allocation may still be in use by queued work
+        CK(cudaFree(b.p));
+    }
     b.p = nullptr, b.cap = 0;
     CK(cudaMalloc(&b.p, want));
     b.cap = want;
@@ -93,10 +115,8 @@ int ensure(tdb_ctx *ctx, DevBuf &b, size_t bytes) {
         if (r_ != TDB_OK) return r_;                \
     } while (0)
 
-// ctrl block layout (unsigned): [0] work counter, [1] next count A, [2] next count B, pad;
-// counters (unsigned long long) at byte 64: 4 per tier x 3 tiers
-constexpr size_t CTRL_BYTES = 64 + 4 * 4 * sizeof(unsigned long long);
-
+// Where the batch lives.  Device pointers always; host pointers only for the host-buffer entry points
+// (then the device arrays are ctx buffers that run_align fills chunk by chunk).
 struct DevBatch {
     const uint8_t *blob;
     size_t blob_bytes;
@@ -109,173 +129,361 @@ struct DevBatch {
     uint8_t *cigar_buf;
     const uint64_t *cigar_off;
     uint32_t *cigar_len;
+    // host sources (nullptr: inputs already resident)
+    const uint8_t *h_blob;
+    const uint64_t *h_seq_off;
+    const uint32_t *h_seq_len;
+    const uint32_t *h_pp, *h_pt;
 };
 
 int check_sizes(tdb_ctx *ctx, size_t blob_bytes, size_t n_seqs, size_t n_pairs) {
-    if (n_seqs >= 0xffffffffull || n_pairs >= 0xffffffffull)
-        return fail(ctx, TDB_E_UNSUPPORTED, "batch too large: n_seqs=%zu n_pairs=%zu (max 2^32-2 per call)", n_seqs,
+    if (n_seqs >= 0x7fffffffull || n_pairs >= 0x7fffffffull)
+        return fail(ctx, TDB_E_UNSUPPORTED, "batch too large: n_seqs=%zu n_pairs=%zu (max 2^31-2 per call)", n_seqs,
                     n_pairs);
     if (blob_bytes / 16 + 2 * n_seqs + 2 >= 0xffffffffull)
         return fail(ctx, TDB_E_UNSUPPORTED, "sequence blob too large for 32-bit word offsets: %zu bytes", blob_bytes);
     return TDB_OK;
 }
 
-// Runs pack + alignment tiers on device-resident inputs.  Leaves results in b.score/status/penalty.
-int run_align_device(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
-    cudaStream_t s = ctx->stream;
+struct Chunk {
+    size_t p0, p1;       // pair range
+    uint32_t s_lo, s_hi; // sequences referenced: [s_lo, s_hi)
+};
+
+uint32_t table_mask(size_t n) {
+    size_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    return (uint32_t)(cap - 1);
+}
+
+// Splits a host batch into pair chunks whose sequence ranges advance with the pair index (true for
+// batches assembled locus by locus), so that a chunk can be aligned while the next one is still in
+// flight over PCIe.  Falls back to a single chunk when the pair list jumps around the sequence table.
+void plan_chunks(const tdb_ctx *ctx, const DevBatch &b, std::vector<Chunk> &out) {
+    out.clear();
+    const size_t n_pairs = b.n_pairs, n_seqs = b.n_seqs;
+    if (!b.h_pp || n_pairs <= ctx->chunk_pairs + ctx->chunk_pairs / 2) {
+        out.push_back({0, n_pairs, 0, (uint32_t)n_seqs});
+        return;
+    }
+    const size_t K = (n_pairs + ctx->chunk_pairs - 1) / ctx->chunk_pairs;
+    const size_t per = (n_pairs + K - 1) / K;
+    out.resize(K);
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < hw; ++t)
+        th.emplace_back([&, t]() {
+            for (size_t k = t; k < K; k += hw) {
+                const size_t p0 = k * per, p1 = std::min(n_pairs, p0 + per);
+                uint32_t lo = 0xffffffffu, hi = 0;
+                for (size_t j = p0; j < p1; ++j) {
+                    const uint32_t a = b.h_pp[j], c = b.h_pt[j];
+                    lo = std::min(lo, std::min(a, c));
+                    hi = std::max(hi, std::max(a, c));
+                }
+                if (lo > hi) lo = hi = 0;
+                hi = (uint32_t)std::min<size_t>((size_t)hi + 1, n_seqs); // out-of-range indices fail on the device
+                lo = std::min(lo, hi);
+                out[k] = {p0, p1, lo, hi};
+            }
+        });
+    for (auto &x : th) x.join();
+    size_t covered = 0;
+    for (const Chunk &c : out) covered += c.s_hi - c.s_lo;
+    if (covered > 2 * n_seqs + 64 * K) {
+        out.clear();
+        out.push_back({0, n_pairs, 0, (uint32_t)n_seqs});
+    }
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+// Pack + duplicate elimination + alignment tiers + scatter.  Leaves results in b.score/status/penalty.
+int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
     const uint32_t n_seqs = (uint32_t)b.n_seqs, n_pairs = (uint32_t)b.n_pairs;
-    memset(&ctx->counters, 0, sizeof(ctx->counters));
-    ctx->counters.pairs = n_pairs;
+    tdb_counters &cn = ctx->counters;
+    memset(&cn, 0, sizeof(cn));
+    cn.pairs = n_pairs;
     CK(cudaEventRecord(ctx->ev[0], s));
     if (n_pairs == 0 || n_seqs == 0) {
         CK(cudaEventRecord(ctx->ev[1], s));
-        CK(cudaEventRecord(ctx->ev[2], s));
         CK(cudaStreamSynchronize(s));
         return TDB_OK;
     }
-    // ---- packed layout: exclusive scan of words per sequence -------------------------------------
-    ENSURE(ctx->woff, ((size_t)n_seqs + 1) * 4);
-    ENSURE(ctx->seq_flag, (size_t)n_seqs);
+    const tdb_penalties &cp = ctx->cfg.penalties;
+    const bool default_pen = cp.mismatch == 8 && cp.gap_opening1 == 4 && cp.gap_extension1 == 2 &&
+                             cp.gap_opening2 == 24 && cp.gap_extension2 == 1;
+    const bool quad_ok = default_pen && !ctx->disable_quad;
+    const bool dedup = !ctx->disable_dedup && !cigar_mode;
+
+    std::vector<Chunk> chunks;
+    plan_chunks(ctx, b, chunks);
+    const size_t K = chunks.size();
+    cn.chunks = K;
+    const bool staged = K == 1; // per-stage CUDA-event timing only when the call is one chunk
+    size_t max_cp = 0, max_cs = 0;
+    for (const Chunk &c : chunks) max_cp = std::max(max_cp, c.p1 - c.p0), max_cs = std::max<size_t>(max_cs, c.s_hi - c.s_lo);
+
+    // ---- buffers ------------------------------------------------------------------------------------
     const size_t max_words = b.blob_bytes / 16 + 2 * (size_t)n_seqs + 2;
     ENSURE(ctx->packed, max_words * 4);
-    {
-        NWordsOp op{b.seq_len};
-        auto it = thrust::make_transform_iterator(thrust::make_counting_iterator<uint32_t>(0), op);
+    ENSURE(ctx->seq_flag, (size_t)n_seqs);
+    ENSURE(ctx->seq_hash, (size_t)n_seqs * 8);
+    ENSURE(ctx->ctrl, sizeof(Ctrl));
+    ENSURE(ctx->list_b, (size_t)n_pairs * 4);
+    const bool want_work = ctx->count_work && !cigar_mode;
+    if (!cigar_mode) {
+        ENSURE(ctx->canon, (size_t)n_seqs * 4);
+        ENSURE(ctx->rep, (size_t)n_pairs * 4);
+        if (want_work) ENSURE(ctx->work, (size_t)n_pairs * 12);
+        ENSURE(ctx->skey_in, max_cp);
+        ENSURE(ctx->skey_out, max_cp);
+        ENSURE(ctx->sval_in, max_cp * 4);
+        ENSURE(ctx->sval_out, max_cp * 4);
+        ENSURE(ctx->list_a, max_cp * 4);
+        if (dedup) ENSURE(ctx->seq_tab, ((size_t)table_mask(max_cs) + 1) * 12);
+        ENSURE(ctx->pair_tab, ((size_t)table_mask(max_cp) + 1) * 12);
         size_t tmp = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, (uint32_t *)ctx->woff.p, (int)n_seqs, s));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint8_t *)nullptr, (uint8_t *)nullptr,
+                                           (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_cp, 0, 8, s));
         ENSURE(ctx->cub_tmp, tmp);
-        CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, it, (uint32_t *)ctx->woff.p, (int)n_seqs, s));
     }
-    {
-        const int threads = 256;
-        const unsigned warps_needed = n_seqs;
-        unsigned blocks = (unsigned)std::min<size_t>(((size_t)warps_needed * 32 + threads - 1) / threads,
-                                                     (size_t)ctx->sm_count * 32);
-        k_pack<<<blocks, threads, 0, s>>>(b.blob, b.blob_bytes, b.seq_off, b.seq_len, (const uint32_t *)ctx->woff.p,
-                                          n_seqs, (uint32_t *)ctx->packed.p, (uint8_t *)ctx->seq_flag.p);
-        CK(cudaGetLastError());
-        ctx->counters.kernel_launches += 2; // scan + pack
+    while (b.h_pp && ctx->up_ev.size() < K) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->up_ev.push_back(e);
     }
-    CK(cudaEventRecord(ctx->ev[1], s));
-    // ---- tiers -------------------------------------------------------------------------------------
-    // 0: four pairs per warp, shared memory (default penalties only)   1: one pair per warp, shared memory
-    // 2,3: one pair per warp, global scratch (long / wide alignments).  A tier that cannot finish a pair
-    // (ring, provenance or score capacity) appends it to the next tier's work list on the device.
-    ENSURE(ctx->ctrl, CTRL_BYTES);
-    CK(cudaMemsetAsync(ctx->ctrl.p, 0, CTRL_BYTES, s));
-    unsigned *ctrl = (unsigned *)ctx->ctrl.p;
-    unsigned long long *cnt64 = (unsigned long long *)((uint8_t *)ctx->ctrl.p + 64);
+    Ctrl *ctrl = (Ctrl *)ctx->ctrl.p;
+    CK(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), s));
+
     AlignParams p;
     memset(&p, 0, sizeof(p));
-    const tdb_penalties &cp = ctx->cfg.penalties;
     p.pn = {cp.mismatch, cp.gap_opening1, cp.gap_extension1, cp.gap_opening2, cp.gap_extension2};
     p.heur = {ctx->cfg.heuristic.kind, ctx->cfg.heuristic.min_wavefront_length,
               ctx->cfg.heuristic.max_distance_threshold, ctx->cfg.heuristic.steps_between_cutoffs};
     p.clip = ctx->cfg.clip_len;
-    p.packed = (const uint32_t *)ctx->packed.p, p.woff = (const uint32_t *)ctx->woff.p;
-    p.seq_flag = (const uint8_t *)ctx->seq_flag.p;
+    p.packed = (const uint32_t *)ctx->packed.p, p.seq_flag = (const uint8_t *)ctx->seq_flag.p;
     p.blob = b.blob, p.seq_off = b.seq_off, p.seq_len = b.seq_len, p.pair_p = b.pp, p.pair_t = b.pt;
     p.out_score = b.score, p.out_status = b.status, p.out_penalty = b.penalty;
+    p.work = want_work ? (uint32_t *)ctx->work.p : nullptr;
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
 
-    const bool default_pen = cp.mismatch == 8 && cp.gap_opening1 == 4 && cp.gap_extension1 == 2 &&
-                             cp.gap_opening2 == 24 && cp.gap_extension2 == 1;
+    // ---- host batches: queue every chunk's upload on the copy stream --------------------------------
+    if (b.h_pp) {
+        uint32_t up = 0; // sequences [0, up) are queued
+        for (size_t k = 0; k < K; ++k) {
+            const Chunk &c = chunks[k];
+            if (c.s_hi > up) {
+                const uint32_t a = up, e = c.s_hi;
+                CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, (size_t)(e - a) * 8, cudaMemcpyHostToDevice, cs));
+                CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
+                const uint64_t b0 = std::min<uint64_t>(b.h_seq_off[a], b.blob_bytes);
+                const uint64_t b1 = e == n_seqs ? b.blob_bytes
+                                                : std::min<uint64_t>(b.h_seq_off[e - 1] + b.h_seq_len[e - 1], b.blob_bytes);
+                if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+                up = e;
+            }
+            CK(cudaMemcpyAsync((uint32_t *)b.pp + c.p0, b.h_pp + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync((uint32_t *)b.pt + c.p0, b.h_pt + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(ctx->up_ev[k], cs));
+        }
+    }
+
+    // ---- chunks ---------------------------------------------------------------------------------------
+    uint32_t packed_upto = 0;
+    for (size_t k = 0; k < K; ++k) {
+        const Chunk &c = chunks[k];
+        const uint32_t cpairs = (uint32_t)(c.p1 - c.p0);
+        if (b.h_pp) CK(cudaStreamWaitEvent(s, ctx->up_ev[k], 0));
+        if (c.s_hi > packed_upto) {
+            const uint32_t cnt = c.s_hi - packed_upto;
+            const unsigned blocks = (unsigned)std::min<size_t>(((size_t)cnt * PK_G + 255) / 256, (size_t)ctx->sm_count * 64);
+            k_pack<<<blocks, 256, 0, s>>>(b.blob, b.blob_bytes, b.seq_off, b.seq_len, packed_upto, c.s_hi, n_seqs,
+                                          (uint32_t *)ctx->packed.p, (uint8_t *)ctx->seq_flag.p,
+                                          (uint64_t *)ctx->seq_hash.p, &ctrl->err);
+            CK(cudaGetLastError());
+            cn.kernel_launches += 1;
+            packed_upto = c.s_hi;
+        }
+        if (staged) CK(cudaEventRecord(ctx->ev[2], s));
+        if (cigar_mode) continue; // CIGAR output lives in the general kernel: no dedup, no shared-memory tiers
+        CK(cudaMemsetAsync((uint8_t *)ctrl + CTRL_CHUNK_OFF, 0, sizeof(Ctrl) - CTRL_CHUNK_OFF, s));
+        const uint32_t ns = c.s_hi - c.s_lo;
+        const uint32_t smask = table_mask(ns), pmask = table_mask(cpairs);
+        unsigned long long *skeys = (unsigned long long *)ctx->seq_tab.p;
+        uint32_t *svals = dedup ? (uint32_t *)(skeys + (size_t)smask + 1) : nullptr;
+        if (dedup && ns) {
+            CK(cudaMemsetAsync(skeys, 0xff, ((size_t)smask + 1) * 12, s));
+            k_seq_insert<<<(ns + 255) / 256, 256, 0, s>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p,
+                                                          c.s_lo, c.s_hi, skeys, svals, smask);
+            CK(cudaGetLastError());
+            cn.kernel_launches += 1;
+        }
+        if (ns) {
+            const unsigned blocks = (unsigned)(((size_t)ns * CN_G + 255) / 256);
+            k_seq_canon<<<blocks, 256, 0, s>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p, b.seq_off,
+                                               b.seq_len, (const uint32_t *)ctx->packed.p, c.s_lo, c.s_hi, skeys, svals,
+                                               smask, (uint32_t *)ctx->canon.p, dedup ? 1 : 0);
+            CK(cudaGetLastError());
+            cn.kernel_launches += 1;
+        }
+        PairTable tb;
+        tb.keys = (unsigned long long *)ctx->pair_tab.p, tb.vals = (uint32_t *)(tb.keys + (size_t)pmask + 1), tb.mask = pmask;
+        CK(cudaMemsetAsync(tb.keys, 0xff, ((size_t)pmask + 1) * 12, s));
+        const unsigned pblocks = (cpairs + 255) / 256;
+        k_pair_insert<<<pblocks, 256, 0, s>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs,
+                                              (const uint32_t *)ctx->canon.p, tb, &ctrl->err);
+        CK(cudaGetLastError());
+        ClassifyOut co;
+        co.rep = (uint32_t *)ctx->rep.p, co.key = (uint8_t *)ctx->skey_in.p, co.val = (uint32_t *)ctx->sval_in.p;
+        co.glist = (uint32_t *)ctx->list_b.p, co.gcount = &ctrl->gcount, co.hist = ctrl->hist;
+        co.out_score = b.score, co.out_status = b.status, co.out_penalty = b.penalty, co.work = p.work;
+        k_pair_classify<<<pblocks, 256, 0, s>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs,
+                                                (const uint32_t *)ctx->canon.p, b.seq_len, (const uint8_t *)ctx->seq_flag.p,
+                                                tb, quad_ok ? 1 : 0, T0_MAXLEN, co);
+        CK(cudaGetLastError());
+        size_t tmp = ctx->cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, (const uint8_t *)ctx->skey_in.p, (uint8_t *)ctx->skey_out.p,
+                                           (const uint32_t *)ctx->sval_in.p, (uint32_t *)ctx->sval_out.p, (int)cpairs, 0, 8, s));
+        k_plan<<<1, 32, 0, s>>>(ctrl->hist, ctrl->seg);
+        CK(cudaGetLastError());
+        cn.kernel_launches += 6; // insert, classify, sort (3 kernels), plan
+        if (staged) CK(cudaEventRecord(ctx->ev[3], s));
+        // tier 0: four pairs per warp, shared memory (default penalties only)
+        p.src1 = (const uint32_t *)ctx->sval_out.p;
+        if (quad_ok) {
+            p.src1_seg = ctrl->seg + 2, p.src2 = nullptr, p.src2_count = nullptr;
+            p.work_counter = &ctrl->wc_quad, p.next_todo = (uint32_t *)ctx->list_a.p, p.next_count = &ctrl->acount;
+            p.counters = ctrl->exec[0];
+            const size_t smem = sizeof(QPair) * (32 / QG) * Q_WARPS;
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->quad_ctas_per_sm,
+                                                             ((size_t)cpairs + 31) / 32 + 1);
+            k_align_quad<8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, s>>>(p);
+            CK(cudaGetLastError());
+            cn.kernel_launches += 1;
+        }
+        if (staged) CK(cudaEventRecord(ctx->ev[4], s));
+        // tier 1: one pair per warp, shared memory
+        {
+            p.src1_seg = ctrl->seg + 0, p.src2 = (const uint32_t *)ctx->list_a.p, p.src2_count = &ctrl->acount;
+            p.work_counter = &ctrl->wc_warp, p.next_todo = (uint32_t *)ctx->list_b.p, p.next_count = &ctrl->gcount;
+            p.counters = ctrl->exec[1];
+            const size_t smem = sizeof(T0Smem) * T0_WARPS;
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->t0_ctas_per_sm,
+                                                             ((size_t)cpairs + T0_WARPS - 1) / T0_WARPS);
+            k_align_warp<<<grid, T0_WARPS * 32, smem, s>>>(p);
+            CK(cudaGetLastError());
+            cn.kernel_launches += 1;
+        }
+        if (staged) CK(cudaEventRecord(ctx->ev[5], s));
+    }
+
+    // ---- global-scratch tiers: pairs too long or too wide for shared memory, once per call ------------
     const uint64_t cap = ctx->cfg.scratch_bytes ? ctx->cfg.scratch_bytes : (48ull << 30);
     const TierCfg gtiers[2] = {
         {10, 1 << 16, 1 << 17, 8u << 20, ctx->sm_count * 8},   // W=1024, S<65536, 8 MiB provenance
         {15, 1 << 18, 1 << 19, 192u << 20, ctx->sm_count * 1}, // W=32768, S<262144, 192 MiB provenance
     };
-    unsigned pending = n_pairs;
-    const uint32_t *todo = nullptr; // nullptr: identity list 0..n_pairs-1
-    bool tier_ran[4] = {false, false, false, false};
-    DevBuf *lists[2] = {&ctx->todo_a, &ctx->todo_b};
-    int flip = 0;
-    for (int t = 0; t < 4 && pending > 0; ++t) {
-        if (cigar_mode && t < 2) continue;                 // CIGAR output lives in the general kernel
-        if (t == 0 && (!default_pen || ctx->disable_quad)) continue;
-        const bool last = t == 3;
-        CK(cudaMemsetAsync(ctrl + 0, 0, 4, s));
-        p.todo = todo, p.n_items = pending, p.n_items_ptr = nullptr, p.work_counter = ctrl + 0;
-        p.next_todo = nullptr, p.next_count = ctrl + 1 + t;
-        if (!last) {
-            ENSURE(*lists[flip], (size_t)pending * 4);
-            p.next_todo = (uint32_t *)lists[flip]->p;
-        }
-        p.counters = cnt64 + 4 * t;
-        CK(cudaEventRecord(ctx->ev[6 + 2 * t], s));
-        if (t == 0) {
-            const size_t smem = sizeof(QPair) * (32 / QG) * Q_WARPS;
-            const unsigned grid = (unsigned)(ctx->sm_count * ctx->quad_ctas_per_sm);
-            k_align_quad<8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, s>>>(p);
-        } else if (t == 1) {
-            const size_t smem = sizeof(T0Smem) * T0_WARPS;
-            const unsigned grid = (unsigned)(ctx->sm_count * ctx->t0_ctas_per_sm);
-            k_align_tier0<<<grid, T0_WARPS * 32, smem, s>>>(p);
+    Ctrl h;
+    CK(cudaMemcpyAsync(&h, ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h.err & ERR_LAYOUT)
+        return fail(ctx, TDB_E_INVALID, "sequence blob layout: sequences must be stored in index order, non-overlapping, inside the blob");
+    if (h.err & ERR_PAIR_INDEX) return fail(ctx, TDB_E_INVALID, "pair index out of range");
+    unsigned pending = cigar_mode ? n_pairs : h.gcount;
+    if (staged) CK(cudaEventRecord(ctx->ev[6], s));
+    for (int g = 0; g < 2 && pending > 0; ++g) {
+        const TierCfg tc = gtiers[g];
+        const size_t stride = global_tier_stride(tc.wlog2, tc.s_cap, tc.ops_cap, tc.prov_cap);
+        uint64_t workers = std::min<uint64_t>((uint64_t)tc.workers, std::max<uint64_t>(1, (cap / 2) / stride));
+        workers = std::min<uint64_t>(workers, pending);
+        workers = (workers + 3) & ~(uint64_t)3; // whole CTAs of 4 warps
+        ENSURE(ctx->scratch[g], stride * (size_t)workers);
+        p.scratch = (uint8_t *)ctx->scratch[g].p, p.scratch_stride = stride;
+        p.wlog2 = tc.wlog2, p.s_cap = tc.s_cap, p.ops_cap = tc.ops_cap, p.prov_cap = tc.prov_cap;
+        p.src1_seg = nullptr, p.src1_count = pending, p.src2 = nullptr, p.src2_count = nullptr;
+        if (g == 0) {
+            p.src1 = cigar_mode ? nullptr : (const uint32_t *)ctx->list_b.p;
+            ENSURE(ctx->list_c, (size_t)pending * 4);
+            p.next_todo = (uint32_t *)ctx->list_c.p, p.next_count = &ctrl->ccount;
         } else {
-            const TierCfg tc = gtiers[t - 2];
-            const size_t stride = global_tier_stride(tc.wlog2, tc.s_cap, tc.ops_cap, tc.prov_cap);
-            uint64_t workers = std::min<uint64_t>((uint64_t)tc.workers, std::max<uint64_t>(1, (cap / 2) / stride));
-            workers = std::min<uint64_t>(workers, pending);
-            workers = (workers + 3) & ~(uint64_t)3; // whole CTAs of 4 warps
-            ENSURE(ctx->scratch[t - 2], stride * (size_t)workers);
-            p.scratch = (uint8_t *)ctx->scratch[t - 2].p, p.scratch_stride = stride;
-            p.wlog2 = tc.wlog2, p.s_cap = tc.s_cap, p.ops_cap = tc.ops_cap, p.prov_cap = tc.prov_cap;
-            const unsigned grid = (unsigned)(workers / 4);
-            if (cigar_mode) k_align_global<true><<<grid, 128, 0, s>>>(p);
-            else k_align_global<false><<<grid, 128, 0, s>>>(p);
+            p.src1 = (const uint32_t *)ctx->list_c.p;
+            p.next_todo = nullptr, p.next_count = nullptr;
         }
+        p.work_counter = &ctrl->wc_g[g], p.counters = ctrl->exec[2 + g];
+        const unsigned grid = (unsigned)(workers / 4);
+        if (cigar_mode) k_align_global<true><<<grid, 128, 0, s>>>(p);
+        else k_align_global<false><<<grid, 128, 0, s>>>(p);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[7 + 2 * t], s));
-        tier_ran[t] = true;
-        ctx->counters.kernel_launches += 1;
+        cn.kernel_launches += 1;
         unsigned next = 0;
-        if (!last) {
-            CK(cudaMemcpyAsync(&next, ctrl + 1 + t, 4, cudaMemcpyDeviceToHost, s));
+        if (g == 0) {
+            CK(cudaMemcpyAsync(&next, &ctrl->ccount, 4, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
         }
-        ctx->counters.tier_pairs[t] = pending - next;
         pending = next;
-        if (!last) todo = (const uint32_t *)lists[flip]->p, flip ^= 1;
     }
-    CK(cudaEventRecord(ctx->ev[2], s));
-    unsigned long long h[16];
-    CK(cudaMemcpyAsync(h, cnt64, sizeof(h), cudaMemcpyDeviceToHost, s));
+    if (staged) CK(cudaEventRecord(ctx->ev[7], s));
+    if (!cigar_mode) {
+        const unsigned blocks = (unsigned)std::min<size_t>(((size_t)n_pairs + 255) / 256, (size_t)ctx->sm_count * 16);
+        k_scatter<<<blocks, 256, 0, s>>>((const uint32_t *)ctx->rep.p, n_pairs, b.score, b.status, b.penalty,
+                                         (const uint32_t *)p.work, ctrl->algo);
+        CK(cudaGetLastError());
+        cn.kernel_launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev[1], s));
+    CK(cudaMemcpyAsync(&h, ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    uint64_t aligned = 0;
     for (int t = 0; t < 4; ++t) {
-        ctx->counters.cells += h[4 * t + 0];
-        ctx->counters.ext16 += h[4 * t + 1];
-        ctx->counters.columns += h[4 * t + 2];
+        cn.exec_cells += h.exec[t][0], cn.exec_ext16 += h.exec[t][1], cn.exec_columns += h.exec[t][2];
+        cn.tier_cells[t] = h.exec[t][0], cn.tier_ext16[t] = h.exec[t][1], cn.tier_columns[t] = h.exec[t][2];
+        cn.tier_pairs[t] = h.exec[t][3];
+        aligned += h.exec[t][3];
     }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->counters.ms_pack = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
-    ctx->counters.ms_align = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
-    ctx->counters.ms_total_device = ms;
-    for (int t = 0; t < 4; ++t)
-        if (tier_ran[t]) {
-            cudaEventElapsedTime(&ms, ctx->ev[6 + 2 * t], ctx->ev[7 + 2 * t]);
-            ctx->counters.ms_tier[t] = ms;
+    if (cigar_mode) {
+        cn.cells = cn.exec_cells, cn.ext16 = cn.exec_ext16, cn.columns = cn.exec_columns;
+    } else {
+        cn.cells = h.algo[0], cn.ext16 = h.algo[1], cn.columns = h.algo[2];
+        cn.pairs_duplicate = n_pairs - h.algo[3];
+        cn.pairs_identical = h.algo[3] >= aligned ? h.algo[3] - aligned : 0;
+    }
+    cn.ms_total_device = elapsed(ctx->ev[0], ctx->ev[1]);
+    if (staged) {
+        cn.ms_pack = elapsed(ctx->ev[0], ctx->ev[2]);
+        if (!cigar_mode) {
+            cn.ms_dedup = elapsed(ctx->ev[2], ctx->ev[3]);
+            cn.ms_tier[0] = elapsed(ctx->ev[3], ctx->ev[4]);
+            cn.ms_tier[1] = elapsed(ctx->ev[4], ctx->ev[5]);
+            cn.ms_scatter = elapsed(ctx->ev[7], ctx->ev[1]);
         }
+        cn.ms_tier[2] = elapsed(ctx->ev[6], ctx->ev[7]);
+        cn.ms_align = cn.ms_tier[0] + cn.ms_tier[1] + cn.ms_tier[2];
+    }
     return TDB_OK;
 }
-
 
 int run_reduce_device(tdb_ctx *ctx, const tdb_trio_locus *dloci, size_t n_loci, const int32_t *dscores, double q,
                       int is_duo, tdb_allele_out *dout, uint8_t *dmask) {
     cudaStream_t s = ctx->stream;
-    CK(cudaEventRecord(ctx->ev[3], s));
+    CK(cudaEventRecord(ctx->ev[8], s));
     if (n_loci) {
         const unsigned threads = 128, blocks = (unsigned)((n_loci + threads - 1) / threads);
         k_reduce<<<blocks, threads, 0, s>>>(dloci, (uint32_t)n_loci, dscores, q, is_duo, dout, dmask);
         CK(cudaGetLastError());
         ctx->counters.kernel_launches += 1;
     }
-    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaEventRecord(ctx->ev[9], s));
     CK(cudaStreamSynchronize(s));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+    const float ms = elapsed(ctx->ev[8], ctx->ev[9]);
     ctx->counters.ms_reduce = ms;
     ctx->counters.ms_total_device += ms;
     return TDB_OK;
@@ -309,11 +517,11 @@ int host_align_common(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, 
     int r = check_sizes(ctx, blob_bytes, n_seqs, n_pairs);
     if (r) return r;
     CK(cudaSetDevice(ctx->dev));
-    UPLOAD(ctx->blob, seq_blob, blob_bytes, 32);
-    UPLOAD(ctx->seq_off, seq_off, n_seqs * 8, 0);
-    UPLOAD(ctx->seq_len, seq_len, n_seqs * 4, 0);
-    UPLOAD(ctx->pair_p, pair_pattern, n_pairs * 4, 0);
-    UPLOAD(ctx->pair_t, pair_text, n_pairs * 4, 0);
+    ENSURE(ctx->blob, blob_bytes + 64);
+    ENSURE(ctx->seq_off, n_seqs * 8 + 8);
+    ENSURE(ctx->seq_len, n_seqs * 4 + 4);
+    ENSURE(ctx->pair_p, n_pairs * 4 + 4);
+    ENSURE(ctx->pair_t, n_pairs * 4 + 4);
     ENSURE(ctx->score, n_pairs * 4 + 4);
     ENSURE(ctx->status, n_pairs * 4 + 4);
     ENSURE(ctx->penalty, n_pairs * 4 + 4);
@@ -322,6 +530,8 @@ int host_align_common(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, 
     b.seq_off = (const uint64_t *)ctx->seq_off.p, b.seq_len = (const uint32_t *)ctx->seq_len.p, b.n_seqs = n_seqs;
     b.pp = (const uint32_t *)ctx->pair_p.p, b.pt = (const uint32_t *)ctx->pair_t.p, b.n_pairs = n_pairs;
     b.score = (int32_t *)ctx->score.p, b.status = (int32_t *)ctx->status.p, b.penalty = (int32_t *)ctx->penalty.p;
+    // the chunked uploads are queued by run_align on the copy stream
+    b.h_blob = seq_blob, b.h_seq_off = seq_off, b.h_seq_len = seq_len, b.h_pp = pair_pattern, b.h_pt = pair_text;
     return TDB_OK;
 }
 
@@ -390,15 +600,16 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     memset(&c->counters, 0, sizeof(c->counters));
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 14 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     const size_t smem = sizeof(T0Smem) * T0_WARPS;
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_align_tier0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_align_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_align_tier0, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k_align_warp, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     int occ = 0;
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_align_tier0, T0_WARPS * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_align_warp, T0_WARPS * 32, smem);
     if (e != cudaSuccess || occ < 1) {
         int code = fail(nullptr, TDB_E_CUDA, "context setup failed: %s (occupancy %d)", cudaGetErrorString(e), occ);
         tdb_destroy(c);
@@ -419,6 +630,11 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         }
         c->quad_ctas_per_sm = qocc;
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
+        c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
+        if (const char *cp = getenv("TDB_CHUNK_PAIRS")) {
+            const long long v = atoll(cp);
+            if (v >= 1024) c->chunk_pairs = (size_t)v;
+        }
     }
     *out = c;
     return TDB_OK;
@@ -427,14 +643,17 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
 void tdb_destroy(tdb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
-    DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->woff, &c->packed, &c->seq_flag, &c->pair_p, &c->pair_t,
-                      &c->score, &c->status, &c->penalty, &c->todo_a, &c->todo_b, &c->ctrl, &c->cub_tmp, &c->loci,
-                      &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
-                      &c->scratch[1]};
+    DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->canon,
+                      &c->pair_p, &c->pair_t, &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->skey_in,
+                      &c->skey_out, &c->sval_in, &c->sval_out, &c->cub_tmp, &c->seq_tab, &c->pair_tab, &c->list_a,
+                      &c->list_b, &c->list_c, &c->ctrl, &c->loci, &c->aout, &c->mask, &c->scores_in, &c->cigar,
+                      &c->cigar_off, &c->cigar_len, &c->scratch[0], &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
-    for (int i = 0; i < 14; ++i)
+    for (int i = 0; i < 16; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->up_ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -475,7 +694,7 @@ int tdb_align_batch(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, co
     DevBatch b;
     r = host_align_common(ctx, seq_blob, blob_bytes, seq_off, seq_len, n_seqs, pair_pattern, pair_text, n_pairs, b);
     if (r) return r;
-    r = run_align_device(ctx, b, false);
+    r = run_align(ctx, b, false);
     if (r) return r;
     if (n_pairs) {
         CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -498,7 +717,7 @@ int tdb_align_batch_device(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_by
     b.blob = seq_blob, b.blob_bytes = blob_bytes, b.seq_off = seq_off, b.seq_len = seq_len, b.n_seqs = n_seqs;
     b.pp = pair_pattern, b.pt = pair_text, b.n_pairs = n_pairs;
     b.score = out_score, b.status = out_status, b.penalty = nullptr;
-    return run_align_device(ctx, b, false);
+    return run_align(ctx, b, false);
 }
 
 int tdb_align_batch_cigar(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
@@ -522,7 +741,7 @@ int tdb_align_batch_cigar(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_byt
     ENSURE(ctx->cigar_len, n_pairs * 4 + 4);
     b.cigar_buf = (uint8_t *)ctx->cigar.p, b.cigar_off = (const uint64_t *)ctx->cigar_off.p;
     b.cigar_len = (uint32_t *)ctx->cigar_len.p;
-    r = run_align_device(ctx, b, true);
+    r = run_align(ctx, b, true);
     if (r) return r;
     if (n_pairs) {
         CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -584,7 +803,7 @@ static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t
     ENSURE(ctx->mask, n_pairs + 16);
     CK(cudaMemsetAsync(ctx->aout.p, 0, n_loci * 2 * sizeof(tdb_allele_out), ctx->stream));
     CK(cudaMemsetAsync(ctx->mask.p, 0, n_pairs + 16, ctx->stream));
-    r = run_align_device(ctx, b, false);
+    r = run_align(ctx, b, false);
     if (r) return r;
     r = run_reduce_device(ctx, (const tdb_trio_locus *)ctx->loci.p, n_loci, b.score, q, is_duo,
                           (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p);
@@ -633,7 +852,7 @@ int tdb_assess_batch_device(tdb_ctx *ctx, int32_t is_duo, const uint8_t *seq_blo
     b.blob = seq_blob, b.blob_bytes = blob_bytes, b.seq_off = seq_off, b.seq_len = seq_len, b.n_seqs = n_seqs;
     b.pp = pair_pattern, b.pt = pair_text, b.n_pairs = n_pairs;
     b.score = dscore, b.status = nullptr, b.penalty = nullptr;
-    r = run_align_device(ctx, b, false);
+    r = run_align(ctx, b, false);
     if (r) return r;
     return run_reduce_device(ctx, loci, n_loci, dscore, parent_quantile, is_duo, out, denovo_mask);
 }

@@ -8,16 +8,15 @@ namespace tdb {
 
 // ------------------------------------------------------------------------------------------------
 // Packing: raw ASCII -> 2-bit words (the role north_star gives locus.rs/read.rs, done at HBM speed).
-// One warp per sequence, lane j builds word j (16 bases).  A sequence containing any byte outside
-// {A,C,G,T} is flagged; pairs touching a flagged sequence take the byte-compare path so that raw byte
-// equality (N==N, case-sensitive) is preserved exactly as WFA2 sees it.
+// Sixteen lanes per sequence, lane j builds word j (16 bases).  A sequence containing any byte
+// outside {A,C,G,T} is flagged; pairs touching a flagged sequence take the byte-compare path so that
+// raw byte equality (N==N, case-sensitive) is preserved exactly as WFA2 sees it.  The same pass
+// produces a 64-bit content hash per sequence (feeds the duplicate elimination below) and checks
+// the blob layout contract (sequences laid out in index order, non-overlapping), which lets the
+// packed offset be pure arithmetic: word offset of sequence i = (seq_off[i] >> 4) + 2 i.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t nwords_of(uint32_t len) { return (len + 15u) / 16u + 1u; }
-
-struct NWordsOp {
-    const uint32_t *len;
-    __host__ __device__ uint32_t operator()(uint32_t i) const { return (len[i] + 15u) / 16u + 1u; }
-};
+__host__ __device__ __forceinline__ uint32_t nwords_of(uint32_t len) { return (len + 15u) / 16u + 1u; }
+__host__ __device__ __forceinline__ uint32_t woff_of(uint64_t off, uint32_t i) { return (uint32_t)(off >> 4) + 2u * i; }
 
 __device__ __forceinline__ uint32_t pack4(uint32_t w) { // 4 ASCII bytes -> 8 bits
     const uint32_t c = (w >> 1) & 0x03030303u;
@@ -27,22 +26,45 @@ __device__ __forceinline__ uint32_t acgt_mask4(uint32_t w) { // 0xff per byte th
     return __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) |
            __vcmpeq4(w, 0x54545454u);
 }
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 33)) * 0xff51afd7ed558ccdull;
+    z = (z ^ (z >> 33)) * 0xc4ceb9fe1a85ec53ull;
+    return z ^ (z >> 33);
+}
+constexpr uint64_t HT_EMPTY = ~0ull;
+
+// error bits raised by the kernels into the ctrl block
+enum { ERR_LAYOUT = 1, ERR_PAIR_INDEX = 2 };
+
+constexpr int PK_G = 16; // lanes per sequence
 
 __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, size_t blob_bytes,
                                               const uint64_t *__restrict__ seq_off,
-                                              const uint32_t *__restrict__ seq_len,
-                                              const uint32_t *__restrict__ woff, uint32_t n_seqs,
-                                              uint32_t *__restrict__ packed, uint8_t *__restrict__ seq_flag) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = warp0; i < n_seqs; i += nwarps) {
+                                              const uint32_t *__restrict__ seq_len, uint32_t s0, uint32_t s1,
+                                              uint32_t n_seqs, uint32_t *__restrict__ packed,
+                                              uint8_t *__restrict__ seq_flag, uint64_t *__restrict__ seq_hash,
+                                              unsigned *__restrict__ err) {
+    const int lane = threadIdx.x & 31, gl = lane & (PK_G - 1);
+    const unsigned gmask = 0xffffu << (lane & 16);
+    const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) / PK_G;
+    const uint32_t ng = (gridDim.x * blockDim.x) / PK_G;
+    for (uint32_t i = s0 + g0; i < s1; i += ng) {
         const uint32_t len = seq_len[i];
         const uint64_t off = seq_off[i];
+        if (gl == 0) {
+            bool bad_layout = off + len > blob_bytes;
+            if (i + 1 < n_seqs) bad_layout |= off + len > seq_off[i + 1];
+            if (bad_layout) atomicOr(err, (unsigned)ERR_LAYOUT);
+        }
+        if (off + len > blob_bytes) { // never read outside the blob; the call fails with ERR_LAYOUT
+            if (gl == 0) seq_flag[i] = 2, seq_hash[i] = 0; // 2: unusable, pairs touching it are skipped
+            continue;
+        }
         const uint32_t nw = nwords_of(len);
-        uint32_t *dst = packed + woff[i];
+        uint32_t *dst = packed + woff_of(off, i);
         bool bad = false;
-        for (uint32_t j = lane; j < nw; j += 32) {
+        uint64_t hs = 0;
+        for (uint32_t j = gl; j < nw; j += PK_G) {
             const uint32_t base = j * 16u;
             uint32_t word = 0;
             if (base < len) {
@@ -78,46 +100,285 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, 
                 }
             }
             dst[j] = word;
+            hs += mix64(((uint64_t)j << 32) | word);
         }
-        const unsigned any_bad = __ballot_sync(TDB_FULL, bad);
-        if (lane == 0) seq_flag[i] = any_bad ? 1 : 0;
+        const unsigned any_bad = __ballot_sync(gmask, bad) & gmask;
+#pragma unroll
+        for (int o = PK_G / 2; o; o >>= 1) hs += __shfl_xor_sync(gmask, hs, o);
+        if (gl == 0) {
+            seq_flag[i] = any_bad ? 1 : 0;
+            uint64_t h = mix64(hs ^ ((uint64_t)len * 0x9e3779b97f4a7c15ull));
+            seq_hash[i] = h == HT_EMPTY ? 0 : h;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Duplicate elimination.  HiFi reads that span a short repeat are mostly error-free copies of the
+// allele they come from, so a locus' pair list holds the same (pattern, text) CONTENT many times
+// (synthetic 30x trio: 3.5 pairs per distinct content).  The alignment is a pure function of the two
+// byte strings, so each distinct content is aligned once and its result copied:
+//   1. sequences -> canonical sequence (lowest index with the same bytes): open-addressing table on
+//      the 64-bit content hash, every hit VERIFIED word by word (a hash collision only costs a missed
+//      merge, never a wrong one);
+//   2. pairs -> representative pair (lowest index with the same (canon pattern, canon text)): exact
+//      64-bit key, no verification needed;
+//   3. representatives are radix-sorted by expected work (|n - m|, the dominant term of the penalty)
+//      so that the four pairs of a warp, and the warps of a wave, run near-identical control flow and
+//      the heaviest pairs start first;
+//   4. after the tiers ran, k_scatter copies score/status/penalty (and the algorithmic work counts)
+//      from each representative to its duplicates.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_seq_insert(const uint64_t *__restrict__ seq_hash,
+                                                    const uint8_t *__restrict__ seq_flag, uint32_t s0, uint32_t s1,
+                                                    unsigned long long *__restrict__ keys,
+                                                    uint32_t *__restrict__ vals, uint32_t mask) {
+    const uint32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s1 || seq_flag[i]) return;
+    const uint64_t h = seq_hash[i];
+    uint32_t slot = (uint32_t)h & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(keys + slot, (unsigned long long)HT_EMPTY, (unsigned long long)h);
+        if (old == HT_EMPTY || old == h) {
+            atomicMin(vals + slot, i);
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+
+constexpr int CN_G = 8; // lanes per sequence in the verification pass
+__global__ void __launch_bounds__(256) k_seq_canon(const uint64_t *__restrict__ seq_hash,
+                                                   const uint8_t *__restrict__ seq_flag,
+                                                   const uint64_t *__restrict__ seq_off,
+                                                   const uint32_t *__restrict__ seq_len,
+                                                   const uint32_t *__restrict__ packed, uint32_t s0, uint32_t s1,
+                                                   const unsigned long long *__restrict__ keys,
+                                                   const uint32_t *__restrict__ vals, uint32_t mask,
+                                                   uint32_t *__restrict__ canon, int dedup) {
+    const int lane = threadIdx.x & 31, gl = lane & (CN_G - 1);
+    const unsigned gmask = 0xffu << (lane & ~(CN_G - 1));
+    const uint32_t i = s0 + (blockIdx.x * blockDim.x + threadIdx.x) / CN_G;
+    if (i >= s1) return; // whole groups leave together
+    uint32_t c = i;
+    if (dedup && !seq_flag[i]) {
+        const uint64_t h = seq_hash[i];
+        uint32_t slot = (uint32_t)h & mask;
+        while (keys[slot] != h) slot = (slot + 1) & mask; // inserted by k_seq_insert: always found
+        c = vals[slot];
+        if (c != i) {
+            const uint32_t len = seq_len[i];
+            bool diff = seq_len[c] != len;
+            if (!diff) {
+                const uint32_t *a = packed + woff_of(seq_off[i], i), *b = packed + woff_of(seq_off[c], c);
+                const uint32_t nw = (len + 15u) / 16u;
+                for (uint32_t j = gl; j < nw; j += CN_G) diff |= a[j] != b[j];
+            }
+            if (__ballot_sync(gmask, diff) & gmask) c = i;
+        }
+    }
+    if (gl == 0) canon[i] = c;
+}
+
+// sort keys of representative pairs: 0 quad tier by descending |n-m| ... ; 255 = not in the sorted list
+constexpr int QL_MAX = 16;  // |n-m| >= QL_MAX: wavefront wider than the quad tier's 32 diagonals
+constexpr int WL_MAX = 40;  // |n-m| >= WL_MAX: wider than the warp tier's 64 diagonals
+constexpr int KEY_WARP = 0; // sorted first: heaviest pairs of the shared-memory tiers
+constexpr int KEY_QUAD0 = 1;
+constexpr int KEY_NONE = 255;
+constexpr int N_HIST = 32;
+
+struct PairTable {
+    unsigned long long *keys;
+    uint32_t *vals;
+    uint32_t mask;
+};
+
+__global__ void __launch_bounds__(256) k_pair_insert(const uint32_t *__restrict__ pair_p,
+                                                     const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1,
+                                                     uint32_t n_seqs, const uint32_t *__restrict__ canon,
+                                                     PairTable tb, unsigned *__restrict__ err) {
+    const uint32_t j = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p1) return;
+    const uint32_t ip = pair_p[j], jt = pair_t[j];
+    if (ip >= n_seqs || jt >= n_seqs) {
+        atomicOr(err, (unsigned)ERR_PAIR_INDEX);
+        return;
+    }
+    const uint32_t cp = canon[ip], ct = canon[jt];
+    if (cp == ct) return;
+    const unsigned long long key = ((unsigned long long)cp << 32) | ct;
+    uint32_t slot = (uint32_t)mix64(key) & tb.mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(tb.keys + slot, (unsigned long long)HT_EMPTY, key);
+        if (old == HT_EMPTY || old == key) {
+            atomicMin(tb.vals + slot, j);
+            return;
+        }
+        slot = (slot + 1) & tb.mask;
+    }
+}
+
+struct ClassifyOut {
+    uint32_t *rep;       // [n_pairs] representative pair of j (itself when unique / identical)
+    uint8_t *key;        // [p1-p0] sort key
+    uint32_t *val;       // [p1-p0] pair index
+    uint32_t *glist;     // pairs routed straight to the global-scratch tiers
+    unsigned *gcount;
+    unsigned *hist;      // [N_HIST]
+    int32_t *out_score, *out_status, *out_penalty;
+    uint32_t *work;      // [3 n_pairs] algorithmic cells, ext16, columns per pair (nullptr: not counted)
+};
+
+__global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restrict__ pair_p,
+                                                       const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1,
+                                                       uint32_t n_seqs, const uint32_t *__restrict__ canon,
+                                                       const uint32_t *__restrict__ seq_len,
+                                                       const uint8_t *__restrict__ seq_flag, PairTable tb,
+                                                       int quad_ok, int max_len16, ClassifyOut o) {
+    __shared__ unsigned sh_hist[N_HIST];
+    if (threadIdx.x < N_HIST) sh_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t j = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p1) {
+        const uint32_t ip = pair_p[j], jt = pair_t[j];
+        int key = KEY_NONE;
+        uint32_t rep = j;
+        // bad pair index (ERR_PAIR_INDEX, raised by k_pair_insert) or a sequence outside the blob (ERR_LAYOUT,
+        // raised by k_pack): the call fails; such pairs never reach an alignment kernel
+        if (ip >= n_seqs || jt >= n_seqs || ((seq_flag[ip] | seq_flag[jt]) & 2)) {
+            o.out_score[j] = 0;
+            if (o.out_status) o.out_status[j] = TDB_STATUS_UNATTAINABLE;
+            if (o.out_penalty) o.out_penalty[j] = INT32_MIN;
+            if (o.work) o.work[3 * (size_t)j] = o.work[3 * (size_t)j + 1] = o.work[3 * (size_t)j + 2] = 0;
+        } else {
+            const uint32_t cp = canon[ip], ct = canon[jt];
+            const int n = (int)seq_len[ip], m = (int)seq_len[jt];
+            if (cp == ct) { // same bytes: penalty 0, every column a match, clipped score 0
+                o.out_score[j] = 0;
+                if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
+                if (o.out_penalty) o.out_penalty[j] = 0;
+                if (o.work) {
+                    o.work[3 * (size_t)j] = 0, o.work[3 * (size_t)j + 1] = (uint32_t)(m >> 4) + 1u;
+                    o.work[3 * (size_t)j + 2] = (uint32_t)m;
+                }
+            } else {
+                const unsigned long long k64 = ((unsigned long long)cp << 32) | ct;
+                uint32_t slot = (uint32_t)mix64(k64) & tb.mask;
+                while (tb.keys[slot] != k64) slot = (slot + 1) & tb.mask;
+                rep = tb.vals[slot];
+                if (rep == j) {
+                    const int L = abs(m - n);
+                    if ((seq_flag[ip] | seq_flag[jt]) || n > max_len16 || m > max_len16 || L >= WL_MAX) {
+                        const unsigned q = atomicAdd(o.gcount, 1u);
+                        o.glist[q] = j;
+                    } else if (!quad_ok || L >= QL_MAX) {
+                        key = KEY_WARP;
+                    } else {
+                        key = KEY_QUAD0 + (QL_MAX - 1 - L);
+                    }
+                }
+            }
+        }
+        o.rep[j] = rep;
+        o.key[j - p0] = (uint8_t)key;
+        o.val[j - p0] = j;
+        if (key != KEY_NONE) atomicAdd(sh_hist + key, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < N_HIST && sh_hist[threadIdx.x]) atomicAdd(o.hist + threadIdx.x, sh_hist[threadIdx.x]);
+}
+
+// Segment table of the sorted list: seg[0] = begin, seg[1] = count of the warp-tier segment;
+// seg[2], seg[3] the same for the quad tier.
+__global__ void k_plan(const unsigned *__restrict__ hist, unsigned *__restrict__ seg) {
+    if (threadIdx.x == 0) {
+        unsigned q = 0;
+        for (int i = KEY_QUAD0; i < KEY_QUAD0 + QL_MAX; ++i) q += hist[i];
+        seg[0] = 0, seg[1] = hist[KEY_WARP];
+        seg[2] = hist[KEY_WARP], seg[3] = q;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restrict__ rep, uint32_t n_pairs,
+                                                 int32_t *__restrict__ score, int32_t *__restrict__ status,
+                                                 int32_t *__restrict__ penalty, const uint32_t *__restrict__ work,
+                                                 unsigned long long *__restrict__ algo) {
+    unsigned long long c = 0, e = 0, t = 0, u = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pairs; j += gridDim.x * blockDim.x) {
+        const uint32_t r = rep[j];
+        if (r != j) {
+            score[j] = score[r];
+            if (status) status[j] = status[r];
+            if (penalty) penalty[j] = penalty[r];
+        } else {
+            ++u;
+        }
+        if (work) c += work[3 * (size_t)r], e += work[3 * (size_t)r + 1], t += work[3 * (size_t)r + 2];
+    }
+    for (int o = 16; o; o >>= 1) {
+        c += __shfl_xor_sync(TDB_FULL, c, o), e += __shfl_xor_sync(TDB_FULL, e, o);
+        t += __shfl_xor_sync(TDB_FULL, t, o), u += __shfl_xor_sync(TDB_FULL, u, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (work) atomicAdd(algo + 0, c), atomicAdd(algo + 1, e), atomicAdd(algo + 2, t);
+        atomicAdd(algo + 3, u);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Alignment tiers.  Persistent warps pull pairs from a device-side counter (work per pair spans three
-// orders of magnitude, so static assignment would leave SMs idle).
+// orders of magnitude, so static assignment would leave SMs idle).  A tier's items come from up to
+// two device-resident lists: a segment of the sorted representative list and the pairs the previous
+// tier could not finish.  All counts live on the device, so a batch is enqueued without host syncs.
 // ------------------------------------------------------------------------------------------------
 struct AlignParams {
     Penalties pn;
     Heur heur;
     int clip;
     const uint32_t *packed;
-    const uint32_t *woff;
     const uint8_t *seq_flag;
     const uint8_t *blob;
     const uint64_t *seq_off;
     const uint32_t *seq_len;
     const uint32_t *pair_p;
     const uint32_t *pair_t;
-    const uint32_t *todo;        // pair ids to process (nullptr: 0..n_items-1)
-    const unsigned *n_items_ptr; // device-side count (nullptr: n_items)
-    unsigned n_items;
+    const uint32_t *src1;      // first item list (nullptr: identity 0..src1_count-1)
+    const unsigned *src1_seg;  // device {begin, count} of the segment of src1 (nullptr: 0, src1_count)
+    unsigned src1_count;
+    const uint32_t *src2;      // second item list (overflow of the previous tier); may be nullptr
+    const unsigned *src2_count;
     unsigned *work_counter;
     uint32_t *next_todo; // pairs this tier could not finish (nullptr on the last tier)
     unsigned *next_count;
     int32_t *out_score;
     int32_t *out_status;
     int32_t *out_penalty;
+    uint32_t *work; // per-pair algorithmic work (cells, ext16, columns); may be nullptr
     uint8_t *cigar_buf;
     const uint64_t *cigar_off;
     uint32_t *cigar_len;
-    unsigned long long *counters; // cells, ext16, columns, pairs finished by this launch
+    unsigned long long *counters; // executed cells, ext16, columns, pairs finished by this launch
     uint8_t *scratch;             // global tiers: per-warp slices
     size_t scratch_stride;
     int wlog2, s_cap, ops_cap;
     unsigned prov_cap;
 };
+
+struct ItemSrc {
+    unsigned b1, c1, total;
+};
+__device__ __forceinline__ ItemSrc item_src(const AlignParams &p) {
+    ItemSrc s;
+    s.b1 = p.src1_seg ? p.src1_seg[0] : 0u;
+    s.c1 = p.src1_seg ? p.src1_seg[1] : p.src1_count;
+    s.total = s.c1 + (p.src2 ? *p.src2_count : 0u);
+    return s;
+}
+__device__ __forceinline__ uint32_t item_at(const AlignParams &p, const ItemSrc &s, unsigned it) {
+    if (it < s.c1) return p.src1 ? p.src1[s.b1 + it] : it;
+    return p.src2[it - s.c1];
+}
 
 constexpr int T0_WLOG2 = 6;
 constexpr int T0_W = 1 << T0_WLOG2;
@@ -125,7 +386,7 @@ constexpr int T0_SCAP = 128;
 constexpr int T0_PROV = 2048;
 constexpr int T0_WARPS = 4;
 constexpr int T0_MAXLEN = 8000; // int16 offsets
-constexpr int WORK_CHUNK = 8;
+constexpr int WORK_CHUNK = 4;
 
 struct __align__(16) T0Smem {
     int16_t M[MS * T0_W];
@@ -158,11 +419,29 @@ __device__ __forceinline__ void defer_pair(const AlignParams &p, uint32_t idx, i
             if (p.out_status) p.out_status[idx] = TDB_STATUS_OOM;
             if (p.out_penalty) p.out_penalty[idx] = INT32_MIN;
             if (p.cigar_len) p.cigar_len[idx] = 0;
+            if (p.work) p.work[3 * (size_t)idx] = p.work[3 * (size_t)idx + 1] = p.work[3 * (size_t)idx + 2] = 0;
         }
     }
 }
 
-__global__ void __launch_bounds__(T0_WARPS * 32) k_align_tier0(const AlignParams p) {
+// result of one finished pair (whole warp calls; ext1 is a per-lane partial count)
+__device__ __forceinline__ void finish_pair(const AlignParams &p, uint32_t idx, int lane, int clipped, int pen,
+                                            const WorkCount &wc1, unsigned long long ext1) {
+    unsigned e = 0;
+    if (p.work) e = __reduce_add_sync(TDB_FULL, (unsigned)ext1);
+    if (lane == 0) {
+        p.out_score[idx] = clipped;
+        if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
+        if (p.out_penalty) p.out_penalty[idx] = pen;
+        if (p.work) {
+            p.work[3 * (size_t)idx] = (uint32_t)wc1.cells, p.work[3 * (size_t)idx + 1] = e;
+            p.work[3 * (size_t)idx + 2] = (uint32_t)wc1.columns;
+        }
+    }
+}
+
+// Warp tier: one pair per warp, wavefront history in shared memory.
+__global__ void __launch_bounds__(T0_WARPS * 32) k_align_warp(const AlignParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     T0Smem &sm = reinterpret_cast<T0Smem *>(smem_raw)[wid];
@@ -171,24 +450,25 @@ __global__ void __launch_bounds__(T0_WARPS * 32) k_align_tier0(const AlignParams
     st.step_lo = sm.step_lo, st.step_base = sm.step_base, st.prov = sm.prov;
     st.ops = reinterpret_cast<uint8_t *>(sm.M);
     st.wlog2 = T0_WLOG2, st.s_cap = T0_SCAP, st.ops_cap = (int)sizeof(sm.M), st.prov_cap = T0_PROV;
-    const unsigned n_items = p.n_items_ptr ? *p.n_items_ptr : p.n_items;
+    const ItemSrc src = item_src(p);
     WorkCount wc = {0, 0, 0};
     unsigned long long lane_ext16 = 0, done = 0;
     for (;;) {
         unsigned b = 0;
         if (lane == 0) b = atomicAdd(p.work_counter, (unsigned)WORK_CHUNK);
         b = __shfl_sync(TDB_FULL, b, 0);
-        if (b >= n_items) break;
-        const unsigned e = min(b + WORK_CHUNK, n_items);
+        if (b >= src.total) break;
+        const unsigned e = min(b + WORK_CHUNK, src.total);
         for (unsigned it = b; it < e; ++it) {
-            const uint32_t idx = p.todo ? p.todo[it] : it;
+            const uint32_t idx = item_at(p, src, it);
             const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
             const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
             if ((p.seq_flag[ip] | p.seq_flag[jt]) || n > T0_MAXLEN || m > T0_MAXLEN) {
                 defer_pair(p, idx, lane);
                 continue;
             }
-            SeqView P = {p.packed + p.woff[ip], nullptr, n}, T = {p.packed + p.woff[jt], nullptr, m};
+            SeqView P = {p.packed + woff_of(p.seq_off[ip], ip), nullptr, n};
+            SeqView T = {p.packed + woff_of(p.seq_off[jt], jt), nullptr, m};
             int pen = 0, clipped = 0;
             WorkCount wc1 = {0, 0, 0}; // work of this attempt: only counted when the tier finishes the pair
             unsigned long long ext1 = 0;
@@ -198,11 +478,7 @@ __global__ void __launch_bounds__(T0_WARPS * 32) k_align_tier0(const AlignParams
             if (r == WFA_OK) {
                 ++done;
                 wc.cells += wc1.cells, wc.columns += wc1.columns, lane_ext16 += ext1;
-                if (lane == 0) {
-                    p.out_score[idx] = clipped;
-                    if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
-                    if (p.out_penalty) p.out_penalty[idx] = pen;
-                }
+                finish_pair(p, idx, lane, clipped, pen, wc1, ext1);
             } else {
                 defer_pair(p, idx, lane);
             }
@@ -235,22 +511,22 @@ __global__ void __launch_bounds__(128) k_align_global(const AlignParams p) {
     st.ops = base, base += align16((size_t)p.ops_cap);
     st.prov = base;
     st.wlog2 = p.wlog2, st.s_cap = p.s_cap, st.ops_cap = p.ops_cap, st.prov_cap = p.prov_cap;
-    const unsigned n_items = p.n_items_ptr ? *p.n_items_ptr : p.n_items;
+    const ItemSrc src = item_src(p);
     WorkCount wc = {0, 0, 0};
     unsigned long long lane_ext16 = 0, done = 0;
     for (;;) {
         unsigned it = 0;
         if (lane == 0) it = atomicAdd(p.work_counter, 1u);
         it = __shfl_sync(TDB_FULL, it, 0);
-        if (it >= n_items) break;
-        const uint32_t idx = p.todo ? p.todo[it] : it;
+        if (it >= src.total) break;
+        const uint32_t idx = item_at(p, src, it);
         const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
         const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
         const bool bytes = (p.seq_flag[ip] | p.seq_flag[jt]) != 0;
         SeqView P, T;
         P.len = n, T.len = m;
-        P.w = bytes ? nullptr : p.packed + p.woff[ip];
-        T.w = bytes ? nullptr : p.packed + p.woff[jt];
+        P.w = bytes ? nullptr : p.packed + woff_of(p.seq_off[ip], ip);
+        T.w = bytes ? nullptr : p.packed + woff_of(p.seq_off[jt], jt);
         P.b = p.blob + p.seq_off[ip];
         T.b = p.blob + p.seq_off[jt];
         int pen = 0, clipped = 0;
@@ -264,11 +540,7 @@ __global__ void __launch_bounds__(128) k_align_global(const AlignParams p) {
         if (r == WFA_OK) {
             ++done;
             wc.cells += wc1.cells, wc.columns += wc1.columns, lane_ext16 += ext1;
-            if (lane == 0) {
-                p.out_score[idx] = clipped;
-                if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
-                if (p.out_penalty) p.out_penalty[idx] = pen;
-            }
+            finish_pair(p, idx, lane, clipped, pen, wc1, ext1);
         } else {
             defer_pair(p, idx, lane);
         }

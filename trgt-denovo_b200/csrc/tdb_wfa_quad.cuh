@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p
     const unsigned gmask = 0xffu << gshift;
     QPair &sm = reinterpret_cast<QPair *>(smem_raw)[wid * (32 / QG) + gid];
     const Penalties pn = {X, O1, E1, O2, E2};
-    const unsigned n_items = p.n_items_ptr ? *p.n_items_ptr : p.n_items;
+    const ItemSrc src = item_src(p);
+    const unsigned n_items = src.total;
     constexpr int PER_FETCH = 32; // pairs per work-counter atomic (8 batches of 4)
     unsigned long long acc_cells = 0, acc_cols = 0, acc_ext = 0, acc_done = 0; // acc_* valid on group lane 0
 
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p
             const unsigned it = bb + gid;
             // ====================== one pair per group ======================
             if (it < n_items) {
-                const uint32_t idx = p.todo ? p.todo[it] : it;
+                const uint32_t idx = item_at(p, src, it);
                 const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
                 const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
                 const int k_end = m - n;
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p
                 int penalty = 0, clipped = 0;
                 unsigned long long cells = 0, cols = 0, ext = 0;
                 if (!overflow) {
-                    const uint32_t *pw = p.packed + p.woff[ip], *tw = p.packed + p.woff[jt];
+                    const uint32_t *pw = p.packed + woff_of(p.seq_off[ip], ip);
+                    const uint32_t *tw = p.packed + woff_of(p.seq_off[jt], jt);
                     const int m0 = extend_group(pw, tw, n, m, 0, 0, gl, gmask, gshift, lane);
                     if (gl == 0) ext += (unsigned)(m0 >> 4) + 1;
                     if (k_end == 0 && m0 >= m) {
@@ -397,11 +399,22 @@ __global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p
                     }
                 }
                 // ---- result ----
+                unsigned ext_pair = 0;
+                if (p.work) { // per-pair algorithmic work: ext is a per-lane partial count
+                    ext_pair = (unsigned)ext;
+                    ext_pair += __shfl_xor_sync(gmask, ext_pair, 1);
+                    ext_pair += __shfl_xor_sync(gmask, ext_pair, 2);
+                    ext_pair += __shfl_xor_sync(gmask, ext_pair, 4);
+                }
                 if (gl == 0) {
                     if (!overflow) {
                         p.out_score[idx] = clipped;
                         if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
                         if (p.out_penalty) p.out_penalty[idx] = penalty;
+                        if (p.work) {
+                            p.work[3 * (size_t)idx] = (uint32_t)cells, p.work[3 * (size_t)idx + 1] = ext_pair;
+                            p.work[3 * (size_t)idx + 2] = (uint32_t)cols;
+                        }
                         acc_cells += cells, acc_cols += cols, acc_done += 1;
                     } else if (p.next_todo) {
                         const unsigned j = atomicAdd(p.next_count, 1u);
