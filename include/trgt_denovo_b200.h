@@ -232,6 +232,7 @@ typedef struct {
     uint64_t pairs_duplicate; /* copies of an already aligned (pattern, text) content */
     uint64_t kernel_launches;
     uint64_t chunks;        /* pipeline chunks the call was cut into */
+    uint64_t host_packed;   /* 1: the caller's CPU threads 2-bit packed the sequences before the upload */
     float ms_pack, ms_dedup, ms_align, ms_scatter, ms_reduce, ms_total_device; /* CUDA-event times */
     float ms_tier[4]; /* per alignment tier (events on the launching stream); [2] covers both global tiers.
                          Stage times are recorded for single-chunk calls only (ms_total_device always). */
@@ -239,6 +240,19 @@ typedef struct {
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 /* Enables exact C/E/T work counting inside the kernels (off by default: it costs atomics). */
 int tdb_set_count_work(tdb_ctx *ctx, int32_t on);
+
+/* The host half of the packing role (north_star: "locus.rs and read.rs pack the reads and alleles ...
+ * into 2-bit packed device batches"): ASCII -> 2-bit words, exactly what the host-buffer batch calls
+ * run on the caller's CPU threads before the upload.  Data re-encoding only, exposed so that a host
+ * can inspect / pre-compute the packed form; needs no GPU.  packed must hold tdb_packed_words()
+ * words; flag[i] = 1 when sequence i has a byte outside {A,C,G,T}.  Returns TDB_OK or TDB_E_INVALID
+ * (layout contract violated).  Layout: base k of sequence i in word (seq_off[i] >> 4) + 2 i + k / 16,
+ * bits 2 (k % 16), code (byte >> 1) & 3. */
+size_t tdb_packed_words(size_t blob_bytes, size_t n_seqs);
+int tdb_host_pack(const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off, const uint32_t *seq_len,
+                  size_t n_seqs, uint32_t *packed, uint8_t *flag);
+/* "avx512bw", "avx2" or "scalar": the instruction set the host packer uses on this CPU. */
+const char *tdb_host_pack_isa(void);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA binding. */
 void *tdb_host_alloc(size_t bytes);

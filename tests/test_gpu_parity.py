@@ -162,6 +162,31 @@ def test_chunked_host_pipeline(tdb, monkeypatch):
     c.close()
 
 
+def test_host_packed_batches(tdb, monkeypatch):
+    """Host batches 2-bit packed by the caller's CPU threads (default for batches >= 8 MB): same scores,
+    including sequences with non-ACGT bytes whose raw bytes are shipped separately."""
+    monkeypatch.setenv("TDB_HOSTPACK_MIN_BYTES", "0")
+    monkeypatch.setenv("TDB_CHUNK_PAIRS", "1024")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_HOSTPACK_MIN_BYTES")
+    monkeypatch.delenv("TDB_CHUNK_PAIRS")
+    rng = random.Random(35)
+    seqs, pp, pt = make_pairs(rng, n_targets=300, reads_per_target=12, max_units=20, err=0.002)
+    cnt = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    assert cnt.host_packed == 1 and cnt.chunks >= 3
+    seqs, pp, pt = make_pairs(rng, n_targets=40, reads_per_target=6, alphabet="ACGTN")  # few flagged: per-sequence copies
+    seqs[0] = seqs[0].lower()
+    cnt = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    assert cnt.host_packed == 1
+    seqs, pp, pt = make_pairs(rng, n_targets=100, reads_per_target=6, err=0.2, alphabet="ACGTN")  # > 256 flagged: whole blob
+    _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    blob = np.frombuffer(b"ACGTACGTAC" * 4, dtype=np.uint8)
+    with pytest.raises(tdb.TdbError):  # layout violations are caught by the host packer too
+        c.align_batch(blob, np.array([0, 5], np.uint64), np.array([10, 10], np.uint32), np.array([0], np.uint32),
+                      np.array([1], np.uint32))
+    c.close()
+
+
 def test_bad_layout_and_bad_pair_index_fail(tdb, ctx):
     blob = np.frombuffer(b"ACGTACGTAC" * 4, dtype=np.uint8)
     ln = np.array([10, 10], np.uint32)

@@ -49,7 +49,7 @@ class Counters(C.Structure):
                 ("ext16", C.c_uint64), ("columns", C.c_uint64), ("exec_cells", C.c_uint64),
                 ("exec_ext16", C.c_uint64), ("exec_columns", C.c_uint64), ("tier_cells", C.c_uint64 * 4),
                 ("tier_ext16", C.c_uint64 * 4), ("tier_columns", C.c_uint64 * 4), ("pairs_identical", C.c_uint64),
-                ("pairs_duplicate", C.c_uint64), ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64),
+                ("pairs_duplicate", C.c_uint64), ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64), ("host_packed", C.c_uint64),
                 ("ms_pack", C.c_float), ("ms_dedup", C.c_float), ("ms_align", C.c_float),
                 ("ms_scatter", C.c_float), ("ms_reduce", C.c_float), ("ms_total_device", C.c_float),
                 ("ms_tier", C.c_float * 4)]
@@ -62,7 +62,7 @@ EXPORTS = [
     "tdb_align_batch_device", "tdb_align_batch_cigar", "tdb_trio_reduce", "tdb_duo_reduce",
     "tdb_trio_batch", "tdb_duo_batch", "tdb_assess_batch_device", "tdb_align_end_to_end", "tdb_score",
     "tdb_cigar_ops", "tdb_cigar_score_clipped", "tdb_get_counters", "tdb_set_count_work",
-    "tdb_host_alloc", "tdb_host_free",
+    "tdb_host_alloc", "tdb_host_free", "tdb_packed_words", "tdb_host_pack", "tdb_host_pack_isa",
 ]
 
 _lib = None
@@ -108,6 +108,10 @@ def lib():
     L.tdb_cigar_score_clipped.argtypes = [vp, i32]
     L.tdb_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.tdb_set_count_work.argtypes = [vp, i32]
+    L.tdb_packed_words.restype = sz
+    L.tdb_packed_words.argtypes = [sz, sz]
+    L.tdb_host_pack.argtypes = [vp, sz, vp, vp, sz, vp, vp]
+    L.tdb_host_pack_isa.restype = C.c_char_p
     L.tdb_host_alloc.restype = vp
     L.tdb_host_alloc.argtypes = [sz]
     L.tdb_host_free.restype = None

@@ -1,10 +1,12 @@
 // tdb_api.cu -- C ABI (include/trgt_denovo_b200.h) over the sm_100a kernels.  No CPU compute path:
 // every entry point that does arithmetic launches CUDA kernels or fails.
 #include "tdb_wfa_quad.cuh"
+#include "tdb_hostpack.h"
 
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -68,6 +70,9 @@ struct tdb_ctx {
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0;
     bool disable_quad = false, disable_dedup = false;
     size_t chunk_pairs = 2u << 20;
+    size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
+    void *h_packed = nullptr, *h_flag = nullptr; // pinned staging of the host packer
+    size_t h_packed_cap = 0, h_flag_cap = 0;
     bool count_work = true;
     tdb_counters counters;
     // single-pair shim state
@@ -149,6 +154,67 @@ struct Chunk {
     size_t p0, p1;       // pair range
     uint32_t s_lo, s_hi; // sequences referenced: [s_lo, s_hi)
 };
+
+// Worker threads that 2-bit pack a host batch block by block, in sequence order, while the main thread
+// queues uploads and kernels for the chunks that are already packed.
+class HostPacker {
+  public:
+    struct Block {
+        uint32_t s0, s1;
+        uint32_t chunk;
+    };
+    HostPacker() = default;
+    HostPacker(const HostPacker &) = delete;
+    ~HostPacker() { join(); }
+    void start(const uint8_t *blob, size_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
+               uint32_t *packed, uint8_t *flag, std::vector<Block> blocks, size_t n_chunks, unsigned n_threads) {
+        blocks_ = std::move(blocks);
+        remaining_ = std::vector<std::atomic<int>>(n_chunks);
+        for (auto &r : remaining_) r.store(0, std::memory_order_relaxed);
+        for (const Block &b : blocks_) remaining_[b.chunk].fetch_add(1, std::memory_order_relaxed);
+        next_.store(0), violations_.store(0);
+        for (unsigned t = 0; t < n_threads; ++t)
+            threads_.emplace_back([=]() {
+                for (;;) {
+                    const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
+                    if (i >= blocks_.size()) return;
+                    const Block &b = blocks_[i];
+                    const size_t v = hostpack_range(blob, blob_bytes, off, len, b.s0, b.s1, n_seqs, packed, flag);
+                    if (v) violations_.fetch_add(v, std::memory_order_relaxed);
+                    remaining_[b.chunk].fetch_sub(1, std::memory_order_release);
+                }
+            });
+    }
+    void wait_chunk(size_t k) const {
+        while (remaining_[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    }
+    size_t violations() const { return violations_.load(); }
+    void join() {
+        next_.store(blocks_.size()); // unclaimed blocks are abandoned (error paths)
+        for (auto &t : threads_) t.join();
+        threads_.clear();
+    }
+
+  private:
+    std::vector<Block> blocks_;
+    std::vector<std::atomic<int>> remaining_;
+    std::atomic<size_t> next_{0}, violations_{0};
+    std::vector<std::thread> threads_;
+};
+
+int ensure_pinned(tdb_ctx *ctx, void *&p, size_t &cap, size_t bytes) {
+    if (bytes <= cap) return TDB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr, cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        p = nullptr;
+        return fail(ctx, TDB_E_OOM, "pinned staging allocation of %zu bytes failed", want);
+    }
+    cap = want;
+    return TDB_OK;
+}
 
 uint32_t table_mask(size_t n) {
     size_t cap = 1024;
@@ -276,42 +342,89 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     p.work = want_work ? (uint32_t *)ctx->work.p : nullptr;
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
 
-    // ---- host batches: queue every chunk's upload on the copy stream --------------------------------
-    if (b.h_pp) {
-        uint32_t up = 0; // sequences [0, up) are queued
+    // ---- host batches: the caller's CPU threads 2-bit pack the sequences chunk by chunk (a quarter of the
+    // ASCII bytes cross PCIe); small batches and CIGAR calls ship the ASCII and pack on the device -------
+    const bool host_pack = b.h_pp && !cigar_mode && b.blob_bytes >= ctx->hostpack_min_bytes;
+    HostPacker packer;
+    std::vector<uint32_t> new_lo(K, 0), new_hi(K, 0); // sequences first needed by chunk k: [new_lo, new_hi)
+    {
+        uint32_t up = 0;
         for (size_t k = 0; k < K; ++k) {
-            const Chunk &c = chunks[k];
-            if (c.s_hi > up) {
-                const uint32_t a = up, e = c.s_hi;
+            new_lo[k] = up;
+            up = std::max(up, chunks[k].s_hi);
+            new_hi[k] = up;
+        }
+    }
+    if (host_pack) {
+        int r = ensure_pinned(ctx, ctx->h_packed, ctx->h_packed_cap, max_words * 4);
+        if (r) return r;
+        r = ensure_pinned(ctx, ctx->h_flag, ctx->h_flag_cap, (size_t)n_seqs);
+        if (r) return r;
+        std::vector<HostPacker::Block> blocks;
+        for (size_t k = 0; k < K; ++k)
+            for (uint32_t a = new_lo[k]; a < new_hi[k]; a += 4096)
+                blocks.push_back({a, std::min(new_hi[k], a + 4096), (uint32_t)k});
+        const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        packer.start(b.h_blob, b.blob_bytes, b.h_seq_off, b.h_seq_len, n_seqs, (uint32_t *)ctx->h_packed,
+                     (uint8_t *)ctx->h_flag, std::move(blocks), K, hw);
+        cn.host_packed = 1;
+    }
+
+    // ---- chunks ---------------------------------------------------------------------------------------
+    for (size_t k = 0; k < K; ++k) {
+        const Chunk &c = chunks[k];
+        const uint32_t cpairs = (uint32_t)(c.p1 - c.p0);
+        const uint32_t a = new_lo[k], e = new_hi[k];
+        if (b.h_pp) { // queue this chunk's upload on the copy stream
+            if (e > a) {
                 CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, (size_t)(e - a) * 8, cudaMemcpyHostToDevice, cs));
                 CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
                 const uint64_t b0 = std::min<uint64_t>(b.h_seq_off[a], b.blob_bytes);
                 const uint64_t b1 = e == n_seqs ? b.blob_bytes
                                                 : std::min<uint64_t>(b.h_seq_off[e - 1] + b.h_seq_len[e - 1], b.blob_bytes);
-                if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
-                up = e;
+                if (!host_pack) {
+                    if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+                } else {
+                    packer.wait_chunk(k);
+                    if (packer.violations())
+                        return fail(ctx, TDB_E_INVALID, "sequence blob layout: sequences must be stored in index order, "
+                                                        "non-overlapping, inside the blob");
+                    const uint8_t *hf = (const uint8_t *)ctx->h_flag;
+                    CK(cudaMemcpyAsync((uint8_t *)ctx->seq_flag.p + a, hf + a, (size_t)(e - a), cudaMemcpyHostToDevice, cs));
+                    const size_t w0 = woff_of(b.h_seq_off[a], a);
+                    const size_t w1 = (size_t)woff_of(b.h_seq_off[e - 1], e - 1) + nwords_of(b.h_seq_len[e - 1]);
+                    CK(cudaMemcpyAsync((uint32_t *)ctx->packed.p + w0, (const uint32_t *)ctx->h_packed + w0, (w1 - w0) * 4,
+                                       cudaMemcpyHostToDevice, cs));
+                    // sequences with bytes outside ACGT are compared as raw bytes on the device: ship those bytes
+                    size_t n_flag = 0;
+                    for (uint32_t i = a; i < e; ++i) n_flag += hf[i] != 0;
+                    if (n_flag > 256) {
+                        if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+                    } else if (n_flag) {
+                        for (uint32_t i = a; i < e; ++i)
+                            if (hf[i] && b.h_seq_len[i])
+                                CK(cudaMemcpyAsync((uint8_t *)b.blob + b.h_seq_off[i], b.h_blob + b.h_seq_off[i], b.h_seq_len[i],
+                                                   cudaMemcpyHostToDevice, cs));
+                    }
+                }
             }
             CK(cudaMemcpyAsync((uint32_t *)b.pp + c.p0, b.h_pp + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
             CK(cudaMemcpyAsync((uint32_t *)b.pt + c.p0, b.h_pt + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
             CK(cudaEventRecord(ctx->up_ev[k], cs));
+            CK(cudaStreamWaitEvent(s, ctx->up_ev[k], 0));
         }
-    }
-
-    // ---- chunks ---------------------------------------------------------------------------------------
-    uint32_t packed_upto = 0;
-    for (size_t k = 0; k < K; ++k) {
-        const Chunk &c = chunks[k];
-        const uint32_t cpairs = (uint32_t)(c.p1 - c.p0);
-        if (b.h_pp) CK(cudaStreamWaitEvent(s, ctx->up_ev[k], 0));
-        if (c.s_hi > packed_upto) {
-            const uint32_t cnt = c.s_hi - packed_upto;
+        if (e > a) {
+            const uint32_t cnt = e - a;
             const unsigned blocks = (unsigned)std::min<size_t>(((size_t)cnt * PK_G + 255) / 256, (size_t)ctx->sm_count * 64);
-            k_pack<<<blocks, 256, 0, s>>>(b.blob, b.blob_bytes, b.seq_off, b.seq_len, packed_upto, c.s_hi, n_seqs,
-                                          (uint32_t *)ctx->packed.p, (uint8_t *)ctx->seq_flag.p,
-                                          (uint64_t *)ctx->seq_hash.p, &ctrl->err);
+            if (host_pack)
+                k_hash<<<blocks, 256, 0, s>>>(b.seq_off, b.seq_len, a, e, (const uint32_t *)ctx->packed.p,
+                                              (uint64_t *)ctx->seq_hash.p);
+            else
+                k_pack<<<blocks, 256, 0, s>>>(b.blob, b.blob_bytes, b.seq_off, b.seq_len, a, e, n_seqs,
+                                              (uint32_t *)ctx->packed.p, (uint8_t *)ctx->seq_flag.p,
+                                              (uint64_t *)ctx->seq_hash.p, &ctrl->err);
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
-            packed_upto = c.s_hi;
         }
         if (staged) CK(cudaEventRecord(ctx->ev[2], s));
         if (cigar_mode) continue; // CIGAR output lives in the general kernel: no dedup, no shared-memory tiers
@@ -631,6 +744,10 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->quad_ctas_per_sm = qocc;
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
+        if (const char *hp = getenv("TDB_HOSTPACK_MIN_BYTES")) {
+            const long long v = atoll(hp); // < 0 disables the host packer
+            c->hostpack_min_bytes = v < 0 ? (size_t)-1 : (size_t)v;
+        }
         if (const char *cp = getenv("TDB_CHUNK_PAIRS")) {
             const long long v = atoll(cp);
             if (v >= 1024) c->chunk_pairs = (size_t)v;
@@ -652,6 +769,8 @@ void tdb_destroy(tdb_ctx *c) {
     for (int i = 0; i < 16; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->up_ev) cudaEventDestroy(e);
+    if (c->h_packed) cudaFreeHost(c->h_packed);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -918,6 +1037,18 @@ int32_t tdb_cigar_score_clipped(const tdb_ctx *ctx, int32_t flank_len) {
     if (last) score -= cost(last, oplen);
     return score;
 }
+
+size_t tdb_packed_words(size_t blob_bytes, size_t n_seqs) { return blob_bytes / 16 + 2 * n_seqs + 2; }
+
+int tdb_host_pack(const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off, const uint32_t *seq_len,
+                  size_t n_seqs, uint32_t *packed, uint8_t *flag) {
+    if (n_seqs && (!seq_off || !seq_len || !packed || !flag)) return TDB_E_INVALID;
+    if (n_seqs >= 0x7fffffffull || blob_bytes / 16 + 2 * n_seqs + 2 >= 0xffffffffull) return TDB_E_UNSUPPORTED;
+    const size_t v = hostpack_range(seq_blob, blob_bytes, seq_off, seq_len, 0, (uint32_t)n_seqs, (uint32_t)n_seqs, packed, flag);
+    return v ? TDB_E_INVALID : TDB_OK;
+}
+
+const char *tdb_host_pack_isa(void) { return hostpack_isa(); }
 
 void *tdb_host_alloc(size_t bytes) {
     void *p = nullptr;

@@ -113,6 +113,30 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, 
     }
 }
 
+// Content hash of sequences that arrive already packed (host batches packed by the caller's CPU threads,
+// tdb_hostpack.cpp).  Same hash as k_pack so both routes feed the duplicate elimination identically.
+__global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
+                                              uint32_t s0, uint32_t s1, const uint32_t *__restrict__ packed,
+                                              uint64_t *__restrict__ seq_hash) {
+    const int lane = threadIdx.x & 31, gl = lane & (PK_G - 1);
+    const unsigned gmask = 0xffffu << (lane & 16);
+    const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) / PK_G;
+    const uint32_t ng = (gridDim.x * blockDim.x) / PK_G;
+    for (uint32_t i = s0 + g0; i < s1; i += ng) {
+        const uint32_t len = seq_len[i];
+        const uint32_t nw = nwords_of(len);
+        const uint32_t *src = packed + woff_of(seq_off[i], i);
+        uint64_t hs = 0;
+        for (uint32_t j = gl; j < nw; j += PK_G) hs += mix64(((uint64_t)j << 32) | __ldg(src + j));
+#pragma unroll
+        for (int o = PK_G / 2; o; o >>= 1) hs += __shfl_xor_sync(gmask, hs, o);
+        if (gl == 0) {
+            const uint64_t h = mix64(hs ^ ((uint64_t)len * 0x9e3779b97f4a7c15ull));
+            seq_hash[i] = h == HT_EMPTY ? 0 : h;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Duplicate elimination.  HiFi reads that span a short repeat are mostly error-free copies of the
 // allele they come from, so a locus' pair list holds the same (pattern, text) CONTENT many times
