@@ -270,7 +270,10 @@ def main():
         step_host()
     barrier()
     e2e_s = time.time() - e0
-    e2e_chunks = ctx.counters().chunks
+    ce = ctx.counters()
+    e2e_chunks = ce.chunks
+    e2e_host = {"host_packed": int(ce.host_packed), "ms_plan": ce.ms_host_plan, "ms_pack_wait": ce.ms_host_pack_wait,
+                "ms_align_call": ce.ms_host_call, "ms_device_span": ce.ms_total_device}
     h2d = batch.blob.size + batch.seq_off.nbytes + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
         batch.pair_text.nbytes + loci_np.nbytes
     d2h = C.sizeof(h_out) + h_mask.nbytes
@@ -371,7 +374,7 @@ def main():
             "work": {"cells": int(cnt.cells), "ext16": int(cnt.ext16), "columns": int(cnt.columns),
                      "exec_cells": int(cnt.exec_cells), "exec_ext16": int(cnt.exec_ext16),
                      "exec_columns": int(cnt.exec_columns)},
-            "e2e_chunks": int(e2e_chunks),
+            "e2e_chunks": int(e2e_chunks), "e2e_host": e2e_host,
             "self_check_vs_oracle": check,
         }
         print(json.dumps(line), flush=True)

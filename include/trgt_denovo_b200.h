@@ -234,6 +234,8 @@ typedef struct {
     uint64_t chunks;        /* pipeline chunks the call was cut into */
     uint64_t host_packed;   /* 1: the caller's CPU threads 2-bit packed the sequences before the upload */
     float ms_pack, ms_dedup, ms_align, ms_scatter, ms_reduce, ms_total_device; /* CUDA-event times */
+    float ms_host_plan, ms_host_pack_wait, ms_host_call; /* host wall clock: chunk planning, time the calling
+                         thread waited for the packer threads, whole run of pack+align (host-buffer calls) */
     float ms_tier[4]; /* per alignment tier (events on the launching stream); [2] covers both global tiers.
                          Stage times are recorded for single-chunk calls only (ms_total_device always). */
 } tdb_counters;
@@ -242,15 +244,16 @@ int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 int tdb_set_count_work(tdb_ctx *ctx, int32_t on);
 
 /* The host half of the packing role (north_star: "locus.rs and read.rs pack the reads and alleles ...
- * into 2-bit packed device batches"): ASCII -> 2-bit words, exactly what the host-buffer batch calls
- * run on the caller's CPU threads before the upload.  Data re-encoding only, exposed so that a host
- * can inspect / pre-compute the packed form; needs no GPU.  packed must hold tdb_packed_words()
- * words; flag[i] = 1 when sequence i has a byte outside {A,C,G,T}.  Returns TDB_OK or TDB_E_INVALID
- * (layout contract violated).  Layout: base k of sequence i in word (seq_off[i] >> 4) + 2 i + k / 16,
- * bits 2 (k % 16), code (byte >> 1) & 3. */
-size_t tdb_packed_words(size_t blob_bytes, size_t n_seqs);
+ * into 2-bit packed device batches"): ASCII blob -> 2-bit stream, exactly what the host-buffer batch
+ * calls run on the caller's CPU threads before the upload.  Data re-encoding only, exposed so that a
+ * host can inspect / pre-compute the packed form; needs no GPU.  Layout: the byte at blob position x
+ * goes to word x / 16, bits 2 (x % 16), code (byte >> 1) & 3 -- independent of sequence boundaries; a
+ * sequence is the window [seq_off, seq_off + seq_len) of the stream.  packed must hold
+ * tdb_packed_words(blob_bytes) words; flag[i] = 1 when sequence i has a byte outside {A,C,G,T}.
+ * Returns TDB_OK or TDB_E_INVALID (layout contract violated). */
+size_t tdb_packed_words(size_t blob_bytes);
 int tdb_host_pack(const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off, const uint32_t *seq_len,
-                  size_t n_seqs, uint32_t *packed, uint8_t *flag);
+                  size_t n_seqs, uint32_t *packed, uint8_t *flag, int n_threads);
 /* "avx512bw", "avx2" or "scalar": the instruction set the host packer uses on this CPU. */
 const char *tdb_host_pack_isa(void);
 

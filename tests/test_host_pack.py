@@ -16,55 +16,55 @@ def L():
 
 
 def _reference_pack(seqs, off):
-    nwords = len(b"".join(seqs)) // 16 + 2 * len(seqs) + 2
-    out = np.zeros(nwords, dtype=np.uint32)
+    blob = b"".join(seqs)
+    out = np.zeros(len(blob) // 16 + 2, dtype=np.uint32)
     flags = np.zeros(len(seqs), dtype=np.uint8)
+    for x, c in enumerate(blob):
+        out[x // 16] |= np.uint32(((c >> 1) & 3) << (2 * (x % 16)))
     for i, s in enumerate(seqs):
-        w0 = (int(off[i]) >> 4) + 2 * i
-        for k, c in enumerate(s):
-            out[w0 + k // 16] |= np.uint32(((c >> 1) & 3) << (2 * (k % 16)))
-            if c not in b"ACGT":
-                flags[i] = 1
+        if any(c not in b"ACGT" for c in s):
+            flags[i] = 1
     return out, flags
 
 
-def _pack(L, seqs):
+def _pack(L, seqs, threads=3):
     blob, off, ln = to_arrays(seqs)
-    n = L.tdb_packed_words(blob.size, len(seqs))
+    n = L.tdb_packed_words(blob.size)
     packed = np.full(n, 0xdeadbeef, dtype=np.uint32)
     flag = np.full(len(seqs), 7, dtype=np.uint8)
     r = L.tdb_host_pack(blob.ctypes.data, blob.size, off.ctypes.data, ln.ctypes.data, len(seqs), packed.ctypes.data,
-                        flag.ctypes.data)
-    return r, packed, flag, off
+                        flag.ctypes.data, threads)
+    return r, packed, flag, off, blob.size
 
 
 def test_host_pack_matches_layout(L):
     rng = random.Random(3)
-    lens = [0, 1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 200, 1000] + [rng.randint(1, 400) for _ in range(300)]
+    lens = [0, 1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 200, 1000, 0, 0, 5] + \
+        [rng.randint(1, 400) for _ in range(300)]
     seqs = [rand_seq(rng, n).encode() for n in lens]
     seqs[5] = seqs[5][:10] + b"N" + seqs[5][11:]
     seqs[20] = seqs[20].lower()
-    r, packed, flag, off = _pack(L, seqs)
-    assert r == 0
-    want, wflag = _reference_pack(seqs, off)
-    assert (flag == wflag).all()
-    # every word a sequence owns (its bases plus one zero word) is written and equal
-    for i, s in enumerate(seqs):
-        w0 = (int(off[i]) >> 4) + 2 * i
-        nw = (len(s) + 15) // 16 + 1
-        assert (packed[w0:w0 + nw] == want[w0:w0 + nw]).all(), i
+    seqs[18] = b"ACGNT"  # right after two empty sequences sharing its offset
+    for cut in (None, 1, 37, 700):  # different blob tails (partial words / partial vectors)
+        ss = seqs if cut is None else seqs[:-1] + [seqs[-1][:cut]]
+        r, packed, flag, off, nbytes = _pack(L, ss)
+        assert r == 0
+        want, wflag = _reference_pack(ss, off)
+        assert (flag == wflag).all()
+        nw = (nbytes + 15) // 16
+        assert (packed[:nw] == want[:nw]).all()
     assert L.tdb_host_pack_isa() in (b"avx512bw", b"avx2", b"scalar")
 
 
 def test_host_pack_rejects_bad_layout(L):
     blob = np.frombuffer(b"ACGT" * 10, dtype=np.uint8)
     ln = np.array([10, 10], np.uint32)
-    packed = np.zeros(L.tdb_packed_words(blob.size, 2), np.uint32)
+    packed = np.zeros(L.tdb_packed_words(blob.size), np.uint32)
     flag = np.zeros(2, np.uint8)
     for offs in ([0, 5], [0, 35]):
         off = np.array(offs, np.uint64)
         assert L.tdb_host_pack(blob.ctypes.data, blob.size, off.ctypes.data, ln.ctypes.data, 2, packed.ctypes.data,
-                               flag.ctypes.data) == -1
+                               flag.ctypes.data, 1) == -1
 
 
 @pytest.mark.parametrize("isa", ["avx2", "scalar"])

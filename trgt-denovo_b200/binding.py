@@ -52,6 +52,7 @@ class Counters(C.Structure):
                 ("pairs_duplicate", C.c_uint64), ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64), ("host_packed", C.c_uint64),
                 ("ms_pack", C.c_float), ("ms_dedup", C.c_float), ("ms_align", C.c_float),
                 ("ms_scatter", C.c_float), ("ms_reduce", C.c_float), ("ms_total_device", C.c_float),
+                ("ms_host_plan", C.c_float), ("ms_host_pack_wait", C.c_float), ("ms_host_call", C.c_float),
                 ("ms_tier", C.c_float * 4)]
 
 
@@ -109,8 +110,8 @@ def lib():
     L.tdb_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.tdb_set_count_work.argtypes = [vp, i32]
     L.tdb_packed_words.restype = sz
-    L.tdb_packed_words.argtypes = [sz, sz]
-    L.tdb_host_pack.argtypes = [vp, sz, vp, vp, sz, vp, vp]
+    L.tdb_packed_words.argtypes = [sz]
+    L.tdb_host_pack.argtypes = [vp, sz, vp, vp, sz, vp, vp, C.c_int]
     L.tdb_host_pack_isa.restype = C.c_char_p
     L.tdb_host_alloc.restype = vp
     L.tdb_host_alloc.argtypes = [sz]

@@ -7,9 +7,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -45,12 +47,14 @@ struct Ctrl {
     unsigned pad0[3];
     unsigned long long exec[4][4]; // executed cells, ext16, columns, pairs finished; per tier
     unsigned long long algo[4];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self
-    // ---- per chunk ----
-    unsigned wc_quad, wc_warp, acount, pad1;
-    unsigned hist[N_HIST];
-    unsigned seg[4];
+    // ---- per chunk (one block per pipeline slot, zeroed before every chunk) ----
+    struct Chunk {
+        unsigned wc_quad, wc_warp, acount, pad1;
+        unsigned hist[N_HIST];
+        unsigned seg[4];
+    } ck[2];
 };
-constexpr size_t CTRL_CHUNK_OFF = offsetof(Ctrl, wc_quad);
+constexpr int N_SLOT = 2;
 
 } // namespace
 
@@ -63,8 +67,15 @@ struct tdb_ctx {
     cudaEvent_t ev[16] = {};
     std::vector<cudaEvent_t> up_ev; // one per in-flight chunk upload
     // grow-only device buffers
-    DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, canon, pair_p, pair_t, score, status, penalty;
-    DevBuf rep, work, skey_in, skey_out, sval_in, sval_out, cub_tmp, seq_tab, pair_tab, list_a, list_b, list_c;
+    DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, pair_p, pair_t, score, status, penalty;
+    DevBuf rep, work, list_b, list_c;
+    // Chunks alternate between two pipeline slots (own stream + own scratch) so that the tail of one chunk's
+    // alignment kernels overlaps the next chunk's duplicate elimination and alignment.
+    struct Slot {
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf canon, skey_in, skey_out, sval_in, sval_out, cub_tmp, seq_tab, pair_tab, list_a;
+    } slot[2];
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0;
@@ -155,50 +166,60 @@ struct Chunk {
     uint32_t s_lo, s_hi; // sequences referenced: [s_lo, s_hi)
 };
 
-// Worker threads that 2-bit pack a host batch block by block, in sequence order, while the main thread
-// queues uploads and kernels for the chunks that are already packed.
+// Worker threads that 2-bit pack a host blob block by block, in byte order, while the calling thread
+// queues uploads and kernels for the chunks whose bytes are already packed.
 class HostPacker {
   public:
-    struct Block {
-        uint32_t s0, s1;
-        uint32_t chunk;
-    };
+    static constexpr uint64_t BLOCK = 256u << 10; // bytes of ASCII per work item (a multiple of 64)
     HostPacker() = default;
     HostPacker(const HostPacker &) = delete;
     ~HostPacker() { join(); }
-    void start(const uint8_t *blob, size_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
-               uint32_t *packed, uint8_t *flag, std::vector<Block> blocks, size_t n_chunks, unsigned n_threads) {
-        blocks_ = std::move(blocks);
-        remaining_ = std::vector<std::atomic<int>>(n_chunks);
-        for (auto &r : remaining_) r.store(0, std::memory_order_relaxed);
-        for (const Block &b : blocks_) remaining_[b.chunk].fetch_add(1, std::memory_order_relaxed);
-        next_.store(0), violations_.store(0);
+    // `pre` tasks (indices 0..n_pre-1 handed to pre_fn) run first on the same threads: the chunk planning
+    // scan shares the cores with the packer instead of competing with it.
+    void start(const uint8_t *blob, uint64_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
+               uint32_t *packed, uint8_t *flag, unsigned n_threads, size_t n_pre, std::function<void(size_t)> pre_fn) {
+        n_blocks_ = packed ? (size_t)((blob_bytes + BLOCK - 1) / BLOCK) : 0;
+        done_ = std::vector<std::atomic<uint8_t>>(n_blocks_);
+        for (auto &d : done_) d.store(0, std::memory_order_relaxed);
+        next_.store(0), next_pre_.store(0), pre_left_.store((long)n_pre);
         for (unsigned t = 0; t < n_threads; ++t)
             threads_.emplace_back([=]() {
                 for (;;) {
+                    const size_t i = next_pre_.fetch_add(1, std::memory_order_relaxed);
+                    if (i >= n_pre) break;
+                    pre_fn(i);
+                    pre_left_.fetch_sub(1, std::memory_order_release);
+                }
+                wait_pre(); // the pre tasks zero the flag array the packer writes into
+                for (;;) {
                     const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
-                    if (i >= blocks_.size()) return;
-                    const Block &b = blocks_[i];
-                    const size_t v = hostpack_range(blob, blob_bytes, off, len, b.s0, b.s1, n_seqs, packed, flag);
-                    if (v) violations_.fetch_add(v, std::memory_order_relaxed);
-                    remaining_[b.chunk].fetch_sub(1, std::memory_order_release);
+                    if (i >= n_blocks_) return;
+                    const uint64_t x0 = (uint64_t)i * BLOCK, x1 = std::min(blob_bytes, x0 + BLOCK);
+                    hostpack_stream(blob, x0, x1, packed, off, len, n_seqs, flag);
+                    done_[i].store(1, std::memory_order_release);
                 }
             });
     }
-    void wait_chunk(size_t k) const {
-        while (remaining_[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    // blocks until blob bytes [b0, b1) are packed
+    void wait_bytes(uint64_t b0, uint64_t b1) const {
+        if (b1 <= b0) return;
+        for (size_t i = (size_t)(b0 / BLOCK); i <= (size_t)((b1 - 1) / BLOCK) && i < n_blocks_; ++i)
+            while (!done_[i].load(std::memory_order_acquire)) std::this_thread::yield();
     }
-    size_t violations() const { return violations_.load(); }
+    void wait_pre() const {
+        while (pre_left_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    }
     void join() {
-        next_.store(blocks_.size()); // unclaimed blocks are abandoned (error paths)
+        next_.store(n_blocks_); // unclaimed blocks are abandoned (error paths)
         for (auto &t : threads_) t.join();
         threads_.clear();
     }
 
   private:
-    std::vector<Block> blocks_;
-    std::vector<std::atomic<int>> remaining_;
-    std::atomic<size_t> next_{0}, violations_{0};
+    size_t n_blocks_ = 0;
+    std::vector<std::atomic<uint8_t>> done_;
+    std::atomic<size_t> next_{0}, next_pre_{0};
+    std::atomic<long> pre_left_{0};
     std::vector<std::thread> threads_;
 };
 
@@ -225,40 +246,37 @@ uint32_t table_mask(size_t n) {
 // Splits a host batch into pair chunks whose sequence ranges advance with the pair index (true for
 // batches assembled locus by locus), so that a chunk can be aligned while the next one is still in
 // flight over PCIe.  Falls back to a single chunk when the pair list jumps around the sequence table.
-void plan_chunks(const tdb_ctx *ctx, const DevBatch &b, std::vector<Chunk> &out) {
+// plan_prepare sizes the chunk table; scan_chunk(k) (any thread) fills chunk k; plan_finish validates.
+void plan_prepare(const tdb_ctx *ctx, const DevBatch &b, std::vector<Chunk> &out) {
     out.clear();
-    const size_t n_pairs = b.n_pairs, n_seqs = b.n_seqs;
+    const size_t n_pairs = b.n_pairs;
     if (!b.h_pp || n_pairs <= ctx->chunk_pairs + ctx->chunk_pairs / 2) {
-        out.push_back({0, n_pairs, 0, (uint32_t)n_seqs});
+        out.push_back({0, n_pairs, 0, (uint32_t)b.n_seqs});
         return;
     }
     const size_t K = (n_pairs + ctx->chunk_pairs - 1) / ctx->chunk_pairs;
     const size_t per = (n_pairs + K - 1) / K;
     out.resize(K);
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < hw; ++t)
-        th.emplace_back([&, t]() {
-            for (size_t k = t; k < K; k += hw) {
-                const size_t p0 = k * per, p1 = std::min(n_pairs, p0 + per);
-                uint32_t lo = 0xffffffffu, hi = 0;
-                for (size_t j = p0; j < p1; ++j) {
-                    const uint32_t a = b.h_pp[j], c = b.h_pt[j];
-                    lo = std::min(lo, std::min(a, c));
-                    hi = std::max(hi, std::max(a, c));
-                }
-                if (lo > hi) lo = hi = 0;
-                hi = (uint32_t)std::min<size_t>((size_t)hi + 1, n_seqs); // out-of-range indices fail on the device
-                lo = std::min(lo, hi);
-                out[k] = {p0, p1, lo, hi};
-            }
-        });
-    for (auto &x : th) x.join();
+    for (size_t k = 0; k < K; ++k) out[k] = {k * per, std::min(n_pairs, (k + 1) * per), 0, 0};
+}
+void scan_chunk(const DevBatch &b, Chunk &c) {
+    uint32_t lo = 0xffffffffu, hi = 0;
+    for (size_t j = c.p0; j < c.p1; ++j) {
+        const uint32_t a = b.h_pp[j], t = b.h_pt[j];
+        lo = std::min(lo, std::min(a, t));
+        hi = std::max(hi, std::max(a, t));
+    }
+    if (lo > hi) lo = hi = 0;
+    hi = (uint32_t)std::min<size_t>((size_t)hi + 1, b.n_seqs); // out-of-range indices fail on the device
+    c.s_lo = std::min(lo, hi), c.s_hi = hi;
+}
+void plan_finish(const DevBatch &b, std::vector<Chunk> &out) {
+    if (out.size() <= 1) return;
     size_t covered = 0;
     for (const Chunk &c : out) covered += c.s_hi - c.s_lo;
-    if (covered > 2 * n_seqs + 64 * K) {
+    if (covered > 2 * b.n_seqs + 64 * out.size()) {
         out.clear();
-        out.push_back({0, n_pairs, 0, (uint32_t)n_seqs});
+        out.push_back({0, b.n_pairs, 0, (uint32_t)b.n_seqs});
     }
 }
 
@@ -290,8 +308,43 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     const bool quad_ok = default_pen && !ctx->disable_quad;
     const bool dedup = !ctx->disable_dedup && !cigar_mode;
 
+    const auto t_call = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    // ---- host batches: the caller's CPU threads 2-bit pack the blob (a quarter of the ASCII bytes cross
+    // PCIe) while this thread plans and queues chunks; small batches and CIGAR calls ship the ASCII and
+    // pack on the device -------------------------------------------------------------------------------
+    const bool host_pack = b.h_pp && !cigar_mode && b.blob_bytes >= ctx->hostpack_min_bytes;
+    HostPacker packer;
     std::vector<Chunk> chunks;
-    plan_chunks(ctx, b, chunks);
+    plan_prepare(ctx, b, chunks);
+    if (host_pack) {
+        int r = ensure_pinned(ctx, ctx->h_packed, ctx->h_packed_cap, (b.blob_bytes / 16 + 2) * 4);
+        if (r) return r;
+        r = ensure_pinned(ctx, ctx->h_flag, ctx->h_flag_cap, (size_t)n_seqs);
+        if (r) return r;
+        cn.host_packed = 1;
+    }
+    if (b.h_pp && (host_pack || chunks.size() > 1)) {
+        // one core stays free for the calling thread, which must react quickly to every finished chunk
+        const unsigned hc = std::thread::hardware_concurrency();
+        const unsigned hw = std::max(1u, std::min(32u, hc > 2 ? hc - 1 : 1u));
+        const size_t K0 = chunks.size(), n_scan = K0 > 1 ? K0 : 0, n_zero = host_pack ? 16 : 0;
+        uint8_t *hflag = (uint8_t *)ctx->h_flag;
+        packer.start(b.h_blob, b.blob_bytes, b.h_seq_off, b.h_seq_len, n_seqs, host_pack ? (uint32_t *)ctx->h_packed : nullptr,
+                     hflag, hw, n_scan + n_zero, [&chunks, &b, n_scan, n_zero, hflag](size_t k) {
+                         if (k < n_scan) {
+                             scan_chunk(b, chunks[k]);
+                         } else { // zero a slice of the flag array
+                             const size_t per = (b.n_seqs + n_zero - 1) / n_zero, z0 = std::min(b.n_seqs, (k - n_scan) * per);
+                             memset(hflag + z0, 0, std::min(b.n_seqs, z0 + per) - z0);
+                         }
+                     });
+        packer.wait_pre();
+    }
+    plan_finish(b, chunks);
+    cn.ms_host_plan = ms_since(t_call);
     const size_t K = chunks.size();
     cn.chunks = K;
     const bool staged = K == 1; // per-stage CUDA-event timing only when the call is one chunk
@@ -299,28 +352,32 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     for (const Chunk &c : chunks) max_cp = std::max(max_cp, c.p1 - c.p0), max_cs = std::max<size_t>(max_cs, c.s_hi - c.s_lo);
 
     // ---- buffers ------------------------------------------------------------------------------------
-    const size_t max_words = b.blob_bytes / 16 + 2 * (size_t)n_seqs + 2;
+    const size_t max_words = b.blob_bytes / 16 + 2;
     ENSURE(ctx->packed, max_words * 4);
     ENSURE(ctx->seq_flag, (size_t)n_seqs);
     ENSURE(ctx->seq_hash, (size_t)n_seqs * 8);
     ENSURE(ctx->ctrl, sizeof(Ctrl));
     ENSURE(ctx->list_b, (size_t)n_pairs * 4);
     const bool want_work = ctx->count_work && !cigar_mode;
+    const int n_slot = K > 1 ? N_SLOT : 1;
     if (!cigar_mode) {
-        ENSURE(ctx->canon, (size_t)n_seqs * 4);
         ENSURE(ctx->rep, (size_t)n_pairs * 4);
         if (want_work) ENSURE(ctx->work, (size_t)n_pairs * 12);
-        ENSURE(ctx->skey_in, max_cp);
-        ENSURE(ctx->skey_out, max_cp);
-        ENSURE(ctx->sval_in, max_cp * 4);
-        ENSURE(ctx->sval_out, max_cp * 4);
-        ENSURE(ctx->list_a, max_cp * 4);
-        if (dedup) ENSURE(ctx->seq_tab, ((size_t)table_mask(max_cs) + 1) * 12);
-        ENSURE(ctx->pair_tab, ((size_t)table_mask(max_cp) + 1) * 12);
         size_t tmp = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint8_t *)nullptr, (uint8_t *)nullptr,
                                            (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_cp, 0, 8, s));
-        ENSURE(ctx->cub_tmp, tmp);
+        for (int i = 0; i < n_slot; ++i) {
+            tdb_ctx::Slot &sl = ctx->slot[i];
+            ENSURE(sl.canon, (size_t)n_seqs * 4);
+            ENSURE(sl.skey_in, max_cp);
+            ENSURE(sl.skey_out, max_cp);
+            ENSURE(sl.sval_in, max_cp * 4);
+            ENSURE(sl.sval_out, max_cp * 4);
+            ENSURE(sl.list_a, max_cp * 4);
+            if (dedup) ENSURE(sl.seq_tab, ((size_t)table_mask(max_cs) + 1) * 12);
+            ENSURE(sl.pair_tab, ((size_t)table_mask(max_cp) + 1) * 12);
+            ENSURE(sl.cub_tmp, tmp);
+        }
     }
     while (b.h_pp && ctx->up_ev.size() < K) {
         cudaEvent_t e;
@@ -329,6 +386,9 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     }
     Ctrl *ctrl = (Ctrl *)ctx->ctrl.p;
     CK(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), s));
+    CK(cudaEventRecord(ctx->ev[10], s)); // the other slot's stream and the copy stream start after the reset
+    for (int i = 1; i < n_slot; ++i) CK(cudaStreamWaitEvent(ctx->slot[i].st, ctx->ev[10], 0));
+    if (b.h_pp) CK(cudaStreamWaitEvent(cs, ctx->ev[10], 0));
 
     AlignParams p;
     memset(&p, 0, sizeof(p));
@@ -342,10 +402,6 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     p.work = want_work ? (uint32_t *)ctx->work.p : nullptr;
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
 
-    // ---- host batches: the caller's CPU threads 2-bit pack the sequences chunk by chunk (a quarter of the
-    // ASCII bytes cross PCIe); small batches and CIGAR calls ship the ASCII and pack on the device -------
-    const bool host_pack = b.h_pp && !cigar_mode && b.blob_bytes >= ctx->hostpack_min_bytes;
-    HostPacker packer;
     std::vector<uint32_t> new_lo(K, 0), new_hi(K, 0); // sequences first needed by chunk k: [new_lo, new_hi)
     {
         uint32_t up = 0;
@@ -355,148 +411,156 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
             new_hi[k] = up;
         }
     }
-    if (host_pack) {
-        int r = ensure_pinned(ctx, ctx->h_packed, ctx->h_packed_cap, max_words * 4);
-        if (r) return r;
-        r = ensure_pinned(ctx, ctx->h_flag, ctx->h_flag_cap, (size_t)n_seqs);
-        if (r) return r;
-        std::vector<HostPacker::Block> blocks;
-        for (size_t k = 0; k < K; ++k)
-            for (uint32_t a = new_lo[k]; a < new_hi[k]; a += 4096)
-                blocks.push_back({a, std::min(new_hi[k], a + 4096), (uint32_t)k});
-        const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-        packer.start(b.h_blob, b.blob_bytes, b.h_seq_off, b.h_seq_len, n_seqs, (uint32_t *)ctx->h_packed,
-                     (uint8_t *)ctx->h_flag, std::move(blocks), K, hw);
-        cn.host_packed = 1;
-    }
 
     // ---- chunks ---------------------------------------------------------------------------------------
     for (size_t k = 0; k < K; ++k) {
         const Chunk &c = chunks[k];
         const uint32_t cpairs = (uint32_t)(c.p1 - c.p0);
         const uint32_t a = new_lo[k], e = new_hi[k];
+        // blob bytes of the new sequences (device batches: offsets unknown on the host -> everything at once)
+        uint64_t b0 = 0, b1 = b.blob_bytes;
+        if (b.h_pp && e > a) {
+            b0 = std::min<uint64_t>(b.h_seq_off[a], b.blob_bytes) & ~(uint64_t)15;
+            b1 = e == n_seqs ? b.blob_bytes : std::min<uint64_t>(b.h_seq_off[e - 1] + b.h_seq_len[e - 1], b.blob_bytes);
+            b1 = std::max(b1, b0);
+        }
         if (b.h_pp) { // queue this chunk's upload on the copy stream
             if (e > a) {
-                CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, (size_t)(e - a) * 8, cudaMemcpyHostToDevice, cs));
+                // one offset beyond the chunk: k_hash checks every sequence against its successor's offset
+                const size_t n_off = (size_t)(e - a) + (e < n_seqs ? 1 : 0);
+                CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, n_off * 8, cudaMemcpyHostToDevice, cs));
                 CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
-                const uint64_t b0 = std::min<uint64_t>(b.h_seq_off[a], b.blob_bytes);
-                const uint64_t b1 = e == n_seqs ? b.blob_bytes
-                                                : std::min<uint64_t>(b.h_seq_off[e - 1] + b.h_seq_len[e - 1], b.blob_bytes);
                 if (!host_pack) {
                     if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
                 } else {
-                    packer.wait_chunk(k);
-                    if (packer.violations())
-                        return fail(ctx, TDB_E_INVALID, "sequence blob layout: sequences must be stored in index order, "
-                                                        "non-overlapping, inside the blob");
+                    const auto t_wait = std::chrono::steady_clock::now();
+                    packer.wait_bytes(b0, b1);
+                    cn.ms_host_pack_wait += ms_since(t_wait);
                     const uint8_t *hf = (const uint8_t *)ctx->h_flag;
                     CK(cudaMemcpyAsync((uint8_t *)ctx->seq_flag.p + a, hf + a, (size_t)(e - a), cudaMemcpyHostToDevice, cs));
-                    const size_t w0 = woff_of(b.h_seq_off[a], a);
-                    const size_t w1 = (size_t)woff_of(b.h_seq_off[e - 1], e - 1) + nwords_of(b.h_seq_len[e - 1]);
-                    CK(cudaMemcpyAsync((uint32_t *)ctx->packed.p + w0, (const uint32_t *)ctx->h_packed + w0, (w1 - w0) * 4,
-                                       cudaMemcpyHostToDevice, cs));
+                    const size_t w0 = (size_t)(b0 >> 4), w1 = (size_t)((b1 + 15) >> 4);
+                    if (w1 > w0)
+                        CK(cudaMemcpyAsync((uint32_t *)ctx->packed.p + w0, (const uint32_t *)ctx->h_packed + w0, (w1 - w0) * 4,
+                                           cudaMemcpyHostToDevice, cs));
                     // sequences with bytes outside ACGT are compared as raw bytes on the device: ship those bytes
                     size_t n_flag = 0;
                     for (uint32_t i = a; i < e; ++i) n_flag += hf[i] != 0;
                     if (n_flag > 256) {
                         if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
                     } else if (n_flag) {
-                        for (uint32_t i = a; i < e; ++i)
-                            if (hf[i] && b.h_seq_len[i])
-                                CK(cudaMemcpyAsync((uint8_t *)b.blob + b.h_seq_off[i], b.h_blob + b.h_seq_off[i], b.h_seq_len[i],
-                                                   cudaMemcpyHostToDevice, cs));
+                        for (uint32_t i = a; i < e; ++i) {
+                            const uint64_t o = b.h_seq_off[i];
+                            if (hf[i] && b.h_seq_len[i] && o <= b.blob_bytes && b.h_seq_len[i] <= b.blob_bytes - o)
+                                CK(cudaMemcpyAsync((uint8_t *)b.blob + o, b.h_blob + o, b.h_seq_len[i], cudaMemcpyHostToDevice, cs));
+                        }
                     }
                 }
             }
             CK(cudaMemcpyAsync((uint32_t *)b.pp + c.p0, b.h_pp + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
             CK(cudaMemcpyAsync((uint32_t *)b.pt + c.p0, b.h_pt + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
-            CK(cudaEventRecord(ctx->up_ev[k], cs));
-            CK(cudaStreamWaitEvent(s, ctx->up_ev[k], 0));
         }
+        // 2-bit packing (unless the host did it) and content hashes of the new sequences: on the copy stream for
+        // host batches, so that sequences are ready in order whichever slot needs them
+        cudaStream_t ps = b.h_pp ? cs : s;
         if (e > a) {
-            const uint32_t cnt = e - a;
-            const unsigned blocks = (unsigned)std::min<size_t>(((size_t)cnt * PK_G + 255) / 256, (size_t)ctx->sm_count * 64);
-            if (host_pack)
-                k_hash<<<blocks, 256, 0, s>>>(b.seq_off, b.seq_len, a, e, (const uint32_t *)ctx->packed.p,
-                                              (uint64_t *)ctx->seq_hash.p);
-            else
-                k_pack<<<blocks, 256, 0, s>>>(b.blob, b.blob_bytes, b.seq_off, b.seq_len, a, e, n_seqs,
-                                              (uint32_t *)ctx->packed.p, (uint8_t *)ctx->seq_flag.p,
-                                              (uint64_t *)ctx->seq_hash.p, &ctrl->err);
+            if (!host_pack) {
+                CK(cudaMemsetAsync((uint8_t *)ctx->seq_flag.p + a, 0, (size_t)(e - a), ps));
+                if (b1 > b0) {
+                    const unsigned blocks = (unsigned)std::min<uint64_t>(((b1 - b0 + 15) / 16 + 255) / 256, (uint64_t)ctx->sm_count * 32);
+                    k_pack<<<blocks, 256, 0, ps>>>(b.blob, b0, b1, b.seq_off, b.seq_len, a, e, (uint32_t *)ctx->packed.p,
+                                                   (uint8_t *)ctx->seq_flag.p);
+                    CK(cudaGetLastError());
+                    cn.kernel_launches += 1;
+                }
+            }
+            const unsigned blocks = (unsigned)std::min<size_t>(((size_t)(e - a) * PK_G + 255) / 256, (size_t)ctx->sm_count * 64);
+            k_hash<<<blocks, 256, 0, ps>>>(b.seq_off, b.seq_len, a, e, n_seqs, b.blob_bytes, (const uint32_t *)ctx->packed.p,
+                                           (uint8_t *)ctx->seq_flag.p, (uint64_t *)ctx->seq_hash.p, &ctrl->err);
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
-        if (staged) CK(cudaEventRecord(ctx->ev[2], s));
+        const int si = (int)(k % (size_t)n_slot);
+        tdb_ctx::Slot &sl = ctx->slot[si];
+        cudaStream_t st = sl.st;
+        if (b.h_pp) {
+            CK(cudaEventRecord(ctx->up_ev[k], cs));
+            CK(cudaStreamWaitEvent(st, ctx->up_ev[k], 0));
+        }
+        if (staged) CK(cudaEventRecord(ctx->ev[2], st));
         if (cigar_mode) continue; // CIGAR output lives in the general kernel: no dedup, no shared-memory tiers
-        CK(cudaMemsetAsync((uint8_t *)ctrl + CTRL_CHUNK_OFF, 0, sizeof(Ctrl) - CTRL_CHUNK_OFF, s));
+        Ctrl::Chunk *ck = &ctrl->ck[si];
+        CK(cudaMemsetAsync(ck, 0, sizeof(Ctrl::Chunk), st));
         const uint32_t ns = c.s_hi - c.s_lo;
         const uint32_t smask = table_mask(ns), pmask = table_mask(cpairs);
-        unsigned long long *skeys = (unsigned long long *)ctx->seq_tab.p;
+        unsigned long long *skeys = (unsigned long long *)sl.seq_tab.p;
         uint32_t *svals = dedup ? (uint32_t *)(skeys + (size_t)smask + 1) : nullptr;
+        uint32_t *canon = (uint32_t *)sl.canon.p;
         if (dedup && ns) {
-            CK(cudaMemsetAsync(skeys, 0xff, ((size_t)smask + 1) * 12, s));
-            k_seq_insert<<<(ns + 255) / 256, 256, 0, s>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p,
-                                                          c.s_lo, c.s_hi, skeys, svals, smask);
+            CK(cudaMemsetAsync(skeys, 0xff, ((size_t)smask + 1) * 12, st));
+            k_seq_insert<<<(ns + 255) / 256, 256, 0, st>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p,
+                                                           c.s_lo, c.s_hi, skeys, svals, smask);
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
         if (ns) {
             const unsigned blocks = (unsigned)(((size_t)ns * CN_G + 255) / 256);
-            k_seq_canon<<<blocks, 256, 0, s>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p, b.seq_off,
-                                               b.seq_len, (const uint32_t *)ctx->packed.p, c.s_lo, c.s_hi, skeys, svals,
-                                               smask, (uint32_t *)ctx->canon.p, dedup ? 1 : 0);
+            k_seq_canon<<<blocks, 256, 0, st>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p, b.seq_off,
+                                                b.seq_len, (const uint32_t *)ctx->packed.p, c.s_lo, c.s_hi, skeys, svals,
+                                                smask, canon, dedup ? 1 : 0);
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
         PairTable tb;
-        tb.keys = (unsigned long long *)ctx->pair_tab.p, tb.vals = (uint32_t *)(tb.keys + (size_t)pmask + 1), tb.mask = pmask;
-        CK(cudaMemsetAsync(tb.keys, 0xff, ((size_t)pmask + 1) * 12, s));
+        tb.keys = (unsigned long long *)sl.pair_tab.p, tb.vals = (uint32_t *)(tb.keys + (size_t)pmask + 1), tb.mask = pmask;
+        CK(cudaMemsetAsync(tb.keys, 0xff, ((size_t)pmask + 1) * 12, st));
         const unsigned pblocks = (cpairs + 255) / 256;
-        k_pair_insert<<<pblocks, 256, 0, s>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs,
-                                              (const uint32_t *)ctx->canon.p, tb, &ctrl->err);
+        k_pair_insert<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, tb, &ctrl->err);
         CK(cudaGetLastError());
         ClassifyOut co;
-        co.rep = (uint32_t *)ctx->rep.p, co.key = (uint8_t *)ctx->skey_in.p, co.val = (uint32_t *)ctx->sval_in.p;
-        co.glist = (uint32_t *)ctx->list_b.p, co.gcount = &ctrl->gcount, co.hist = ctrl->hist;
+        co.rep = (uint32_t *)ctx->rep.p, co.key = (uint8_t *)sl.skey_in.p, co.val = (uint32_t *)sl.sval_in.p;
+        co.glist = (uint32_t *)ctx->list_b.p, co.gcount = &ctrl->gcount, co.hist = ck->hist;
         co.out_score = b.score, co.out_status = b.status, co.out_penalty = b.penalty, co.work = p.work;
-        k_pair_classify<<<pblocks, 256, 0, s>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs,
-                                                (const uint32_t *)ctx->canon.p, b.seq_len, (const uint8_t *)ctx->seq_flag.p,
-                                                tb, quad_ok ? 1 : 0, T0_MAXLEN, co);
+        k_pair_classify<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, b.seq_len,
+                                                 (const uint8_t *)ctx->seq_flag.p, tb, quad_ok ? 1 : 0, T0_MAXLEN, co);
         CK(cudaGetLastError());
-        size_t tmp = ctx->cub_tmp.cap;
-        CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, (const uint8_t *)ctx->skey_in.p, (uint8_t *)ctx->skey_out.p,
-                                           (const uint32_t *)ctx->sval_in.p, (uint32_t *)ctx->sval_out.p, (int)cpairs, 0, 8, s));
-        k_plan<<<1, 32, 0, s>>>(ctrl->hist, ctrl->seg);
+        size_t tmp = sl.cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(sl.cub_tmp.p, tmp, (const uint8_t *)sl.skey_in.p, (uint8_t *)sl.skey_out.p,
+                                           (const uint32_t *)sl.sval_in.p, (uint32_t *)sl.sval_out.p, (int)cpairs, 0, 8, st));
+        k_plan<<<1, 32, 0, st>>>(ck->hist, ck->seg);
         CK(cudaGetLastError());
         cn.kernel_launches += 6; // insert, classify, sort (3 kernels), plan
-        if (staged) CK(cudaEventRecord(ctx->ev[3], s));
+        if (staged) CK(cudaEventRecord(ctx->ev[3], st));
         // tier 0: four pairs per warp, shared memory (default penalties only)
-        p.src1 = (const uint32_t *)ctx->sval_out.p;
+        p.src1 = (const uint32_t *)sl.sval_out.p;
         if (quad_ok) {
-            p.src1_seg = ctrl->seg + 2, p.src2 = nullptr, p.src2_count = nullptr;
-            p.work_counter = &ctrl->wc_quad, p.next_todo = (uint32_t *)ctx->list_a.p, p.next_count = &ctrl->acount;
+            p.src1_seg = ck->seg + 2, p.src2 = nullptr, p.src2_count = nullptr;
+            p.work_counter = &ck->wc_quad, p.next_todo = (uint32_t *)sl.list_a.p, p.next_count = &ck->acount;
             p.counters = ctrl->exec[0];
             const size_t smem = sizeof(QPair) * (32 / QG) * Q_WARPS;
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->quad_ctas_per_sm,
                                                              ((size_t)cpairs + 31) / 32 + 1);
-            k_align_quad<8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, s>>>(p);
+            k_align_quad<8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, st>>>(p);
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
-        if (staged) CK(cudaEventRecord(ctx->ev[4], s));
-        // tier 1: one pair per warp, shared memory
+        if (staged) CK(cudaEventRecord(ctx->ev[4], st));
+        // tier 1: one pair per warp, shared memory; the quad tier's leftovers (the heaviest pairs) go first
         {
-            p.src1_seg = ctrl->seg + 0, p.src2 = (const uint32_t *)ctx->list_a.p, p.src2_count = &ctrl->acount;
-            p.work_counter = &ctrl->wc_warp, p.next_todo = (uint32_t *)ctx->list_b.p, p.next_count = &ctrl->gcount;
+            p.src1_seg = ck->seg + 0, p.src2 = (const uint32_t *)sl.list_a.p, p.src2_count = &ck->acount;
+            p.work_counter = &ck->wc_warp, p.next_todo = (uint32_t *)ctx->list_b.p, p.next_count = &ctrl->gcount;
             p.counters = ctrl->exec[1];
             const size_t smem = sizeof(T0Smem) * T0_WARPS;
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->t0_ctas_per_sm,
                                                              ((size_t)cpairs + T0_WARPS - 1) / T0_WARPS);
-            k_align_warp<<<grid, T0_WARPS * 32, smem, s>>>(p);
+            k_align_warp<<<grid, T0_WARPS * 32, smem, st>>>(p);
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
-        if (staged) CK(cudaEventRecord(ctx->ev[5], s));
+        if (staged) CK(cudaEventRecord(ctx->ev[5], st));
+    }
+    for (int i = 1; i < n_slot; ++i) { // join the other slot's stream
+        CK(cudaEventRecord(ctx->slot[i].done, ctx->slot[i].st));
+        CK(cudaStreamWaitEvent(s, ctx->slot[i].done, 0));
     }
 
     // ---- global-scratch tiers: pairs too long or too wide for shared memory, once per call ------------
@@ -570,6 +634,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         cn.pairs_identical = h.algo[3] >= aligned ? h.algo[3] - aligned : 0;
     }
     cn.ms_total_device = elapsed(ctx->ev[0], ctx->ev[1]);
+    cn.ms_host_call = ms_since(t_call);
     if (staged) {
         cn.ms_pack = elapsed(ctx->ev[0], ctx->ev[2]);
         if (!cigar_mode) {
@@ -714,6 +779,9 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
     memset(&c->counters, 0, sizeof(c->counters));
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    c->slot[0].st = c->stream;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->slot[1].st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[1].done, cudaEventDisableTiming);
     for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     const size_t smem = sizeof(T0Smem) * T0_WARPS;
     if (e == cudaSuccess)
@@ -760,12 +828,18 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
 void tdb_destroy(tdb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
-    DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->canon,
-                      &c->pair_p, &c->pair_t, &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->skey_in,
-                      &c->skey_out, &c->sval_in, &c->sval_out, &c->cub_tmp, &c->seq_tab, &c->pair_tab, &c->list_a,
-                      &c->list_b, &c->list_c, &c->ctrl, &c->loci, &c->aout, &c->mask, &c->scores_in, &c->cigar,
-                      &c->cigar_off, &c->cigar_len, &c->scratch[0], &c->scratch[1]};
+    DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->pair_p, &c->pair_t,
+                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->ctrl, &c->loci,
+                      &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
+                      &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
+    for (auto &sl : c->slot) {
+        DevBuf *sb[] = {&sl.canon, &sl.skey_in, &sl.skey_out, &sl.sval_in, &sl.sval_out, &sl.cub_tmp, &sl.seq_tab,
+                        &sl.pair_tab, &sl.list_a};
+        for (DevBuf *b : sb) b->release();
+    }
+    if (c->slot[1].st) cudaStreamDestroy(c->slot[1].st);
+    if (c->slot[1].done) cudaEventDestroy(c->slot[1].done);
     for (int i = 0; i < 16; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->up_ev) cudaEventDestroy(e);
@@ -1038,14 +1112,42 @@ int32_t tdb_cigar_score_clipped(const tdb_ctx *ctx, int32_t flank_len) {
     return score;
 }
 
-size_t tdb_packed_words(size_t blob_bytes, size_t n_seqs) { return blob_bytes / 16 + 2 * n_seqs + 2; }
+size_t tdb_packed_words(size_t blob_bytes) { return blob_bytes / 16 + 2; }
 
 int tdb_host_pack(const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off, const uint32_t *seq_len,
-                  size_t n_seqs, uint32_t *packed, uint8_t *flag) {
-    if (n_seqs && (!seq_off || !seq_len || !packed || !flag)) return TDB_E_INVALID;
-    if (n_seqs >= 0x7fffffffull || blob_bytes / 16 + 2 * n_seqs + 2 >= 0xffffffffull) return TDB_E_UNSUPPORTED;
-    const size_t v = hostpack_range(seq_blob, blob_bytes, seq_off, seq_len, 0, (uint32_t)n_seqs, (uint32_t)n_seqs, packed, flag);
-    return v ? TDB_E_INVALID : TDB_OK;
+                  size_t n_seqs, uint32_t *packed, uint8_t *flag, int n_threads) {
+    if ((blob_bytes && (!seq_blob || !packed)) || (n_seqs && (!seq_off || !seq_len || !flag))) return TDB_E_INVALID;
+    if (n_seqs >= 0x7fffffffull || blob_bytes / 16 + 2 >= 0xffffffffull) return TDB_E_UNSUPPORTED;
+    const uint32_t n = (uint32_t)n_seqs;
+    const unsigned nt = (unsigned)std::max(1, std::min(n_threads, 256));
+    const uint64_t BLK = HostPacker::BLOCK;
+    std::atomic<uint64_t> next{0};
+    std::atomic<uint32_t> next_seq{0};
+    std::atomic<size_t> violations{0};
+    auto run = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(fn);
+        fn();
+        for (auto &x : th) x.join();
+    };
+    run([&]() { // layout contract first: the packer's owner search needs ascending offsets
+        for (;;) {
+            const uint32_t a = next_seq.fetch_add(65536);
+            if (a >= n) return;
+            const uint32_t e = (uint32_t)std::min<uint64_t>(n, (uint64_t)a + 65536);
+            violations += hostpack_check_layout(seq_off, seq_len, a, e, n, blob_bytes);
+            memset(flag + a, 0, e - a);
+        }
+    });
+    if (violations.load()) return TDB_E_INVALID;
+    run([&]() {
+        for (;;) {
+            const uint64_t x0 = next.fetch_add(BLK);
+            if (x0 >= blob_bytes) return;
+            hostpack_stream(seq_blob, x0, std::min<uint64_t>(blob_bytes, x0 + BLK), packed, seq_off, seq_len, n, flag);
+        }
+    });
+    return TDB_OK;
 }
 
 const char *tdb_host_pack_isa(void) { return hostpack_isa(); }

@@ -8,16 +8,14 @@ namespace tdb {
 
 // ------------------------------------------------------------------------------------------------
 // Packing: raw ASCII -> 2-bit words (the role north_star gives locus.rs/read.rs, done at HBM speed).
-// Sixteen lanes per sequence, lane j builds word j (16 bases).  A sequence containing any byte
-// outside {A,C,G,T} is flagged; pairs touching a flagged sequence take the byte-compare path so that
-// raw byte equality (N==N, case-sensitive) is preserved exactly as WFA2 sees it.  The same pass
-// produces a 64-bit content hash per sequence (feeds the duplicate elimination below) and checks
-// the blob layout contract (sequences laid out in index order, non-overlapping), which lets the
-// packed offset be pure arithmetic: word offset of sequence i = (seq_off[i] >> 4) + 2 i.
+// The blob is packed as ONE stream, independent of sequence boundaries: the byte at blob position x
+// goes to word x/16, bits 2*(x%16), code (byte >> 1) & 3.  A sequence is a window of that stream
+// (word seq_off/16, shift seq_off%16); the aligners read it with a funnel shift, so no per-sequence
+// padding or offset table exists.  One thread packs 16 bytes into one word: fully coalesced 16-byte
+// loads and 4-byte stores.  A byte outside {A,C,G,T} flags the sequence that owns it (binary search
+// in seq_off, rare); pairs touching a flagged sequence take the byte-compare path so that raw byte
+// equality (N==N, case-sensitive) is preserved exactly as WFA2 sees it.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t nwords_of(uint32_t len) { return (len + 15u) / 16u + 1u; }
-__host__ __device__ __forceinline__ uint32_t woff_of(uint64_t off, uint32_t i) { return (uint32_t)(off >> 4) + 2u * i; }
-
 __device__ __forceinline__ uint32_t pack4(uint32_t w) { // 4 ASCII bytes -> 8 bits
     const uint32_t c = (w >> 1) & 0x03030303u;
     return (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu;
@@ -36,14 +34,88 @@ constexpr uint64_t HT_EMPTY = ~0ull;
 // error bits raised by the kernels into the ctrl block
 enum { ERR_LAYOUT = 1, ERR_PAIR_INDEX = 2 };
 
+// Sets flag = 1 on the sequence of [s_lo, s_hi) that owns blob position x (seq_off sorted ascending).
+__device__ inline void flag_owner(uint64_t x, const uint64_t *__restrict__ seq_off,
+                                  const uint32_t *__restrict__ seq_len, uint32_t s_lo, uint32_t s_hi,
+                                  uint8_t *__restrict__ seq_flag) {
+    uint32_t lo = s_lo, hi = s_hi; // last i in [s_lo, s_hi) with seq_off[i] <= x
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (seq_off[mid] <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    // zero-length sequences may share an offset with their successor: walk back over them
+    for (uint32_t i = lo; i > s_lo;) {
+        --i;
+        const uint64_t o = seq_off[i];
+        if (x < o + seq_len[i]) {
+            seq_flag[i] |= 1;
+            return;
+        }
+        if (o + seq_len[i] <= x && seq_len[i] != 0) return;
+    }
+}
+
+// Packs blob bytes [b0, b1) (b0 a multiple of 16).  seq_flag of [s_lo, s_hi) must be zeroed before.
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, uint64_t b0, uint64_t b1,
+                                              const uint64_t *__restrict__ seq_off,
+                                              const uint32_t *__restrict__ seq_len, uint32_t s_lo, uint32_t s_hi,
+                                              uint32_t *__restrict__ packed, uint8_t *__restrict__ seq_flag) {
+    const uint64_t ngroups = (b1 - b0 + 15) / 16;
+    const bool aligned = (((uintptr_t)blob) & 15) == 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x0 = b0 + g * 16;
+        uint32_t q[4];
+        const uint32_t cnt = (uint32_t)min((uint64_t)16, b1 - x0);
+        if (aligned && cnt == 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(blob + x0));
+            q[0] = v.x, q[1] = v.y, q[2] = v.z, q[3] = v.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint32_t w = 0;
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t bi = (uint32_t)(t * 4 + u);
+                    if (bi < cnt) w |= (uint32_t)blob[x0 + bi] << (8 * u);
+                }
+                q[t] = w;
+            }
+        }
+        uint32_t word = 0, badm = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int rem = (int)cnt - 4 * t;
+            const uint32_t need = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
+            const uint32_t bad4 = ~acgt_mask4(q[t]) & need; // 0xff per offending byte
+            badm |= (((bad4 >> 7) & 1u) | ((bad4 >> 14) & 2u) | ((bad4 >> 21) & 4u) | ((bad4 >> 28) & 8u)) << (4 * t);
+            word |= pack4(q[t] & need) << (8 * t);
+        }
+        packed[x0 >> 4] = word;
+        while (badm) { // rare: flag the owning sequences
+            const int k = __ffs(badm) - 1;
+            badm &= badm - 1;
+            flag_owner(x0 + (uint64_t)k, seq_off, seq_len, s_lo, s_hi, seq_flag);
+        }
+    }
+}
+
+// Word j (bases 16j .. 16j+15) of a sequence in the packed stream, bases past the end masked to zero.
+__device__ __forceinline__ uint32_t seq_word(const uint32_t *__restrict__ packed, uint64_t off, uint32_t len, uint32_t j) {
+    const uint64_t x = off + 16ull * j;
+    const uint32_t *w = packed + (x >> 4);
+    const uint32_t v = __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(x & 15) << 1);
+    const uint32_t rem = len - 16u * j;
+    return rem >= 16u ? v : (v & ((1u << (2u * rem)) - 1u));
+}
+
 constexpr int PK_G = 16; // lanes per sequence
 
-__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, size_t blob_bytes,
-                                              const uint64_t *__restrict__ seq_off,
-                                              const uint32_t *__restrict__ seq_len, uint32_t s0, uint32_t s1,
-                                              uint32_t n_seqs, uint32_t *__restrict__ packed,
-                                              uint8_t *__restrict__ seq_flag, uint64_t *__restrict__ seq_hash,
-                                              unsigned *__restrict__ err) {
+// 64-bit content hash per sequence (feeds the duplicate elimination below) + the blob layout contract
+// (sequences in index order, non-overlapping, inside the blob: what makes chunked uploads possible).
+__global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
+                                              uint32_t s0, uint32_t s1, uint32_t n_seqs, uint64_t blob_bytes,
+                                              const uint32_t *__restrict__ packed, uint8_t *__restrict__ seq_flag,
+                                              uint64_t *__restrict__ seq_hash, unsigned *__restrict__ err) {
     const int lane = threadIdx.x & 31, gl = lane & (PK_G - 1);
     const unsigned gmask = 0xffffu << (lane & 16);
     const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) / PK_G;
@@ -51,83 +123,17 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, 
     for (uint32_t i = s0 + g0; i < s1; i += ng) {
         const uint32_t len = seq_len[i];
         const uint64_t off = seq_off[i];
+        const bool outside = off > blob_bytes || (uint64_t)len > blob_bytes - off;
         if (gl == 0) {
-            bool bad_layout = off + len > blob_bytes;
-            if (i + 1 < n_seqs) bad_layout |= off + len > seq_off[i + 1];
+            bool bad_layout = outside;
+            if (!outside && i + 1 < n_seqs) bad_layout = off + len > seq_off[i + 1];
             if (bad_layout) atomicOr(err, (unsigned)ERR_LAYOUT);
+            if (outside) seq_flag[i] = 2, seq_hash[i] = 0; // 2: unusable, pairs touching it are skipped
         }
-        if (off + len > blob_bytes) { // never read outside the blob; the call fails with ERR_LAYOUT
-            if (gl == 0) seq_flag[i] = 2, seq_hash[i] = 0; // 2: unusable, pairs touching it are skipped
-            continue;
-        }
-        const uint32_t nw = nwords_of(len);
-        uint32_t *dst = packed + woff_of(off, i);
-        bool bad = false;
+        if (outside) continue;
+        const uint32_t nw = (len + 15u) / 16u;
         uint64_t hs = 0;
-        for (uint32_t j = gl; j < nw; j += PK_G) {
-            const uint32_t base = j * 16u;
-            uint32_t word = 0;
-            if (base < len) {
-                const uint32_t cnt = min(16u, len - base);
-                const uint8_t *src = blob + off + base;
-                uint32_t q[4];
-                if (off + base + 20 <= blob_bytes) { // aligned word loads + byte funnel shift
-                    const uintptr_t a = (uintptr_t)src;
-                    const uint32_t *ap = (const uint32_t *)(a & ~(uintptr_t)3);
-                    const uint32_t sh = (uint32_t)(a & 3) * 8u;
-                    uint32_t r[5];
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) r[t] = __ldg(ap + t);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) q[t] = __funnelshift_r(r[t], r[t + 1], sh);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        uint32_t w = 0;
-                        for (int u = 0; u < 4; ++u) {
-                            const uint32_t bi = (uint32_t)(t * 4 + u);
-                            if (bi < cnt) w |= (uint32_t)src[bi] << (8 * u);
-                        }
-                        q[t] = w;
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int rem = (int)cnt - 4 * t; // bytes of this quad that belong to the sequence
-                    const uint32_t need = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
-                    bad |= (~acgt_mask4(q[t]) & need) != 0;
-                    word |= pack4(q[t] & need) << (8 * t);
-                }
-            }
-            dst[j] = word;
-            hs += mix64(((uint64_t)j << 32) | word);
-        }
-        const unsigned any_bad = __ballot_sync(gmask, bad) & gmask;
-#pragma unroll
-        for (int o = PK_G / 2; o; o >>= 1) hs += __shfl_xor_sync(gmask, hs, o);
-        if (gl == 0) {
-            seq_flag[i] = any_bad ? 1 : 0;
-            uint64_t h = mix64(hs ^ ((uint64_t)len * 0x9e3779b97f4a7c15ull));
-            seq_hash[i] = h == HT_EMPTY ? 0 : h;
-        }
-    }
-}
-
-// Content hash of sequences that arrive already packed (host batches packed by the caller's CPU threads,
-// tdb_hostpack.cpp).  Same hash as k_pack so both routes feed the duplicate elimination identically.
-__global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
-                                              uint32_t s0, uint32_t s1, const uint32_t *__restrict__ packed,
-                                              uint64_t *__restrict__ seq_hash) {
-    const int lane = threadIdx.x & 31, gl = lane & (PK_G - 1);
-    const unsigned gmask = 0xffffu << (lane & 16);
-    const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) / PK_G;
-    const uint32_t ng = (gridDim.x * blockDim.x) / PK_G;
-    for (uint32_t i = s0 + g0; i < s1; i += ng) {
-        const uint32_t len = seq_len[i];
-        const uint32_t nw = nwords_of(len);
-        const uint32_t *src = packed + woff_of(seq_off[i], i);
-        uint64_t hs = 0;
-        for (uint32_t j = gl; j < nw; j += PK_G) hs += mix64(((uint64_t)j << 32) | __ldg(src + j));
+        for (uint32_t j = gl; j < nw; j += PK_G) hs += mix64(((uint64_t)j << 32) | seq_word(packed, off, len, j));
 #pragma unroll
         for (int o = PK_G / 2; o; o >>= 1) hs += __shfl_xor_sync(gmask, hs, o);
         if (gl == 0) {
@@ -194,9 +200,9 @@ __global__ void __launch_bounds__(256) k_seq_canon(const uint64_t *__restrict__ 
             const uint32_t len = seq_len[i];
             bool diff = seq_len[c] != len;
             if (!diff) {
-                const uint32_t *a = packed + woff_of(seq_off[i], i), *b = packed + woff_of(seq_off[c], c);
+                const uint64_t oi = seq_off[i], oc = seq_off[c];
                 const uint32_t nw = (len + 15u) / 16u;
-                for (uint32_t j = gl; j < nw; j += CN_G) diff |= a[j] != b[j];
+                for (uint32_t j = gl; j < nw; j += CN_G) diff |= seq_word(packed, oi, len, j) != seq_word(packed, oc, len, j);
             }
             if (__ballot_sync(gmask, diff) & gmask) c = i;
         }
@@ -390,18 +396,20 @@ struct AlignParams {
 };
 
 struct ItemSrc {
-    unsigned b1, c1, total;
+    unsigned b1, c2, total;
 };
+// src2 (what the previous tier could not finish: the heaviest pairs) is served before src1
 __device__ __forceinline__ ItemSrc item_src(const AlignParams &p) {
     ItemSrc s;
     s.b1 = p.src1_seg ? p.src1_seg[0] : 0u;
-    s.c1 = p.src1_seg ? p.src1_seg[1] : p.src1_count;
-    s.total = s.c1 + (p.src2 ? *p.src2_count : 0u);
+    s.c2 = p.src2 ? *p.src2_count : 0u;
+    s.total = s.c2 + (p.src1_seg ? p.src1_seg[1] : p.src1_count);
     return s;
 }
 __device__ __forceinline__ uint32_t item_at(const AlignParams &p, const ItemSrc &s, unsigned it) {
-    if (it < s.c1) return p.src1 ? p.src1[s.b1 + it] : it;
-    return p.src2[it - s.c1];
+    if (it < s.c2) return p.src2[it];
+    it -= s.c2;
+    return p.src1 ? p.src1[s.b1 + it] : it;
 }
 
 constexpr int T0_WLOG2 = 6;
@@ -491,8 +499,9 @@ __global__ void __launch_bounds__(T0_WARPS * 32) k_align_warp(const AlignParams 
                 defer_pair(p, idx, lane);
                 continue;
             }
-            SeqView P = {p.packed + woff_of(p.seq_off[ip], ip), nullptr, n};
-            SeqView T = {p.packed + woff_of(p.seq_off[jt], jt), nullptr, m};
+            const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
+            SeqView P = {p.packed + (poff >> 4), nullptr, n, (int)(poff & 15)};
+            SeqView T = {p.packed + (toff >> 4), nullptr, m, (int)(toff & 15)};
             int pen = 0, clipped = 0;
             WorkCount wc1 = {0, 0, 0}; // work of this attempt: only counted when the tier finishes the pair
             unsigned long long ext1 = 0;
@@ -546,13 +555,13 @@ __global__ void __launch_bounds__(128) k_align_global(const AlignParams p) {
         const uint32_t idx = item_at(p, src, it);
         const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
         const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
-        const bool bytes = (p.seq_flag[ip] | p.seq_flag[jt]) != 0;
         SeqView P, T;
         P.len = n, T.len = m;
-        P.w = bytes ? nullptr : p.packed + woff_of(p.seq_off[ip], ip);
-        T.w = bytes ? nullptr : p.packed + woff_of(p.seq_off[jt], jt);
-        P.b = p.blob + p.seq_off[ip];
-        T.b = p.blob + p.seq_off[jt];
+        const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
+        P.w = p.packed + (poff >> 4), P.sh = (int)(poff & 15);
+        T.w = p.packed + (toff >> 4), T.sh = (int)(toff & 15);
+        P.b = p.seq_flag[ip] ? p.blob + poff : nullptr; // raw bytes only where 2 bits lose information
+        T.b = p.seq_flag[jt] ? p.blob + toff : nullptr;
         int pen = 0, clipped = 0;
         uint8_t *cig = WANT_CIGAR ? p.cigar_buf + p.cigar_off[idx] : nullptr;
         uint32_t *cl = WANT_CIGAR ? p.cigar_len + idx : nullptr;

@@ -27,13 +27,24 @@ struct Heur {
     int kind, min_len, max_dist, steps;
 };
 
-// A sequence as the kernels see it: 2-bit packed words (16 bases per uint32, base i at bits 2*(i%16))
-// when both sequences of the pair are pure ACGT, else the raw bytes (raw byte equality, 'N'=='N').
+// A sequence as the kernels see it: a window of the 2-bit packed blob (the byte at blob position x is
+// packed into word x/16 at bits 2*(x%16); base i of the sequence is at blob position seq_off + i, so
+// w points at word seq_off/16 and sh = seq_off%16 is added to every base index),
+// plus the raw bytes (b != nullptr) when the sequence holds a byte outside ACGT.  A pair is compared
+// 16 bases per instruction on the packed words when both sides are pure ACGT; otherwise byte by byte
+// (raw byte equality, 'N'=='N', case-sensitive), the pure-ACGT side decoded from its packed form.
 struct SeqView {
     const uint32_t *w;
     const uint8_t *b;
     int len;
+    int sh;
 };
+__device__ __forceinline__ uint32_t base_at(const SeqView &S, int i) {
+    if (S.b) return S.b[i];
+    const int x = S.sh + i;
+    const uint32_t code = (__ldg(S.w + (x >> 4)) >> ((x & 15) << 1)) & 3u;
+    return (0x47544341u >> (code << 3)) & 0xffu; // (byte >> 1) & 3: A 0, C 1, T 2, G 3
+}
 
 // provenance byte: bits 0-2 source of M, bits 3..6: I1,I2,D1,D2 came from "extend" (else "open")
 enum { PM_NONE = 0, PM_I1 = 1, PM_I2 = 2, PM_D1 = 3, PM_D2 = 4, PM_X = 5 };
@@ -88,9 +99,9 @@ __device__ __forceinline__ int extend_lane(const SeqView &P, const SeqView &T, i
                                            unsigned long long &ncmp) {
     const int room = min(P.len - v, T.len - h);
     int eq = 0;
-    if (P.w) {
+    if (!P.b && !T.b) {
         while (eq < room) {
-            const uint32_t x = get16(P.w, v + eq) ^ get16(T.w, h + eq);
+            const uint32_t x = get16(P.w, P.sh + v + eq) ^ get16(T.w, T.sh + h + eq);
             if (x) {
                 eq += (__ffs(x) - 1) >> 1;
                 break;
@@ -101,7 +112,7 @@ __device__ __forceinline__ int extend_lane(const SeqView &P, const SeqView &T, i
         ncmp += (eq >> 4) + 1; // E of SURVEY.md 8(d): 16-base compares, at least one per live diagonal
         return eq;
     }
-    while (eq < room && P.b[v + eq] == T.b[h + eq]) ++eq;
+    while (eq < room && base_at(P, v + eq) == base_at(T, h + eq)) ++eq;
     ncmp += (eq >> 4) + 1;
     return eq;
 }
@@ -109,11 +120,11 @@ __device__ __forceinline__ int extend_lane(const SeqView &P, const SeqView &T, i
 // Whole-warp extension of ONE diagonal (v,h uniform): lane l compares bases [16l, 16l+16) per round.
 __device__ __forceinline__ int extend_coop(const SeqView &P, const SeqView &T, int v, int h, int lane) {
     const int room = min(P.len - v, T.len - h);
-    if (P.w) {
+    if (!P.b && !T.b) {
         for (int base = 0; base < room; base += 512) {
             const int off = base + lane * 16;
             uint32_t x = 1u;
-            if (off < room) x = get16(P.w, v + off) ^ get16(T.w, h + off);
+            if (off < room) x = get16(P.w, P.sh + v + off) ^ get16(T.w, T.sh + h + off);
             const unsigned bal = __ballot_sync(TDB_FULL, x != 0);
             if (bal) {
                 const int l = __ffs(bal) - 1;
@@ -125,7 +136,7 @@ __device__ __forceinline__ int extend_coop(const SeqView &P, const SeqView &T, i
     }
     for (int base = 0; base < room; base += 32) {
         const int off = base + lane;
-        const bool ne = off >= room || P.b[v + off] != T.b[h + off];
+        const bool ne = off >= room || base_at(P, v + off) != base_at(T, h + off);
         const unsigned bal = __ballot_sync(TDB_FULL, ne);
         if (bal) return min(base + __ffs(bal) - 1, room);
     }

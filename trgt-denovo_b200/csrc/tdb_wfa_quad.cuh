@@ -51,13 +51,13 @@ __device__ __forceinline__ unsigned qballot(unsigned gmask, int gshift, bool pre
 }
 
 // Eight lanes extend one diagonal: lane l compares bases [16l, 16l+16) per round.
-__device__ __forceinline__ int extend_group(const uint32_t *pw, const uint32_t *tw, int n, int m, int v, int h,
-                                            int gl, unsigned gmask, int gshift, int lane) {
+__device__ __forceinline__ int extend_group(const uint32_t *pw, const uint32_t *tw, int psh, int tsh, int n, int m,
+                                            int v, int h, int gl, unsigned gmask, int gshift, int lane) {
     const int room = min(n - v, m - h);
     for (int base = 0; base < room; base += 16 * QG) {
         const int off = base + gl * 16;
         uint32_t x = 1u;
-        if (off < room) x = get16(pw, v + off) ^ get16(tw, h + off);
+        if (off < room) x = get16(pw, psh + v + off) ^ get16(tw, tsh + h + off);
         const unsigned bal = qballot(gmask, gshift, x != 0);
         if (bal) {
             const int l = __ffs(bal) - 1;
@@ -99,9 +99,10 @@ __global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p
                 int penalty = 0, clipped = 0;
                 unsigned long long cells = 0, cols = 0, ext = 0;
                 if (!overflow) {
-                    const uint32_t *pw = p.packed + woff_of(p.seq_off[ip], ip);
-                    const uint32_t *tw = p.packed + woff_of(p.seq_off[jt], jt);
-                    const int m0 = extend_group(pw, tw, n, m, 0, 0, gl, gmask, gshift, lane);
+                    const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
+                    const uint32_t *pw = p.packed + (poff >> 4), *tw = p.packed + (toff >> 4);
+                    const int psh = (int)(poff & 15), tsh = (int)(toff & 15);
+                    const int m0 = extend_group(pw, tw, psh, tsh, n, m, 0, 0, gl, gmask, gshift, lane);
                     if (gl == 0) ext += (unsigned)(m0 >> 4) + 1;
                     if (k_end == 0 && m0 >= m) {
                         cols = (unsigned)m; // identical: penalty 0, clipped score 0
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p
                                         const int v = mv - k, room = min(n - v, m - mv);
                                         int eq = 0;
                                         while (eq < room) {
-                                            const uint32_t x = get16(pw, v + eq) ^ get16(tw, mv + eq);
+                                            const uint32_t x = get16(pw, psh + v + eq) ^ get16(tw, tsh + mv + eq);
                                             if (x) {
                                                 eq += (__ffs(x) - 1) >> 1;
                                                 break;
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p
                             bool in_m = true;
                             for (int i = nops - 1; i >= -1; --i) {
                                 if (in_m) {
-                                    const int eq = extend_group(pw, tw, n, m, v, h, gl, gmask, gshift, lane);
+                                    const int eq = extend_group(pw, tw, psh, tsh, n, m, v, h, gl, gmask, gshift, lane);
                                     acc.emit('M', eq, pn);
                                     v += eq, h += eq;
                                 }
