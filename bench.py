@@ -235,6 +235,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------------
+    # one untimed counting step: exact algorithmic C/E/T of the workload (every pair as the CPU oracle counts it)
+    ctx.set_count_work(True)
+    algo = step_device()
+    algo_work = {"cells": int(algo.cells), "ext16": int(algo.ext16), "columns": int(algo.columns)}
+    ctx.set_count_work(False)
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local_rank)
@@ -324,7 +329,8 @@ def main():
         k_s = max(k_ms, 1e-6) * 1e-3
         ops = (INT_OPS_PER_CELL * cnt.tier_cells[ti] + INT_OPS_PER_EXT * cnt.tier_ext16[ti] +
                INT_OPS_PER_COL * cnt.tier_columns[ti])
-        ops_algo = INT_OPS_PER_CELL * cnt.cells + INT_OPS_PER_EXT * cnt.ext16 + INT_OPS_PER_COL * cnt.columns
+        ops_algo = (INT_OPS_PER_CELL * algo_work["cells"] + INT_OPS_PER_EXT * algo_work["ext16"] +
+                    INT_OPS_PER_COL * algo_work["columns"])
         clk = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         int_peak = n_sm * 128 * clk
@@ -371,7 +377,8 @@ def main():
             "breakdown_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "tier_pairs": [int(x) for x in cnt.tier_pairs],
             "pairs_identical": int(cnt.pairs_identical), "pairs_duplicate": int(cnt.pairs_duplicate),
-            "work": {"cells": int(cnt.cells), "ext16": int(cnt.ext16), "columns": int(cnt.columns),
+            "pairs_closed_form": int(cnt.pairs_closed_form),
+            "work": {"cells": algo_work["cells"], "ext16": algo_work["ext16"], "columns": algo_work["columns"],
                      "exec_cells": int(cnt.exec_cells), "exec_ext16": int(cnt.exec_ext16),
                      "exec_columns": int(cnt.exec_columns)},
             "e2e_chunks": int(e2e_chunks), "e2e_host": e2e_host,

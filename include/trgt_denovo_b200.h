@@ -230,6 +230,8 @@ typedef struct {
     uint64_t tier_cells[4], tier_ext16[4], tier_columns[4]; /* executed work per tier */
     uint64_t pairs_identical; /* pattern bytes == text bytes: resolved without an alignment */
     uint64_t pairs_duplicate; /* copies of an already aligned (pattern, text) content */
+    uint64_t pairs_closed_form; /* one substitution / one gap of <= 5 bases: scored in closed form (0 while
+                                   exact work counting is on) */
     uint64_t kernel_launches;
     uint64_t chunks;        /* pipeline chunks the call was cut into */
     uint64_t host_packed;   /* 1: the caller's CPU threads 2-bit packed the sequences before the upload */
@@ -240,7 +242,10 @@ typedef struct {
                          Stage times are recorded for single-chunk calls only (ms_total_device always). */
 } tdb_counters;
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
-/* Enables exact C/E/T work counting inside the kernels (off by default: it costs atomics). */
+/* Exact algorithmic work counting (cells / ext16 / columns of tdb_counters: every pair counted as the CPU
+ * oracle counts it, duplicates included).  Off by default: it routes every non-identical content through
+ * the wavefront kernels (no closed form) and keeps per-pair work records.  The exec_* / tier_* counters of
+ * the work the kernels executed are always maintained. */
 int tdb_set_count_work(tdb_ctx *ctx, int32_t on);
 
 /* The host half of the packing role (north_star: "locus.rs and read.rs pack the reads and alleles ...

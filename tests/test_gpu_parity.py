@@ -68,12 +68,23 @@ def _check_batch(ctx, seqs, pp, pt, clip, heuristic=tdo.DEFAULT_HEURISTIC, cigar
     blob, off, ln = to_arrays(seqs)
     ctx.set_clip_len(clip)
     want, wst, wtot = tdo.align_batch(blob, off, ln, pp, pt, clip, heuristic=heuristic, n_threads=8)
+    assert (wst == 0).all()
+    # production mode: closed form for single-substitution / single-short-gap contents, no work records
+    ctx.set_count_work(False)
+    got, st = ctx.align_batch(blob, off, ln, pp, pt)
+    fast = ctx.counters()
+    assert (st == wst).all()
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, f"{len(bad)} score mismatches (closed form on), first pair {bad[:5]}: gpu {got[bad[:5]]} oracle {want[bad[:5]]}"
+    assert sum(fast.tier_pairs) + fast.pairs_identical + fast.pairs_duplicate + fast.pairs_closed_form == len(pp)
+    # counting mode: every content through the wavefront kernels
+    ctx.set_count_work(True)
     got, st = ctx.align_batch(blob, off, ln, pp, pt)
     cnt = ctx.counters()
-    assert (wst == 0).all()
     assert (st == wst).all()
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, f"{len(bad)} score mismatches, first pair {bad[:5]}: gpu {got[bad[:5]]} oracle {want[bad[:5]]}"
+    assert cnt.pairs_closed_form == 0
     # exact algorithmic work accounting agrees with the oracle (C, E, T)
     assert (cnt.cells, cnt.ext16, cnt.columns) == (wtot.cells, wtot.ext16, wtot.columns)
     if cigars:
@@ -144,6 +155,37 @@ def test_duplicate_heavy_batch_counts(ctx):
     cnt = _check_batch(ctx, seqs, pp, pt, 50)
     assert cnt.pairs_duplicate + cnt.pairs_identical > 0.3 * len(pp) and cnt.pairs_duplicate > 0
     assert cnt.exec_cells < cnt.cells and cnt.exec_columns < cnt.columns
+
+
+@pytest.mark.parametrize("clip", [50, 0, 7])
+def test_closed_form_pairs(tdb, clip):
+    """Single substitution / single gap of 1..5 bases anywhere (inside and outside the clip window, at the very
+    ends, inside repeats where the gap can slide): the closed form must equal the wavefront result."""
+    rng = random.Random(40 + clip)
+    seqs, pp, pt = [], [], []
+    for _ in range(3000):
+        k = rng.randint(1, 6)
+        motif = rand_seq(rng, k)
+        lf, rf = rand_seq(rng, rng.randint(0, 60)), rand_seq(rng, rng.randint(0, 60))
+        t = lf + motif * rng.randint(0, 30) + rf or "A"
+        mode = rng.random()
+        if mode < 0.35:
+            i = rng.randrange(len(t))
+            p = t[:i] + rng.choice("ACGT") + t[i + 1:]
+        elif mode < 0.9:
+            i, d = rng.randrange(len(t) + 1), rng.randint(1, 6)
+            p = t[:i] + rand_seq(rng, d) + t[i:] if rng.random() < 0.5 else t[:i] + t[i + d:]
+        else:
+            p = mutate(rng, t, 0.02)
+        pt.append(len(seqs)); seqs.append(t.encode())
+        pp.append(len(seqs)); seqs.append((p or "C").encode())
+    c = tdb.Context()
+    cnt = _check_batch(c, seqs, np.array(pp, np.uint32), np.array(pt, np.uint32), clip, cigars=False)
+    c.set_count_work(False)
+    blob, off, ln = to_arrays(seqs)
+    c.align_batch(blob, off, ln, np.array(pp, np.uint32), np.array(pt, np.uint32))
+    assert c.counters().pairs_closed_form > 1000
+    c.close()
 
 
 def test_chunked_host_pipeline(tdb, monkeypatch):

@@ -36,7 +36,7 @@ class Context:
     """One tdb_ctx: bound to one GPU, single owner (like a thread-local WFAligner)."""
 
     def __init__(self, device_id=0, penalties=(8, 4, 2, 24, 1), heuristic=(1, 10, 50, 1), clip_len=50,
-                 scratch_bytes=0):
+                 scratch_bytes=0, count_work=False):
         L = B.lib()
         cfg = B.Config()
         L.tdb_default_config(C.byref(cfg))
@@ -50,6 +50,8 @@ class Context:
         if r != B.OK:
             raise B.TdbError(r, L.tdb_last_error(None).decode())
         self._h = h
+        if count_work:
+            L.tdb_set_count_work(h, 1)
         self.penalties = tuple(penalties)
         self.clip_len = clip_len
         self.device_id = device_id
@@ -71,6 +73,10 @@ class Context:
 
     def set_heuristic(self, heuristic):
         self._check(B.lib().tdb_set_heuristic(self._h, C.byref(B.Heuristic(*heuristic))))
+
+    def set_count_work(self, on):
+        """Exact algorithmic C/E/T counting (tdb_set_count_work): every content goes through the wavefronts."""
+        self._check(B.lib().tdb_set_count_work(self._h, int(bool(on))))
 
     def counters(self):
         c = B.Counters()

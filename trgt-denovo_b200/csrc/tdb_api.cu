@@ -44,7 +44,8 @@ struct Ctrl {
     unsigned gcount;   // pairs queued for the global-scratch tier (listB)
     unsigned ccount;   // pairs the first global tier could not finish (listC)
     unsigned wc_g[2];  // work counters of the two global tiers
-    unsigned pad0[3];
+    unsigned n_closed; // pairs resolved in closed form (k_pair_classify)
+    unsigned pad0[2];
     unsigned long long exec[4][4]; // executed cells, ext16, columns, pairs finished; per tier
     unsigned long long algo[4];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self
     // ---- per chunk (one block per pipeline slot, zeroed before every chunk) ----
@@ -79,12 +80,12 @@ struct tdb_ctx {
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0;
-    bool disable_quad = false, disable_dedup = false;
+    bool disable_quad = false, disable_dedup = false, disable_closed_form = false;
     size_t chunk_pairs = 2u << 20;
     size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
     void *h_packed = nullptr, *h_flag = nullptr; // pinned staging of the host packer
     size_t h_packed_cap = 0, h_flag_cap = 0;
-    bool count_work = true;
+    bool count_work = false;
     tdb_counters counters;
     // single-pair shim state
     std::vector<uint8_t> last_cigar;
@@ -359,6 +360,13 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     ENSURE(ctx->ctrl, sizeof(Ctrl));
     ENSURE(ctx->list_b, (size_t)n_pairs * 4);
     const bool want_work = ctx->count_work && !cigar_mode;
+    // closed form for single-substitution / single-short-gap pairs: production penalties, wf-adaptive unable to
+    // act before score 14 (or off), and no exact work counting requested
+    const tdb_heuristic &hh = ctx->cfg.heuristic;
+    ClosedFormCfg cf;
+    cf.enabled = default_pen && !ctx->count_work && !ctx->disable_closed_form &&
+                 (hh.kind == TDB_HEURISTIC_NONE || hh.min_wavefront_length >= 10);
+    cf.clip = ctx->cfg.clip_len;
     const int n_slot = K > 1 ? N_SLOT : 1;
     if (!cigar_mode) {
         ENSURE(ctx->rep, (size_t)n_pairs * 4);
@@ -518,10 +526,11 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         CK(cudaGetLastError());
         ClassifyOut co;
         co.rep = (uint32_t *)ctx->rep.p, co.key = (uint8_t *)sl.skey_in.p, co.val = (uint32_t *)sl.sval_in.p;
-        co.glist = (uint32_t *)ctx->list_b.p, co.gcount = &ctrl->gcount, co.hist = ck->hist;
+        co.glist = (uint32_t *)ctx->list_b.p, co.gcount = &ctrl->gcount, co.hist = ck->hist, co.n_closed = &ctrl->n_closed;
         co.out_score = b.score, co.out_status = b.status, co.out_penalty = b.penalty, co.work = p.work;
         k_pair_classify<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, b.seq_len,
-                                                 (const uint8_t *)ctx->seq_flag.p, tb, quad_ok ? 1 : 0, T0_MAXLEN, co);
+                                                 (const uint8_t *)ctx->seq_flag.p, b.seq_off, (const uint32_t *)ctx->packed.p,
+                                                 tb, quad_ok ? 1 : 0, T0_MAXLEN, cf, co);
         CK(cudaGetLastError());
         size_t tmp = sl.cub_tmp.cap;
         CK(cub::DeviceRadixSort::SortPairs(sl.cub_tmp.p, tmp, (const uint8_t *)sl.skey_in.p, (uint8_t *)sl.skey_out.p,
@@ -631,7 +640,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     } else {
         cn.cells = h.algo[0], cn.ext16 = h.algo[1], cn.columns = h.algo[2];
         cn.pairs_duplicate = n_pairs - h.algo[3];
-        cn.pairs_identical = h.algo[3] >= aligned ? h.algo[3] - aligned : 0;
+        cn.pairs_closed_form = h.n_closed;
+        cn.pairs_identical = h.algo[3] >= aligned + h.n_closed ? h.algo[3] - aligned - h.n_closed : 0;
     }
     cn.ms_total_device = elapsed(ctx->ev[0], ctx->ev[1]);
     cn.ms_host_call = ms_since(t_call);
@@ -812,6 +822,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->quad_ctas_per_sm = qocc;
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
+        c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
         if (const char *hp = getenv("TDB_HOSTPACK_MIN_BYTES")) {
             const long long v = atoll(hp); // < 0 disables the host packer
             c->hostpack_min_bytes = v < 0 ? (size_t)-1 : (size_t)v;

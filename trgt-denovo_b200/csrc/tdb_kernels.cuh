@@ -249,6 +249,72 @@ __global__ void __launch_bounds__(256) k_pair_insert(const uint32_t *__restrict_
     }
 }
 
+// Closed form for the two commonest non-identical contents (53 % of the aligned pairs of the 30x trio):
+// one substitution, or one gap of <= CF_MAXGAP bases, everything else matching.  With the production
+// penalties (8,4,2,24,1) such a pair has penalty 8 resp. 4+2L <= 14, which is optimal (any alignment of
+// lengths differing by L pays at least one gap of L), unique up to WFA's placement rule -- the gap /
+// substitution sits where diagonal 0 stops matching, because wavefront M[0] only keeps its furthest
+// point -- and beyond the reach of wf-adaptive: the cut-off needs a wavefront of >= 10 diagonals, and
+// M[s] spans at most s-3 diagonals for s <= 12, the last score whose cut-off could matter.  The clipped
+// score follows from the column positions (src/aligner.rs:320-357).  Checked against the CPU checker on
+// > 10^5 pairs (tests/test_gpu_parity.py, profiles/closed_form_check.py).  Not used when exact work
+// counting is on: C/E/T of a pair are only known by running the wavefronts.
+constexpr int CF_MAXGAP = 5;
+struct ClosedFormCfg {
+    int enabled, clip;
+};
+__device__ inline bool closed_form(const uint32_t *__restrict__ packed, uint64_t poff, int n, uint64_t toff, int m,
+                                   int clip, int &pen, int &clipped) {
+    const int L = abs(m - n);
+    if (L > CF_MAXGAP) return false;
+    const uint32_t *pw = packed + (poff >> 4), *tw = packed + (toff >> 4);
+    const int psh = (int)(poff & 15), tsh = (int)(toff & 15);
+    const int lim = min(n, m);
+    int p = 0;
+    while (p < lim) {
+        const uint32_t x = get16(pw, psh + p) ^ get16(tw, tsh + p);
+        if (x) {
+            p += (__ffs(x) - 1) >> 1;
+            break;
+        }
+        p += 16;
+    }
+    p = min(p, lim);
+    int v0, h0;
+    if (L == 0) {
+        if (p >= n) { // same bytes under two canonical ids (duplicate elimination off)
+            pen = 0, clipped = 0;
+            return true;
+        }
+        v0 = h0 = p + 1;
+    } else if (m > n) {
+        v0 = p, h0 = p + L;
+    } else {
+        v0 = p + L, h0 = p;
+    }
+    const int room = n - v0; // == m - h0
+    int q = 0;
+    while (q < room) {
+        const uint32_t x = get16(pw, psh + v0 + q) ^ get16(tw, tsh + h0 + q);
+        if (x) {
+            q += (__ffs(x) - 1) >> 1;
+            break;
+        }
+        q += 16;
+    }
+    if (q < room) return false;
+    const int cols = max(n, m), wb = clip, we = cols - clip;
+    if (L == 0) {
+        pen = 8;
+        clipped = (p >= wb && p < we) ? -8 : 0;
+    } else {
+        pen = 4 + 2 * L;
+        const int len = min(p + L, we) - max(p, wb);
+        clipped = len > 0 ? -min(4 + 2 * len, 24 + len) : 0;
+    }
+    return true;
+}
+
 struct ClassifyOut {
     uint32_t *rep;       // [n_pairs] representative pair of j (itself when unique / identical)
     uint8_t *key;        // [p1-p0] sort key
@@ -256,6 +322,7 @@ struct ClassifyOut {
     uint32_t *glist;     // pairs routed straight to the global-scratch tiers
     unsigned *gcount;
     unsigned *hist;      // [N_HIST]
+    unsigned *n_closed;  // pairs resolved by closed_form
     int32_t *out_score, *out_status, *out_penalty;
     uint32_t *work;      // [3 n_pairs] algorithmic cells, ext16, columns per pair (nullptr: not counted)
 };
@@ -264,10 +331,12 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
                                                        const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1,
                                                        uint32_t n_seqs, const uint32_t *__restrict__ canon,
                                                        const uint32_t *__restrict__ seq_len,
-                                                       const uint8_t *__restrict__ seq_flag, PairTable tb,
-                                                       int quad_ok, int max_len16, ClassifyOut o) {
-    __shared__ unsigned sh_hist[N_HIST];
-    if (threadIdx.x < N_HIST) sh_hist[threadIdx.x] = 0;
+                                                       const uint8_t *__restrict__ seq_flag,
+                                                       const uint64_t *__restrict__ seq_off,
+                                                       const uint32_t *__restrict__ packed, PairTable tb,
+                                                       int quad_ok, int max_len16, ClosedFormCfg cf, ClassifyOut o) {
+    __shared__ unsigned sh_hist[N_HIST + 1];
+    if (threadIdx.x <= N_HIST) sh_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t j = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j < p1) {
@@ -299,7 +368,14 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
                 rep = tb.vals[slot];
                 if (rep == j) {
                     const int L = abs(m - n);
-                    if ((seq_flag[ip] | seq_flag[jt]) || n > max_len16 || m > max_len16 || L >= WL_MAX) {
+                    int pen = 0, clipped = 0;
+                    if (cf.enabled && !(seq_flag[ip] | seq_flag[jt]) &&
+                        closed_form(packed, seq_off[ip], n, seq_off[jt], m, cf.clip, pen, clipped)) {
+                        o.out_score[j] = clipped;
+                        if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
+                        if (o.out_penalty) o.out_penalty[j] = pen;
+                        atomicAdd(sh_hist + N_HIST, 1u);
+                    } else if ((seq_flag[ip] | seq_flag[jt]) || n > max_len16 || m > max_len16 || L >= WL_MAX) {
                         const unsigned q = atomicAdd(o.gcount, 1u);
                         o.glist[q] = j;
                     } else if (!quad_ok || L >= QL_MAX) {
@@ -317,6 +393,7 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
     }
     __syncthreads();
     if (threadIdx.x < N_HIST && sh_hist[threadIdx.x]) atomicAdd(o.hist + threadIdx.x, sh_hist[threadIdx.x]);
+    if (threadIdx.x == N_HIST && sh_hist[N_HIST]) atomicAdd(o.n_closed, sh_hist[N_HIST]);
 }
 
 // Segment table of the sorted list: seg[0] = begin, seg[1] = count of the warp-tier segment;
