@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrgt_denovo_b200.so")
+# TDB_LIB: load another build of the same library (tuning sweeps); the default is the in-tree build
+LIB_PATH = os.environ.get("TDB_LIB") or os.path.join(_HERE, "libtrgt_denovo_b200.so")
 
 OK = 0
 E_INVALID, E_NO_DEVICE, E_CUDA, E_OOM, E_UNSUPPORTED = -1, -2, -3, -4, -5

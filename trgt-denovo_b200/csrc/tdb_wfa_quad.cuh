@@ -18,13 +18,29 @@
 
 namespace tdb {
 
-constexpr int QG = 8;        // lanes per pair
-constexpr int QW = 32;       // widest wavefront handled here
-constexpr int Q_MAR = 512;   // M arena entries
-constexpr int Q_SCAP = 96;   // scores 0..95
-constexpr int Q_PROV = 736;  // provenance bytes
+// capacities (overridable at build time for tuning sweeps, profiles/run_gpu_sweep.sh)
+#ifndef TDB_Q_MAR
+#define TDB_Q_MAR 512
+#endif
+#ifndef TDB_Q_SCAP
+#define TDB_Q_SCAP 96
+#endif
+#ifndef TDB_Q_PROV
+#define TDB_Q_PROV 736
+#endif
+#ifndef TDB_Q_WARPS
+#define TDB_Q_WARPS 2
+#endif
+#ifndef TDB_Q_MINB
+#define TDB_Q_MINB 1
+#endif
+constexpr int QG = 8;                // lanes per pair
+constexpr int QW = 32;               // widest wavefront handled here
+constexpr int Q_MAR = TDB_Q_MAR;     // M arena entries (power of two)
+constexpr int Q_SCAP = TDB_Q_SCAP;   // scores 0..Q_SCAP-1
+constexpr int Q_PROV = TDB_Q_PROV;   // provenance bytes
 constexpr int Q_MAXLEN = 8000;
-constexpr int Q_WARPS = 2;
+constexpr int Q_WARPS = TDB_Q_WARPS;
 constexpr int Q_NULL = -16384;
 
 struct __align__(16) QPair {
@@ -69,7 +85,7 @@ __device__ __forceinline__ int extend_group(const uint32_t *pw, const uint32_t *
 }
 
 template <int X, int O1, int E1, int O2, int E2>
-__global__ void __launch_bounds__(Q_WARPS * 32) k_align_quad(const AlignParams p) {
+__global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const AlignParams p) {
     static_assert(X < 32 && O1 + E1 < 32 && O2 + E2 < 32 && E1 < 4 && E2 < 2, "ring sizes");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
