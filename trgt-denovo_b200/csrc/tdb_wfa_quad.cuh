@@ -62,26 +62,35 @@ struct QIn { // one input wavefront, group-uniform
     unsigned span1;
 };
 
-__device__ __forceinline__ unsigned qballot(unsigned gmask, int gshift, bool pred) {
-    return (__ballot_sync(gmask, pred) >> gshift) & 0xffu;
+// All 32 lanes vote; a group reads its own byte.  Every collective in this kernel is full-warp: the four
+// groups run in LOCKSTEP -- one warp-uniform control flow (same score s, same loop trip counts, taken as
+// the maximum over the groups) with per-group predicates -- so that every issued instruction serves four
+// pairs.  (Group-masked collectives made the groups diverge for good and issue one after the other:
+// ncu r01c showed 8 active threads on every vote.)
+__device__ __forceinline__ unsigned qballot(int gshift, bool pred) {
+    return (__ballot_sync(TDB_FULL, pred) >> gshift) & 0xffu;
 }
 
-// Eight lanes extend one diagonal: lane l compares bases [16l, 16l+16) per round.
-__device__ __forceinline__ int extend_group(const uint32_t *pw, const uint32_t *tw, int psh, int tsh, int n, int m,
-                                            int v, int h, int gl, unsigned gmask, int gshift, int lane) {
-    const int room = min(n - v, m - h);
-    for (int base = 0; base < room; base += 16 * QG) {
+// Eight lanes extend one diagonal per group: lane l compares bases [16l, 16l+16) per round.  `on` is
+// group-uniform; groups that are off (or done) idle through the remaining rounds.
+__device__ __forceinline__ int extend_groups(const uint32_t *pw, const uint32_t *tw, int psh, int tsh, int n, int m,
+                                             int v, int h, bool on, int gl, int gshift, int lane) {
+    const int room = on ? min(n - v, m - h) : 0;
+    int res = room;
+    bool busy = on && room > 0;
+    for (int base = 0; __any_sync(TDB_FULL, busy); base += 16 * QG) {
         const int off = base + gl * 16;
-        uint32_t x = 1u;
-        if (off < room) x = get16(pw, psh + v + off) ^ get16(tw, tsh + h + off);
-        const unsigned bal = qballot(gmask, gshift, x != 0);
-        if (bal) {
-            const int l = __ffs(bal) - 1;
-            const uint32_t xl = __shfl_sync(gmask, x, (lane & ~(QG - 1)) + l);
-            return min(base + l * 16 + ((__ffs(xl) - 1) >> 1), room);
+        uint32_t x = 1u; // lanes past the end report a mismatch at their first base: caps the run at `room`
+        if (busy && off < room) x = get16(pw, psh + v + off) ^ get16(tw, tsh + h + off);
+        const unsigned bal = qballot(gshift, x != 0);
+        const int l = bal ? __ffs(bal) - 1 : 0;
+        const uint32_t xl = __shfl_sync(TDB_FULL, x, (lane & ~(QG - 1)) + l);
+        if (busy && bal) {
+            res = min(base + l * 16 + ((__ffs(xl) - 1) >> 1), room);
+            busy = false;
         }
     }
-    return room;
+    return res;
 }
 
 template <int X, int O1, int E1, int O2, int E2>
@@ -90,7 +99,6 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gl = lane & (QG - 1), gid = lane / QG, gshift = gid * QG;
-    const unsigned gmask = 0xffu << gshift;
     QPair &sm = reinterpret_cast<QPair *>(smem_raw)[wid * (32 / QG) + gid];
     const Penalties pn = {X, O1, E1, O2, E2};
     const ItemSrc src = item_src(p);
@@ -104,325 +112,354 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
         fb = __shfl_sync(TDB_FULL, fb, 0);
         if (fb >= n_items) break;
         for (unsigned bb = fb; bb < fb + PER_FETCH && bb < n_items; bb += 32 / QG) {
+            // ====================== one pair per group, four groups in lockstep ======================
             const unsigned it = bb + gid;
-            // ====================== one pair per group ======================
-            if (it < n_items) {
-                const uint32_t idx = item_at(p, src, it);
+            const bool have = it < n_items;
+            uint32_t idx = 0;
+            int n = 0, m = 0, psh = 0, tsh = 0;
+            const uint32_t *pw = p.packed, *tw = p.packed;
+            bool overflow = false;
+            if (have) {
+                idx = item_at(p, src, it);
                 const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
-                const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
-                const int k_end = m - n;
-                bool overflow = (p.seq_flag[ip] | p.seq_flag[jt]) || n > Q_MAXLEN || m > Q_MAXLEN;
-                int penalty = 0, clipped = 0;
-                unsigned long long cells = 0, cols = 0, ext = 0;
-                if (!overflow) {
-                    const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
-                    const uint32_t *pw = p.packed + (poff >> 4), *tw = p.packed + (toff >> 4);
-                    const int psh = (int)(poff & 15), tsh = (int)(toff & 15);
-                    const int m0 = extend_group(pw, tw, psh, tsh, n, m, 0, 0, gl, gmask, gshift, lane);
-                    if (gl == 0) ext += (unsigned)(m0 >> 4) + 1;
-                    if (k_end == 0 && m0 >= m) {
-                        cols = (unsigned)m; // identical: penalty 0, clipped score 0
-                    } else {
-                        // ---------------- wavefront loop ----------------
-                        if (gl == 0) {
-                            sm.m_off[0] = 0, sm.m_lo[0] = 0, sm.m_hi[0] = 0;
-                            sm.marena[0] = (int16_t)m0;
-                            sm.step_lo[0] = 0, sm.step_base[0] = 0;
-                            sm.prov[0] = 0;
-                        }
-                        unsigned Mm = 1u, I1m = 0, I2m = 0, D1m = 0, D2m = 0; // bit j <-> score s-j exists
-                        unsigned mhead = 1, prov_used = 1;
-                        int steps_wait = p.heur.steps - (p.heur.kind == 1 ? 1 : 0);
-                        int s = 0;
-                        __syncwarp(gmask);
-                        for (;;) {
-                            // advance to the next score with a non-null input (register-only null steps)
-                            bool live;
-                            do {
-                                ++s;
-                                Mm <<= 1, I1m <<= 1, I2m <<= 1, D1m <<= 1, D2m <<= 1;
-                                live = (Mm & ((1u << X) | (1u << (O1 + E1)) | (1u << (O2 + E2)))) |
-                                       ((I1m | D1m) & (1u << E1)) | ((I2m | D2m) & (1u << E2));
-                            } while (!live && s < Q_SCAP);
-                            if (s >= Q_SCAP) {
-                                overflow = true;
-                                break;
-                            }
-                            // ---- inputs ----
-                            QIn mx, mo1, mo2, i1e, i2e, d1e, d2e;
+                n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
+                overflow = (p.seq_flag[ip] | p.seq_flag[jt]) || n > Q_MAXLEN || m > Q_MAXLEN;
+                const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
+                pw = p.packed + (poff >> 4), tw = p.packed + (toff >> 4);
+                psh = (int)(poff & 15), tsh = (int)(toff & 15);
+            }
+            const int k_end = m - n;
+            const bool usable = have && !overflow;
+            int penalty = 0, clipped = 0;
+            unsigned long long cells = 0, cols = 0, ext = 0;
+            const int m0 = extend_groups(pw, tw, psh, tsh, n, m, 0, 0, usable, gl, gshift, lane);
+            if (usable && gl == 0) ext += (unsigned)(m0 >> 4) + 1;
+            const bool identical = usable && k_end == 0 && m0 >= m;
+            if (identical) cols = (unsigned)m; // penalty 0, clipped score 0
+            bool running = usable && !identical;
+            // ---------------- wavefront loop (score s is warp-uniform) ----------------
+            if (running && gl == 0) {
+                sm.m_off[0] = 0, sm.m_lo[0] = 0, sm.m_hi[0] = 0;
+                sm.marena[0] = (int16_t)m0;
+                sm.step_lo[0] = 0, sm.step_base[0] = 0;
+                sm.prov[0] = 0;
+            }
+            unsigned Mm = 1u, I1m = 0, I2m = 0, D1m = 0, D2m = 0; // bit j <-> score s-j exists
+            unsigned mhead = 1, prov_used = 1;
+            int steps_wait = p.heur.steps - (p.heur.kind == 1 ? 1 : 0);
+            int s = 0;
+            __syncwarp();
+            while (__any_sync(TDB_FULL, running)) {
+                ++s;
+                if (s >= Q_SCAP) { // warp-uniform
+                    if (running) overflow = true, running = false;
+                    break;
+                }
+                Mm <<= 1, I1m <<= 1, I2m <<= 1, D1m <<= 1, D2m <<= 1;
+                bool live = running && ((Mm & ((1u << X) | (1u << (O1 + E1)) | (1u << (O2 + E2)))) |
+                                        ((I1m | D1m) & (1u << E1)) | ((I2m | D2m) & (1u << E2))) != 0;
+                if (!__any_sync(TDB_FULL, live)) continue; // null step for every group: registers only
+                // ---- inputs ----
+                QIn mx, mo1, mo2, i1e, i2e, d1e, d2e;
 #define TDB_QM(w, lag)                                                              \
     w.p = sm.marena, w.base = 0, w.lo = 1, w.span1 = 0;                             \
-    if (Mm & (1u << (lag))) {                                                       \
+    if (live && (Mm & (1u << (lag)))) {                                             \
         const int sl = (s - (lag)) & 31;                                            \
         const int l_ = sm.m_lo[sl];                                                 \
         w.lo = l_, w.span1 = (unsigned)(sm.m_hi[sl] - l_ + 1), w.base = (int)sm.m_off[sl] - l_; \
     }
-                            TDB_QM(mx, X)
-                            TDB_QM(mo1, O1 + E1)
-                            TDB_QM(mo2, O2 + E2)
+                TDB_QM(mx, X)
+                TDB_QM(mo1, O1 + E1)
+                TDB_QM(mo2, O2 + E2)
 #undef TDB_QM
 #define TDB_QG(w, msk, lag, row0, rmask)                                            \
     w.p = sm.gap[0], w.base = 0, w.lo = 1, w.span1 = 0;                             \
-    if (msk & (1u << (lag))) {                                                      \
+    if (live && (msk & (1u << (lag)))) {                                            \
         const int r_ = (row0) + ((s - (lag)) & (rmask));                            \
         const int l_ = sm.g_lo[r_];                                                 \
         w.p = sm.gap[r_], w.lo = l_, w.span1 = (unsigned)(sm.g_hi[r_] - l_ + 1);    \
     }
-                            TDB_QG(i1e, I1m, E1, 0, 3)
-                            TDB_QG(d1e, D1m, E1, 4, 3)
-                            TDB_QG(i2e, I2m, E2, 8, 1)
-                            TDB_QG(d2e, D2m, E2, 10, 1)
+                TDB_QG(i1e, I1m, E1, 0, 3)
+                TDB_QG(d1e, D1m, E1, 4, 3)
+                TDB_QG(i2e, I2m, E2, 8, 1)
+                TDB_QG(d2e, D2m, E2, 10, 1)
 #undef TDB_QG
-                            int lo = INT32_MAX, hi = INT32_MIN;
+                int lo = INT32_MAX, hi = INT32_MIN;
 #define TDB_LIM(w, dl, dh)                                              \
     if ((w).span1) {                                                    \
         lo = min(lo, (w).lo + (dl));                                    \
         hi = max(hi, (w).lo + (int)(w).span1 - 1 + (dh));               \
     }
-                            TDB_LIM(mx, 0, 0)
-                            TDB_LIM(mo1, -1, 1)
-                            TDB_LIM(mo2, -1, 1)
-                            TDB_LIM(i1e, 1, 1)
-                            TDB_LIM(i2e, 1, 1)
-                            TDB_LIM(d1e, -1, -1)
-                            TDB_LIM(d2e, -1, -1)
+                TDB_LIM(mx, 0, 0)
+                TDB_LIM(mo1, -1, 1)
+                TDB_LIM(mo2, -1, 1)
+                TDB_LIM(i1e, 1, 1)
+                TDB_LIM(i2e, 1, 1)
+                TDB_LIM(d1e, -1, -1)
+                TDB_LIM(d2e, -1, -1)
 #undef TDB_LIM
-                            lo = max(lo, -n - 1), hi = min(hi, m + 1);
-                            const int width = hi - lo + 1;
-                            // arena room: everything from the oldest live M wavefront up to the new one
-                            const unsigned livem = Mm & 0x03fffffeu; // lags 1..25
-                            unsigned tail = mhead;
-                            if (livem) tail = sm.m_off[(s - (31 - __clz(livem))) & 31];
-                            if (width > QW || prov_used + (unsigned)width > Q_PROV ||
-                                ((mhead - tail) & 0xffffu) + (unsigned)width > Q_MAR) {
-                                overflow = true;
-                                break;
-                            }
-                            const bool has_i1 = mo1.span1 || i1e.span1, has_d1 = mo1.span1 || d1e.span1;
-                            const bool has_i2 = mo2.span1 || i2e.span1, has_d2 = mo2.span1 || d2e.span1;
-                            int16_t *I1o = sm.gap[0 + (s & 3)], *D1o = sm.gap[4 + (s & 3)];
-                            int16_t *I2o = sm.gap[8 + (s & 1)], *D2o = sm.gap[10 + (s & 1)];
-                            uint8_t *pv = sm.prov + prov_used;
-                            cells += (unsigned)width;
-                            int tl_m = INT32_MAX, th_m = INT32_MIN, tl_i1 = INT32_MAX, th_i1 = INT32_MIN,
-                                tl_i2 = INT32_MAX, th_i2 = INT32_MIN, tl_d1 = INT32_MAX, th_d1 = INT32_MIN,
-                                tl_d2 = INT32_MAX, th_d2 = INT32_MIN;
-                            int lane_min_d = 1 << 30;
-                            bool fin = false;
-                            for (int kb = lo; kb <= hi; kb += QG) {
-                                const int k = kb + gl;
-                                const bool act = k <= hi;
-                                int ins1 = Q_NULL, ins2 = Q_NULL, del1 = Q_NULL, del2 = Q_NULL, mv = Q_NULL;
-                                bool vm = false;
-                                if (act) {
+                int width = 0;
+                if (live) {
+                    lo = max(lo, -n - 1), hi = min(hi, m + 1);
+                    width = hi - lo + 1;
+                    // arena room: everything from the oldest live M wavefront up to the new one
+                    const unsigned livem = Mm & 0x03fffffeu; // lags 1..25
+                    unsigned tail = mhead;
+                    if (livem) tail = sm.m_off[(s - (31 - __clz(livem))) & 31];
+                    if (width > QW || prov_used + (unsigned)width > Q_PROV ||
+                        ((mhead - tail) & 0xffffu) + (unsigned)width > Q_MAR) {
+                        overflow = true, running = false, live = false, width = 0; // this group drops out
+                    }
+                }
+                if (!live) lo = 0, hi = -1;
+                const bool has_i1 = mo1.span1 || i1e.span1, has_d1 = mo1.span1 || d1e.span1;
+                const bool has_i2 = mo2.span1 || i2e.span1, has_d2 = mo2.span1 || d2e.span1;
+                int16_t *I1o = sm.gap[0 + (s & 3)], *D1o = sm.gap[4 + (s & 3)];
+                int16_t *I2o = sm.gap[8 + (s & 1)], *D2o = sm.gap[10 + (s & 1)];
+                uint8_t *pv = sm.prov + prov_used;
+                cells += (unsigned)width;
+                int tl_m = INT32_MAX, th_m = INT32_MIN, tl_i1 = INT32_MAX, th_i1 = INT32_MIN,
+                    tl_i2 = INT32_MAX, th_i2 = INT32_MIN, tl_d1 = INT32_MAX, th_d1 = INT32_MIN,
+                    tl_d2 = INT32_MAX, th_d2 = INT32_MIN;
+                int lane_min_d = 1 << 30;
+                bool fin = false;
+                const int n_iter = __reduce_max_sync(TDB_FULL, (width + QG - 1) / QG);
+                for (int itk = 0; itk < n_iter; ++itk) {
+                    const int kb = lo + itk * QG;
+                    const int k = kb + gl;
+                    const bool act = k <= hi; // false everywhere in groups that are not live (hi = -1 < lo = 0)
+                    int ins1 = Q_NULL, ins2 = Q_NULL, del1 = Q_NULL, del2 = Q_NULL, mv = Q_NULL;
+                    bool vm = false;
+                    int ev = 0, eroom = 0; // extension state of this lane's diagonal
+                    if (act) {
 #define TDB_RDM(w, kk) (((unsigned)((kk) - (w).lo) < (w).span1) ? (int)sm.marena[((w).base + (kk)) & (Q_MAR - 1)] : Q_NULL)
 #define TDB_RDG(w, kk) (((unsigned)((kk) - (w).lo) < (w).span1) ? (int)(w).p[(kk) & (QW - 1)] : Q_NULL)
-                                    int b = 0, o, e;
-                                    o = TDB_RDM(mo1, k - 1), e = TDB_RDG(i1e, k - 1);
-                                    if (e >= o) ins1 = e, b |= PB_I1E; else ins1 = o;
-                                    ins1 += 1;
-                                    o = TDB_RDM(mo2, k - 1), e = TDB_RDG(i2e, k - 1);
-                                    if (e >= o) ins2 = e, b |= PB_I2E; else ins2 = o;
-                                    ins2 += 1;
-                                    o = TDB_RDM(mo1, k + 1), e = TDB_RDG(d1e, k + 1);
-                                    if (e >= o) del1 = e, b |= PB_D1E; else del1 = o;
-                                    o = TDB_RDM(mo2, k + 1), e = TDB_RDG(d2e, k + 1);
-                                    if (e >= o) del2 = e, b |= PB_D2E; else del2 = o;
-                                    const int mis = TDB_RDM(mx, k) + 1;
+                        int b = 0, o, e;
+                        o = TDB_RDM(mo1, k - 1), e = TDB_RDG(i1e, k - 1);
+                        if (e >= o) ins1 = e, b |= PB_I1E; else ins1 = o;
+                        ins1 += 1;
+                        o = TDB_RDM(mo2, k - 1), e = TDB_RDG(i2e, k - 1);
+                        if (e >= o) ins2 = e, b |= PB_I2E; else ins2 = o;
+                        ins2 += 1;
+                        o = TDB_RDM(mo1, k + 1), e = TDB_RDG(d1e, k + 1);
+                        if (e >= o) del1 = e, b |= PB_D1E; else del1 = o;
+                        o = TDB_RDM(mo2, k + 1), e = TDB_RDG(d2e, k + 1);
+                        if (e >= o) del2 = e, b |= PB_D2E; else del2 = o;
+                        const int mis = TDB_RDM(mx, k) + 1;
 #undef TDB_RDM
 #undef TDB_RDG
-                                    mv = max(max(max(ins1, ins2), max(del1, del2)), mis);
-                                    int src = PM_NONE; // later tests override: priority X > D2 > D1 > I2 > I1
-                                    if (mv == ins1) src = PM_I1;
-                                    if (mv == ins2) src = PM_I2;
-                                    if (mv == del1) src = PM_D1;
-                                    if (mv == del2) src = PM_D2;
-                                    if (mv == mis) src = PM_X;
-                                    pv[k - lo] = (uint8_t)(b | src);
-                                    if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = Q_NULL;
-                                    vm = mv >= 0;
-                                    if (vm) { // extend at once (trimming never changes offsets)
-                                        const int v = mv - k, room = min(n - v, m - mv);
-                                        int eq = 0;
-                                        while (eq < room) {
-                                            const uint32_t x = get16(pw, psh + v + eq) ^ get16(tw, tsh + mv + eq);
-                                            if (x) {
-                                                eq += (__ffs(x) - 1) >> 1;
-                                                break;
-                                            }
-                                            eq += 16;
-                                        }
-                                        eq = min(eq, room);
-                                        ext += (unsigned)(eq >> 4) + 1;
-                                        mv += eq;
-                                        lane_min_d = min(lane_min_d, max(n - (mv - k), m - mv));
-                                        fin |= (k == k_end) && (mv >= m);
-                                    }
-                                    sm.marena[(mhead + (unsigned)(k - lo)) & (Q_MAR - 1)] = (int16_t)mv;
-                                    if (has_i1) I1o[k & (QW - 1)] = (int16_t)ins1;
-                                    if (has_i2) I2o[k & (QW - 1)] = (int16_t)ins2;
-                                    if (has_d1) D1o[k & (QW - 1)] = (int16_t)del1;
-                                    if (has_d2) D2o[k & (QW - 1)] = (int16_t)del2;
-                                }
-                                unsigned bal = qballot(gmask, gshift, vm);
-                                if (bal) tl_m = min(tl_m, kb + __ffs(bal) - 1), th_m = kb + 31 - __clz(bal);
+                        mv = max(max(max(ins1, ins2), max(del1, del2)), mis);
+                        int srcm = PM_NONE; // later tests override: priority X > D2 > D1 > I2 > I1
+                        if (mv == ins1) srcm = PM_I1;
+                        if (mv == ins2) srcm = PM_I2;
+                        if (mv == del1) srcm = PM_D1;
+                        if (mv == del2) srcm = PM_D2;
+                        if (mv == mis) srcm = PM_X;
+                        pv[k - lo] = (uint8_t)(b | srcm);
+                        if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = Q_NULL;
+                        vm = mv >= 0;
+                        if (vm) ev = mv - k, eroom = min(n - ev, m - mv);
+                    }
+                    // extend at once (trimming never changes offsets); one warp-uniform loop for all lanes
+                    int eq = 0;
+                    bool ebusy = vm && eroom > 0;
+                    while (__any_sync(TDB_FULL, ebusy)) {
+                        if (ebusy) {
+                            const uint32_t x = get16(pw, psh + ev + eq) ^ get16(tw, tsh + mv + eq);
+                            if (x) eq += (__ffs(x) - 1) >> 1, ebusy = false;
+                            else eq += 16, ebusy = eq < eroom;
+                        }
+                    }
+                    if (act) {
+                        if (vm) {
+                            eq = min(eq, eroom);
+                            ext += (unsigned)(eq >> 4) + 1;
+                            mv += eq;
+                            lane_min_d = min(lane_min_d, max(n - (mv - k), m - mv));
+                            fin |= (k == k_end) && (mv >= m);
+                        }
+                        sm.marena[(mhead + (unsigned)(k - lo)) & (Q_MAR - 1)] = (int16_t)mv;
+                        if (has_i1) I1o[k & (QW - 1)] = (int16_t)ins1;
+                        if (has_i2) I2o[k & (QW - 1)] = (int16_t)ins2;
+                        if (has_d1) D1o[k & (QW - 1)] = (int16_t)del1;
+                        if (has_d2) D2o[k & (QW - 1)] = (int16_t)del2;
+                    }
+                    // trim_ends (A.2): first / last diagonal whose offset lies inside the DP matrix
+                    unsigned bal = qballot(gshift, vm);
+                    if (bal) tl_m = min(tl_m, kb + __ffs(bal) - 1), th_m = kb + 31 - __clz(bal);
 #define TDB_TRIM(has, val, tl, th)                                                                                     \
-    if (has) {                                                                                                         \
-        bal = qballot(gmask, gshift, act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n);     \
+    {                                                                                                                  \
+        bal = qballot(gshift, (has) && act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n);   \
         if (bal) tl = min(tl, kb + __ffs(bal) - 1), th = kb + 31 - __clz(bal);                                         \
     }
-                                TDB_TRIM(has_i1, ins1, tl_i1, th_i1)
-                                TDB_TRIM(has_i2, ins2, tl_i2, th_i2)
-                                TDB_TRIM(has_d1, del1, tl_d1, th_d1)
-                                TDB_TRIM(has_d2, del2, tl_d2, th_d2)
+                    TDB_TRIM(has_i1, ins1, tl_i1, th_i1)
+                    TDB_TRIM(has_i2, ins2, tl_i2, th_i2)
+                    TDB_TRIM(has_d1, del1, tl_d1, th_d1)
+                    TDB_TRIM(has_d2, del2, tl_d2, th_d2)
 #undef TDB_TRIM
-                            }
-                            if (gl == 0) sm.step_lo[s] = (int16_t)lo, sm.step_base[s] = (uint16_t)prov_used;
-                            prov_used += (unsigned)width;
-                            __syncwarp(gmask);
-                            if (qballot(gmask, gshift, fin)) {
-                                penalty = s;
-                                break;
-                            }
-                            // ---- wf-adaptive cut-off + equate (A.3) ----
-                            int mlo = tl_m, mhi = th_m; // empty when mlo > mhi
-                            if (p.heur.kind == 1 && mlo <= mhi) {
-                                --steps_wait;
-                                if (steps_wait <= 0 && (mhi - mlo + 1) >= p.heur.min_len) {
-                                    int md = lane_min_d;
-                                    md = min(md, __shfl_xor_sync(gmask, md, 1));
-                                    md = min(md, __shfl_xor_sync(gmask, md, 2));
-                                    md = min(md, __shfl_xor_sync(gmask, md, 4));
-                                    const int min_d = min(max(n, m), md), thr = p.heur.max_dist;
-                                    const int abase = (int)mhead - lo;
+                }
+                if (live && gl == 0) sm.step_lo[s] = (int16_t)lo, sm.step_base[s] = (uint16_t)prov_used;
+                prov_used += (unsigned)width;
+                __syncwarp();
+                const bool done_now = qballot(gshift, fin) != 0; // group-uniform
+                if (live && done_now) penalty = s, running = false;
+                const bool cont = live && !done_now;
+                // ---- wf-adaptive cut-off + equate (A.3) ----
+                int mlo = tl_m, mhi = th_m; // empty when mlo > mhi
+                const bool heur_on = cont && p.heur.kind == 1 && mlo <= mhi;
+                if (heur_on) --steps_wait;
+                const bool cut = heur_on && steps_wait <= 0 && (mhi - mlo + 1) >= p.heur.min_len;
+                if (__any_sync(TDB_FULL, cut)) {
+                    int md = lane_min_d;
+                    md = min(md, __shfl_xor_sync(TDB_FULL, md, 1));
+                    md = min(md, __shfl_xor_sync(TDB_FULL, md, 2));
+                    md = min(md, __shfl_xor_sync(TDB_FULL, md, 4));
+                    const int min_d = min(max(n, m), md), thr = p.heur.max_dist;
+                    const int abase = (int)mhead - lo;
 #define TDB_DIST_OK(kk, okv)                                                                  \
     {                                                                                         \
         const int off_ = (int)sm.marena[(abase + (kk)) & (Q_MAR - 1)];                        \
         const int d_ = off_ >= 0 ? max(n - (off_ - (kk)), m - off_) : (1 << 30);              \
         okv = d_ - min_d <= thr;                                                              \
     }
-                                    const int top_limit = min(k_end, mhi);
-                                    int new_lo = mlo;
-                                    if (top_limit > mlo) {
-                                        int first_ok = INT32_MAX;
-                                        for (int kb = mlo; kb < top_limit && first_ok == INT32_MAX; kb += QG) {
-                                            const int k = kb + gl;
-                                            bool ok = false;
-                                            if (k < top_limit) TDB_DIST_OK(k, ok)
-                                            const unsigned bal = qballot(gmask, gshift, ok);
-                                            if (bal) first_ok = kb + __ffs(bal) - 1;
-                                        }
-                                        new_lo = min(first_ok, top_limit);
-                                    }
-                                    const int bot_limit = max(k_end, new_lo);
-                                    int new_hi = mhi;
-                                    if (bot_limit < mhi) {
-                                        int last_ok = INT32_MIN;
-                                        for (int kt = mhi; kt > bot_limit && last_ok == INT32_MIN; kt -= QG) {
-                                            const int k = kt - gl;
-                                            bool ok = false;
-                                            if (k > bot_limit) TDB_DIST_OK(k, ok)
-                                            const unsigned bal = qballot(gmask, gshift, ok);
-                                            if (bal) last_ok = kt - (__ffs(bal) - 1);
-                                        }
-                                        new_hi = max(last_ok, bot_limit);
-                                    }
-#undef TDB_DIST_OK
-                                    mlo = new_lo, mhi = new_hi;
-                                    steps_wait = p.heur.steps;
-                                }
-                                if (mlo <= mhi) { // equate
-                                    tl_i1 = max(tl_i1, mlo), th_i1 = min(th_i1, mhi);
-                                    tl_i2 = max(tl_i2, mlo), th_i2 = min(th_i2, mhi);
-                                    tl_d1 = max(tl_d1, mlo), th_d1 = min(th_d1, mhi);
-                                    tl_d2 = max(tl_d2, mlo), th_d2 = min(th_d2, mhi);
-                                }
-                            }
-                            // ---- publish metadata of score s ----
-                            if (mlo <= mhi) Mm |= 1u;
-                            if (tl_i1 <= th_i1) I1m |= 1u;
-                            if (tl_i2 <= th_i2) I2m |= 1u;
-                            if (tl_d1 <= th_d1) D1m |= 1u;
-                            if (tl_d2 <= th_d2) D2m |= 1u;
-                            if (gl == 0) {
-                                const int sl = s & 31;
-                                sm.m_lo[sl] = (int16_t)mlo, sm.m_hi[sl] = (int16_t)mhi;
-                                sm.m_off[sl] = (uint16_t)(mhead + (unsigned)(mlo - lo));
-                                sm.g_lo[0 + (s & 3)] = (int16_t)tl_i1, sm.g_hi[0 + (s & 3)] = (int16_t)th_i1;
-                                sm.g_lo[4 + (s & 3)] = (int16_t)tl_d1, sm.g_hi[4 + (s & 3)] = (int16_t)th_d1;
-                                sm.g_lo[8 + (s & 1)] = (int16_t)tl_i2, sm.g_hi[8 + (s & 1)] = (int16_t)th_i2;
-                                sm.g_lo[10 + (s & 1)] = (int16_t)tl_d2, sm.g_hi[10 + (s & 1)] = (int16_t)th_d2;
-                            }
-                            if (mlo <= mhi) mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
-                            __syncwarp(gmask);
+                    const int top_limit = min(k_end, mhi);
+                    int new_lo = mlo;
+                    {
+                        int first_ok = INT32_MAX;
+                        bool scan = cut && top_limit > mlo;
+                        for (int kb = mlo; __any_sync(TDB_FULL, scan); kb += QG) {
+                            const int k = kb + gl;
+                            bool ok = false;
+                            if (scan && k < top_limit) TDB_DIST_OK(k, ok)
+                            const unsigned bal = qballot(gshift, ok);
+                            if (scan && bal) first_ok = kb + __ffs(bal) - 1;
+                            scan = scan && first_ok == INT32_MAX && kb + QG < top_limit;
                         }
-                        // ---------------- backtrace + forward replay ----------------
-                        if (!overflow) {
-                            uint8_t *ops = reinterpret_cast<uint8_t *>(sm.marena); // arena is dead now
-                            int nops = 0, n_del = 0;
-                            {
-                                int comp = -1, cs = penalty, k = k_end;
-                                while (!(comp < 0 && cs == 0)) {
-                                    const int b = sm.prov[(unsigned)sm.step_base[cs] + (unsigned)(k - (int)sm.step_lo[cs])];
-                                    int op;
-                                    if (comp < 0) {
-                                        const int src = b & 7;
-                                        if (src == PM_X) op = OP_X, cs -= X;
-                                        else op = OP_CLOSE, comp = src - 1;
-                                    } else if (comp == CI1 || comp == CI2) {
-                                        op = OP_I;
-                                        const bool ex = b & (comp == CI1 ? PB_I1E : PB_I2E);
-                                        const int e = comp == CI1 ? E1 : E2, o = comp == CI1 ? O1 : O2;
-                                        if (ex) cs -= e; else cs -= o + e, comp = -1;
-                                        k -= 1;
-                                    } else {
-                                        op = OP_D;
-                                        ++n_del;
-                                        const bool ex = b & (comp == CD1 ? PB_D1E : PB_D2E);
-                                        const int e = comp == CD1 ? E1 : E2, o = comp == CD1 ? O1 : O2;
-                                        if (ex) cs -= e; else cs -= o + e, comp = -1;
-                                        k += 1;
-                                    }
-                                    if (gl == 0) ops[nops] = (uint8_t)op;
-                                    ++nops;
-                                }
-                            }
-                            __syncwarp(gmask);
-                            ClipAcc acc;
-                            acc.init(m + n_del, p.clip);
-                            int v = 0, h = 0;
-                            bool in_m = true;
-                            for (int i = nops - 1; i >= -1; --i) {
-                                if (in_m) {
-                                    const int eq = extend_group(pw, tw, psh, tsh, n, m, v, h, gl, gmask, gshift, lane);
-                                    acc.emit('M', eq, pn);
-                                    v += eq, h += eq;
-                                }
-                                if (i < 0) break;
-                                const int op = ops[i];
-                                if (op == OP_CLOSE) {
-                                    in_m = true;
-                                    continue;
-                                }
+                        if (cut && top_limit > mlo) new_lo = min(first_ok, top_limit);
+                    }
+                    const int bot_limit = max(k_end, new_lo);
+                    int new_hi = mhi;
+                    {
+                        int last_ok = INT32_MIN;
+                        bool scan = cut && bot_limit < mhi;
+                        for (int kt = mhi; __any_sync(TDB_FULL, scan); kt -= QG) {
+                            const int k = kt - gl;
+                            bool ok = false;
+                            if (scan && k > bot_limit) TDB_DIST_OK(k, ok)
+                            const unsigned bal = qballot(gshift, ok);
+                            if (scan && bal) last_ok = kt - (__ffs(bal) - 1);
+                            scan = scan && last_ok == INT32_MIN && kt - QG > bot_limit;
+                        }
+                        if (cut && bot_limit < mhi) new_hi = max(last_ok, bot_limit);
+                    }
+#undef TDB_DIST_OK
+                    if (cut) mlo = new_lo, mhi = new_hi, steps_wait = p.heur.steps;
+                }
+                if (heur_on && mlo <= mhi) { // equate
+                    tl_i1 = max(tl_i1, mlo), th_i1 = min(th_i1, mhi);
+                    tl_i2 = max(tl_i2, mlo), th_i2 = min(th_i2, mhi);
+                    tl_d1 = max(tl_d1, mlo), th_d1 = min(th_d1, mhi);
+                    tl_d2 = max(tl_d2, mlo), th_d2 = min(th_d2, mhi);
+                }
+                // ---- publish metadata of score s ----
+                if (cont) {
+                    if (mlo <= mhi) Mm |= 1u;
+                    if (tl_i1 <= th_i1) I1m |= 1u;
+                    if (tl_i2 <= th_i2) I2m |= 1u;
+                    if (tl_d1 <= th_d1) D1m |= 1u;
+                    if (tl_d2 <= th_d2) D2m |= 1u;
+                    if (gl == 0) {
+                        const int sl = s & 31;
+                        sm.m_lo[sl] = (int16_t)mlo, sm.m_hi[sl] = (int16_t)mhi;
+                        sm.m_off[sl] = (uint16_t)(mhead + (unsigned)(mlo - lo));
+                        sm.g_lo[0 + (s & 3)] = (int16_t)tl_i1, sm.g_hi[0 + (s & 3)] = (int16_t)th_i1;
+                        sm.g_lo[4 + (s & 3)] = (int16_t)tl_d1, sm.g_hi[4 + (s & 3)] = (int16_t)th_d1;
+                        sm.g_lo[8 + (s & 1)] = (int16_t)tl_i2, sm.g_hi[8 + (s & 1)] = (int16_t)th_i2;
+                        sm.g_lo[10 + (s & 1)] = (int16_t)tl_d2, sm.g_hi[10 + (s & 1)] = (int16_t)th_d2;
+                    }
+                    if (mlo <= mhi) mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
+                }
+                __syncwarp();
+            }
+            // ---------------- backtrace + forward replay (groups that found an alignment) ----------------
+            const bool aligned = usable && !identical && !overflow;
+            uint8_t *ops = reinterpret_cast<uint8_t *>(sm.marena); // arena is dead now
+            int nops = 0, n_del = 0;
+            {
+                int comp = -1, cs = penalty, k = k_end;
+                bool walking = aligned && !(comp < 0 && cs == 0);
+                while (__any_sync(TDB_FULL, walking)) {
+                    if (walking) {
+                        const int b = sm.prov[(unsigned)sm.step_base[cs] + (unsigned)(k - (int)sm.step_lo[cs])];
+                        int op;
+                        if (comp < 0) {
+                            const int srcm = b & 7;
+                            if (srcm == PM_X) op = OP_X, cs -= X;
+                            else op = OP_CLOSE, comp = srcm - 1;
+                        } else if (comp == CI1 || comp == CI2) {
+                            op = OP_I;
+                            const bool ex = b & (comp == CI1 ? PB_I1E : PB_I2E);
+                            const int e = comp == CI1 ? E1 : E2, o = comp == CI1 ? O1 : O2;
+                            if (ex) cs -= e; else cs -= o + e, comp = -1;
+                            k -= 1;
+                        } else {
+                            op = OP_D;
+                            ++n_del;
+                            const bool ex = b & (comp == CD1 ? PB_D1E : PB_D2E);
+                            const int e = comp == CD1 ? E1 : E2, o = comp == CD1 ? O1 : O2;
+                            if (ex) cs -= e; else cs -= o + e, comp = -1;
+                            k += 1;
+                        }
+                        if (gl == 0) ops[nops] = (uint8_t)op;
+                        ++nops;
+                        walking = !(comp < 0 && cs == 0);
+                    }
+                }
+            }
+            __syncwarp();
+            {
+                ClipAcc acc;
+                acc.init(m + n_del, p.clip);
+                int v = 0, h = 0, i = nops - 1;
+                bool in_m = true, replay = aligned;
+                while (__any_sync(TDB_FULL, replay)) {
+                    const int eq = extend_groups(pw, tw, psh, tsh, n, m, v, h, replay && in_m, gl, gshift, lane);
+                    if (replay) {
+                        if (in_m) {
+                            acc.emit('M', eq, pn);
+                            v += eq, h += eq;
+                        }
+                        if (i < 0) {
+                            replay = false;
+                        } else {
+                            const int op = ops[i];
+                            --i;
+                            if (op == OP_CLOSE) {
+                                in_m = true;
+                            } else {
                                 acc.emit(op == OP_X ? 'X' : (op == OP_I ? 'I' : 'D'), 1, pn);
-                                if (op == OP_X) ++v, ++h;
+                                if (op == OP_X) ++v, ++h, in_m = true;
                                 else if (op == OP_I) ++h, in_m = false;
                                 else ++v, in_m = false;
                             }
-                            clipped = acc.finish(pn);
-                            cols = (unsigned)acc.col;
-                            __syncwarp(gmask);
                         }
                     }
                 }
-                // ---- result ----
-                unsigned ext_pair = 0;
-                if (p.work) { // per-pair algorithmic work: ext is a per-lane partial count
-                    ext_pair = (unsigned)ext;
-                    ext_pair += __shfl_xor_sync(gmask, ext_pair, 1);
-                    ext_pair += __shfl_xor_sync(gmask, ext_pair, 2);
-                    ext_pair += __shfl_xor_sync(gmask, ext_pair, 4);
+                if (aligned) {
+                    clipped = acc.finish(pn);
+                    cols = (unsigned)acc.col;
                 }
+            }
+            __syncwarp();
+            // ---- result ----
+            unsigned ext_pair = 0;
+            if (p.work) { // per-pair algorithmic work: ext is a per-lane partial count (warp-uniform branch)
+                ext_pair = (unsigned)ext;
+                ext_pair += __shfl_xor_sync(TDB_FULL, ext_pair, 1);
+                ext_pair += __shfl_xor_sync(TDB_FULL, ext_pair, 2);
+                ext_pair += __shfl_xor_sync(TDB_FULL, ext_pair, 4);
+            }
+            if (have) {
                 if (gl == 0) {
                     if (!overflow) {
                         p.out_score[idx] = clipped;
