@@ -71,7 +71,8 @@ struct tdb_ctx {
     DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, pair_p, pair_t, score, status, penalty;
     DevBuf rep, work, list_b, list_c;
     // Chunks alternate between two pipeline slots (own stream + own scratch) so that the tail of one chunk's
-    // alignment kernels overlaps the next chunk's duplicate elimination and alignment.
+    // alignment kernels overlaps the next chunk's duplicate elimination and alignment.  (3 and 4 slots, and a
+    // warp tier deferred to a call-wide list, were measured and made no difference: profiles/r01/NOTES.md.)
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
