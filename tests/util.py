@@ -55,3 +55,48 @@ def to_arrays(seqs):
     if len(seqs):
         offs[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
     return blob, offs, lens
+
+
+def make_family_loci(rng: random.Random, n_loci: int, duo=False, missing_rate=0.05, denovo_rate=0.15,
+                     reads_per_allele=8, err=0.004):
+    """Synthetic per-locus inputs as `load_alleles` would see them (TRGT VCF alleles + spanning reads with AL/HP
+    tags): -> (loci, father, mother, child) lists (duo: father entries are None and unused)."""
+    from importlib import import_module
+    import trgt_denovo_b200  # noqa: F401
+    R = import_module("trgt_denovo_b200.rows")
+    loci, fam = [], {"f": [], "m": [], "c": []}
+    for li in range(n_loci):
+        lf, motif, rf = str_locus(rng)
+        base = rng.randint(3, 30)
+        chrom = rng.choice(["chr1", "chr7", "chrX", "chrY"])
+        loci.append(R.Locus(chrom=chrom, start=1000 * li + 17, end=1000 * li + 17 + base * len(motif),
+                            motifs=[motif], trid=f"TR{li:05d}_{motif}"))
+        units = {}
+        for s in "fm":
+            n_all = 1 if rng.random() < 0.15 else 2
+            units[s] = [max(1, base + rng.randint(-2, 2)) for _ in range(n_all)]
+        cu = [rng.choice(units["m"]), rng.choice(units["f"])]
+        if rng.random() < 0.15:
+            cu = cu[:1]
+        if rng.random() < denovo_rate:
+            k = rng.randrange(len(cu))
+            cu[k] = max(1, cu[k] + rng.choice([-1, 1]) * rng.randint(1, 8))
+        units["c"] = cu
+        for s in "fmc":
+            if rng.random() < missing_rate:
+                fam[s].append(None)
+                continue
+            seqs = [(lf + motif * u + rf).encode() for u in units[s]]
+            reads = []
+            for ai, u in enumerate(units[s]):
+                for k in range(max(1, int(rng.gauss(reads_per_allele, 2)))):
+                    uu = max(1, u + (rng.choice([-1, 1]) if rng.random() < 0.05 else 0))
+                    bases = mutate(rng, lf + motif * uu + rf, err).encode()
+                    reads.append(R.Read(name=f"{s}{li}_{ai}_{k}/ccs", bases=bases, classification=ai,
+                                        haplotype=rng.choice([1, 2, None, None])))
+            rng.shuffle(reads)
+            fam[s].append(R.SampleInput(allele_seqs=seqs, motif_counts=[str(u) for u in units[s]],
+                                        allele_lengths=[str(u * len(motif)) for u in units[s]],
+                                        genotype_indices=list(range(1, len(seqs) + 1)), reads=reads,
+                                        karyotype=rng.choice(["XX", "XY"])))
+    return loci, fam["f"], fam["m"], fam["c"]

@@ -26,3 +26,4 @@ from .aligner import (  # noqa: F401
     create_aligner_with_scoring,
 )
 from .batch import SeqBatch  # noqa: F401
+from . import rows, shard  # noqa: F401  (per-locus pipeline above the hot path; locus sharding)
