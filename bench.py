@@ -169,6 +169,8 @@ def main():
         entry.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     from importlib import import_module
@@ -191,6 +193,8 @@ def main():
         f"of reads in {time.time() - t0:.1f}s")
     n_loci, n_pairs, n_seqs = batch.n_loci, batch.n_pairs, batch.n_seqs
     ctx = tdb.Context(device_id=local_rank, clip_len=args.clip)
+    if world > 1:
+        ctx.set_host_threads(max(1, threads - 1))  # the ranks share the host's cores
     h = ctx._h
 
     # ---- device-resident copies (plumbing via torch) ----------------------------------------------

@@ -113,6 +113,9 @@ void tdb_destroy(tdb_ctx *ctx);
 const char *tdb_last_error(const tdb_ctx *ctx);
 
 int tdb_set_clip_len(tdb_ctx *ctx, int32_t clip_len);
+/* CPU threads the host-buffer calls may use for 2-bit packing and chunk planning (default: all hardware
+ * threads but one; with one ctx per GPU on a shared host give each its share, e.g. cores / n_gpus). */
+int tdb_set_host_threads(tdb_ctx *ctx, int32_t n_threads);
 int tdb_set_heuristic(tdb_ctx *ctx, const tdb_heuristic *h);
 
 /*

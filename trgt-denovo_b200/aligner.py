@@ -71,6 +71,9 @@ class Context:
         self._check(B.lib().tdb_set_clip_len(self._h, clip_len))
         self.clip_len = clip_len
 
+    def set_host_threads(self, n_threads):
+        self._check(B.lib().tdb_set_host_threads(self._h, int(n_threads)))
+
     def set_heuristic(self, heuristic):
         self._check(B.lib().tdb_set_heuristic(self._h, C.byref(B.Heuristic(*heuristic))))
 

@@ -60,7 +60,7 @@ class Counters(C.Structure):
 # every symbol include/trgt_denovo_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tdb_default_config", "tdb_abi_version", "tdb_device_count", "tdb_create", "tdb_destroy",
-    "tdb_last_error", "tdb_set_clip_len", "tdb_set_heuristic", "tdb_align_batch",
+    "tdb_last_error", "tdb_set_clip_len", "tdb_set_host_threads", "tdb_set_heuristic", "tdb_align_batch",
     "tdb_align_batch_device", "tdb_align_batch_cigar", "tdb_trio_reduce", "tdb_duo_reduce",
     "tdb_trio_batch", "tdb_duo_batch", "tdb_assess_batch_device", "tdb_align_end_to_end", "tdb_score",
     "tdb_cigar_ops", "tdb_cigar_score_clipped", "tdb_get_counters", "tdb_set_count_work",
@@ -89,6 +89,7 @@ def lib():
     L.tdb_last_error.restype = C.c_char_p
     L.tdb_last_error.argtypes = [vp]
     L.tdb_set_clip_len.argtypes = [vp, i32]
+    L.tdb_set_host_threads.argtypes = [vp, i32]
     L.tdb_set_heuristic.argtypes = [vp, C.POINTER(Heuristic)]
     batch = [vp, vp, sz, u64p, vp, sz, vp, vp, sz]
     L.tdb_align_batch.argtypes = batch + [vp, vp]

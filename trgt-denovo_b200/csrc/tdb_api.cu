@@ -84,6 +84,7 @@ struct tdb_ctx {
     bool disable_quad = false, disable_dedup = false, disable_closed_form = false;
     size_t chunk_pairs = 2u << 20;
     size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
+    int host_threads = 0;                 // 0: all hardware threads but one
     void *h_packed = nullptr, *h_flag = nullptr; // pinned staging of the host packer
     size_t h_packed_cap = 0, h_flag_cap = 0;
     bool count_work = false;
@@ -331,7 +332,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     if (b.h_pp && (host_pack || chunks.size() > 1)) {
         // one core stays free for the calling thread, which must react quickly to every finished chunk
         const unsigned hc = std::thread::hardware_concurrency();
-        const unsigned hw = std::max(1u, std::min(32u, hc > 2 ? hc - 1 : 1u));
+        const unsigned hw = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::max(1u, std::min(32u, hc > 2 ? hc - 1 : 1u));
         const size_t K0 = chunks.size(), n_scan = K0 > 1 ? K0 : 0, n_zero = host_pack ? 16 : 0;
         uint8_t *hflag = (uint8_t *)ctx->h_flag;
         packer.start(b.h_blob, b.blob_bytes, b.h_seq_off, b.h_seq_len, n_seqs, host_pack ? (uint32_t *)ctx->h_packed : nullptr,
@@ -824,6 +825,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
         c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
+        if (const char *ht = getenv("TDB_HOST_THREADS")) c->host_threads = std::max(0, std::min(256, atoi(ht)));
         if (const char *hp = getenv("TDB_HOSTPACK_MIN_BYTES")) {
             const long long v = atoll(hp); // < 0 disables the host packer
             c->hostpack_min_bytes = v < 0 ? (size_t)-1 : (size_t)v;
@@ -868,6 +870,13 @@ int tdb_set_clip_len(tdb_ctx *ctx, int32_t clip_len) {
     if (!ctx) return TDB_E_INVALID;
     if (clip_len < 0) return fail(ctx, TDB_E_INVALID, "clip_len must be >= 0");
     ctx->cfg.clip_len = clip_len;
+    return TDB_OK;
+}
+
+int tdb_set_host_threads(tdb_ctx *ctx, int32_t n_threads) {
+    if (!ctx) return TDB_E_INVALID;
+    if (n_threads < 0 || n_threads > 256) return fail(ctx, TDB_E_INVALID, "host threads must be in 0..256");
+    ctx->host_threads = n_threads;
     return TDB_OK;
 }
 
