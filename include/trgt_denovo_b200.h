@@ -233,7 +233,7 @@ typedef struct {
     uint64_t tier_cells[4], tier_ext16[4], tier_columns[4]; /* executed work per tier */
     uint64_t pairs_identical; /* pattern bytes == text bytes: resolved without an alignment */
     uint64_t pairs_duplicate; /* copies of an already aligned (pattern, text) content */
-    uint64_t pairs_closed_form; /* one substitution / one gap of <= 5 bases: scored in closed form (0 while
+    uint64_t pairs_closed_form; /* one substitution / one gap of <= 20 bases: scored in closed form (0 while
                                    exact work counting is on) */
     uint64_t kernel_launches;
     uint64_t chunks;        /* pipeline chunks the call was cut into */

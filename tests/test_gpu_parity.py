@@ -167,13 +167,17 @@ def test_closed_form_pairs(tdb, clip):
         k = rng.randint(1, 6)
         motif = rand_seq(rng, k)
         lf, rf = rand_seq(rng, rng.randint(0, 60)), rand_seq(rng, rng.randint(0, 60))
-        t = lf + motif * rng.randint(0, 30) + rf or "A"
+        t = lf + motif * rng.randint(0, 90) + rf or "A"  # repeats long enough for wf-adaptive to act
         mode = rng.random()
-        if mode < 0.35:
+        if mode < 0.2:
             i = rng.randrange(len(t))
             p = t[:i] + rng.choice("ACGT") + t[i + 1:]
+        elif mode < 0.5:  # whole motif units in or out (the gap can slide inside the repeat)
+            u = rng.randint(1, max(1, 22 // k))
+            j = len(lf) + k * rng.randint(0, 5)
+            p = t[:j] + motif * u + t[j:] if rng.random() < 0.5 else t[:j] + t[j + k * u:]
         elif mode < 0.9:
-            i, d = rng.randrange(len(t) + 1), rng.randint(1, 6)
+            i, d = rng.randrange(len(t) + 1), rng.randint(1, 24)  # beyond CF_MAXGAP = 20 too
             p = t[:i] + rand_seq(rng, d) + t[i:] if rng.random() < 0.5 else t[:i] + t[i + d:]
         else:
             p = mutate(rng, t, 0.02)

@@ -252,17 +252,24 @@ __global__ void __launch_bounds__(256) k_pair_insert(const uint32_t *__restrict_
     }
 }
 
-// Closed form for the two commonest non-identical contents (53 % of the aligned pairs of the 30x trio):
-// one substitution, or one gap of <= CF_MAXGAP bases, everything else matching.  With the production
-// penalties (8,4,2,24,1) such a pair has penalty 8 resp. 4+2L <= 14, which is optimal (any alignment of
-// lengths differing by L pays at least one gap of L), unique up to WFA's placement rule -- the gap /
-// substitution sits where diagonal 0 stops matching, because wavefront M[0] only keeps its furthest
-// point -- and beyond the reach of wf-adaptive: the cut-off needs a wavefront of >= 10 diagonals, and
-// M[s] spans at most s-3 diagonals for s <= 12, the last score whose cut-off could matter.  The clipped
-// score follows from the column positions (src/aligner.rs:320-357).  Checked against the CPU checker on
-// > 10^5 pairs (tests/test_gpu_parity.py, profiles/closed_form_check.py).  Not used when exact work
-// counting is on: C/E/T of a pair are only known by running the wavefronts.
-constexpr int CF_MAXGAP = 5;
+// Closed form for the commonest non-identical contents (about two thirds of the aligned pairs of the 30x
+// trio, and the heaviest ones): one substitution, or one gap of L <= CF_MAXGAP bases, everything else matching.
+// With the production penalties (8,4,2,24,1):
+//  * the penalty is 8 resp. 4+2L, which is optimal: two sequences whose lengths differ by L need gaps of net
+//    length L, a single first-piece gap is the cheapest way (<= the second piece 24+L for L <= 20), and any
+//    further edit costs more;
+//  * the path with that penalty is unique: the gap / substitution starts where diagonal 0 stops matching,
+//    because wavefront M[0] only keeps its furthest point;
+//  * wf-adaptive cannot remove it: at score 4+2j the gap chain sits on the OUTERMOST diagonal of M (+j for an
+//    insertion, -j for a deletion; the second-piece chain only overtakes it beyond score 44), and the cut-off
+//    never drops the top diagonal while it is <= k_end nor the bottom one while it is >= k_end (SURVEY A.3:
+//    the scans stop at min(k_end, hi) resp. max(k_end, lo)).  For L > 20 the optimum runs through the
+//    second-piece chain, which is an INNER diagonal for its first 20 steps and can be cut -- measured: the
+//    closed form then disagrees with the wavefronts on 1.4 % of such pairs, so it is not used there.
+// The clipped score follows from the column positions (src/aligner.rs:320-357).  Checked against the CPU
+// checker on > 3*10^5 pairs (tests/test_gpu_parity.py, profiles/closed_form_check.py).  Not used when exact
+// work counting is on: C/E/T of a pair are only known by running the wavefronts.
+constexpr int CF_MAXGAP = 20;
 struct ClosedFormCfg {
     int enabled, clip;
 };
