@@ -476,14 +476,14 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
             if (!host_pack) {
                 CK(cudaMemsetAsync((uint8_t *)ctx->seq_flag.p + a, 0, (size_t)(e - a), ps));
                 if (b1 > b0) {
-                    const unsigned blocks = (unsigned)std::min<uint64_t>(((b1 - b0 + 15) / 16 + 255) / 256, (uint64_t)ctx->sm_count * 32);
+                    const unsigned blocks = (unsigned)std::min<uint64_t>(((b1 - b0 + 15) / 16 + 511) / 512, (uint64_t)ctx->sm_count * 32);
                     k_pack<<<blocks, 256, 0, ps>>>(b.blob, b0, b1, b.seq_off, b.seq_len, a, e, (uint32_t *)ctx->packed.p,
                                                    (uint8_t *)ctx->seq_flag.p);
                     CK(cudaGetLastError());
                     cn.kernel_launches += 1;
                 }
             }
-            const unsigned blocks = (unsigned)std::min<size_t>(((size_t)(e - a) * PK_G + 255) / 256, (size_t)ctx->sm_count * 64);
+            const unsigned blocks = (unsigned)(((size_t)(e - a) + 255) / 256);
             k_hash<<<blocks, 256, 0, ps>>>(b.seq_off, b.seq_len, a, e, n_seqs, b.blob_bytes, (const uint32_t *)ctx->packed.p,
                                            (uint8_t *)ctx->seq_flag.p, (uint64_t *)ctx->seq_hash.p, &ctrl->err);
             CK(cudaGetLastError());
@@ -513,7 +513,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
             cn.kernel_launches += 1;
         }
         if (ns) {
-            const unsigned blocks = (unsigned)(((size_t)ns * CN_G + 255) / 256);
+            const unsigned blocks = (unsigned)(((size_t)ns + 255) / 256);
             k_seq_canon<<<blocks, 256, 0, st>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p, b.seq_off,
                                                 b.seq_len, (const uint32_t *)ctx->packed.p, c.s_lo, c.s_hi, skeys, svals,
                                                 smask, canon, dedup ? 1 : 0);

@@ -56,45 +56,66 @@ __device__ inline void flag_owner(uint64_t x, const uint64_t *__restrict__ seq_o
     }
 }
 
+__device__ __forceinline__ void load16(const uint8_t *__restrict__ blob, uint64_t x0, uint32_t cnt, bool aligned,
+                                       uint32_t q[4]) {
+    if (aligned && cnt == 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(blob + x0));
+        q[0] = v.x, q[1] = v.y, q[2] = v.z, q[3] = v.w;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t w = 0;
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t bi = (uint32_t)(t * 4 + u);
+                if (bi < cnt) w |= (uint32_t)blob[x0 + bi] << (8 * u);
+            }
+            q[t] = w;
+        }
+    }
+}
+__device__ __forceinline__ uint32_t pack16(const uint32_t q[4], uint32_t cnt, uint32_t &badm) {
+    uint32_t word = 0;
+    badm = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int rem = (int)cnt - 4 * t;
+        const uint32_t need = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
+        const uint32_t bad4 = ~acgt_mask4(q[t]) & need; // 0xff per offending byte
+        badm |= (((bad4 >> 7) & 1u) | ((bad4 >> 14) & 2u) | ((bad4 >> 21) & 4u) | ((bad4 >> 28) & 8u)) << (4 * t);
+        word |= pack4(q[t] & need) << (8 * t);
+    }
+    return word;
+}
+
 // Packs blob bytes [b0, b1) (b0 a multiple of 16).  seq_flag of [s_lo, s_hi) must be zeroed before.
+// Two 16-byte groups per thread (a whole block covers a contiguous 8 KB), both loads issued before use.
 __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ blob, uint64_t b0, uint64_t b1,
                                               const uint64_t *__restrict__ seq_off,
                                               const uint32_t *__restrict__ seq_len, uint32_t s_lo, uint32_t s_hi,
                                               uint32_t *__restrict__ packed, uint8_t *__restrict__ seq_flag) {
     const uint64_t ngroups = (b1 - b0 + 15) / 16;
     const bool aligned = (((uintptr_t)blob) & 15) == 0;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t x0 = b0 + g * 16;
-        uint32_t q[4];
-        const uint32_t cnt = (uint32_t)min((uint64_t)16, b1 - x0);
-        if (aligned && cnt == 16) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(blob + x0));
-            q[0] = v.x, q[1] = v.y, q[2] = v.z, q[3] = v.w;
-        } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                uint32_t w = 0;
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t bi = (uint32_t)(t * 4 + u);
-                    if (bi < cnt) w |= (uint32_t)blob[x0 + bi] << (8 * u);
-                }
-                q[t] = w;
-            }
+    const uint64_t stride = (uint64_t)gridDim.x * 512;
+    for (uint64_t g0 = (uint64_t)blockIdx.x * 512 + threadIdx.x; g0 < ngroups; g0 += stride) {
+        const uint64_t g1 = g0 + 256;
+        const uint64_t xa = b0 + g0 * 16, xb = b0 + g1 * 16;
+        const uint32_t ca = (uint32_t)min((uint64_t)16, b1 - xa);
+        const uint32_t cb = g1 < ngroups ? (uint32_t)min((uint64_t)16, b1 - xb) : 0u;
+        uint32_t qa[4], qb[4] = {0, 0, 0, 0};
+        load16(blob, xa, ca, aligned, qa);
+        if (cb) load16(blob, xb, cb, aligned, qb);
+        uint32_t bada, badb = 0;
+        packed[xa >> 4] = pack16(qa, ca, bada);
+        if (cb) packed[xb >> 4] = pack16(qb, cb, badb);
+        while (bada) { // rare: flag the owning sequences
+            const int k = __ffs(bada) - 1;
+            bada &= bada - 1;
+            flag_owner(xa + (uint64_t)k, seq_off, seq_len, s_lo, s_hi, seq_flag);
         }
-        uint32_t word = 0, badm = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int rem = (int)cnt - 4 * t;
-            const uint32_t need = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
-            const uint32_t bad4 = ~acgt_mask4(q[t]) & need; // 0xff per offending byte
-            badm |= (((bad4 >> 7) & 1u) | ((bad4 >> 14) & 2u) | ((bad4 >> 21) & 4u) | ((bad4 >> 28) & 8u)) << (4 * t);
-            word |= pack4(q[t] & need) << (8 * t);
-        }
-        packed[x0 >> 4] = word;
-        while (badm) { // rare: flag the owning sequences
-            const int k = __ffs(badm) - 1;
-            badm &= badm - 1;
-            flag_owner(x0 + (uint64_t)k, seq_off, seq_len, s_lo, s_hi, seq_flag);
+        while (badb) {
+            const int k = __ffs(badb) - 1;
+            badb &= badb - 1;
+            flag_owner(xb + (uint64_t)k, seq_off, seq_len, s_lo, s_hi, seq_flag);
         }
     }
 }
@@ -108,39 +129,41 @@ __device__ __forceinline__ uint32_t seq_word(const uint32_t *__restrict__ packed
     return rem >= 16u ? v : (v & ((1u << (2u * rem)) - 1u));
 }
 
-constexpr int PK_G = 16; // lanes per sequence
-
 // 64-bit content hash per sequence (feeds the duplicate elimination below) + the blob layout contract
 // (sequences in index order, non-overlapping, inside the blob: what makes chunked uploads possible).
+// One thread per sequence: neighbouring threads walk neighbouring stretches of the packed stream, so a
+// warp's loads stay inside a few cache lines that L1 keeps across the ~10 iterations.
 __global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ seq_len,
                                               uint32_t s0, uint32_t s1, uint32_t n_seqs, uint64_t blob_bytes,
                                               const uint32_t *__restrict__ packed, uint8_t *__restrict__ seq_flag,
                                               uint64_t *__restrict__ seq_hash, unsigned *__restrict__ err) {
-    const int lane = threadIdx.x & 31, gl = lane & (PK_G - 1);
-    const unsigned gmask = 0xffffu << (lane & 16);
-    const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) / PK_G;
-    const uint32_t ng = (gridDim.x * blockDim.x) / PK_G;
-    for (uint32_t i = s0 + g0; i < s1; i += ng) {
-        const uint32_t len = seq_len[i];
-        const uint64_t off = seq_off[i];
-        const bool outside = off > blob_bytes || (uint64_t)len > blob_bytes - off;
-        if (gl == 0) {
-            bool bad_layout = outside;
-            if (!outside && i + 1 < n_seqs) bad_layout = off + len > seq_off[i + 1];
-            if (bad_layout) atomicOr(err, (unsigned)ERR_LAYOUT);
-            if (outside) seq_flag[i] = 2, seq_hash[i] = 0; // 2: unusable, pairs touching it are skipped
-        }
-        if (outside) continue;
-        const uint32_t nw = (len + 15u) / 16u;
-        uint64_t hs = 0;
-        for (uint32_t j = gl; j < nw; j += PK_G) hs += mix64(((uint64_t)j << 32) | seq_word(packed, off, len, j));
-#pragma unroll
-        for (int o = PK_G / 2; o; o >>= 1) hs += __shfl_xor_sync(gmask, hs, o);
-        if (gl == 0) {
-            const uint64_t h = mix64(hs ^ ((uint64_t)len * 0x9e3779b97f4a7c15ull));
-            seq_hash[i] = h == HT_EMPTY ? 0 : h;
-        }
+    const uint32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s1) return;
+    const uint32_t len = seq_len[i];
+    const uint64_t off = seq_off[i];
+    const bool outside = off > blob_bytes || (uint64_t)len > blob_bytes - off;
+    bool bad_layout = outside;
+    if (!outside && i + 1 < n_seqs) bad_layout = off + len > seq_off[i + 1];
+    if (bad_layout) atomicOr(err, (unsigned)ERR_LAYOUT);
+    if (outside) { // 2: unusable, pairs touching it are skipped
+        seq_flag[i] = 2, seq_hash[i] = 0;
+        return;
     }
+    const uint32_t nw = (len + 15u) / 16u;
+    const uint32_t *w = packed + (off >> 4);
+    const uint32_t sh = (uint32_t)(off & 15) << 1;
+    uint64_t hs = 0;
+    uint32_t lo = nw ? __ldg(w) : 0u;
+    for (uint32_t j = 0; j < nw; ++j) {
+        const uint32_t hi = __ldg(w + j + 1);
+        uint32_t v = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        const uint32_t rem = len - 16u * j;
+        if (rem < 16u) v &= (1u << (2u * rem)) - 1u;
+        hs += mix64(((uint64_t)j << 32) | v);
+    }
+    const uint64_t h = mix64(hs ^ ((uint64_t)len * 0x9e3779b97f4a7c15ull));
+    seq_hash[i] = h == HT_EMPTY ? 0 : h;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -177,7 +200,6 @@ __global__ void __launch_bounds__(256) k_seq_insert(const uint64_t *__restrict__
     }
 }
 
-constexpr int CN_G = 8; // lanes per sequence in the verification pass
 __global__ void __launch_bounds__(256) k_seq_canon(const uint64_t *__restrict__ seq_hash,
                                                    const uint8_t *__restrict__ seq_flag,
                                                    const uint64_t *__restrict__ seq_off,
@@ -186,28 +208,26 @@ __global__ void __launch_bounds__(256) k_seq_canon(const uint64_t *__restrict__ 
                                                    const unsigned long long *__restrict__ keys,
                                                    const uint32_t *__restrict__ vals, uint32_t mask,
                                                    uint32_t *__restrict__ canon, int dedup) {
-    const int lane = threadIdx.x & 31, gl = lane & (CN_G - 1);
-    const unsigned gmask = 0xffu << (lane & ~(CN_G - 1));
-    const uint32_t i = s0 + (blockIdx.x * blockDim.x + threadIdx.x) / CN_G;
-    if (i >= s1) return; // whole groups leave together
+    const uint32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s1) return;
     uint32_t c = i;
     if (dedup && !seq_flag[i]) {
         const uint64_t h = seq_hash[i];
         uint32_t slot = (uint32_t)h & mask;
         while (keys[slot] != h) slot = (slot + 1) & mask; // inserted by k_seq_insert: always found
         c = vals[slot];
-        if (c != i) {
+        if (c != i) { // verify the hash hit word by word
             const uint32_t len = seq_len[i];
             bool diff = seq_len[c] != len;
             if (!diff) {
                 const uint64_t oi = seq_off[i], oc = seq_off[c];
                 const uint32_t nw = (len + 15u) / 16u;
-                for (uint32_t j = gl; j < nw; j += CN_G) diff |= seq_word(packed, oi, len, j) != seq_word(packed, oc, len, j);
+                for (uint32_t j = 0; j < nw && !diff; ++j) diff = seq_word(packed, oi, len, j) != seq_word(packed, oc, len, j);
             }
-            if (__ballot_sync(gmask, diff) & gmask) c = i;
+            if (diff) c = i;
         }
     }
-    if (gl == 0) canon[i] = c;
+    canon[i] = c;
 }
 
 // sort keys of representative pairs: 0 quad tier by descending |n-m| ... ; 255 = not in the sorted list
