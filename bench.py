@@ -281,10 +281,13 @@ def main():
     e2e_s = time.time() - e0
     ce = ctx.counters()
     e2e_chunks = ce.chunks
-    e2e_host = {"host_packed": int(ce.host_packed), "ms_plan": ce.ms_host_plan, "ms_pack_wait": ce.ms_host_pack_wait,
+    e2e_host = {"host_packed": int(ce.host_packed), "align_bytes_h2d": int(ce.bytes_h2d), "ms_plan": ce.ms_host_plan, "ms_pack_wait": ce.ms_host_pack_wait,
                 "ms_align_call": ce.ms_host_call, "ms_device_span": ce.ms_total_device}
-    h2d = batch.blob.size + batch.seq_off.nbytes + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
+    # bytes that actually cross PCIe per step: what the library copied for the alignment stage (2-bit packed
+    # sequences, tables, run-length encoded pair lists) plus the locus descriptors
+    host_input_bytes = batch.blob.size + batch.seq_off.nbytes + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
         batch.pair_text.nbytes + loci_np.nbytes
+    h2d = int(ce.bytes_h2d) + loci_np.nbytes
     d2h = C.sizeof(h_out) + h_mask.nbytes
 
     # ---- quick self-check of the step's result against the oracle (outside the timed regions) --------
@@ -372,6 +375,7 @@ def main():
             "wall_ms_per_step": wall_ms_max / args.steps,
             "e2e": {"value": tot_loci * args.steps / (e2e_ms_max * 1e-3), "unit": "loci/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "host_input_bytes_per_step": int(host_input_bytes),
                     "ms_per_step": e2e_ms_max / args.steps,
                     "alignments_per_sec": tot_pairs * args.steps / (e2e_ms_max * 1e-3)},
             "gpu_launches": int(launches),

@@ -238,6 +238,7 @@ typedef struct {
     uint64_t kernel_launches;
     uint64_t chunks;        /* pipeline chunks the call was cut into */
     uint64_t host_packed;   /* 1: the caller's CPU threads 2-bit packed the sequences before the upload */
+    uint64_t bytes_h2d;     /* bytes the alignment stage actually copied host -> device (host-buffer calls) */
     float ms_pack, ms_dedup, ms_align, ms_scatter, ms_reduce, ms_total_device; /* CUDA-event times */
     float ms_host_plan, ms_host_pack_wait, ms_host_call; /* host wall clock: chunk planning, time the calling
                          thread waited for the packer threads, whole run of pack+align (host-buffer calls) */

@@ -81,12 +81,13 @@ struct tdb_ctx {
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0;
-    bool disable_quad = false, disable_dedup = false, disable_closed_form = false;
+    bool disable_quad = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
     size_t chunk_pairs = 2u << 20;
     size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
     int host_threads = 0;                 // 0: all hardware threads but one
-    void *h_packed = nullptr, *h_flag = nullptr; // pinned staging of the host packer
-    size_t h_packed_cap = 0, h_flag_cap = 0;
+    void *h_packed = nullptr, *h_flag = nullptr, *h_runs = nullptr; // pinned staging of the host packer / planner
+    size_t h_packed_cap = 0, h_flag_cap = 0, h_runs_cap = 0;
+    DevBuf runs;
     bool count_work = false;
     tdb_counters counters;
     // single-pair shim state
@@ -164,9 +165,15 @@ int check_sizes(tdb_ctx *ctx, size_t blob_bytes, size_t n_seqs, size_t n_pairs) 
     return TDB_OK;
 }
 
+constexpr int SCAN_PARTS = 4; // a chunk's pair list is scanned by this many independent tasks
 struct Chunk {
     size_t p0, p1;       // pair range
     uint32_t s_lo, s_hi; // sequences referenced: [s_lo, s_hi)
+    size_t run0 = 0;     // this chunk's slice of the run buffer (SCAN_PARTS sub-slices of run_cap runs)
+    uint32_t run_cap = 0, n_runs = 0;
+    uint32_t part_runs[SCAN_PARTS] = {}, part_lo[SCAN_PARTS] = {}, part_hi[SCAN_PARTS] = {};
+    bool part_ok[SCAN_PARTS] = {};
+    bool rle = false;    // pair list shipped as runs
 };
 
 // Worker threads that 2-bit pack a host blob block by block, in byte order, while the calling thread
@@ -260,21 +267,50 @@ void plan_prepare(const tdb_ctx *ctx, const DevBatch &b, std::vector<Chunk> &out
     const size_t K = (n_pairs + ctx->chunk_pairs - 1) / ctx->chunk_pairs;
     const size_t per = (n_pairs + K - 1) / K;
     out.resize(K);
-    for (size_t k = 0; k < K; ++k) out[k] = {k * per, std::min(n_pairs, (k + 1) * per), 0, 0};
+    size_t run0 = 0;
+    for (size_t k = 0; k < K; ++k) {
+        out[k] = {k * per, std::min(n_pairs, (k + 1) * per), 0, 0};
+        out[k].run0 = run0, out[k].run_cap = (uint32_t)((out[k].p1 - out[k].p0) / (4 * SCAN_PARTS) + 16);
+        run0 += (size_t)out[k].run_cap * SCAN_PARTS;
+    }
 }
-void scan_chunk(const DevBatch &b, Chunk &c) {
+// Part `part` of a chunk's pair list: the sequence range it touches and, when `runs` is given, its run-length
+// encoding (consecutive patterns against one text).  A part whose runs do not fit a quarter of its pairs makes
+// the whole chunk travel as plain arrays.
+void scan_chunk_part(const DevBatch &b, Chunk &c, int part, PairRun *runs) {
+    const size_t len = c.p1 - c.p0, q0 = c.p0 + len * part / SCAN_PARTS, q1 = c.p0 + len * (part + 1) / SCAN_PARTS;
     uint32_t lo = 0xffffffffu, hi = 0;
-    for (size_t j = c.p0; j < c.p1; ++j) {
+    PairRun *out = runs ? runs + c.run0 + (size_t)c.run_cap * part : nullptr;
+    uint32_t n_runs = 0, next_p = 0, cur_t = 0;
+    bool ok = runs != nullptr;
+    for (size_t j = q0; j < q1; ++j) {
         const uint32_t a = b.h_pp[j], t = b.h_pt[j];
         lo = std::min(lo, std::min(a, t));
         hi = std::max(hi, std::max(a, t));
+        if (ok && (n_runs == 0 || a != next_p || t != cur_t)) {
+            if (n_runs == c.run_cap) ok = false;
+            else out[n_runs++] = {(uint32_t)(j - c.p0), a, t};
+        }
+        next_p = a + 1, cur_t = t;
     }
+    c.part_lo[part] = lo, c.part_hi[part] = hi, c.part_runs[part] = n_runs, c.part_ok[part] = ok;
+}
+void finish_chunk_scan(const DevBatch &b, Chunk &c) {
+    uint32_t lo = 0xffffffffu, hi = 0;
+    c.rle = true, c.n_runs = 0;
+    for (int p = 0; p < SCAN_PARTS; ++p) {
+        lo = std::min(lo, c.part_lo[p]), hi = std::max(hi, c.part_hi[p]);
+        c.rle = c.rle && c.part_ok[p];
+        c.n_runs += c.part_runs[p];
+    }
+    c.rle = c.rle && c.n_runs > 0;
     if (lo > hi) lo = hi = 0;
     hi = (uint32_t)std::min<size_t>((size_t)hi + 1, b.n_seqs); // out-of-range indices fail on the device
     c.s_lo = std::min(lo, hi), c.s_hi = hi;
 }
 void plan_finish(const DevBatch &b, std::vector<Chunk> &out) {
     if (out.size() <= 1) return;
+    for (Chunk &c : out) finish_chunk_scan(b, c);
     size_t covered = 0;
     for (const Chunk &c : out) covered += c.s_hi - c.s_lo;
     if (covered > 2 * b.n_seqs + 64 * out.size()) {
@@ -333,12 +369,20 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         // one core stays free for the calling thread, which must react quickly to every finished chunk
         const unsigned hc = std::thread::hardware_concurrency();
         const unsigned hw = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::max(1u, std::min(32u, hc > 2 ? hc - 1 : 1u));
-        const size_t K0 = chunks.size(), n_scan = K0 > 1 ? K0 : 0, n_zero = host_pack ? 16 : 0;
+        const size_t K0 = chunks.size(), n_scan = K0 > 1 ? K0 * SCAN_PARTS : 0, n_zero = host_pack ? 16 : 0;
+        PairRun *hruns = nullptr;
+        if (n_scan && !ctx->disable_rle) { // pair lists travel run-length encoded
+            const size_t total = chunks.back().run0 + (size_t)chunks.back().run_cap * SCAN_PARTS;
+            int r = ensure_pinned(ctx, ctx->h_runs, ctx->h_runs_cap, total * sizeof(PairRun));
+            if (r) return r;
+            ENSURE(ctx->runs, total * sizeof(PairRun));
+            hruns = (PairRun *)ctx->h_runs;
+        }
         uint8_t *hflag = (uint8_t *)ctx->h_flag;
         packer.start(b.h_blob, b.blob_bytes, b.h_seq_off, b.h_seq_len, n_seqs, host_pack ? (uint32_t *)ctx->h_packed : nullptr,
-                     hflag, hw, n_scan + n_zero, [&chunks, &b, n_scan, n_zero, hflag](size_t k) {
+                     hflag, hw, n_scan + n_zero, [&chunks, &b, n_scan, n_zero, hflag, hruns](size_t k) {
                          if (k < n_scan) {
-                             scan_chunk(b, chunks[k]);
+                             scan_chunk_part(b, chunks[k / SCAN_PARTS], (int)(k % SCAN_PARTS), hruns);
                          } else { // zero a slice of the flag array
                              const size_t per = (b.n_seqs + n_zero - 1) / n_zero, z0 = std::min(b.n_seqs, (k - n_scan) * per);
                              memset(hflag + z0, 0, std::min(b.n_seqs, z0 + per) - z0);
@@ -440,34 +484,59 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                 const size_t n_off = (size_t)(e - a) + (e < n_seqs ? 1 : 0);
                 CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, n_off * 8, cudaMemcpyHostToDevice, cs));
                 CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
+                cn.bytes_h2d += n_off * 8 + (uint64_t)(e - a) * 4;
                 if (!host_pack) {
                     if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+                    cn.bytes_h2d += b1 - b0;
                 } else {
                     const auto t_wait = std::chrono::steady_clock::now();
                     packer.wait_bytes(b0, b1);
                     cn.ms_host_pack_wait += ms_since(t_wait);
                     const uint8_t *hf = (const uint8_t *)ctx->h_flag;
                     CK(cudaMemcpyAsync((uint8_t *)ctx->seq_flag.p + a, hf + a, (size_t)(e - a), cudaMemcpyHostToDevice, cs));
+                    cn.bytes_h2d += (uint64_t)(e - a);
                     const size_t w0 = (size_t)(b0 >> 4), w1 = (size_t)((b1 + 15) >> 4);
                     if (w1 > w0)
                         CK(cudaMemcpyAsync((uint32_t *)ctx->packed.p + w0, (const uint32_t *)ctx->h_packed + w0, (w1 - w0) * 4,
                                            cudaMemcpyHostToDevice, cs));
+                    cn.bytes_h2d += (uint64_t)(w1 - w0) * 4;
                     // sequences with bytes outside ACGT are compared as raw bytes on the device: ship those bytes
                     size_t n_flag = 0;
                     for (uint32_t i = a; i < e; ++i) n_flag += hf[i] != 0;
                     if (n_flag > 256) {
                         if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+                        cn.bytes_h2d += b1 - b0;
                     } else if (n_flag) {
                         for (uint32_t i = a; i < e; ++i) {
                             const uint64_t o = b.h_seq_off[i];
                             if (hf[i] && b.h_seq_len[i] && o <= b.blob_bytes && b.h_seq_len[i] <= b.blob_bytes - o)
+{
                                 CK(cudaMemcpyAsync((uint8_t *)b.blob + o, b.h_blob + o, b.h_seq_len[i], cudaMemcpyHostToDevice, cs));
+                                cn.bytes_h2d += b.h_seq_len[i];
+                            }
                         }
                     }
                 }
             }
-            CK(cudaMemcpyAsync((uint32_t *)b.pp + c.p0, b.h_pp + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync((uint32_t *)b.pt + c.p0, b.h_pt + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
+            if (c.rle) {
+                PairRun *dr = (PairRun *)ctx->runs.p + c.run0; // the parts' sub-slices land back to back
+                size_t at = 0;
+                for (int pt = 0; pt < SCAN_PARTS; ++pt) {
+                    if (!c.part_runs[pt]) continue;
+                    CK(cudaMemcpyAsync(dr + at, (const PairRun *)ctx->h_runs + c.run0 + (size_t)c.run_cap * pt,
+                                       (size_t)c.part_runs[pt] * sizeof(PairRun), cudaMemcpyHostToDevice, cs));
+                    at += c.part_runs[pt];
+                }
+                k_expand_runs<<<(cpairs + 255) / 256, 256, 0, cs>>>(dr, c.n_runs, (uint32_t)c.p0, cpairs, (uint32_t *)b.pp,
+                                                                     (uint32_t *)b.pt);
+                CK(cudaGetLastError());
+                cn.kernel_launches += 1;
+                cn.bytes_h2d += (uint64_t)c.n_runs * sizeof(PairRun);
+            } else {
+                CK(cudaMemcpyAsync((uint32_t *)b.pp + c.p0, b.h_pp + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
+                CK(cudaMemcpyAsync((uint32_t *)b.pt + c.p0, b.h_pt + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
+                cn.bytes_h2d += (uint64_t)(c.p1 - c.p0) * 8;
+            }
         }
         // 2-bit packing (unless the host did it) and content hashes of the new sequences: on the copy stream for
         // host batches, so that sequences are ready in order whichever slot needs them
@@ -825,6 +894,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
         c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
+        c->disable_rle = getenv("TDB_DISABLE_RLE") != nullptr;
         if (const char *ht = getenv("TDB_HOST_THREADS")) c->host_threads = std::max(0, std::min(256, atoi(ht)));
         if (const char *hp = getenv("TDB_HOSTPACK_MIN_BYTES")) {
             const long long v = atoll(hp); // < 0 disables the host packer
@@ -843,7 +913,7 @@ void tdb_destroy(tdb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
     DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->pair_p, &c->pair_t,
-                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->ctrl, &c->loci,
+                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->ctrl, &c->loci, &c->runs,
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
@@ -859,6 +929,7 @@ void tdb_destroy(tdb_ctx *c) {
     for (cudaEvent_t e : c->up_ev) cudaEventDestroy(e);
     if (c->h_packed) cudaFreeHost(c->h_packed);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->h_runs) cudaFreeHost(c->h_runs);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;

@@ -166,6 +166,29 @@ __global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_o
     seq_hash[i] = h == HT_EMPTY ? 0 : h;
 }
 
+// Pair lists are runs -- "reads r .. r+c-1 of one allele against target t" is how align_alleleset /
+// align_allele (src/denovo.rs:22-54) visit them -- so a host batch ships them run-length encoded
+// (12 bytes per run instead of 8 bytes per pair) and this kernel expands them next to the data.
+struct PairRun {
+    uint32_t begin; // first pair of the run, relative to the chunk
+    uint32_t pattern0, text;
+};
+__global__ void __launch_bounds__(256) k_expand_runs(const PairRun *__restrict__ runs, uint32_t n_runs, uint32_t p0,
+                                                     uint32_t n_pairs, uint32_t *__restrict__ pair_p,
+                                                     uint32_t *__restrict__ pair_t) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pairs) return;
+    uint32_t lo = 0, hi = n_runs; // last run with begin <= j
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (runs[mid].begin <= j) lo = mid;
+        else hi = mid;
+    }
+    const PairRun r = runs[lo];
+    pair_p[p0 + j] = r.pattern0 + (j - r.begin);
+    pair_t[p0 + j] = r.text;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Duplicate elimination.  HiFi reads that span a short repeat are mostly error-free copies of the
 // allele they come from, so a locus' pair list holds the same (pattern, text) CONTENT many times
