@@ -73,16 +73,28 @@ __device__ __forceinline__ void load16(const uint8_t *__restrict__ blob, uint64_
         }
     }
 }
+// 16 bytes -> one packed word; badm gets one bit per byte outside {A,C,G,T}.  Validity is a round trip: the
+// byte the 2-bit code stands for (one PRMT from the table 'A','C','T','G') must equal the byte itself.
 __device__ __forceinline__ uint32_t pack16(const uint32_t q[4], uint32_t cnt, uint32_t &badm) {
-    uint32_t word = 0;
-    badm = 0;
+    uint32_t word = 0, anydiff = 0, diff[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int rem = (int)cnt - 4 * t;
         const uint32_t need = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
-        const uint32_t bad4 = ~acgt_mask4(q[t]) & need; // 0xff per offending byte
-        badm |= (((bad4 >> 7) & 1u) | ((bad4 >> 14) & 2u) | ((bad4 >> 21) & 4u) | ((bad4 >> 28) & 8u)) << (4 * t);
-        word |= pack4(q[t] & need) << (8 * t);
+        const uint32_t p8 = pack4(q[t] & need);
+        const uint32_t y = (p8 | (p8 << 4)) & 0x0f0fu;
+        const uint32_t sel = (y | (y << 2)) & 0x3333u; // the four codes as PRMT selector nibbles
+        diff[t] = (q[t] ^ __byte_perm(0x47544341u, 0u, sel)) & need;
+        anydiff |= diff[t];
+        word |= p8 << (8 * t);
+    }
+    badm = 0;
+    if (anydiff) { // rare
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t nz = (diff[t] | ((diff[t] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u; // 0x80 per bad byte
+            badm |= (((nz >> 7) & 1u) | ((nz >> 14) & 2u) | ((nz >> 21) & 4u) | ((nz >> 28) & 8u)) << (4 * t);
+        }
     }
     return word;
 }
