@@ -274,6 +274,20 @@ def test_edge_cases(ctx):
         _check_batch(ctx, seqs, pp, pt, clip)
 
 
+def test_empty_and_very_long_sequences(ctx):
+    """Zero-length sequences (pure gap alignments) and sequences beyond the int16 tiers' 8000-base limit."""
+    rng = random.Random(55)
+    long_t = rand_seq(rng, 9000)
+    seqs = [b"", b"ACGT", b"", b"A" * 30, b"A", long_t.encode(), mutate(rng, long_t, 0.01).encode(),
+            (long_t[:4000] + long_t[4300:]).encode(), b"ACGTTGCA" * 1200, b"ACGTTGCA" * 1190]
+    pairs = [(0, 1), (1, 0), (0, 2), (0, 3), (3, 0), (4, 0), (6, 5), (5, 6), (7, 5), (5, 7), (9, 8), (8, 9), (5, 5)]
+    pp = np.array([p for p, _ in pairs], np.uint32)
+    pt = np.array([t for _, t in pairs], np.uint32)
+    for clip in (50, 0):
+        cnt = _check_batch(ctx, seqs, pp, pt, clip)
+    assert cnt.tier_pairs[2] + cnt.tier_pairs[3] >= 4
+
+
 def test_empty_batch(ctx):
     z8, z4 = np.zeros(0, np.uint64), np.zeros(0, np.uint32)
     got, st = ctx.align_batch(np.zeros(0, np.uint8), z8, z4, z4, z4)

@@ -249,7 +249,7 @@ int ensure_pinned(tdb_ctx *ctx, void *&p, size_t &cap, size_t bytes) {
 
 uint32_t table_mask(size_t n) {
     size_t cap = 1024;
-    while (cap < 2 * n) cap <<= 1;
+    while (cap < n + n / 2) cap <<= 1; // load factor 0.33 .. 0.67
     return (uint32_t)(cap - 1);
 }
 
