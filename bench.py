@@ -346,9 +346,19 @@ def main():
                                         (batch.seq_len[batch.pair_text[:200000]].astype(np.int64) + 3) // 4)) + 16.0
         algo_bytes = mean_pair_bytes * float(cnt.tier_pairs[ti])
         step_s = dev_ms / args.steps * 1e-3
+        # DRAM traffic of that kernel per launch: bytes per aligned pair from the committed ncu --set full capture
+        # (profiles/r01/traffic.json, written by profiles/summarize_final.py) x the pairs this launch aligned
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+        if os.path.exists(tj):
+            tinfo = json.load(open(tj)).get(names[tiers[ti]])
+            if tinfo:
+                traffic = tinfo["dram_bytes_per_pair"] * float(cnt.tier_pairs[ti])
+                traffic_src = tinfo["source"] + ", per-pair bytes scaled to this launch"
         roofline = {
             "bound": "hbm", "kernel": names[tiers[ti]], "achieved": algo_bytes / k_s / 1e9,
-            "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / k_s / 1e9 / hbm_peak, "traffic": None,
+            "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / k_s / 1e9 / hbm_peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
             "note": "HBM is not the binding roofline for this integer DP (SURVEY.md 8d); see int_issue",
             "int_issue": {"bound": "int32_issue", "achieved": ops / k_s, "peak": int_peak, "unit": "lane-int-ops/s",
