@@ -184,13 +184,25 @@ class HostPacker {
     HostPacker() = default;
     HostPacker(const HostPacker &) = delete;
     ~HostPacker() { join(); }
-    // `pre` tasks (indices 0..n_pre-1 handed to pre_fn) run first on the same threads: the chunk planning
-    // scan shares the cores with the packer instead of competing with it.
+    // Work order on the shared threads: `n_pre` barrier tasks first (they zero the flag array the packer writes
+    // into), then, chunk by chunk, the scan parts of chunk k (pair list -> sequence range + run-length encoding)
+    // followed by that chunk's share of the pack blocks -- so the first chunk is ready after a K-th of the work
+    // and planning never holds up packing.
     void start(const uint8_t *blob, uint64_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
-               uint32_t *packed, uint8_t *flag, unsigned n_threads, size_t n_pre, std::function<void(size_t)> pre_fn) {
+               uint32_t *packed, uint8_t *flag, unsigned n_threads, size_t n_pre, std::function<void(size_t)> pre_fn,
+               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn) {
         n_blocks_ = packed ? (size_t)((blob_bytes + BLOCK - 1) / BLOCK) : 0;
         done_ = std::vector<std::atomic<uint8_t>>(n_blocks_);
         for (auto &d : done_) d.store(0, std::memory_order_relaxed);
+        scan_left_ = std::vector<std::atomic<int>>(n_scan_chunks);
+        for (auto &x : scan_left_) x.store(parts, std::memory_order_relaxed);
+        tasks_.clear();
+        const size_t groups = std::max<size_t>(1, n_scan_chunks);
+        for (size_t k = 0; k < groups; ++k) {
+            if (k < n_scan_chunks)
+                for (int pt = 0; pt < parts; ++pt) tasks_.push_back({1, (uint32_t)k, (uint32_t)pt});
+            for (size_t i = n_blocks_ * k / groups; i < n_blocks_ * (k + 1) / groups; ++i) tasks_.push_back({2, (uint32_t)i, 0});
+        }
         next_.store(0), next_pre_.store(0), pre_left_.store((long)n_pre);
         for (unsigned t = 0; t < n_threads; ++t)
             threads_.emplace_back([=]() {
@@ -200,13 +212,19 @@ class HostPacker {
                     pre_fn(i);
                     pre_left_.fetch_sub(1, std::memory_order_release);
                 }
-                wait_pre(); // the pre tasks zero the flag array the packer writes into
+                while (pre_left_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
                 for (;;) {
                     const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
-                    if (i >= n_blocks_) return;
-                    const uint64_t x0 = (uint64_t)i * BLOCK, x1 = std::min(blob_bytes, x0 + BLOCK);
-                    hostpack_stream(blob, x0, x1, packed, off, len, n_seqs, flag);
-                    done_[i].store(1, std::memory_order_release);
+                    if (i >= tasks_.size()) return;
+                    const Task tk = tasks_[i];
+                    if (tk.kind == 1) {
+                        scan_fn(tk.a, (int)tk.b);
+                        scan_left_[tk.a].fetch_sub(1, std::memory_order_release);
+                    } else {
+                        const uint64_t x0 = (uint64_t)tk.a * BLOCK, x1 = std::min(blob_bytes, x0 + BLOCK);
+                        hostpack_stream(blob, x0, x1, packed, off, len, n_seqs, flag);
+                        done_[tk.a].store(1, std::memory_order_release);
+                    }
                 }
             });
     }
@@ -216,18 +234,25 @@ class HostPacker {
         for (size_t i = (size_t)(b0 / BLOCK); i <= (size_t)((b1 - 1) / BLOCK) && i < n_blocks_; ++i)
             while (!done_[i].load(std::memory_order_acquire)) std::this_thread::yield();
     }
-    void wait_pre() const {
-        while (pre_left_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    void wait_scan(size_t k) const {
+        if (k >= scan_left_.size()) return;
+        while (scan_left_[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
     }
     void join() {
-        next_.store(n_blocks_); // unclaimed blocks are abandoned (error paths)
+        next_.store(tasks_.size()); // unclaimed tasks are abandoned (error paths)
         for (auto &t : threads_) t.join();
         threads_.clear();
     }
 
   private:
+    struct Task {
+        uint8_t kind; // 1 scan part (a = chunk, b = part), 2 pack block a
+        uint32_t a, b;
+    };
     size_t n_blocks_ = 0;
+    std::vector<Task> tasks_;
     std::vector<std::atomic<uint8_t>> done_;
+    std::vector<std::atomic<int>> scan_left_;
     std::atomic<size_t> next_{0}, next_pre_{0};
     std::atomic<long> pre_left_{0};
     std::vector<std::thread> threads_;
@@ -308,17 +333,6 @@ void finish_chunk_scan(const DevBatch &b, Chunk &c) {
     hi = (uint32_t)std::min<size_t>((size_t)hi + 1, b.n_seqs); // out-of-range indices fail on the device
     c.s_lo = std::min(lo, hi), c.s_hi = hi;
 }
-void plan_finish(const DevBatch &b, std::vector<Chunk> &out) {
-    if (out.size() <= 1) return;
-    for (Chunk &c : out) finish_chunk_scan(b, c);
-    size_t covered = 0;
-    for (const Chunk &c : out) covered += c.s_hi - c.s_lo;
-    if (covered > 2 * b.n_seqs + 64 * out.size()) {
-        out.clear();
-        out.push_back({0, b.n_pairs, 0, (uint32_t)b.n_seqs});
-    }
-}
-
 float elapsed(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
@@ -365,13 +379,15 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         if (r) return r;
         cn.host_packed = 1;
     }
-    if (b.h_pp && (host_pack || chunks.size() > 1)) {
+    const bool lazy_scan = b.h_pp && chunks.size() > 1;
+    std::vector<Chunk> scan_chunks = chunks; // what the worker threads fill in; `chunks` is the calling thread's copy
+    if (b.h_pp && (host_pack || lazy_scan)) {
         // one core stays free for the calling thread, which must react quickly to every finished chunk
         const unsigned hc = std::thread::hardware_concurrency();
         const unsigned hw = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::max(1u, std::min(32u, hc > 2 ? hc - 1 : 1u));
-        const size_t K0 = chunks.size(), n_scan = K0 > 1 ? K0 * SCAN_PARTS : 0, n_zero = host_pack ? 16 : 0;
+        const size_t n_zero = host_pack ? 16 : 0;
         PairRun *hruns = nullptr;
-        if (n_scan && !ctx->disable_rle) { // pair lists travel run-length encoded
+        if (lazy_scan && !ctx->disable_rle) { // pair lists travel run-length encoded
             const size_t total = chunks.back().run0 + (size_t)chunks.back().run_cap * SCAN_PARTS;
             int r = ensure_pinned(ctx, ctx->h_runs, ctx->h_runs_cap, total * sizeof(PairRun));
             if (r) return r;
@@ -380,23 +396,33 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         }
         uint8_t *hflag = (uint8_t *)ctx->h_flag;
         packer.start(b.h_blob, b.blob_bytes, b.h_seq_off, b.h_seq_len, n_seqs, host_pack ? (uint32_t *)ctx->h_packed : nullptr,
-                     hflag, hw, n_scan + n_zero, [&chunks, &b, n_scan, n_zero, hflag, hruns](size_t k) {
-                         if (k < n_scan) {
-                             scan_chunk_part(b, chunks[k / SCAN_PARTS], (int)(k % SCAN_PARTS), hruns);
-                         } else { // zero a slice of the flag array
-                             const size_t per = (b.n_seqs + n_zero - 1) / n_zero, z0 = std::min(b.n_seqs, (k - n_scan) * per);
-                             memset(hflag + z0, 0, std::min(b.n_seqs, z0 + per) - z0);
-                         }
-                     });
-        packer.wait_pre();
+                     hflag, hw, n_zero,
+                     [&b, n_zero, hflag](size_t k) { // zero a slice of the flag array
+                         const size_t per = (b.n_seqs + n_zero - 1) / n_zero, z0 = std::min(b.n_seqs, k * per);
+                         memset(hflag + z0, 0, std::min(b.n_seqs, z0 + per) - z0);
+                     },
+                     lazy_scan ? chunks.size() : 0, SCAN_PARTS,
+                     [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); });
     }
-    plan_finish(b, chunks);
+    if (lazy_scan) {
+        // The first chunk tells whether the pair list walks the sequence table in order; if it does not (a chunk
+        // would touch a large share of all sequences) the batch runs as one chunk.
+        packer.wait_scan(0);
+        chunks[0] = scan_chunks[0];
+        finish_chunk_scan(b, chunks[0]);
+        if ((size_t)(chunks[0].s_hi - chunks[0].s_lo) > 4 * (b.n_seqs / chunks.size()) + 64) {
+            chunks.clear();
+            chunks.push_back({0, b.n_pairs, 0, (uint32_t)b.n_seqs});
+        }
+    }
+    const bool scanned_lazily = lazy_scan && chunks.size() > 1;
     cn.ms_host_plan = ms_since(t_call);
     const size_t K = chunks.size();
     cn.chunks = K;
     const bool staged = K == 1; // per-stage CUDA-event timing only when the call is one chunk
     size_t max_cp = 0, max_cs = 0;
-    for (const Chunk &c : chunks) max_cp = std::max(max_cp, c.p1 - c.p0), max_cs = std::max<size_t>(max_cs, c.s_hi - c.s_lo);
+    for (const Chunk &c : chunks) max_cp = std::max(max_cp, c.p1 - c.p0);
+    max_cs = n_seqs; // chunk sequence ranges are only known as the scan proceeds: size for the worst case
 
     // ---- buffers ------------------------------------------------------------------------------------
     const size_t max_words = b.blob_bytes / 16 + 2;
@@ -406,8 +432,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     ENSURE(ctx->ctrl, sizeof(Ctrl));
     ENSURE(ctx->list_b, (size_t)n_pairs * 4);
     const bool want_work = ctx->count_work && !cigar_mode;
-    // closed form for single-substitution / single-short-gap pairs: production penalties, wf-adaptive unable to
-    // act before score 14 (or off), and no exact work counting requested
+    // closed form for single-substitution / single-gap (<= 20 bases) contents: production penalties, wf-adaptive
+    // or no heuristic, and no exact work counting requested (derivation at closed_form, tdb_kernels.cuh)
     const tdb_heuristic &hh = ctx->cfg.heuristic;
     ClosedFormCfg cf;
     cf.enabled = default_pen && !ctx->count_work && !ctx->disable_closed_form &&
@@ -456,21 +482,21 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     p.work = want_work ? (uint32_t *)ctx->work.p : nullptr;
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
 
-    std::vector<uint32_t> new_lo(K, 0), new_hi(K, 0); // sequences first needed by chunk k: [new_lo, new_hi)
-    {
-        uint32_t up = 0;
-        for (size_t k = 0; k < K; ++k) {
-            new_lo[k] = up;
-            up = std::max(up, chunks[k].s_hi);
-            new_hi[k] = up;
-        }
-    }
+    uint32_t seq_up = 0; // sequences [0, seq_up) are uploaded / packed
 
     // ---- chunks ---------------------------------------------------------------------------------------
     for (size_t k = 0; k < K; ++k) {
+        if (scanned_lazily && k > 0) {
+            const auto t_wait = std::chrono::steady_clock::now();
+            packer.wait_scan(k);
+            cn.ms_host_pack_wait += ms_since(t_wait);
+            chunks[k] = scan_chunks[k];
+            finish_chunk_scan(b, chunks[k]);
+        }
         const Chunk &c = chunks[k];
         const uint32_t cpairs = (uint32_t)(c.p1 - c.p0);
-        const uint32_t a = new_lo[k], e = new_hi[k];
+        const uint32_t a = seq_up, e = std::max(seq_up, c.s_hi); // sequences first needed by this chunk: [a, e)
+        seq_up = e;
         // blob bytes of the new sequences (device batches: offsets unknown on the host -> everything at once)
         uint64_t b0 = 0, b1 = b.blob_bytes;
         if (b.h_pp && e > a) {
