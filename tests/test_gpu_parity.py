@@ -135,6 +135,32 @@ def test_quad_tier_disabled_gives_same_scores(tdb, monkeypatch):
     c.close()
 
 
+def test_tier1_variants_give_same_scores(tdb, monkeypatch):
+    """Tier 1 has two implementations (one pair per warp -- the default -- and an opt-in two pairs per warp in
+    lockstep): both must agree with the oracle on wide-wavefront pairs."""
+    rng = random.Random(36)
+    seqs, pp, pt = [], [], []
+    for _ in range(200):
+        lf, rf, motif = rand_seq(rng, 50), rand_seq(rng, 50), rand_seq(rng, rng.randint(2, 6))
+        t = lf + motif * rng.randint(10, 60) + rf
+        for _ in range(4):
+            u = rng.randint(16, 45) // len(motif) + 1
+            src = lf + motif * max(1, t.count(motif) + rng.choice([-u, u])) + rf
+            pp.append(len(seqs) + 1); pt.append(len(seqs))
+            seqs.append(t.encode()); seqs.append(mutate(rng, src, 0.004).encode())
+    pp, pt = np.array(pp, np.uint32), np.array(pt, np.uint32)
+    c = tdb.Context()
+    cnt = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    assert cnt.tier_pairs[1] > 100
+    c.close()
+    monkeypatch.setenv("TDB_ENABLE_DUO", "1")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_ENABLE_DUO")
+    cnt2 = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    assert cnt2.tier_pairs[1] > 100
+    c.close()
+
+
 def test_dedup_disabled_gives_same_scores(tdb, monkeypatch):
     """Duplicate elimination must be invisible: every pair aligned on its own gives the same scores."""
     rng = random.Random(32)

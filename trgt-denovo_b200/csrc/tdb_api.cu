@@ -80,8 +80,8 @@ struct tdb_ctx {
     } slot[2];
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
-    int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0;
-    bool disable_quad = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
+    int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0;
+    bool disable_quad = false, disable_duo = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
     size_t chunk_pairs = 2u << 20;
     size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
     int host_threads = 0;                 // 0: all hardware threads but one
@@ -642,23 +642,30 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
             p.src1_seg = ck->seg + 2, p.src2 = nullptr, p.src2_count = nullptr;
             p.work_counter = &ck->wc_quad, p.next_todo = (uint32_t *)sl.list_a.p, p.next_count = &ck->acount;
             p.counters = ctrl->exec[0];
-            const size_t smem = sizeof(QPair) * (32 / QG) * Q_WARPS;
+            const size_t smem = lock_smem_bytes<QuadCfg>();
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->quad_ctas_per_sm,
                                                              ((size_t)cpairs + 31) / 32 + 1);
-            k_align_quad<8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, st>>>(p);
+            k_align_lock<QuadCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, st>>>(p);
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
         if (staged) CK(cudaEventRecord(ctx->ev[4], st));
-        // tier 1: one pair per warp, shared memory; the quad tier's leftovers (the heaviest pairs) go first
+        // tier 1: wavefronts up to 64 diagonals, shared memory, one pair per warp; the quad tier's leftovers (the
+        // heaviest pairs) go first.  (TDB_ENABLE_DUO: two pairs per warp in lockstep, production penalties only.)
         {
             p.src1_seg = ck->seg + 0, p.src2 = (const uint32_t *)sl.list_a.p, p.src2_count = &ck->acount;
             p.work_counter = &ck->wc_warp, p.next_todo = (uint32_t *)ctx->list_b.p, p.next_count = &ctrl->gcount;
             p.counters = ctrl->exec[1];
-            const size_t smem = sizeof(T0Smem) * T0_WARPS;
-            const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->t0_ctas_per_sm,
-                                                             ((size_t)cpairs + T0_WARPS - 1) / T0_WARPS);
-            k_align_warp<<<grid, T0_WARPS * 32, smem, st>>>(p);
+            if (default_pen && !ctx->disable_duo) {
+                const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->duo_ctas_per_sm,
+                                                                 ((size_t)cpairs + 3) / 4 + 1);
+                k_align_lock<DuoCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, lock_smem_bytes<DuoCfg>(), st>>>(p);
+            } else {
+                const size_t smem = sizeof(T0Smem) * T0_WARPS;
+                const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->t0_ctas_per_sm,
+                                                                 ((size_t)cpairs + T0_WARPS - 1) / T0_WARPS);
+                k_align_warp<<<grid, T0_WARPS * 32, smem, st>>>(p);
+            }
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
@@ -905,19 +912,26 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
     }
     c->t0_ctas_per_sm = occ;
     {
-        const size_t qsmem = sizeof(QPair) * (32 / QG) * Q_WARPS;
-        auto kq = k_align_quad<8, 4, 2, 24, 1>;
-        e = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kq, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        int qocc = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qocc, kq, Q_WARPS * 32, qsmem);
-        if (e != cudaSuccess || qocc < 1) {
-            int code = fail(nullptr, TDB_E_CUDA, "quad kernel setup failed: %s (occupancy %d)", cudaGetErrorString(e), qocc);
+        auto setup = [&](auto kern, size_t smem, int &occ_out) {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            int occ2 = 0;
+            if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern, Q_WARPS * 32, smem);
+            occ_out = occ2;
+            return e2;
+        };
+        e = setup(k_align_lock<QuadCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<QuadCfg>(), c->quad_ctas_per_sm);
+        if (e == cudaSuccess) e = setup(k_align_lock<DuoCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<DuoCfg>(), c->duo_ctas_per_sm);
+        if (e != cudaSuccess || c->quad_ctas_per_sm < 1 || c->duo_ctas_per_sm < 1) {
+            int code = fail(nullptr, TDB_E_CUDA, "lockstep kernel setup failed: %s (occupancy %d / %d)", cudaGetErrorString(e),
+                            c->quad_ctas_per_sm, c->duo_ctas_per_sm);
             tdb_destroy(c);
             return code;
         }
-        c->quad_ctas_per_sm = qocc;
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
+        // the two-pairs-per-warp lockstep variant of tier 1 measures the same as one pair per warp (wide wavefronts
+        // already fill the lanes) and overflows a little more often (FIFO arena): opt-in, kept for experiments
+        c->disable_duo = getenv("TDB_ENABLE_DUO") == nullptr;
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
         c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
         c->disable_rle = getenv("TDB_DISABLE_RLE") != nullptr;

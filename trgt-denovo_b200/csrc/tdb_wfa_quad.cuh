@@ -34,26 +34,32 @@ namespace tdb {
 #ifndef TDB_Q_MINB
 #define TDB_Q_MINB 1
 #endif
-constexpr int QG = 8;                // lanes per pair
-constexpr int QW = 32;               // widest wavefront handled here
-constexpr int Q_MAR = TDB_Q_MAR;     // M arena entries (power of two)
-constexpr int Q_SCAP = TDB_Q_SCAP;   // scores 0..Q_SCAP-1
-constexpr int Q_PROV = TDB_Q_PROV;   // provenance bytes
+// Geometry of a lockstep configuration: G lanes per pair (32/G pairs per warp), wavefronts up to W
+// diagonals, M arena of MAR entries (power of two), scores < SCAP, PROV provenance bytes.
+template <int G_, int W_, int MAR_, int SCAP_, int PROV_>
+struct LockCfg {
+    static constexpr int G = G_, W = W_, MAR = MAR_, SCAP = SCAP_, PROV = PROV_;
+};
+using QuadCfg = LockCfg<8, 32, TDB_Q_MAR, TDB_Q_SCAP, TDB_Q_PROV>; // tier 0: four pairs per warp
+using DuoCfg = LockCfg<16, 64, 1024, 128, 2048>;                    // tier 1: two pairs per warp
 constexpr int Q_MAXLEN = 8000;
 constexpr int Q_WARPS = TDB_Q_WARPS;
 constexpr int Q_NULL = -16384;
 
-struct __align__(16) QPair {
-    int16_t marena[Q_MAR];        // FIFO arena of M wavefronts; reused as the op stream at backtrace
-    int16_t gap[12][QW];          // I1[4], D1[4], I2[2], D2[2] rings indexed by score
+template <class C>
+struct __align__(16) QPairT {
+    int16_t marena[C::MAR];       // FIFO arena of M wavefronts; reused as the op stream at backtrace
+    int16_t gap[12][C::W];        // I1[4], D1[4], I2[2], D2[2] rings indexed by score
     uint16_t m_off[32];           // arena index of diagonal m_lo (free-running, masked on access)
     int16_t m_lo[32], m_hi[32];   // valid range of M[s], slot s & 31
     int16_t g_lo[12], g_hi[12];
-    int16_t step_lo[Q_SCAP];      // computed lo of score s (provenance row origin)
-    uint16_t step_base[Q_SCAP];
-    uint8_t prov[Q_PROV];
+    int16_t step_lo[C::SCAP];     // computed lo of score s (provenance row origin)
+    uint16_t step_base[C::SCAP];
+    uint8_t prov[C::PROV];
 };
-static_assert(sizeof(QPair) % 16 == 0, "QPair must keep 16-byte alignment");
+static_assert(sizeof(QPairT<QuadCfg>) % 16 == 0 && sizeof(QPairT<DuoCfg>) % 16 == 0, "pair state keeps 16-byte alignment");
+template <class C>
+constexpr size_t lock_smem_bytes() { return sizeof(QPairT<C>) * (32 / C::G) * Q_WARPS; }
 
 struct QIn { // one input wavefront, group-uniform
     const int16_t *p; // element for diagonal k at p[(base + k) & amask]
@@ -67,12 +73,14 @@ struct QIn { // one input wavefront, group-uniform
 // the maximum over the groups) with per-group predicates -- so that every issued instruction serves four
 // pairs.  (Group-masked collectives made the groups diverge for good and issue one after the other:
 // ncu r01c showed 8 active threads on every vote.)
+template <int QG>
 __device__ __forceinline__ unsigned qballot(int gshift, bool pred) {
-    return (__ballot_sync(TDB_FULL, pred) >> gshift) & 0xffu;
+    return (__ballot_sync(TDB_FULL, pred) >> gshift) & ((QG == 32) ? 0xffffffffu : ((1u << QG) - 1u));
 }
 
-// Eight lanes extend one diagonal per group: lane l compares bases [16l, 16l+16) per round.  `on` is
+// The lanes of a group extend one diagonal: lane l compares bases [16l, 16l+16) per round.  `on` is
 // group-uniform; groups that are off (or done) idle through the remaining rounds.
+template <int QG>
 __device__ __forceinline__ int extend_groups(const uint32_t *pw, const uint32_t *tw, int psh, int tsh, int n, int m,
                                              int v, int h, bool on, int gl, int gshift, int lane) {
     const int room = on ? min(n - v, m - h) : 0;
@@ -82,7 +90,7 @@ __device__ __forceinline__ int extend_groups(const uint32_t *pw, const uint32_t 
         const int off = base + gl * 16;
         uint32_t x = 1u; // lanes past the end report a mismatch at their first base: caps the run at `room`
         if (busy && off < room) x = get16(pw, psh + v + off) ^ get16(tw, tsh + h + off);
-        const unsigned bal = qballot(gshift, x != 0);
+        const unsigned bal = qballot<QG>(gshift, x != 0);
         const int l = bal ? __ffs(bal) - 1 : 0;
         const uint32_t xl = __shfl_sync(TDB_FULL, x, (lane & ~(QG - 1)) + l);
         if (busy && bal) {
@@ -93,9 +101,11 @@ __device__ __forceinline__ int extend_groups(const uint32_t *pw, const uint32_t 
     return res;
 }
 
-template <int X, int O1, int E1, int O2, int E2>
-__global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const AlignParams p) {
+template <class C, int X, int O1, int E1, int O2, int E2>
+__global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const AlignParams p) {
     static_assert(X < 32 && O1 + E1 < 32 && O2 + E2 < 32 && E1 < 4 && E2 < 2, "ring sizes");
+    constexpr int QG = C::G, QW = C::W, Q_MAR = C::MAR, Q_SCAP = C::SCAP, Q_PROV = C::PROV;
+    using QPair = QPairT<C>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gl = lane & (QG - 1), gid = lane / QG, gshift = gid * QG;
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
     const Penalties pn = {X, O1, E1, O2, E2};
     const ItemSrc src = item_src(p);
     const unsigned n_items = src.total;
-    constexpr int PER_FETCH = 32; // pairs per work-counter atomic (8 batches of 4)
+    constexpr int PER_FETCH = QG == 8 ? 32 : 8; // pairs per work-counter atomic (8 batches of four / 4 of two)
     unsigned long long acc_cells = 0, acc_cols = 0, acc_ext = 0, acc_done = 0; // acc_* valid on group lane 0
 
     for (;;) {
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
             const bool usable = have && !overflow;
             int penalty = 0, clipped = 0;
             unsigned long long cells = 0, cols = 0, ext = 0;
-            const int m0 = extend_groups(pw, tw, psh, tsh, n, m, 0, 0, usable, gl, gshift, lane);
+            const int m0 = extend_groups<QG>(pw, tw, psh, tsh, n, m, 0, 0, usable, gl, gshift, lane);
             if (usable && gl == 0) ext += (unsigned)(m0 >> 4) + 1;
             const bool identical = usable && k_end == 0 && m0 >= m;
             if (identical) cols = (unsigned)m; // penalty 0, clipped score 0
@@ -285,11 +295,11 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
                         if (has_d2) D2o[k & (QW - 1)] = (int16_t)del2;
                     }
                     // trim_ends (A.2): first / last diagonal whose offset lies inside the DP matrix
-                    unsigned bal = qballot(gshift, vm);
+                    unsigned bal = qballot<QG>(gshift, vm);
                     if (bal) tl_m = min(tl_m, kb + __ffs(bal) - 1), th_m = kb + 31 - __clz(bal);
 #define TDB_TRIM(has, val, tl, th)                                                                                     \
     {                                                                                                                  \
-        bal = qballot(gshift, (has) && act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n);   \
+        bal = qballot<QG>(gshift, (has) && act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n);   \
         if (bal) tl = min(tl, kb + __ffs(bal) - 1), th = kb + 31 - __clz(bal);                                         \
     }
                     TDB_TRIM(has_i1, ins1, tl_i1, th_i1)
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
                 if (live && gl == 0) sm.step_lo[s] = (int16_t)lo, sm.step_base[s] = (uint16_t)prov_used;
                 prov_used += (unsigned)width;
                 __syncwarp();
-                const bool done_now = qballot(gshift, fin) != 0; // group-uniform
+                const bool done_now = qballot<QG>(gshift, fin) != 0; // group-uniform
                 if (live && done_now) penalty = s, running = false;
                 const bool cont = live && !done_now;
                 // ---- wf-adaptive cut-off + equate (A.3) ----
@@ -311,9 +321,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
                 const bool cut = heur_on && steps_wait <= 0 && (mhi - mlo + 1) >= p.heur.min_len;
                 if (__any_sync(TDB_FULL, cut)) {
                     int md = lane_min_d;
-                    md = min(md, __shfl_xor_sync(TDB_FULL, md, 1));
-                    md = min(md, __shfl_xor_sync(TDB_FULL, md, 2));
-                    md = min(md, __shfl_xor_sync(TDB_FULL, md, 4));
+#pragma unroll
+                    for (int o = 1; o < QG; o <<= 1) md = min(md, __shfl_xor_sync(TDB_FULL, md, o));
                     const int min_d = min(max(n, m), md), thr = p.heur.max_dist;
                     const int abase = (int)mhead - lo;
 #define TDB_DIST_OK(kk, okv)                                                                  \
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
                             const int k = kb + gl;
                             bool ok = false;
                             if (scan && k < top_limit) TDB_DIST_OK(k, ok)
-                            const unsigned bal = qballot(gshift, ok);
+                            const unsigned bal = qballot<QG>(gshift, ok);
                             if (scan && bal) first_ok = kb + __ffs(bal) - 1;
                             scan = scan && first_ok == INT32_MAX && kb + QG < top_limit;
                         }
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
                             const int k = kt - gl;
                             bool ok = false;
                             if (scan && k > bot_limit) TDB_DIST_OK(k, ok)
-                            const unsigned bal = qballot(gshift, ok);
+                            const unsigned bal = qballot<QG>(gshift, ok);
                             if (scan && bal) last_ok = kt - (__ffs(bal) - 1);
                             scan = scan && last_ok == INT32_MIN && kt - QG > bot_limit;
                         }
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
                 int v = 0, h = 0, i = nops - 1;
                 bool in_m = true, replay = aligned;
                 while (__any_sync(TDB_FULL, replay)) {
-                    const int eq = extend_groups(pw, tw, psh, tsh, n, m, v, h, replay && in_m, gl, gshift, lane);
+                    const int eq = extend_groups<QG>(pw, tw, psh, tsh, n, m, v, h, replay && in_m, gl, gshift, lane);
                     if (replay) {
                         if (in_m) {
                             acc.emit('M', eq, pn);
@@ -455,9 +464,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_quad(const A
             unsigned ext_pair = 0;
             if (p.work) { // per-pair algorithmic work: ext is a per-lane partial count (warp-uniform branch)
                 ext_pair = (unsigned)ext;
-                ext_pair += __shfl_xor_sync(TDB_FULL, ext_pair, 1);
-                ext_pair += __shfl_xor_sync(TDB_FULL, ext_pair, 2);
-                ext_pair += __shfl_xor_sync(TDB_FULL, ext_pair, 4);
+#pragma unroll
+                for (int o = 1; o < QG; o <<= 1) ext_pair += __shfl_xor_sync(TDB_FULL, ext_pair, o);
             }
             if (have) {
                 if (gl == 0) {
