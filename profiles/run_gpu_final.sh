@@ -19,6 +19,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-fil
 echo launches rc=$?
 CMD="python bench.py --loci 30000 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain30k_$tag.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_align_quad -s 3 -c 1 -f -o gpurun_out/prof_quad_$tag $CMD > gpurun_out/ncu_quad_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_align_lock -s 3 -c 1 -f -o gpurun_out/prof_quad_$tag $CMD > gpurun_out/ncu_quad_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_align_warp -s 3 -c 1 -f -o gpurun_out/prof_warp_$tag $CMD > gpurun_out/ncu_warp_$tag.log 2>&1
 echo full rc=$?

@@ -36,7 +36,7 @@ for kern, ti in (("quad", 0), ("warp", 1)):
         return x * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(un, 1)
     b = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
     pairs = plain["tier_pairs"][ti]
-    traffic["k_align_" + kern] = {"dram_bytes_per_launch": b, "pairs_in_launch": pairs, "dram_bytes_per_pair": b / max(1, pairs),
+    traffic[{"quad": "k_align_lock<QuadCfg>", "warp": "k_align_warp"}[kern]] = {"dram_bytes_per_launch": b, "pairs_in_launch": pairs, "dram_bytes_per_pair": b / max(1, pairs),
                                   "source": f"ncu --set full, prof_{kern}_{tag}.ncu-rep (30 000-locus step)"}
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
