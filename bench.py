@@ -221,8 +221,14 @@ def main():
             raise RuntimeError(L.tdb_last_error(h).decode())
         return ctx.counters()
 
-    h_out = (B.AlleleOut * (2 * n_loci))()
-    h_mask = np.zeros(n_pairs, dtype=np.uint8)
+    # results land in pinned host memory too (tdb_host_alloc), like the inputs
+    out_bytes = C.sizeof(B.AlleleOut) * 2 * n_loci
+    h_out_ptr = L.tdb_host_alloc(out_bytes)
+    h_mask_ptr = L.tdb_host_alloc(max(1, n_pairs))
+    if not h_out_ptr or not h_mask_ptr:
+        raise SystemExit("pinned host allocation failed")
+    h_out = (B.AlleleOut * (2 * n_loci)).from_address(h_out_ptr)
+    h_mask = np.frombuffer((C.c_uint8 * max(1, n_pairs)).from_address(h_mask_ptr), dtype=np.uint8)
 
     def step_host():
         r = L.tdb_trio_batch if not args.duo else L.tdb_duo_batch
@@ -281,8 +287,9 @@ def main():
     e2e_s = time.time() - e0
     ce = ctx.counters()
     e2e_chunks = ce.chunks
-    e2e_host = {"host_packed": int(ce.host_packed), "align_bytes_h2d": int(ce.bytes_h2d), "ms_plan": ce.ms_host_plan, "ms_pack_wait": ce.ms_host_pack_wait,
-                "ms_align_call": ce.ms_host_call, "ms_device_span": ce.ms_total_device}
+    e2e_host = {"host_packed": int(ce.host_packed), "align_bytes_h2d": int(ce.bytes_h2d), "ascii_bytes_taken_over": int(ce.bytes_raw), "ms_plan": ce.ms_host_plan, "ms_pack_wait": ce.ms_host_pack_wait,
+                "ms_align_call": ce.ms_host_call, "ms_device_span": ce.ms_total_device,
+                "ms_last_block_packed": ce.ms_host_packed, "ms_last_chunk_queued": ce.ms_host_enqueued}
     # bytes that actually cross PCIe per step: what the library copied for the alignment stage (2-bit packed
     # sequences, tables, run-length encoded pair lists) plus the locus descriptors
     host_input_bytes = batch.blob.size + batch.seq_off.nbytes + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \

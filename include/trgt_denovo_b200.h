@@ -239,9 +239,13 @@ typedef struct {
     uint64_t chunks;        /* pipeline chunks the call was cut into */
     uint64_t host_packed;   /* 1: the caller's CPU threads 2-bit packed the sequences before the upload */
     uint64_t bytes_h2d;     /* bytes the alignment stage actually copied host -> device (host-buffer calls) */
+    uint64_t bytes_raw;     /* ... of which ASCII blocks the calling thread took over from the host packer while the
+                               copy engine was idle (packed on the GPU instead) */
     float ms_pack, ms_dedup, ms_align, ms_scatter, ms_reduce, ms_total_device; /* CUDA-event times */
     float ms_host_plan, ms_host_pack_wait, ms_host_call; /* host wall clock: chunk planning, time the calling
                          thread waited for the packer threads, whole run of pack+align (host-buffer calls) */
+    float ms_host_packed, ms_host_enqueued; /* since the start of the call: last block packed by the worker threads,
+                         last chunk queued by the calling thread */
     float ms_tier[4]; /* per alignment tier (events on the launching stream); [2] covers both global tiers.
                          Stage times are recorded for single-chunk calls only (ms_total_device always). */
 } tdb_counters;

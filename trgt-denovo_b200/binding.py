@@ -50,10 +50,11 @@ class Counters(C.Structure):
                 ("ext16", C.c_uint64), ("columns", C.c_uint64), ("exec_cells", C.c_uint64),
                 ("exec_ext16", C.c_uint64), ("exec_columns", C.c_uint64), ("tier_cells", C.c_uint64 * 4),
                 ("tier_ext16", C.c_uint64 * 4), ("tier_columns", C.c_uint64 * 4), ("pairs_identical", C.c_uint64),
-                ("pairs_duplicate", C.c_uint64), ("pairs_closed_form", C.c_uint64), ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64), ("host_packed", C.c_uint64), ("bytes_h2d", C.c_uint64),
+                ("pairs_duplicate", C.c_uint64), ("pairs_closed_form", C.c_uint64), ("kernel_launches", C.c_uint64), ("chunks", C.c_uint64), ("host_packed", C.c_uint64), ("bytes_h2d", C.c_uint64), ("bytes_raw", C.c_uint64),
                 ("ms_pack", C.c_float), ("ms_dedup", C.c_float), ("ms_align", C.c_float),
                 ("ms_scatter", C.c_float), ("ms_reduce", C.c_float), ("ms_total_device", C.c_float),
                 ("ms_host_plan", C.c_float), ("ms_host_pack_wait", C.c_float), ("ms_host_call", C.c_float),
+                ("ms_host_packed", C.c_float), ("ms_host_enqueued", C.c_float),
                 ("ms_tier", C.c_float * 4)]
 
 

@@ -88,6 +88,10 @@ struct tdb_ctx {
     void *h_packed = nullptr, *h_flag = nullptr, *h_runs = nullptr; // pinned staging of the host packer / planner
     size_t h_packed_cap = 0, h_flag_cap = 0, h_runs_cap = 0;
     DevBuf runs;
+    // host-pack mode, opt-in (TDB_RAW_EVERY=n): every n-th 256 KB block ships as ASCII and is packed on the GPU.
+    // Measured slower on the B200 host at every share tried (profiles/r01/NOTES.md): off by default.
+    bool allow_steal = false;
+    int steal_div = 0;
     bool count_work = false;
     tdb_counters counters;
     // single-pair shim state
@@ -190,10 +194,13 @@ class HostPacker {
     // and planning never holds up packing.
     void start(const uint8_t *blob, uint64_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
                uint32_t *packed, uint8_t *flag, unsigned n_threads, size_t n_pre, std::function<void(size_t)> pre_fn,
-               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn) {
+               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn, int raw_every) {
         n_blocks_ = packed ? (size_t)((blob_bytes + BLOCK - 1) / BLOCK) : 0;
         done_ = std::vector<std::atomic<uint8_t>>(n_blocks_);
-        for (auto &d : done_) d.store(0, std::memory_order_relaxed);
+        // every raw_every-th block is left to the GPU: it crosses PCIe as ASCII (1 byte of host memory traffic per
+        // base instead of 1.5 for read + write + DMA of the packed form) and k_pack packs it there
+        for (size_t i = 0; i < n_blocks_; ++i)
+            done_[i].store(raw_every > 1 && i % (size_t)raw_every == (size_t)raw_every - 1 ? RAW : PENDING, std::memory_order_relaxed);
         scan_left_ = std::vector<std::atomic<int>>(n_scan_chunks);
         for (auto &x : scan_left_) x.store(parts, std::memory_order_relaxed);
         tasks_.clear();
@@ -201,7 +208,8 @@ class HostPacker {
         for (size_t k = 0; k < groups; ++k) {
             if (k < n_scan_chunks)
                 for (int pt = 0; pt < parts; ++pt) tasks_.push_back({1, (uint32_t)k, (uint32_t)pt});
-            for (size_t i = n_blocks_ * k / groups; i < n_blocks_ * (k + 1) / groups; ++i) tasks_.push_back({2, (uint32_t)i, 0});
+            for (size_t i = n_blocks_ * k / groups; i < n_blocks_ * (k + 1) / groups; ++i)
+                if (done_[i].load(std::memory_order_relaxed) == PENDING) tasks_.push_back({2, (uint32_t)i, 0});
         }
         next_.store(0), next_pre_.store(0), pre_left_.store((long)n_pre);
         for (unsigned t = 0; t < n_threads; ++t)
@@ -221,18 +229,25 @@ class HostPacker {
                         scan_fn(tk.a, (int)tk.b);
                         scan_left_[tk.a].fetch_sub(1, std::memory_order_release);
                     } else {
+                        uint8_t expect = PENDING;
+                        if (!done_[tk.a].compare_exchange_strong(expect, BUSY, std::memory_order_acq_rel)) continue; // stolen
                         const uint64_t x0 = (uint64_t)tk.a * BLOCK, x1 = std::min(blob_bytes, x0 + BLOCK);
                         hostpack_stream(blob, x0, x1, packed, off, len, n_seqs, flag);
-                        done_[tk.a].store(1, std::memory_order_release);
+                        done_[tk.a].store(PACKED, std::memory_order_release);
+                        last_pack_ns_.store(std::chrono::steady_clock::now().time_since_epoch().count(), std::memory_order_relaxed);
                     }
                 }
             });
     }
-    // blocks until blob bytes [b0, b1) are packed
-    void wait_bytes(uint64_t b0, uint64_t b1) const {
-        if (b1 <= b0) return;
-        for (size_t i = (size_t)(b0 / BLOCK); i <= (size_t)((b1 - 1) / BLOCK) && i < n_blocks_; ++i)
-            while (!done_[i].load(std::memory_order_acquire)) std::this_thread::yield();
+    enum : uint8_t { PENDING = 0, PACKED = 1, RAW = 2, BUSY = 3 };
+    uint8_t peek(size_t i) const { return done_[i].load(std::memory_order_acquire); }
+    // State of block i for the calling thread: RAW (left to the GPU) or PACKED (waits for the worker that is on it).
+    uint8_t acquire(size_t i) const {
+        for (;;) {
+            const uint8_t st = done_[i].load(std::memory_order_acquire);
+            if (st == PACKED || st == RAW) return st;
+            std::this_thread::yield();
+        }
     }
     void wait_scan(size_t k) const {
         if (k >= scan_left_.size()) return;
@@ -255,7 +270,11 @@ class HostPacker {
     std::vector<std::atomic<int>> scan_left_;
     std::atomic<size_t> next_{0}, next_pre_{0};
     std::atomic<long> pre_left_{0};
+    std::atomic<long long> last_pack_ns_{0};
     std::vector<std::thread> threads_;
+
+  public:
+    long long last_pack_ns() const { return last_pack_ns_.load(); }
 };
 
 int ensure_pinned(tdb_ctx *ctx, void *&p, size_t &cap, size_t bytes) {
@@ -402,7 +421,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                          memset(hflag + z0, 0, std::min(b.n_seqs, z0 + per) - z0);
                      },
                      lazy_scan ? chunks.size() : 0, SCAN_PARTS,
-                     [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); });
+                     [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); },
+                     ctx->allow_steal && chunks.size() > 1 ? ctx->steal_div : 0);
     }
     if (lazy_scan) {
         // The first chunk tells whether the pair list walks the sequence table in order; if it does not (a chunk
@@ -483,6 +503,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
 
     uint32_t seq_up = 0; // sequences [0, seq_up) are uploaded / packed
+    std::vector<std::pair<uint64_t, uint64_t>> raw_ranges; // this chunk's byte ranges shipped as ASCII in host-pack mode
 
     // ---- chunks ---------------------------------------------------------------------------------------
     for (size_t k = 0; k < K; ++k) {
@@ -515,28 +536,48 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                     if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
                     cn.bytes_h2d += b1 - b0;
                 } else {
-                    const auto t_wait = std::chrono::steady_clock::now();
-                    packer.wait_bytes(b0, b1);
-                    cn.ms_host_pack_wait += ms_since(t_wait);
                     const uint8_t *hf = (const uint8_t *)ctx->h_flag;
+                    // Walk this chunk's blocks: packed ones ship as 2-bit words, the share left to the GPU ships as
+                    // ASCII for k_pack.  Runs of equal state become one copy.
+                    raw_ranges.clear();
+                    const auto t_wait = std::chrono::steady_clock::now();
+                    if (b1 > b0) {
+                        const uint64_t BLK = HostPacker::BLOCK;
+                        size_t i = (size_t)(b0 / BLK);
+                        const size_t i_end = (size_t)((b1 - 1) / BLK);
+                        while (i <= i_end) {
+                            const uint8_t st0 = packer.acquire(i);
+                            size_t j = i + 1; // extend the run of equal state
+                            while (j <= i_end && packer.peek(j) == st0) ++j;
+                            const uint64_t x0 = std::max<uint64_t>(b0, (uint64_t)i * BLK), x1 = std::min<uint64_t>(b1, (uint64_t)j * BLK);
+                            if (st0 == HostPacker::PACKED) {
+                                const size_t w0 = (size_t)(x0 >> 4), w1 = (size_t)((x1 + 15) >> 4);
+                                CK(cudaMemcpyAsync((uint32_t *)ctx->packed.p + w0, (const uint32_t *)ctx->h_packed + w0, (w1 - w0) * 4,
+                                                   cudaMemcpyHostToDevice, cs));
+                                cn.bytes_h2d += (uint64_t)(w1 - w0) * 4;
+                            } else {
+                                CK(cudaMemcpyAsync((uint8_t *)b.blob + x0, b.h_blob + x0, x1 - x0, cudaMemcpyHostToDevice, cs));
+                                cn.bytes_h2d += x1 - x0;
+                                cn.bytes_raw += x1 - x0;
+                                raw_ranges.push_back({x0, x1});
+                            }
+                            i = j;
+                        }
+                    }
+                    cn.ms_host_pack_wait += ms_since(t_wait);
                     CK(cudaMemcpyAsync((uint8_t *)ctx->seq_flag.p + a, hf + a, (size_t)(e - a), cudaMemcpyHostToDevice, cs));
                     cn.bytes_h2d += (uint64_t)(e - a);
-                    const size_t w0 = (size_t)(b0 >> 4), w1 = (size_t)((b1 + 15) >> 4);
-                    if (w1 > w0)
-                        CK(cudaMemcpyAsync((uint32_t *)ctx->packed.p + w0, (const uint32_t *)ctx->h_packed + w0, (w1 - w0) * 4,
-                                           cudaMemcpyHostToDevice, cs));
-                    cn.bytes_h2d += (uint64_t)(w1 - w0) * 4;
                     // sequences with bytes outside ACGT are compared as raw bytes on the device: ship those bytes
                     size_t n_flag = 0;
-                    for (uint32_t i = a; i < e; ++i) n_flag += hf[i] != 0;
+                    if (memchr(hf + a, 1, (size_t)(e - a))) // almost always absent: one vectorised pass
+                        for (uint32_t i = a; i < e; ++i) n_flag += hf[i] != 0;
                     if (n_flag > 256) {
                         if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
                         cn.bytes_h2d += b1 - b0;
                     } else if (n_flag) {
                         for (uint32_t i = a; i < e; ++i) {
                             const uint64_t o = b.h_seq_off[i];
-                            if (hf[i] && b.h_seq_len[i] && o <= b.blob_bytes && b.h_seq_len[i] <= b.blob_bytes - o)
-{
+                            if (hf[i] && b.h_seq_len[i] && o <= b.blob_bytes && b.h_seq_len[i] <= b.blob_bytes - o) {
                                 CK(cudaMemcpyAsync((uint8_t *)b.blob + o, b.h_blob + o, b.h_seq_len[i], cudaMemcpyHostToDevice, cs));
                                 cn.bytes_h2d += b.h_seq_len[i];
                             }
@@ -568,6 +609,14 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         // host batches, so that sequences are ready in order whichever slot needs them
         cudaStream_t ps = b.h_pp ? cs : s;
         if (e > a) {
+            for (const auto &rr : raw_ranges) { // blocks taken over from the host packer: 2-bit pack them here
+                const uint64_t x0 = rr.first & ~(uint64_t)15, x1 = rr.second;
+                const unsigned blocks = (unsigned)std::min<uint64_t>(((x1 - x0 + 15) / 16 + 511) / 512, (uint64_t)ctx->sm_count * 32);
+                k_pack<<<blocks, 256, 0, ps>>>(b.blob, x0, x1, b.seq_off, b.seq_len, a, e, (uint32_t *)ctx->packed.p,
+                                               (uint8_t *)ctx->seq_flag.p);
+                CK(cudaGetLastError());
+                cn.kernel_launches += 1;
+            }
             if (!host_pack) {
                 CK(cudaMemsetAsync((uint8_t *)ctx->seq_flag.p + a, 0, (size_t)(e - a), ps));
                 if (b1 > b0) {
@@ -671,6 +720,10 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         }
         if (staged) CK(cudaEventRecord(ctx->ev[5], st));
     }
+    cn.ms_host_enqueued = ms_since(t_call);
+    if (packer.last_pack_ns())
+        cn.ms_host_packed = std::chrono::duration<float, std::milli>(
+                                std::chrono::steady_clock::duration(packer.last_pack_ns()) - t_call.time_since_epoch()).count();
     for (int i = 1; i < n_slot; ++i) { // join the other slot's stream
         CK(cudaEventRecord(ctx->slot[i].done, ctx->slot[i].st));
         CK(cudaStreamWaitEvent(s, ctx->slot[i].done, 0));
@@ -935,6 +988,10 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
         c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
         c->disable_rle = getenv("TDB_DISABLE_RLE") != nullptr;
+        if (const char *sd = getenv("TDB_RAW_EVERY")) {
+            c->steal_div = atoi(sd);
+            c->allow_steal = c->steal_div > 1;
+        }
         if (const char *ht = getenv("TDB_HOST_THREADS")) c->host_threads = std::max(0, std::min(256, atoi(ht)));
         if (const char *hp = getenv("TDB_HOSTPACK_MIN_BYTES")) {
             const long long v = atoll(hp); // < 0 disables the host packer
