@@ -20,10 +20,6 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w) { // 4 ASCII bytes -> 8 bi
     const uint32_t c = (w >> 1) & 0x03030303u;
     return (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu;
 }
-__device__ __forceinline__ uint32_t acgt_mask4(uint32_t w) { // 0xff per byte that is one of ACGT
-    return __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) |
-           __vcmpeq4(w, 0x54545454u);
-}
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 33)) * 0xff51afd7ed558ccdull;
     z = (z ^ (z >> 33)) * 0xc4ceb9fe1a85ec53ull;
