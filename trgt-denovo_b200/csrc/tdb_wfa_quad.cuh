@@ -46,13 +46,20 @@ constexpr int Q_MAXLEN = 8000;
 constexpr int Q_WARPS = TDB_Q_WARPS;
 constexpr int Q_NULL = -16384;
 
+struct __align__(8) QMMeta {
+    int16_t lo, hi;  // valid range
+    uint16_t off;    // arena index of diagonal lo (free-running, masked on access)
+    uint16_t pad;
+};
+struct __align__(4) QGMeta {
+    int16_t lo, hi;
+};
 template <class C>
 struct __align__(16) QPairT {
     int16_t marena[C::MAR];       // FIFO arena of M wavefronts; reused as the op stream at backtrace
     int16_t gap[12][C::W];        // I1[4], D1[4], I2[2], D2[2] rings indexed by score
-    uint16_t m_off[32];           // arena index of diagonal m_lo (free-running, masked on access)
-    int16_t m_lo[32], m_hi[32];   // valid range of M[s], slot s & 31
-    int16_t g_lo[12], g_hi[12];
+    QMMeta mmeta[32];             // valid range + arena position of M[s], slot s & 31 (one 8-byte load)
+    QGMeta gmeta[12];             // valid range of the gap wavefronts (one 4-byte load)
     int16_t step_lo[C::SCAP];     // computed lo of score s (provenance row origin)
     uint16_t step_base[C::SCAP];
     uint8_t prov[C::PROV];
@@ -60,6 +67,25 @@ struct __align__(16) QPairT {
 static_assert(sizeof(QPairT<QuadCfg>) % 16 == 0 && sizeof(QPairT<DuoCfg>) % 16 == 0, "pair state keeps 16-byte alignment");
 template <class C>
 constexpr size_t lock_smem_bytes() { return sizeof(QPairT<C>) * (32 / C::G) * Q_WARPS; }
+
+// Bit mask over the (at most W) diagonals of one wavefront; first / last set bit = trimmed range.
+template <int W>
+struct QMask {
+    static_assert(W == 32 || W == 64, "wavefront width");
+    unsigned long long bits = 0; // W == 32 only uses the low word (the compiler drops the rest)
+    __device__ __forceinline__ void add(unsigned group_bits, int shift) {
+        if (W == 32) bits = (unsigned)bits | (group_bits << shift);
+        else bits |= (unsigned long long)group_bits << shift;
+    }
+    __device__ __forceinline__ void range(int lo, int &first, int &last) const {
+        if (W == 32) {
+            const unsigned b = (unsigned)bits;
+            first = b ? lo + __ffs(b) - 1 : INT32_MAX, last = b ? lo + 31 - __clz(b) : INT32_MIN;
+        } else {
+            first = bits ? lo + __ffsll((long long)bits) - 1 : INT32_MAX, last = bits ? lo + 63 - __clzll((long long)bits) : INT32_MIN;
+        }
+    }
+};
 
 struct QIn { // one input wavefront, group-uniform
     const int16_t *p; // element for diagonal k at p[(base + k) & amask]
@@ -141,7 +167,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
             const int k_end = m - n;
             const bool usable = have && !overflow;
             int penalty = 0, clipped = 0;
-            unsigned long long cells = 0, cols = 0, ext = 0;
+            unsigned cells = 0, cols = 0, ext = 0; // per pair: far below 2^32
             const int m0 = extend_groups<QG>(pw, tw, psh, tsh, n, m, 0, 0, usable, gl, gshift, lane);
             if (usable && gl == 0) ext += (unsigned)(m0 >> 4) + 1;
             const bool identical = usable && k_end == 0 && m0 >= m;
@@ -149,7 +175,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
             bool running = usable && !identical;
             // ---------------- wavefront loop (score s is warp-uniform) ----------------
             if (running && gl == 0) {
-                sm.m_off[0] = 0, sm.m_lo[0] = 0, sm.m_hi[0] = 0;
+                sm.mmeta[0] = QMMeta{0, 0, 0, 0};
                 sm.marena[0] = (int16_t)m0;
                 sm.step_lo[0] = 0, sm.step_base[0] = 0;
                 sm.prov[0] = 0;
@@ -174,9 +200,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
 #define TDB_QM(w, lag)                                                              \
     w.p = sm.marena, w.base = 0, w.lo = 1, w.span1 = 0;                             \
     if (live && (Mm & (1u << (lag)))) {                                             \
-        const int sl = (s - (lag)) & 31;                                            \
-        const int l_ = sm.m_lo[sl];                                                 \
-        w.lo = l_, w.span1 = (unsigned)(sm.m_hi[sl] - l_ + 1), w.base = (int)sm.m_off[sl] - l_; \
+        const QMMeta mm_ = sm.mmeta[(s - (lag)) & 31];                              \
+        w.lo = mm_.lo, w.span1 = (unsigned)(mm_.hi - mm_.lo + 1), w.base = (int)mm_.off - mm_.lo; \
     }
                 TDB_QM(mx, X)
                 TDB_QM(mo1, O1 + E1)
@@ -186,8 +211,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
     w.p = sm.gap[0], w.base = 0, w.lo = 1, w.span1 = 0;                             \
     if (live && (msk & (1u << (lag)))) {                                            \
         const int r_ = (row0) + ((s - (lag)) & (rmask));                            \
-        const int l_ = sm.g_lo[r_];                                                 \
-        w.p = sm.gap[r_], w.lo = l_, w.span1 = (unsigned)(sm.g_hi[r_] - l_ + 1);    \
+        const QGMeta gm_ = sm.gmeta[r_];                                            \
+        w.p = sm.gap[r_], w.lo = gm_.lo, w.span1 = (unsigned)(gm_.hi - gm_.lo + 1); \
     }
                 TDB_QG(i1e, I1m, E1, 0, 3)
                 TDB_QG(d1e, D1m, E1, 4, 3)
@@ -215,22 +240,19 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                     // arena room: everything from the oldest live M wavefront up to the new one
                     const unsigned livem = Mm & 0x03fffffeu; // lags 1..25
                     unsigned tail = mhead;
-                    if (livem) tail = sm.m_off[(s - (31 - __clz(livem))) & 31];
+                    if (livem) tail = sm.mmeta[(s - (31 - __clz(livem))) & 31].off;
                     if (width > QW || prov_used + (unsigned)width > Q_PROV ||
                         ((mhead - tail) & 0xffffu) + (unsigned)width > Q_MAR) {
                         overflow = true, running = false, live = false, width = 0; // this group drops out
                     }
                 }
                 if (!live) lo = 0, hi = -1;
-                const bool has_i1 = mo1.span1 || i1e.span1, has_d1 = mo1.span1 || d1e.span1;
-                const bool has_i2 = mo2.span1 || i2e.span1, has_d2 = mo2.span1 || d2e.span1;
                 int16_t *I1o = sm.gap[0 + (s & 3)], *D1o = sm.gap[4 + (s & 3)];
                 int16_t *I2o = sm.gap[8 + (s & 1)], *D2o = sm.gap[10 + (s & 1)];
                 uint8_t *pv = sm.prov + prov_used;
                 cells += (unsigned)width;
-                int tl_m = INT32_MAX, th_m = INT32_MIN, tl_i1 = INT32_MAX, th_i1 = INT32_MIN,
-                    tl_i2 = INT32_MAX, th_i2 = INT32_MIN, tl_d1 = INT32_MAX, th_d1 = INT32_MIN,
-                    tl_d2 = INT32_MAX, th_d2 = INT32_MIN;
+                // validity masks of this score's wavefronts, bit = diagonal - lo (a wavefront spans at most QW diagonals)
+                QMask<QW> vmask_m, vmask_i1, vmask_i2, vmask_d1, vmask_d2;
                 int lane_min_d = 1 << 30;
                 bool fin = false;
                 const int n_iter = __reduce_max_sync(TDB_FULL, (width + QG - 1) / QG);
@@ -289,25 +311,29 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                             fin |= (k == k_end) && (mv >= m);
                         }
                         sm.marena[(mhead + (unsigned)(k - lo)) & (Q_MAR - 1)] = (int16_t)mv;
-                        if (has_i1) I1o[k & (QW - 1)] = (int16_t)ins1;
-                        if (has_i2) I2o[k & (QW - 1)] = (int16_t)ins2;
-                        if (has_d1) D1o[k & (QW - 1)] = (int16_t)del1;
-                        if (has_d2) D2o[k & (QW - 1)] = (int16_t)del2;
+                        // a component without a source only holds NULL+1 here: never valid, so its range stays empty
+                        I1o[k & (QW - 1)] = (int16_t)ins1;
+                        I2o[k & (QW - 1)] = (int16_t)ins2;
+                        D1o[k & (QW - 1)] = (int16_t)del1;
+                        D2o[k & (QW - 1)] = (int16_t)del2;
                     }
-                    // trim_ends (A.2): first / last diagonal whose offset lies inside the DP matrix
-                    unsigned bal = qballot<QG>(gshift, vm);
-                    if (bal) tl_m = min(tl_m, kb + __ffs(bal) - 1), th_m = kb + 31 - __clz(bal);
-#define TDB_TRIM(has, val, tl, th)                                                                                     \
-    {                                                                                                                  \
-        bal = qballot<QG>(gshift, (has) && act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n);   \
-        if (bal) tl = min(tl, kb + __ffs(bal) - 1), th = kb + 31 - __clz(bal);                                         \
-    }
-                    TDB_TRIM(has_i1, ins1, tl_i1, th_i1)
-                    TDB_TRIM(has_i2, ins2, tl_i2, th_i2)
-                    TDB_TRIM(has_d1, del1, tl_d1, th_d1)
-                    TDB_TRIM(has_d2, del2, tl_d2, th_d2)
-#undef TDB_TRIM
+                    // which cells lie inside the DP matrix: collected per score, trimmed once below (A.2)
+                    const int sh = itk * QG;
+                    vmask_m.add(qballot<QG>(gshift, vm), sh);
+#define TDB_VALID(val) (act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n)
+                    vmask_i1.add(qballot<QG>(gshift, TDB_VALID(ins1)), sh);
+                    vmask_i2.add(qballot<QG>(gshift, TDB_VALID(ins2)), sh);
+                    vmask_d1.add(qballot<QG>(gshift, TDB_VALID(del1)), sh);
+                    vmask_d2.add(qballot<QG>(gshift, TDB_VALID(del2)), sh);
+#undef TDB_VALID
                 }
+                // trim_ends (A.2): first / last diagonal whose offset lies inside the DP matrix
+                int tl_m, th_m, tl_i1, th_i1, tl_i2, th_i2, tl_d1, th_d1, tl_d2, th_d2;
+                vmask_m.range(lo, tl_m, th_m);
+                vmask_i1.range(lo, tl_i1, th_i1);
+                vmask_i2.range(lo, tl_i2, th_i2);
+                vmask_d1.range(lo, tl_d1, th_d1);
+                vmask_d2.range(lo, tl_d2, th_d2);
                 if (live && gl == 0) sm.step_lo[s] = (int16_t)lo, sm.step_base[s] = (uint16_t)prov_used;
                 prov_used += (unsigned)width;
                 __syncwarp();
@@ -378,13 +404,11 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                     if (tl_d1 <= th_d1) D1m |= 1u;
                     if (tl_d2 <= th_d2) D2m |= 1u;
                     if (gl == 0) {
-                        const int sl = s & 31;
-                        sm.m_lo[sl] = (int16_t)mlo, sm.m_hi[sl] = (int16_t)mhi;
-                        sm.m_off[sl] = (uint16_t)(mhead + (unsigned)(mlo - lo));
-                        sm.g_lo[0 + (s & 3)] = (int16_t)tl_i1, sm.g_hi[0 + (s & 3)] = (int16_t)th_i1;
-                        sm.g_lo[4 + (s & 3)] = (int16_t)tl_d1, sm.g_hi[4 + (s & 3)] = (int16_t)th_d1;
-                        sm.g_lo[8 + (s & 1)] = (int16_t)tl_i2, sm.g_hi[8 + (s & 1)] = (int16_t)th_i2;
-                        sm.g_lo[10 + (s & 1)] = (int16_t)tl_d2, sm.g_hi[10 + (s & 1)] = (int16_t)th_d2;
+                        sm.mmeta[s & 31] = QMMeta{(int16_t)mlo, (int16_t)mhi, (uint16_t)(mhead + (unsigned)(mlo - lo)), 0};
+                        sm.gmeta[0 + (s & 3)] = QGMeta{(int16_t)tl_i1, (int16_t)th_i1};
+                        sm.gmeta[4 + (s & 3)] = QGMeta{(int16_t)tl_d1, (int16_t)th_d1};
+                        sm.gmeta[8 + (s & 1)] = QGMeta{(int16_t)tl_i2, (int16_t)th_i2};
+                        sm.gmeta[10 + (s & 1)] = QGMeta{(int16_t)tl_d2, (int16_t)th_d2};
                     }
                     if (mlo <= mhi) mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
                 }
