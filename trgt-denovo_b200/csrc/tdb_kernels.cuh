@@ -623,12 +623,15 @@ __global__ void __launch_bounds__(T0_WARPS * 32) k_align_warp(const AlignParams 
     const ItemSrc src = item_src(p);
     WorkCount wc = {0, 0, 0};
     unsigned long long lane_ext16 = 0, done = 0;
+    // pairs per work-counter atomic: one when a launch has only a few pairs per warp (they are few and heavy)
+    const unsigned n_warps = gridDim.x * (blockDim.x >> 5);
+    const unsigned chunk = src.total >= n_warps * 16u ? (unsigned)WORK_CHUNK : 1u;
     for (;;) {
         unsigned b = 0;
-        if (lane == 0) b = atomicAdd(p.work_counter, (unsigned)WORK_CHUNK);
+        if (lane == 0) b = atomicAdd(p.work_counter, chunk);
         b = __shfl_sync(TDB_FULL, b, 0);
         if (b >= src.total) break;
-        const unsigned e = min(b + WORK_CHUNK, src.total);
+        const unsigned e = min(b + chunk, src.total);
         for (unsigned it = b; it < e; ++it) {
             const uint32_t idx = item_at(p, src, it);
             const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];

@@ -139,15 +139,20 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
     const Penalties pn = {X, O1, E1, O2, E2};
     const ItemSrc src = item_src(p);
     const unsigned n_items = src.total;
-    constexpr int PER_FETCH = QG == 8 ? 32 : 8; // pairs per work-counter atomic (8 batches of four / 4 of two)
+    // pairs per work-counter atomic: 8 batches when there is plenty of work, fewer when a launch (a pipeline
+    // chunk) only has a few batches per warp -- coarse grabs then leave warps idle behind the heaviest ones
+    constexpr int PER_BATCH = 32 / QG, MAX_FETCH = 8 * PER_BATCH;
+    const unsigned n_warps = gridDim.x * (blockDim.x >> 5);
+    const unsigned per_fetch =
+        (unsigned)PER_BATCH * max(1u, min((unsigned)(MAX_FETCH / PER_BATCH), n_items / (n_warps * 8u * (unsigned)PER_BATCH)));
     unsigned long long acc_cells = 0, acc_cols = 0, acc_ext = 0, acc_done = 0; // acc_* valid on group lane 0
 
     for (;;) {
         unsigned fb = 0;
-        if (lane == 0) fb = atomicAdd(p.work_counter, (unsigned)PER_FETCH);
+        if (lane == 0) fb = atomicAdd(p.work_counter, per_fetch);
         fb = __shfl_sync(TDB_FULL, fb, 0);
         if (fb >= n_items) break;
-        for (unsigned bb = fb; bb < fb + PER_FETCH && bb < n_items; bb += 32 / QG) {
+        for (unsigned bb = fb; bb < fb + per_fetch && bb < n_items; bb += 32 / QG) {
             // ====================== one pair per group, four groups in lockstep ======================
             const unsigned it = bb + gid;
             const bool have = it < n_items;
