@@ -186,6 +186,16 @@ def main():
 
     # ---- workload: this rank's shard -----------------------------------------------------------------
     threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    # every rank keeps its shard in pinned host memory for the e2e leg (about 22 KB per locus with the packed
+    # staging and the result buffers): never ask one box for more than 80 % of what it has free
+    try:
+        import psutil
+        fit = int(0.8 * psutil.virtual_memory().available / max(1, world) / 22e3)
+        if args.loci > fit:
+            log(f"[rank {rank}] {args.loci} loci per GPU x {world} ranks does not fit the host memory; using {fit}")
+            args.loci = max(1000, fit)
+    except ImportError:
+        pass
     params = S.config("duo_genome" if args.duo else "trio_genome", pinned=1)
     t0 = time.time()
     batch = S.generate(params, rank * args.loci, (rank + 1) * args.loci, threads)

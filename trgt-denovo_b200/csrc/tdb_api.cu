@@ -88,10 +88,12 @@ struct tdb_ctx {
     void *h_packed = nullptr, *h_flag = nullptr, *h_runs = nullptr; // pinned staging of the host packer / planner
     size_t h_packed_cap = 0, h_flag_cap = 0, h_runs_cap = 0;
     DevBuf runs;
-    // host-pack mode, opt-in (TDB_RAW_EVERY=n): every n-th 256 KB block ships as ASCII and is packed on the GPU.
-    // Measured slower on the B200 host at every share tried (profiles/r01/NOTES.md): off by default.
-    bool allow_steal = false;
-    int steal_div = 0;
+    // host-pack mode: every steal_div-th pipeline chunk ships as ASCII (where the workers have not reached it yet) and
+    // is packed on the GPU.  Automatic: on (every 2nd chunk) when the call has at most 8 packer threads -- several
+    // ranks sharing one host -- where it measured +10 % e2e; off with more threads, where it measured nothing
+    // (profiles/r01/NOTES.md).  TDB_RAW_EVERY=n forces it (n < 2: off).
+    bool steal_forced = false, allow_steal = false;
+    int steal_div = 2;
     bool count_work = false;
     tdb_counters counters;
     // single-pair shim state
@@ -194,13 +196,10 @@ class HostPacker {
     // and planning never holds up packing.
     void start(const uint8_t *blob, uint64_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
                uint32_t *packed, uint8_t *flag, unsigned n_threads, size_t n_pre, std::function<void(size_t)> pre_fn,
-               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn, int raw_every) {
+               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn) {
         n_blocks_ = packed ? (size_t)((blob_bytes + BLOCK - 1) / BLOCK) : 0;
         done_ = std::vector<std::atomic<uint8_t>>(n_blocks_);
-        // every raw_every-th block is left to the GPU: it crosses PCIe as ASCII (1 byte of host memory traffic per
-        // base instead of 1.5 for read + write + DMA of the packed form) and k_pack packs it there
-        for (size_t i = 0; i < n_blocks_; ++i)
-            done_[i].store(raw_every > 1 && i % (size_t)raw_every == (size_t)raw_every - 1 ? RAW : PENDING, std::memory_order_relaxed);
+        for (auto &d : done_) d.store(PENDING, std::memory_order_relaxed);
         scan_left_ = std::vector<std::atomic<int>>(n_scan_chunks);
         for (auto &x : scan_left_) x.store(parts, std::memory_order_relaxed);
         tasks_.clear();
@@ -241,6 +240,11 @@ class HostPacker {
     }
     enum : uint8_t { PENDING = 0, PACKED = 1, RAW = 2, BUSY = 3 };
     uint8_t peek(size_t i) const { return done_[i].load(std::memory_order_acquire); }
+    // The calling thread takes a block no worker has started: it ships as ASCII and the GPU packs it.
+    bool try_steal(size_t i) {
+        uint8_t st = PENDING;
+        return done_[i].compare_exchange_strong(st, RAW, std::memory_order_acq_rel);
+    }
     // State of block i for the calling thread: RAW (left to the GPU) or PACKED (waits for the worker that is on it).
     uint8_t acquire(size_t i) const {
         for (;;) {
@@ -404,6 +408,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         // one core stays free for the calling thread, which must react quickly to every finished chunk
         const unsigned hc = std::thread::hardware_concurrency();
         const unsigned hw = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::max(1u, std::min(32u, hc > 2 ? hc - 1 : 1u));
+        if (!ctx->steal_forced) ctx->allow_steal = hw <= 8;
         const size_t n_zero = host_pack ? 16 : 0;
         PairRun *hruns = nullptr;
         if (lazy_scan && !ctx->disable_rle) { // pair lists travel run-length encoded
@@ -421,8 +426,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                          memset(hflag + z0, 0, std::min(b.n_seqs, z0 + per) - z0);
                      },
                      lazy_scan ? chunks.size() : 0, SCAN_PARTS,
-                     [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); },
-                     ctx->allow_steal && chunks.size() > 1 ? ctx->steal_div : 0);
+                     [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); });
     }
     if (lazy_scan) {
         // The first chunk tells whether the pair list walks the sequence table in order; if it does not (a chunk
@@ -545,6 +549,11 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                         const uint64_t BLK = HostPacker::BLOCK;
                         size_t i = (size_t)(b0 / BLK);
                         const size_t i_end = (size_t)((b1 - 1) / BLK);
+                        // Every steal_div-th chunk is left to the GPU where the workers have not reached it yet: its
+                        // blocks cross PCIe as ASCII in one copy and k_pack packs them.  Pays when the host threads are
+                        // the bottleneck and the link has room (several ranks sharing one host's cores).
+                        if (ctx->allow_steal && K > 1 && k % (size_t)ctx->steal_div == (size_t)ctx->steal_div - 1)
+                            for (size_t q = i; q <= i_end; ++q) packer.try_steal(q);
                         while (i <= i_end) {
                             const uint8_t st0 = packer.acquire(i);
                             size_t j = i + 1; // extend the run of equal state
@@ -989,8 +998,9 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
         c->disable_rle = getenv("TDB_DISABLE_RLE") != nullptr;
         if (const char *sd = getenv("TDB_RAW_EVERY")) {
-            c->steal_div = atoi(sd);
-            c->allow_steal = c->steal_div > 1;
+            c->steal_forced = true;
+            c->allow_steal = atoi(sd) > 1;
+            c->steal_div = std::max(2, atoi(sd));
         }
         if (const char *ht = getenv("TDB_HOST_THREADS")) c->host_threads = std::max(0, std::min(256, atoi(ht)));
         if (const char *hp = getenv("TDB_HOSTPACK_MIN_BYTES")) {
