@@ -252,6 +252,20 @@ def test_host_packed_batches(tdb, monkeypatch):
     assert cnt.host_packed == 1
     seqs, pp, pt = make_pairs(rng, n_targets=100, reads_per_target=6, err=0.2, alphabet="ACGTN")  # > 256 flagged: whole blob
     _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    # every 2nd chunk left to the GPU as ASCII (what thread-starved ranks do automatically)
+    monkeypatch.setenv("TDB_HOSTPACK_MIN_BYTES", "0")
+    monkeypatch.setenv("TDB_CHUNK_PAIRS", "1024")
+    monkeypatch.setenv("TDB_RAW_EVERY", "2")
+    monkeypatch.setenv("TDB_TEST_RAW_BLOCKS", "2")  # deterministic: every 2nd 256 KB block is never packed on the host
+    c2 = tdb.Context()
+    seqs, pp, pt = make_pairs(rng, n_targets=600, reads_per_target=12, max_units=30, err=0.002, alphabet="ACGT")
+    seqs[7] = seqs[7][:30] + b"N" + seqs[7][31:]
+    seqs[len(seqs) // 2] = seqs[len(seqs) // 2].lower()
+    cnt = _check_batch(c2, seqs, pp, pt, 50, cigars=False)
+    for v in ("TDB_HOSTPACK_MIN_BYTES", "TDB_CHUNK_PAIRS", "TDB_RAW_EVERY", "TDB_TEST_RAW_BLOCKS"):
+        monkeypatch.delenv(v)
+    assert cnt.host_packed == 1 and cnt.chunks >= 4 and cnt.bytes_raw > 0
+    c2.close()
     blob = np.frombuffer(b"ACGTACGTAC" * 4, dtype=np.uint8)
     with pytest.raises(tdb.TdbError):  # layout violations are caught by the host packer too
         c.align_batch(blob, np.array([0, 5], np.uint64), np.array([10, 10], np.uint32), np.array([0], np.uint32),

@@ -196,10 +196,13 @@ class HostPacker {
     // and planning never holds up packing.
     void start(const uint8_t *blob, uint64_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
                uint32_t *packed, uint8_t *flag, unsigned n_threads, size_t n_pre, std::function<void(size_t)> pre_fn,
-               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn) {
+               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn, int raw_every_block) {
         n_blocks_ = packed ? (size_t)((blob_bytes + BLOCK - 1) / BLOCK) : 0;
         done_ = std::vector<std::atomic<uint8_t>>(n_blocks_);
-        for (auto &d : done_) d.store(PENDING, std::memory_order_relaxed);
+        // raw_every_block (tests only): every n-th block is left to the GPU from the start, whatever the timing
+        for (size_t i = 0; i < n_blocks_; ++i)
+            done_[i].store(raw_every_block > 1 && i % (size_t)raw_every_block == (size_t)raw_every_block - 1 ? RAW : PENDING,
+                           std::memory_order_relaxed);
         scan_left_ = std::vector<std::atomic<int>>(n_scan_chunks);
         for (auto &x : scan_left_) x.store(parts, std::memory_order_relaxed);
         tasks_.clear();
@@ -426,7 +429,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                          memset(hflag + z0, 0, std::min(b.n_seqs, z0 + per) - z0);
                      },
                      lazy_scan ? chunks.size() : 0, SCAN_PARTS,
-                     [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); });
+                     [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); },
+                     getenv("TDB_TEST_RAW_BLOCKS") ? atoi(getenv("TDB_TEST_RAW_BLOCKS")) : 0);
     }
     if (lazy_scan) {
         // The first chunk tells whether the pair list walks the sequence table in order; if it does not (a chunk
