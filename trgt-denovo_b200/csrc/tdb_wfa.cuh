@@ -2,7 +2,7 @@
 //
 // One warp aligns one (read, target) pair: lanes own diagonals of the current wavefront, the
 // wavefront history (26-score window for M, e+1 for the gap components) lives in a ring indexed by
-// (score, k mod W) -- in shared memory for the common short pairs (tier 0) or in a per-warp slice of
+// (score, k mod W) -- in shared memory for pairs of moderate width (k_align_warp) or in a per-warp slice of
 // global scratch for long / wide pairs (tiers 1,2).  One provenance byte per computed cell is kept so
 // that the alignment path can be rebuilt on the device and the flank-clipped score
 // (reference: src/aligner.rs:320-357) produced without ever materialising a CIGAR in HBM.
@@ -69,7 +69,7 @@ struct OffTraits<int32_t> {
     static constexpr int NULLV = INT32_MIN / 2;
 };
 
-// Storage handed to the aligner (shared memory for tier 0, global scratch otherwise).
+// Storage handed to the aligner (shared memory for k_align_warp, global scratch for k_align_global).
 template <typename OffT, typename StepLoT, typename StepBaseT>
 struct Storage {
     OffT *M;           // [MS][W]

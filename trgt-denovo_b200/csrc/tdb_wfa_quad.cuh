@@ -1,18 +1,17 @@
-// tdb_wfa_quad.cuh -- tier 0 of the alignment path: FOUR pairs per warp, eight lanes per pair.
+// tdb_wfa_quad.cuh -- k_align_lock: several pairs per warp in LOCKSTEP (tier 0: four pairs, eight lanes each).
 //
-// Why: on the genome-wide trio the median pair has penalty 6 and wavefront width 3 (42 % are
-// identical), so a warp per pair leaves 27+ lanes idle and the kernel is bound by the instruction
-// issue of its warp-uniform bookkeeping (ncu r01: issue active 72 %, 3.5 k warp-instructions / pair).
-// Here a warp runs four consecutive pairs in lock-step -- consecutive pairs are reads of the same
-// parental allele against the same child allele, so their control flow is nearly identical -- and
-// every bookkeeping instruction serves four pairs.  Further:
-//   * existence of the last 26 M / gap wavefronts is tracked in register bit-masks, so the null
-//     score steps of the 2-piece-affine recurrence (most steps, penalties 8/6/25) touch no memory;
-//   * the M history lives in a FIFO arena (only non-null wavefronts occupy shared memory), which
-//     lets a pair with width <= 32 fit in 3 KB and keeps >= 17 warps resident per SM;
-//   * penalties are compile-time constants (the reference hard-wires 8,4,2,24,1:
-//     src/commands/shared.rs:39-51, src/model.rs:13-23), other penalties use the general tiers.
-// Semantics are exactly those of wfa_align_warp (tdb_wfa.cuh): SURVEY.md Appendix A.1-A.4.
+// Why: after duplicate elimination and the closed forms the typical pair still has a penalty around 20 and
+// wavefronts 3..16 diagonals wide, so a warp per pair leaves most lanes idle and the kernel is bound by the
+// instruction issue of its per-score bookkeeping.  Here a warp runs 32/G consecutive pairs of the work-sorted
+// list (same |n-m|, usually the same locus: near-identical control flow) under ONE warp-uniform control flow, so
+// that every bookkeeping instruction serves all of them.  Further:
+//   * existence of the last 26 M / gap wavefronts is tracked in register bit-masks, so the null score steps of
+//     the 2-piece-affine recurrence (most steps, penalties 8/6/25) touch no memory;
+//   * the M history lives in a FIFO arena (only non-null wavefronts occupy shared memory), which lets a pair
+//     with width <= 32 fit in 3 KB and keeps 16 warps resident per SM;
+//   * penalties are compile-time constants (the reference hard-wires 8,4,2,24,1: src/commands/shared.rs:39-51,
+//     src/model.rs:13-23); other penalties use the general tiers (wfa_align_warp, tdb_wfa.cuh).
+// Semantics are exactly those of wfa_align_warp: SURVEY.md Appendix A.1-A.4.
 #pragma once
 #include "tdb_kernels.cuh"
 
