@@ -17,6 +17,10 @@ CMD="python bench.py --loci 100000 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$tag.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launch_$tag.log 2>&1
 echo launches rc=$?
+# the judged command itself (937k loci): first 150 launches = the counting step, the warm-ups and the timed steps
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-file gpurun_out/launches_full_$tag.csv $CMD > gpurun_out/ncu_launch_full_$tag.log 2>&1
+echo launches_full rc=$?
 CMD="python bench.py --loci 30000 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain30k_$tag.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_align_lock -s 3 -c 1 -f -o gpurun_out/prof_quad_$tag $CMD > gpurun_out/ncu_quad_$tag.log 2>&1

@@ -5,21 +5,26 @@ import csv, json, os, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01g"
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles", "r01")
-for f in (f"bench_full_{tag}.json", f"bench_ref_{tag}.json", f"launches_{tag}.csv"):
-    subprocess.check_call(["cp", os.path.join(G, f), os.path.join(P, f)])
-rows = list(csv.reader(open(os.path.join(G, f"launches_{tag}.csv"))))
-h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
-ki, vi = rows[h].index("Kernel Name"), rows[h].index("Metric Value")
-t, c = {}, {}
-for r in rows[h + 1:]:
-    if len(r) > vi:
-        k = r[ki][:70]
-        t[k] = t.get(k, 0.0) + float(r[vi].replace(",", "")); c[k] = c.get(k, 0) + 1
-tot = sum(t.values())
-with open(os.path.join(P, f"launches_{tag}_summary.txt"), "w") as o:
-    o.write("# ncu --metrics gpu__time_duration.sum, first 120 launches of: python bench.py --loci 100000 --steps 1 --warmup 3 --no-cpu-baseline\n# (cold-cache, serialised: compare shares)\n")
-    for k, v in sorted(t.items(), key=lambda x: -x[1]):
-        o.write(f"{v/1e6:10.3f} ms {100*v/tot:5.1f}% n={c[k]:3d} {k}\n")
+for f in (f"bench_full_{tag}.json", f"bench_ref_{tag}.json", f"launches_{tag}.csv", f"launches_full_{tag}.csv"):
+    if os.path.exists(os.path.join(G, f)):
+        subprocess.check_call(["cp", os.path.join(G, f), os.path.join(P, f)])
+for name, what in ((f"launches_{tag}", "first 120 launches of: python bench.py --loci 100000 --steps 1 --warmup 3 --no-cpu-baseline"),
+                   (f"launches_full_{tag}", "first 150 launches of: python bench.py --steps 3 --warmup 3 --no-cpu-baseline (the judged 937k-locus configuration)")):
+    if not os.path.exists(os.path.join(G, name + ".csv")):
+        continue
+    rows = list(csv.reader(open(os.path.join(G, name + ".csv"))))
+    h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    ki, vi = rows[h].index("Kernel Name"), rows[h].index("Metric Value")
+    t, c = {}, {}
+    for r in rows[h + 1:]:
+        if len(r) > vi:
+            k = r[ki][:70]
+            t[k] = t.get(k, 0.0) + float(r[vi].replace(",", "")); c[k] = c.get(k, 0) + 1
+    tot = sum(t.values())
+    with open(os.path.join(P, name + "_summary.txt"), "w") as o:
+        o.write(f"# ncu --metrics gpu__time_duration.sum, {what}\n# (cold-cache, serialised: compare shares)\n")
+        for k, v in sorted(t.items(), key=lambda x: -x[1]):
+            o.write(f"{v/1e6:10.3f} ms {100*v/tot:5.1f}% n={c[k]:3d} {k}\n")
 plain = json.loads([l for l in open(os.path.join(G, f"plain30k_{tag}.log")) if l.startswith("{")][-1])
 traffic = {}
 for kern, ti in (("quad", 0), ("warp", 1)):
