@@ -221,9 +221,17 @@ def main():
     d_score = torch.zeros(n_pairs, dtype=torch.int32, device=dev)
     d_mask = torch.zeros(n_pairs, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
+    # The generator appends sequences back to back, as a host filling one byte vector does: that is the ABI's
+    # dense layout (seq_off = NULL, offsets derived on the device).  TDB_BENCH_DENSE=0 passes explicit offsets.
+    ends = np.cumsum(batch.seq_len, dtype=np.uint64)
+    dense = bool(n_seqs == 0 or (batch.seq_off[0] == 0 and np.array_equal(batch.seq_off[1:], ends[:-1])))
+    del ends
+    dense = dense and os.environ.get("TDB_BENCH_DENSE", "1") != "0"
+    h_off_ptr = None if dense else batch.seq_off.ctypes.data
+    d_off_ptr = None if dense else d_off.data_ptr()
 
     def step_device():
-        r = L.tdb_assess_batch_device(h, int(args.duo), d_blob.data_ptr(), batch.blob.size, d_off.data_ptr(),
+        r = L.tdb_assess_batch_device(h, int(args.duo), d_blob.data_ptr(), batch.blob.size, d_off_ptr,
                                       d_len.data_ptr(), n_seqs, d_pp.data_ptr(), d_pt.data_ptr(), n_pairs,
                                       d_loci.data_ptr(), n_loci, args.quantile, d_out.data_ptr(), d_score.data_ptr(),
                                       d_mask.data_ptr())
@@ -242,7 +250,7 @@ def main():
 
     def step_host():
         r = L.tdb_trio_batch if not args.duo else L.tdb_duo_batch
-        rc = r(h, batch.blob.ctypes.data, batch.blob.size, batch.seq_off.ctypes.data, batch.seq_len.ctypes.data,
+        rc = r(h, batch.blob.ctypes.data, batch.blob.size, h_off_ptr, batch.seq_len.ctypes.data,
                n_seqs, batch.pair_pattern.ctypes.data, batch.pair_text.ctypes.data, n_pairs, batch.loci_ptr, n_loci,
                args.quantile, C.cast(h_out, C.c_void_p), None, h_mask.ctypes.data)
         if rc != 0:
@@ -302,7 +310,7 @@ def main():
                 "ms_last_block_packed": ce.ms_host_packed, "ms_last_chunk_queued": ce.ms_host_enqueued}
     # bytes that actually cross PCIe per step: what the library copied for the alignment stage (2-bit packed
     # sequences, tables, run-length encoded pair lists) plus the locus descriptors
-    host_input_bytes = batch.blob.size + batch.seq_off.nbytes + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
+    host_input_bytes = batch.blob.size + (0 if dense else batch.seq_off.nbytes) + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
         batch.pair_text.nbytes + loci_np.nbytes
     h2d = int(ce.bytes_h2d) + loci_np.nbytes
     d2h = C.sizeof(h_out) + h_mask.nbytes
@@ -396,6 +404,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(args), "loci_per_gpu": n_loci, "pairs_per_gpu": n_pairs,
                        "clip_len": args.clip, "parent_quantile": args.quantile, "sharding": f"loci x{world}, no collective",
+                       "layout": "dense (seq_off = NULL)" if dense else "explicit seq_off",
                        "l2": "inputs larger than L2 (no flush needed)"},
             "alignments_per_sec": tot_pairs * args.steps / (dev_ms_max * 1e-3),
             "gcups": batch.sum_nm * args.steps / (dev_ms * 1e-3) / 1e9,

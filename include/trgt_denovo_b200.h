@@ -124,7 +124,10 @@ int tdb_set_heuristic(tdb_ctx *ctx, const tdb_heuristic *h);
  * `seq_blob`; sequence i is seq_blob[seq_off[i] .. seq_off[i]+seq_len[i]).  Layout contract (checked
  * on the device, TDB_E_INVALID otherwise): sequences are stored in index order and do not overlap
  * (seq_off[i] + seq_len[i] <= seq_off[i+1] <= blob_bytes) -- what appending reads and alleles locus
- * by locus produces.  Pair j aligns
+ * by locus produces.  seq_off == NULL (every batch entry point, host or device) declares the DENSE
+ * layout that appending to one byte vector gives: seq_off[0] = 0, seq_off[i+1] = seq_off[i] +
+ * seq_len[i]; the offsets are then derived on the device by a prefix sum of seq_len and never cross
+ * PCIe (8 bytes per sequence less to upload: prefer it).  Pair j aligns
  * pattern = sequence pair_pattern[j] (the read) against text = sequence pair_text[j] (the target).
  * out_score[j]  = cigar_score_clipped(clip_len) (<= 0), written when out_status[j] == 0;
  * out_status[j] = WFA2 status.  out_status may be NULL.

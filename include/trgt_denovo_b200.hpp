@@ -189,11 +189,10 @@ inline std::string serialize_with_precision(double v) {
 namespace detail {
 
 struct Batch { // sequence blob + pair list in the reference's visiting order (src/denovo.rs:29-37,48-52)
-    std::string blob;
-    std::vector<uint64_t> off;
+    std::string blob; // sequences back to back: the ABI's dense layout (seq_off = NULL)
     std::vector<uint32_t> len, pp, pt;
     uint32_t seq(const std::string &s) {
-        off.push_back(blob.size()), len.push_back((uint32_t)s.size());
+        len.push_back((uint32_t)s.size());
         blob += s;
         return (uint32_t)len.size() - 1;
     }
@@ -267,7 +266,7 @@ inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, co
         if (!b.pp.empty()) {
             scores.resize(b.pp.size()), status.resize(b.pp.size());
             aligner.set_clip_len(params.clip_len);
-            aligner.check(tdb_align_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), b.off.data(), b.len.data(),
+            aligner.check(tdb_align_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), nullptr, b.len.data(),
                                           b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), scores.data(), status.data()));
         }
     }
@@ -481,7 +480,7 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
     std::vector<uint8_t> mask(b.pp.size() + 1);
     if (!todo.empty()) {
         aligner.set_clip_len(params.clip_len);
-        aligner.check(tdb_trio_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), b.off.data(), b.len.data(),
+        aligner.check(tdb_trio_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), nullptr, b.len.data(),
                                      b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
                                      params.parent_quantile, out.data(), nullptr, mask.data()));
     }
@@ -608,7 +607,7 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
     std::vector<uint8_t> mask(b.pp.size() + 1);
     if (!todo.empty()) {
         aligner.set_clip_len(params.clip_len);
-        aligner.check(tdb_duo_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), b.off.data(), b.len.data(),
+        aligner.check(tdb_duo_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), nullptr, b.len.data(),
                                     b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
                                     params.parent_quantile, out.data(), nullptr, mask.data()));
     }

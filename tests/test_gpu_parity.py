@@ -77,6 +77,10 @@ def _check_batch(ctx, seqs, pp, pt, clip, heuristic=tdo.DEFAULT_HEURISTIC, cigar
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, f"{len(bad)} score mismatches (closed form on), first pair {bad[:5]}: gpu {got[bad[:5]]} oracle {want[bad[:5]]}"
     assert sum(fast.tier_pairs) + fast.pairs_identical + fast.pairs_duplicate + fast.pairs_closed_form == len(pp)
+    # dense layout (seq_off = NULL): to_arrays lays the sequences back to back, the device derives the offsets
+    got, st = ctx.align_batch(blob, None, ln, pp, pt)
+    assert (st == wst).all() and (got == want).all()
+    assert ctx.counters().bytes_h2d <= fast.bytes_h2d - 8 * (int(max(pp.max(), pt.max())) if len(pp) else 0)
     # counting mode: every content through the wavefront kernels
     ctx.set_count_work(True)
     got, st = ctx.align_batch(blob, off, ln, pp, pt)
@@ -271,6 +275,43 @@ def test_host_packed_batches(tdb, monkeypatch):
         c.align_batch(blob, np.array([0, 5], np.uint64), np.array([10, 10], np.uint32), np.array([0], np.uint32),
                       np.array([1], np.uint32))
     c.close()
+
+
+def test_dense_layout(tdb, ctx):
+    """seq_off = NULL on the host and device entry points; gaps between sequences need explicit offsets; a dense
+    call whose lengths overrun the blob fails."""
+    rng = random.Random(37)
+    seqs, pp, pt = make_pairs(rng, n_targets=50, reads_per_target=8, err=0.01)
+    blob, off, ln = to_arrays(seqs)
+    want, _, _ = tdo.align_batch(blob, off, ln, pp, pt, 50)
+    ctx.set_clip_len(50)
+    ctx.set_count_work(False)
+    got, st = ctx.align_batch(blob, None, ln, pp, pt)
+    assert (got == want).all() and (st == 0).all()
+    g2, st2, pen2, cigs = ctx.align_batch_cigar(blob, None, ln, pp, pt)
+    assert (g2 == want).all()
+    # device-resident entry point
+    import torch
+    dev = lambda a: torch.from_numpy(np.array(a)).cuda()
+    d_blob = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
+    d_blob[:blob.size] = dev(blob)
+    d_ln, d_pp, d_pt = dev(ln.view(np.int32)), dev(pp.view(np.int32)), dev(pt.view(np.int32))
+    d_sc = torch.zeros(len(pp), dtype=torch.int32, device="cuda")
+    d_st = torch.zeros(len(pp), dtype=torch.int32, device="cuda")
+    rc = tdb.lib().tdb_align_batch_device(ctx._h, d_blob.data_ptr(), blob.size, None, d_ln.data_ptr(), len(ln),
+                                                  d_pp.data_ptr(), d_pt.data_ptr(), len(pp), d_sc.data_ptr(),
+                                                  d_st.data_ptr())
+    assert rc == 0
+    assert (d_sc.cpu().numpy() == want).all()
+    # explicit offsets with gaps between the sequences still work and differ from the dense reading
+    gap_seqs = [s + b"TTTT" for s in seqs]
+    gblob, goff, _ = to_arrays(gap_seqs)
+    got, st = ctx.align_batch(gblob, goff, ln, pp, pt)
+    assert (got == want).all()
+    with pytest.raises(tdb.TdbError):  # dense lengths overrun the blob
+        ctx.align_batch(blob[:blob.size // 2], None, ln, pp, pt)
+    got, st = ctx.align_batch(blob, None, ln, pp, pt)
+    assert (got == want).all()
 
 
 def test_bad_layout_and_bad_pair_index_fail(tdb, ctx):

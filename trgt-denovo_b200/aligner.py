@@ -146,7 +146,9 @@ class Context:
 
 
 def _canon(blob, seq_off, seq_len, pp, pt):
-    return (np.ascontiguousarray(blob, dtype=np.uint8), np.ascontiguousarray(seq_off, dtype=np.uint64),
+    # seq_off None: dense layout (sequences back to back), the library derives the offsets
+    return (np.ascontiguousarray(blob, dtype=np.uint8),
+            None if seq_off is None else np.ascontiguousarray(seq_off, dtype=np.uint64),
             np.ascontiguousarray(seq_len, dtype=np.uint32), np.ascontiguousarray(pp, dtype=np.uint32),
             np.ascontiguousarray(pt, dtype=np.uint32))
 

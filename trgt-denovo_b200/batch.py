@@ -30,10 +30,8 @@ class SeqBatch:
         return len(self._pp)
 
     def arrays(self):
-        """-> blob uint8, seq_off uint64, seq_len uint32, pair_pattern uint32, pair_text uint32"""
+        """-> blob uint8, seq_off (None: dense layout), seq_len uint32, pair_pattern uint32, pair_text uint32"""
         blob = np.frombuffer(b"".join(self._chunks), dtype=np.uint8)
         lens = np.array(self._lens, dtype=np.uint32)
-        offs = np.zeros(len(lens), dtype=np.uint64)
-        if len(lens):
-            offs[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
+        offs = None  # dense layout: sequences back to back, the library derives the offsets
         return (blob, offs, lens, np.array(self._pp, dtype=np.uint32), np.array(self._pt, dtype=np.uint32))

@@ -4,6 +4,8 @@
 #include "tdb_hostpack.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <atomic>
@@ -12,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -69,7 +72,7 @@ struct tdb_ctx {
     std::vector<cudaEvent_t> up_ev; // one per in-flight chunk upload
     // grow-only device buffers
     DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, pair_p, pair_t, score, status, penalty;
-    DevBuf rep, work, list_b, list_c;
+    DevBuf rep, work, list_b, list_c, scan_tmp;
     // Chunks alternate between two pipeline slots (own stream + own scratch) so that the tail of one chunk's
     // alignment kernels overlaps the next chunk's duplicate elimination and alignment.  (3 and 4 slots, and a
     // warp tier deferred to a call-wide list, were measured and made no difference: profiles/r01/NOTES.md.)
@@ -196,7 +199,8 @@ class HostPacker {
     // and planning never holds up packing.
     void start(const uint8_t *blob, uint64_t blob_bytes, const uint64_t *off, const uint32_t *len, uint32_t n_seqs,
                uint32_t *packed, uint8_t *flag, unsigned n_threads, size_t n_pre, std::function<void(size_t)> pre_fn,
-               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn, int raw_every_block) {
+               size_t n_scan_chunks, int parts, std::function<void(size_t, int)> scan_fn, int raw_every_block,
+               const uint64_t *(*make_off)(void *) = nullptr, void *make_arg = nullptr) {
         n_blocks_ = packed ? (size_t)((blob_bytes + BLOCK - 1) / BLOCK) : 0;
         done_ = std::vector<std::atomic<uint8_t>>(n_blocks_);
         // raw_every_block (tests only): every n-th block is left to the GPU from the start, whatever the timing
@@ -234,7 +238,7 @@ class HostPacker {
                         uint8_t expect = PENDING;
                         if (!done_[tk.a].compare_exchange_strong(expect, BUSY, std::memory_order_acq_rel)) continue; // stolen
                         const uint64_t x0 = (uint64_t)tk.a * BLOCK, x1 = std::min(blob_bytes, x0 + BLOCK);
-                        hostpack_stream(blob, x0, x1, packed, off, len, n_seqs, flag);
+                        hostpack_stream(blob, x0, x1, packed, off, len, n_seqs, flag, make_off, make_arg);
                         done_[tk.a].store(PACKED, std::memory_order_release);
                         last_pack_ns_.store(std::chrono::steady_clock::now().time_since_epoch().count(), std::memory_order_relaxed);
                     }
@@ -304,6 +308,43 @@ uint32_t table_mask(size_t n) {
     return (uint32_t)(cap - 1);
 }
 
+// Dense layout (seq_off == NULL at the ABI): sequence i starts where sequence i-1 ends, sequence 0 at byte 0.
+// The device derives the offsets with a prefix sum of the lengths; the host needs them only to find the owner
+// of a byte outside ACGT, and builds the table the first time such a byte turns up.
+struct DenseOffsets {
+    const uint32_t *len = nullptr;
+    size_t n = 0;
+    std::once_flag once;
+    std::vector<uint64_t> off;
+    const uint64_t *get() {
+        std::call_once(once, [this]() {
+            off.resize(n + 1);
+            uint64_t s = 0;
+            for (size_t i = 0; i < n; ++i) off[i] = s, s += len[i];
+            off[n] = s;
+        });
+        return off.data();
+    }
+    static const uint64_t *thunk(void *self) { return static_cast<DenseOffsets *>(self)->get(); }
+};
+struct LenTo64 {
+    __host__ __device__ __forceinline__ uint64_t operator()(uint32_t x) const { return (uint64_t)x; }
+};
+// d_off[i] = base + sum of d_len[0 .. i) for i in [0, n)
+int scan_offsets(tdb_ctx *ctx, const uint32_t *d_len, uint64_t *d_off, size_t n, uint64_t base, cudaStream_t st) {
+    size_t tmp = ctx->scan_tmp.cap;
+    CK(cub::DeviceScan::ExclusiveScan(ctx->scan_tmp.p, tmp, thrust::make_transform_iterator(d_len, LenTo64()), d_off,
+                                      cub::Sum(), base, (int)n, st));
+    return TDB_OK;
+}
+int scan_offsets_reserve(tdb_ctx *ctx, size_t n_max) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveScan(nullptr, tmp, thrust::make_transform_iterator((const uint32_t *)nullptr, LenTo64()),
+                                      (uint64_t *)nullptr, cub::Sum(), (uint64_t)0, (int)n_max, ctx->stream));
+    ENSURE(ctx->scan_tmp, tmp + 16);
+    return TDB_OK;
+}
+
 // Splits a host batch into pair chunks whose sequence ranges advance with the pair index (true for
 // batches assembled locus by locus), so that a chunk can be aligned while the next one is still in
 // flight over PCIe.  Falls back to a single chunk when the pair list jumps around the sequence table.
@@ -369,7 +410,8 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
 }
 
 // Pack + duplicate elimination + alignment tiers + scatter.  Leaves results in b.score/status/penalty.
-int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
+int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
+    DevBatch b = b_in;
     cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
     const uint32_t n_seqs = (uint32_t)b.n_seqs, n_pairs = (uint32_t)b.n_pairs;
     tdb_counters &cn = ctx->counters;
@@ -380,6 +422,15 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         CK(cudaEventRecord(ctx->ev[1], s));
         CK(cudaStreamSynchronize(s));
         return TDB_OK;
+    }
+    if (!b.h_pp && !b.seq_off) { // device batch in the dense layout: offsets = prefix sum of the lengths
+        ENSURE(ctx->seq_off, (size_t)n_seqs * 8 + 8);
+        int r = scan_offsets_reserve(ctx, n_seqs);
+        if (r) return r;
+        r = scan_offsets(ctx, b.seq_len, (uint64_t *)ctx->seq_off.p, n_seqs, 0, s);
+        if (r) return r;
+        b.seq_off = (const uint64_t *)ctx->seq_off.p;
+        cn.kernel_launches += 1;
     }
     const tdb_penalties &cp = ctx->cfg.penalties;
     const bool default_pen = cp.mismatch == 8 && cp.gap_opening1 == 4 && cp.gap_extension1 == 2 &&
@@ -395,9 +446,16 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     // PCIe) while this thread plans and queues chunks; small batches and CIGAR calls ship the ASCII and
     // pack on the device -------------------------------------------------------------------------------
     const bool host_pack = b.h_pp && !cigar_mode && b.blob_bytes >= ctx->hostpack_min_bytes;
+    const bool dense = b.h_pp && !b.h_seq_off; // host batch without offsets: sequences back to back
+    DenseOffsets dense_off; // declared before the packer: its threads may call into it
+    dense_off.len = b.h_seq_len, dense_off.n = n_seqs;
     HostPacker packer;
     std::vector<Chunk> chunks;
     plan_prepare(ctx, b, chunks);
+    if (dense) {
+        int r = scan_offsets_reserve(ctx, (size_t)n_seqs + 1);
+        if (r) return r;
+    }
     if (host_pack) {
         int r = ensure_pinned(ctx, ctx->h_packed, ctx->h_packed_cap, (b.blob_bytes / 16 + 2) * 4);
         if (r) return r;
@@ -430,7 +488,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                      },
                      lazy_scan ? chunks.size() : 0, SCAN_PARTS,
                      [&scan_chunks, &b, hruns](size_t k, int part) { scan_chunk_part(b, scan_chunks[k], part, hruns); },
-                     getenv("TDB_TEST_RAW_BLOCKS") ? atoi(getenv("TDB_TEST_RAW_BLOCKS")) : 0);
+                     getenv("TDB_TEST_RAW_BLOCKS") ? atoi(getenv("TDB_TEST_RAW_BLOCKS")) : 0,
+                     dense ? &DenseOffsets::thunk : nullptr, &dense_off);
     }
     if (lazy_scan) {
         // The first chunk tells whether the pair list walks the sequence table in order; if it does not (a chunk
@@ -511,6 +570,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
 
     uint32_t seq_up = 0; // sequences [0, seq_up) are uploaded / packed
+    uint64_t dense_pos = 0; // dense layout: byte offset of sequence seq_up
     std::vector<std::pair<uint64_t, uint64_t>> raw_ranges; // this chunk's byte ranges shipped as ASCII in host-pack mode
 
     // ---- chunks ---------------------------------------------------------------------------------------
@@ -528,18 +588,36 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
         seq_up = e;
         // blob bytes of the new sequences (device batches: offsets unknown on the host -> everything at once)
         uint64_t b0 = 0, b1 = b.blob_bytes;
+        const uint64_t off_a = dense_pos;
         if (b.h_pp && e > a) {
-            b0 = std::min<uint64_t>(b.h_seq_off[a], b.blob_bytes) & ~(uint64_t)15;
-            b1 = e == n_seqs ? b.blob_bytes : std::min<uint64_t>(b.h_seq_off[e - 1] + b.h_seq_len[e - 1], b.blob_bytes);
+            uint64_t first = 0, end = 0;
+            if (dense) {
+                uint64_t sum = 0;
+                for (uint32_t i = a; i < e; ++i) sum += b.h_seq_len[i];
+                first = off_a, end = off_a + sum;
+                dense_pos = end;
+            } else {
+                first = b.h_seq_off[a], end = b.h_seq_off[e - 1] + b.h_seq_len[e - 1];
+            }
+            b0 = std::min<uint64_t>(first, b.blob_bytes) & ~(uint64_t)15;
+            b1 = e == n_seqs ? b.blob_bytes : std::min<uint64_t>(end, b.blob_bytes);
             b1 = std::max(b1, b0);
         }
         if (b.h_pp) { // queue this chunk's upload on the copy stream
             if (e > a) {
                 // one offset beyond the chunk: k_hash checks every sequence against its successor's offset
                 const size_t n_off = (size_t)(e - a) + (e < n_seqs ? 1 : 0);
-                CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, n_off * 8, cudaMemcpyHostToDevice, cs));
-                CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
-                cn.bytes_h2d += n_off * 8 + (uint64_t)(e - a) * 4;
+                if (dense) { // lengths only (one beyond the chunk feeds the scan's last output); offsets by prefix sum
+                    CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, n_off * 4, cudaMemcpyHostToDevice, cs));
+                    int r = scan_offsets(ctx, b.seq_len + a, (uint64_t *)b.seq_off + a, n_off, off_a, cs);
+                    if (r) return r;
+                    cn.kernel_launches += 1;
+                    cn.bytes_h2d += n_off * 4;
+                } else {
+                    CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, n_off * 8, cudaMemcpyHostToDevice, cs));
+                    CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
+                    cn.bytes_h2d += n_off * 8 + (uint64_t)(e - a) * 4;
+                }
                 if (!host_pack) {
                     if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
                     cn.bytes_h2d += b1 - b0;
@@ -569,8 +647,6 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                                                    cudaMemcpyHostToDevice, cs));
                                 cn.bytes_h2d += (uint64_t)(w1 - w0) * 4;
                             } else {
-                                CK(cudaMemcpyAsync((uint8_t *)b.blob + x0, b.h_blob + x0, x1 - x0, cudaMemcpyHostToDevice, cs));
-                                cn.bytes_h2d += x1 - x0;
                                 cn.bytes_raw += x1 - x0;
                                 raw_ranges.push_back({x0, x1});
                             }
@@ -578,18 +654,32 @@ int run_align(tdb_ctx *ctx, const DevBatch &b, bool cigar_mode) {
                         }
                     }
                     cn.ms_host_pack_wait += ms_since(t_wait);
-                    CK(cudaMemcpyAsync((uint8_t *)ctx->seq_flag.p + a, hf + a, (size_t)(e - a), cudaMemcpyHostToDevice, cs));
-                    cn.bytes_h2d += (uint64_t)(e - a);
+                    // A chunk with a share left to the GPU ships its ASCII whole: a sequence k_pack flags there may
+                    // reach into a neighbouring host-packed block, and flagged sequences are compared as raw bytes.
+                    const bool chunk_raw = !raw_ranges.empty();
+                    if (chunk_raw) {
+                        CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+                        cn.bytes_h2d += b1 - b0;
+                    }
+                    // flags found by the host packers (almost always none: one vectorised pass instead of a copy)
+                    const bool any_flag = memchr(hf + a, 1, (size_t)(e - a)) != nullptr;
+                    if (any_flag) {
+                        CK(cudaMemcpyAsync((uint8_t *)ctx->seq_flag.p + a, hf + a, (size_t)(e - a), cudaMemcpyHostToDevice, cs));
+                        cn.bytes_h2d += (uint64_t)(e - a);
+                    } else {
+                        CK(cudaMemsetAsync((uint8_t *)ctx->seq_flag.p + a, 0, (size_t)(e - a), cs));
+                    }
                     // sequences with bytes outside ACGT are compared as raw bytes on the device: ship those bytes
                     size_t n_flag = 0;
-                    if (memchr(hf + a, 1, (size_t)(e - a))) // almost always absent: one vectorised pass
+                    if (any_flag && !chunk_raw)
                         for (uint32_t i = a; i < e; ++i) n_flag += hf[i] != 0;
+                    const uint64_t *hoff = !n_flag ? nullptr : dense ? dense_off.get() : b.h_seq_off;
                     if (n_flag > 256) {
                         if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
                         cn.bytes_h2d += b1 - b0;
                     } else if (n_flag) {
                         for (uint32_t i = a; i < e; ++i) {
-                            const uint64_t o = b.h_seq_off[i];
+                            const uint64_t o = hoff[i];
                             if (hf[i] && b.h_seq_len[i] && o <= b.blob_bytes && b.h_seq_len[i] <= b.blob_bytes - o) {
                                 CK(cudaMemcpyAsync((uint8_t *)b.blob + o, b.h_blob + o, b.h_seq_len[i], cudaMemcpyHostToDevice, cs));
                                 cn.bytes_h2d += b.h_seq_len[i];
@@ -863,9 +953,10 @@ int validate_common(tdb_ctx *ctx, const void *blob, const void *off, const void 
                     size_t n_seqs, size_t n_pairs, const void *out_score) {
     if (!ctx) return TDB_E_INVALID;
     ctx->err.clear();
-    if ((n_seqs && (!off || !len)) || (n_pairs && (!pp || !pt || !out_score)) || (n_pairs && !n_seqs))
+    // off == NULL selects the dense layout: sequence i starts where sequence i-1 ends, sequence 0 at byte 0
+    if ((n_seqs && !len) || (n_pairs && (!pp || !pt || !out_score)) || (n_pairs && !n_seqs))
         return fail(ctx, TDB_E_INVALID, "null pointer argument");
-    (void)blob;
+    (void)blob, (void)off;
     return TDB_OK;
 }
 
@@ -1024,7 +1115,7 @@ void tdb_destroy(tdb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
     DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->pair_p, &c->pair_t,
-                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->ctrl, &c->loci, &c->runs,
+                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->scan_tmp, &c->ctrl, &c->loci, &c->runs,
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();

@@ -31,10 +31,16 @@ void flag_owner(uint64_t x, const uint64_t *seq_off, const uint32_t *seq_len, ui
 }
 
 struct Owner {
-    const uint64_t *seq_off;
+    mutable const uint64_t *seq_off; // null for a dense layout until a byte outside ACGT asks for it
     const uint32_t *seq_len;
     uint32_t n_seqs;
     uint8_t *flag;
+    const uint64_t *(*make_off)(void *);
+    void *arg;
+    const uint64_t *off() const {
+        if (!seq_off) seq_off = make_off(arg);
+        return seq_off;
+    }
 };
 
 // All three variants pack bytes [x0, x1) of the blob into words [x0/16, ceil(x1/16)); x0 % 64 == 0.
@@ -43,7 +49,7 @@ void pack_scalar(const uint8_t *blob, uint64_t x0, uint64_t x1, uint32_t *packed
         uint32_t w = 0;
         for (uint32_t k = 0; k < 16u && x + k < x1; ++k) {
             const uint8_t c = blob[x + k];
-            if (!is_acgt(c)) flag_owner(x + k, ow.seq_off, ow.seq_len, ow.n_seqs, ow.flag);
+            if (!is_acgt(c)) flag_owner(x + k, ow.off(), ow.seq_len, ow.n_seqs, ow.flag);
             w |= (uint32_t)((c >> 1) & 3u) << (2 * k);
         }
         packed[x >> 4] = w;
@@ -71,7 +77,7 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *blob, uint64_t x0,
         while (bad) {
             const int k = __builtin_ctz(bad);
             bad &= bad - 1;
-            flag_owner(x + (uint64_t)k, ow.seq_off, ow.seq_len, ow.n_seqs, ow.flag);
+            flag_owner(x + (uint64_t)k, ow.off(), ow.seq_len, ow.n_seqs, ow.flag);
         }
     }
     if (x < x1) pack_scalar(blob, x, x1, packed, ow);
@@ -110,7 +116,7 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) void pack_avx512(const uint
         while (bad) {
             const int k = __builtin_ctzll(bad);
             bad &= bad - 1;
-            flag_owner(x + (uint64_t)k, ow.seq_off, ow.seq_len, ow.n_seqs, ow.flag);
+            flag_owner(x + (uint64_t)k, ow.off(), ow.seq_len, ow.n_seqs, ow.flag);
         }
     }
     _mm_sfence(); // order the streaming stores before the block is published as done
@@ -150,8 +156,9 @@ const Dispatch &dispatch() {
 const char *hostpack_isa() { return dispatch().name; }
 
 void hostpack_stream(const uint8_t *blob, uint64_t x0, uint64_t x1, uint32_t *packed, const uint64_t *seq_off,
-                     const uint32_t *seq_len, uint32_t n_seqs, uint8_t *flag) {
-    const Owner ow = {seq_off, seq_len, n_seqs, flag};
+                     const uint32_t *seq_len, uint32_t n_seqs, uint8_t *flag, const uint64_t *(*make_off)(void *),
+                     void *make_arg) {
+    const Owner ow = {seq_off, seq_len, n_seqs, flag, make_off, make_arg};
     if (x1 > x0) dispatch().fn(blob, x0, x1, packed, ow);
 }
 

@@ -236,9 +236,7 @@ class _BatchBuilder:
     def arrays(self):
         blob = np.frombuffer(b"".join(self.chunks), dtype=np.uint8) if self.chunks else np.zeros(0, np.uint8)
         lens = np.array(self.lens, dtype=np.uint32)
-        offs = np.zeros(len(lens), dtype=np.uint64)
-        if len(lens):
-            offs[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
+        offs = None  # dense layout: sequences back to back, the library derives the offsets
         return blob, offs, lens, np.array(self.pp, dtype=np.uint32), np.array(self.pt, dtype=np.uint32)
 
 
