@@ -276,13 +276,15 @@ def main():
     barrier()
     w0 = time.time()
     dev_ms, launches = 0.0, 0
-    stage = {k: 0.0 for k in ("pack", "dedup", "align_quad", "align_warp", "align_global", "scatter", "reduce")}
+    stage = {k: 0.0 for k in ("pack", "dedup", "align_thread", "align_quad", "align_warp", "align_global", "scatter",
+                              "reduce")}
     cnt = None
     for _ in range(args.steps):
         cnt = step_device()
         dev_ms += cnt.ms_total_device
         stage["pack"] += cnt.ms_pack
         stage["dedup"] += cnt.ms_dedup
+        stage["align_thread"] += cnt.ms_thread_tier
         stage["align_quad"] += cnt.ms_tier[0]
         stage["align_warp"] += cnt.ms_tier[1]
         stage["align_global"] += cnt.ms_tier[2]
@@ -354,13 +356,17 @@ def main():
     if rank == 0:
         # roofline of the dominant kernel, per launch, rank 0's shard.  Work = what THAT launch executed
         # (representative pairs only; duplicates are copied, not aligned), SURVEY.md 8(d) accounting.
-        tiers = ("align_quad", "align_warp", "align_global")
-        names = {"align_quad": "k_align_lock<QuadCfg>", "align_warp": "k_align_warp", "align_global": "k_align_global"}
-        ti = max(range(3), key=lambda i: stage[tiers[i]])
+        tiers = ("align_quad", "align_warp", "align_global", "align_thread")
+        names = {"align_quad": "k_align_lock<QuadCfg>", "align_warp": "k_align_warp", "align_global": "k_align_global",
+                 "align_thread": "k_align_thread"}
+        ti = max(range(4), key=lambda i: stage[tiers[i]])
         k_ms = stage[tiers[ti]] / args.steps
         k_s = max(k_ms, 1e-6) * 1e-3
-        ops = (INT_OPS_PER_CELL * cnt.tier_cells[ti] + INT_OPS_PER_EXT * cnt.tier_ext16[ti] +
-               INT_OPS_PER_COL * cnt.tier_columns[ti])
+        t_pairs = [int(x) for x in cnt.tier_pairs[:3]] + [int(cnt.thread_pairs)]
+        t_cells = [int(x) for x in cnt.tier_cells[:3]] + [int(cnt.thread_cells)]
+        t_ext = [int(x) for x in cnt.tier_ext16[:3]] + [int(cnt.thread_ext16)]
+        t_cols = [int(x) for x in cnt.tier_columns[:3]] + [int(cnt.thread_columns)]
+        ops = INT_OPS_PER_CELL * t_cells[ti] + INT_OPS_PER_EXT * t_ext[ti] + INT_OPS_PER_COL * t_cols[ti]
         ops_algo = (INT_OPS_PER_CELL * algo_work["cells"] + INT_OPS_PER_EXT * algo_work["ext16"] +
                     INT_OPS_PER_COL * algo_work["columns"])
         clk = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
@@ -369,7 +375,7 @@ def main():
         # algorithmic HBM bytes of the launch: 2-bit sequences + 16 B descriptor/result per pair it aligned
         mean_pair_bytes = float(np.mean((batch.seq_len[batch.pair_pattern[:200000]].astype(np.int64) + 3) // 4 +
                                         (batch.seq_len[batch.pair_text[:200000]].astype(np.int64) + 3) // 4)) + 16.0
-        algo_bytes = mean_pair_bytes * float(cnt.tier_pairs[ti])
+        algo_bytes = mean_pair_bytes * float(t_pairs[ti])
         step_s = dev_ms / args.steps * 1e-3
         # DRAM traffic of that kernel per launch: bytes per aligned pair from the committed ncu --set full capture
         # (profiles/r01/traffic.json, written by profiles/summarize_final.py) x the pairs this launch aligned
@@ -378,7 +384,7 @@ def main():
         if os.path.exists(tj):
             tinfo = json.load(open(tj)).get(names[tiers[ti]])
             if tinfo:
-                traffic = tinfo["dram_bytes_per_pair"] * float(cnt.tier_pairs[ti])
+                traffic = tinfo["dram_bytes_per_pair"] * float(t_pairs[ti])
                 traffic_src = tinfo["source"] + ", per-pair bytes scaled to this launch"
         roofline = {
             "bound": "hbm", "kernel": names[tiers[ti]], "achieved": algo_bytes / k_s / 1e9,
@@ -391,7 +397,7 @@ def main():
                           "peak_source": f"{n_sm} SM x 128 lanes x {clk / 1e6:.0f} MHz (clock observed under load)",
                           "accounting": "24*C + 8*E + 4*T of the pairs this launch aligned (counted exactly on "
                                         "the device), over its CUDA-event duration",
-                          "pairs_aligned_by_kernel": int(cnt.tier_pairs[ti])},
+                          "pairs_aligned_by_kernel": t_pairs[ti]},
             "whole_step_algorithmic": {"ops_per_s": ops_algo / step_s, "frac_of_int_peak": ops_algo / step_s / int_peak,
                                        "note": "every pair counted as the CPU oracle counts it (duplicates "
                                                "included) over the whole device step"},
@@ -419,7 +425,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "breakdown_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-            "tier_pairs": [int(x) for x in cnt.tier_pairs],
+            "tier_pairs": [int(x) for x in cnt.tier_pairs], "thread_tier_pairs": int(cnt.thread_pairs),
             "pairs_identical": int(cnt.pairs_identical), "pairs_duplicate": int(cnt.pairs_duplicate),
             "pairs_closed_form": int(cnt.pairs_closed_form),
             "work": {"cells": algo_work["cells"], "ext16": algo_work["ext16"], "columns": algo_work["columns"],

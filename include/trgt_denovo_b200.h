@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define TDB_ABI_VERSION 2
+#define TDB_ABI_VERSION 3
 
 /* return codes */
 #define TDB_OK 0
@@ -251,6 +251,9 @@ typedef struct {
                          last chunk queued by the calling thread */
     float ms_tier[4]; /* per alignment tier (events on the launching stream); [2] covers both global tiers.
                          Stage times are recorded for single-chunk calls only (ms_total_device always). */
+    float ms_thread_tier;   /* the thread-per-pair tier that runs in front of tier 0 */
+    uint64_t thread_pairs;  /* pairs ALIGNED by the thread-per-pair tier (final penalty <= 24), and the work */
+    uint64_t thread_cells, thread_ext16, thread_columns; /* it executed (also included in exec_*) */
 } tdb_counters;
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 /* Exact algorithmic work counting (cells / ext16 / columns of tdb_counters: every pair counted as the CPU

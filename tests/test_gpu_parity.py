@@ -76,7 +76,7 @@ def _check_batch(ctx, seqs, pp, pt, clip, heuristic=tdo.DEFAULT_HEURISTIC, cigar
     assert (st == wst).all()
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, f"{len(bad)} score mismatches (closed form on), first pair {bad[:5]}: gpu {got[bad[:5]]} oracle {want[bad[:5]]}"
-    assert sum(fast.tier_pairs) + fast.pairs_identical + fast.pairs_duplicate + fast.pairs_closed_form == len(pp)
+    assert sum(fast.tier_pairs) + fast.thread_pairs + fast.pairs_identical + fast.pairs_duplicate + fast.pairs_closed_form == len(pp)
     # dense layout (seq_off = NULL): to_arrays lays the sequences back to back, the device derives the offsets
     got, st = ctx.align_batch(blob, None, ln, pp, pt)
     assert (st == wst).all() and (got == want).all()
@@ -107,10 +107,10 @@ def test_str_pairs_bit_exact(ctx, clip):
     rng = random.Random(100 + clip)
     seqs, pp, pt = make_pairs(rng, n_targets=300, reads_per_target=12)
     cnt = _check_batch(ctx, seqs, pp, pt, clip)
-    aligned = sum(cnt.tier_pairs)
+    aligned = sum(cnt.tier_pairs) + cnt.thread_pairs
     assert aligned + cnt.pairs_identical + cnt.pairs_duplicate == len(pp)
-    assert cnt.tier_pairs[0] + cnt.tier_pairs[1] > 0.8 * aligned  # the shared-memory tiers carry the bulk
-    assert cnt.tier_pairs[0] > 0 and cnt.tier_pairs[1] > 0
+    assert cnt.thread_pairs + cnt.tier_pairs[0] + cnt.tier_pairs[1] > 0.8 * aligned  # the shared-memory tiers carry the bulk
+    assert cnt.thread_pairs > 0 and cnt.tier_pairs[0] > 0 and cnt.tier_pairs[1] > 0
 
 
 def test_random_divergent_pairs(ctx):
@@ -136,6 +136,39 @@ def test_quad_tier_disabled_gives_same_scores(tdb, monkeypatch):
     monkeypatch.delenv("TDB_DISABLE_QUAD")
     cnt = _check_batch(c, seqs, pp, pt, 50)
     assert cnt.tier_pairs[0] == 0
+    c.close()
+
+
+def test_thread_tier_disabled_gives_same_scores(tdb, monkeypatch):
+    """The thread-per-pair tier takes the lightest pairs (final penalty <= 24) in front of the lockstep tier: the
+    lockstep tier alone must give the same scores and work counts, and with it on most light pairs end there."""
+    rng = random.Random(38)
+    seqs, pp, pt = make_pairs(rng, n_targets=150, reads_per_target=12, max_units=25, err=0.006)
+    monkeypatch.setenv("TDB_DISABLE_THREAD_TIER", "1")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_DISABLE_THREAD_TIER")
+    cnt = _check_batch(c, seqs, pp, pt, 50)
+    assert cnt.thread_pairs == 0 and cnt.tier_pairs[0] > 0
+    c.close()
+    c = tdb.Context()
+    cnt2 = _check_batch(c, seqs, pp, pt, 50)
+    assert cnt2.thread_pairs > 0.3 * cnt.tier_pairs[0]
+    assert cnt2.thread_pairs + sum(cnt2.tier_pairs) == sum(cnt.tier_pairs)
+    # every length from empty upwards, tiny clip windows, heuristic off: the tier's range guards
+    seqs, pp, pt = [], [], []
+    for L in list(range(0, 40)) + [63, 64, 65, 200]:
+        for _ in range(6):
+            t = rand_seq(rng, L)
+            p = mutate(rng, t, rng.choice([0.02, 0.05, 0.1])) if L else rng.choice(["", "A", "ACG"])
+            pt.append(len(seqs)); seqs.append(t.encode())
+            pp.append(len(seqs)); seqs.append(p.encode())
+    for clip in (0, 3, 50):
+        _check_batch(c, seqs, np.array(pp, np.uint32), np.array(pt, np.uint32), clip)
+    c.close()
+    c = tdb.Context(heuristic=(0, 0, 0, 0))
+    seqs, pp, pt = make_pairs(rng, n_targets=60, reads_per_target=8, max_units=30, err=0.01)
+    cnt3 = _check_batch(c, seqs, pp, pt, 50, heuristic=tdo.NO_HEURISTIC)
+    assert cnt3.thread_pairs > 0
     c.close()
 
 

@@ -1,6 +1,7 @@
 // tdb_api.cu -- C ABI (include/trgt_denovo_b200.h) over the sm_100a kernels.  No CPU compute path:
 // every entry point that does arithmetic launches CUDA kernels or fails.
 #include "tdb_wfa_quad.cuh"
+#include "tdb_wfa_thread.cuh"
 #include "tdb_hostpack.h"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -49,13 +50,14 @@ struct Ctrl {
     unsigned wc_g[2];  // work counters of the two global tiers
     unsigned n_closed; // pairs resolved in closed form (k_pair_classify)
     unsigned pad0[2];
-    unsigned long long exec[4][4]; // executed cells, ext16, columns, pairs finished; per tier
+    unsigned long long exec[5][4]; // executed cells, ext16, columns, pairs finished; per tier ([4]: thread-per-pair tier)
     unsigned long long algo[4];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self
     // ---- per chunk (one block per pipeline slot, zeroed before every chunk) ----
     struct Chunk {
-        unsigned wc_quad, wc_warp, acount, pad1;
+        unsigned wc_quad, wc_warp, acount, wc_mini;
+        unsigned mcount, pad1[3]; // mcount: pairs the thread-per-pair tier handed on
         unsigned hist[N_HIST];
-        unsigned seg[4];
+        unsigned seg[8];
     } ck[2];
 };
 constexpr int N_SLOT = 2;
@@ -79,11 +81,12 @@ struct tdb_ctx {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf canon, skey_in, skey_out, sval_in, sval_out, cub_tmp, seq_tab, pair_tab, list_a;
+        DevBuf canon, skey_in, skey_out, sval_in, sval_out, cub_tmp, seq_tab, pair_tab, list_a, list_m;
     } slot[2];
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
-    int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0;
+    int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0, mini_ctas_per_sm = 0;
+    bool disable_mini = false;
     bool disable_quad = false, disable_duo = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
     size_t chunk_pairs = 2u << 20;
     size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
@@ -436,6 +439,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     const bool default_pen = cp.mismatch == 8 && cp.gap_opening1 == 4 && cp.gap_extension1 == 2 &&
                              cp.gap_opening2 == 24 && cp.gap_extension2 == 1;
     const bool quad_ok = default_pen && !ctx->disable_quad;
+    const bool mini_ok = quad_ok && !ctx->disable_mini; // its leftovers go to the lockstep tier
     const bool dedup = !ctx->disable_dedup && !cigar_mode;
 
     const auto t_call = std::chrono::steady_clock::now();
@@ -541,6 +545,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             ENSURE(sl.sval_in, max_cp * 4);
             ENSURE(sl.sval_out, max_cp * 4);
             ENSURE(sl.list_a, max_cp * 4);
+            if (mini_ok) ENSURE(sl.list_m, max_cp * 4);
             if (dedup) ENSURE(sl.seq_tab, ((size_t)table_mask(max_cs) + 1) * 12);
             ENSURE(sl.pair_tab, ((size_t)table_mask(max_cp) + 1) * 12);
             ENSURE(sl.cub_tmp, tmp);
@@ -779,7 +784,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         co.out_score = b.score, co.out_status = b.status, co.out_penalty = b.penalty, co.work = p.work;
         k_pair_classify<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, b.seq_len,
                                                  (const uint8_t *)ctx->seq_flag.p, b.seq_off, (const uint32_t *)ctx->packed.p,
-                                                 tb, quad_ok ? 1 : 0, T0_MAXLEN, cf, co);
+                                                 tb, quad_ok ? 1 : 0, mini_ok ? 1 : 0, T0_MAXLEN, cf, co);
         CK(cudaGetLastError());
         size_t tmp = sl.cub_tmp.cap;
         CK(cub::DeviceRadixSort::SortPairs(sl.cub_tmp.p, tmp, (const uint8_t *)sl.skey_in.p, (uint8_t *)sl.skey_out.p,
@@ -788,10 +793,23 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         CK(cudaGetLastError());
         cn.kernel_launches += 6; // insert, classify, sort (3 kernels), plan
         if (staged) CK(cudaEventRecord(ctx->ev[3], st));
-        // tier 0: four pairs per warp, shared memory (default penalties only)
         p.src1 = (const uint32_t *)sl.sval_out.p;
+        // thread-per-pair tier: the lightest pairs (|n-m| < 8), up to penalty 24; the rest moves on to tier 0
+        if (mini_ok) {
+            p.src1_seg = ck->seg + 4, p.src2 = nullptr, p.src2_count = nullptr;
+            p.work_counter = &ck->wc_mini, p.next_todo = (uint32_t *)sl.list_m.p, p.next_count = &ck->mcount;
+            p.counters = ctrl->exec[4];
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->mini_ctas_per_sm,
+                                                             ((size_t)cpairs + TH_NT - 1) / TH_NT + 1);
+            k_align_thread<8, 4, 2, 24, 1><<<grid, TH_NT, th_smem_bytes(), st>>>(p);
+            CK(cudaGetLastError());
+            cn.kernel_launches += 1;
+        }
+        if (staged) CK(cudaEventRecord(ctx->ev[11], st));
+        // tier 0: four pairs per warp, shared memory (default penalties only)
         if (quad_ok) {
-            p.src1_seg = ck->seg + 2, p.src2 = nullptr, p.src2_count = nullptr;
+            p.src1_seg = ck->seg + 2;
+            p.src2 = mini_ok ? (const uint32_t *)sl.list_m.p : nullptr, p.src2_count = mini_ok ? &ck->mcount : nullptr;
             p.work_counter = &ck->wc_quad, p.next_todo = (uint32_t *)sl.list_a.p, p.next_count = &ck->acount;
             p.counters = ctrl->exec[0];
             const size_t smem = lock_smem_bytes<QuadCfg>();
@@ -895,6 +913,10 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         cn.tier_pairs[t] = h.exec[t][3];
         aligned += h.exec[t][3];
     }
+    cn.exec_cells += h.exec[4][0], cn.exec_ext16 += h.exec[4][1], cn.exec_columns += h.exec[4][2];
+    cn.thread_cells = h.exec[4][0], cn.thread_ext16 = h.exec[4][1], cn.thread_columns = h.exec[4][2];
+    cn.thread_pairs = h.exec[4][3];
+    aligned += h.exec[4][3];
     if (cigar_mode) {
         cn.cells = cn.exec_cells, cn.ext16 = cn.exec_ext16, cn.columns = cn.exec_columns;
     } else {
@@ -909,12 +931,13 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         cn.ms_pack = elapsed(ctx->ev[0], ctx->ev[2]);
         if (!cigar_mode) {
             cn.ms_dedup = elapsed(ctx->ev[2], ctx->ev[3]);
-            cn.ms_tier[0] = elapsed(ctx->ev[3], ctx->ev[4]);
+            cn.ms_thread_tier = elapsed(ctx->ev[3], ctx->ev[11]);
+            cn.ms_tier[0] = elapsed(ctx->ev[11], ctx->ev[4]);
             cn.ms_tier[1] = elapsed(ctx->ev[4], ctx->ev[5]);
             cn.ms_scatter = elapsed(ctx->ev[7], ctx->ev[1]);
         }
         cn.ms_tier[2] = elapsed(ctx->ev[6], ctx->ev[7]);
-        cn.ms_align = cn.ms_tier[0] + cn.ms_tier[1] + cn.ms_tier[2];
+        cn.ms_align = cn.ms_thread_tier + cn.ms_tier[0] + cn.ms_tier[1] + cn.ms_tier[2];
     }
     return TDB_OK;
 }
@@ -1085,7 +1108,23 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
             tdb_destroy(c);
             return code;
         }
+        {
+            cudaError_t e2 = cudaFuncSetAttribute(k_align_thread<8, 4, 2, 24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)th_smem_bytes());
+            if (e2 == cudaSuccess)
+                e2 = cudaFuncSetAttribute(k_align_thread<8, 4, 2, 24, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (e2 == cudaSuccess)
+                e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->mini_ctas_per_sm, k_align_thread<8, 4, 2, 24, 1>, TH_NT,
+                                                                   th_smem_bytes());
+            if (e2 != cudaSuccess || c->mini_ctas_per_sm < 1) {
+                int code = fail(nullptr, TDB_E_CUDA, "thread-per-pair kernel setup failed: %s (occupancy %d)",
+                                cudaGetErrorString(e2), c->mini_ctas_per_sm);
+                tdb_destroy(c);
+                return code;
+            }
+        }
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
+        c->disable_mini = getenv("TDB_DISABLE_THREAD_TIER") != nullptr;
         // the two-pairs-per-warp lockstep variant of tier 1 measures the same as one pair per warp (wide wavefronts
         // already fill the lanes) and overflows a little more often (FIFO arena): opt-in, kept for experiments
         c->disable_duo = getenv("TDB_ENABLE_DUO") == nullptr;
@@ -1121,7 +1160,7 @@ void tdb_destroy(tdb_ctx *c) {
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
         DevBuf *sb[] = {&sl.canon, &sl.skey_in, &sl.skey_out, &sl.sval_in, &sl.sval_out, &sl.cub_tmp, &sl.seq_tab,
-                        &sl.pair_tab, &sl.list_a};
+                        &sl.pair_tab, &sl.list_a, &sl.list_m};
         for (DevBuf *b : sb) b->release();
     }
     if (c->slot[1].st) cudaStreamDestroy(c->slot[1].st);

@@ -269,7 +269,11 @@ constexpr int QL_MAX = TDB_QL_MAX; // |n-m| >= QL_MAX: wavefront wider than the 
 constexpr int WL_MAX = 40;  // |n-m| >= WL_MAX: wider than the warp tier's 64 diagonals
 constexpr int KEY_WARP = 0; // sorted first: heaviest pairs of the shared-memory tiers
 constexpr int KEY_QUAD0 = 1;
+constexpr int ML_MAX = 8;       // |n-m| < ML_MAX and both sequences >= ML_MINLEN bases: thread-per-pair tier first
+constexpr int ML_MINLEN = 16;
+constexpr int KEY_MINI0 = KEY_QUAD0 + QL_MAX; // sorted last: the lightest pairs
 constexpr int KEY_NONE = 255;
+static_assert(KEY_MINI0 + ML_MAX <= 32, "histogram size");
 constexpr int N_HIST = 32;
 
 struct PairTable {
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
                                                        const uint8_t *__restrict__ seq_flag,
                                                        const uint64_t *__restrict__ seq_off,
                                                        const uint32_t *__restrict__ packed, PairTable tb,
-                                                       int quad_ok, int max_len16, ClosedFormCfg cf, ClassifyOut o) {
+                                                       int quad_ok, int mini_ok, int max_len16, ClosedFormCfg cf, ClassifyOut o) {
     __shared__ unsigned sh_hist[N_HIST + 1];
     if (threadIdx.x <= N_HIST) sh_hist[threadIdx.x] = 0;
     __syncthreads();
@@ -441,6 +445,8 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
                         o.glist[q] = j;
                     } else if (!quad_ok || L >= QL_MAX) {
                         key = KEY_WARP;
+                    } else if (mini_ok && L < ML_MAX && n >= ML_MINLEN && m >= ML_MINLEN) {
+                        key = KEY_MINI0 + (ML_MAX - 1 - L);
                     } else {
                         key = KEY_QUAD0 + (QL_MAX - 1 - L);
                     }
@@ -458,13 +464,15 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
 }
 
 // Segment table of the sorted list: seg[0] = begin, seg[1] = count of the warp-tier segment;
-// seg[2], seg[3] the same for the quad tier.
+// seg[2], seg[3] the same for the lockstep (quad) tier; seg[4], seg[5] for the thread-per-pair tier.
 __global__ void k_plan(const unsigned *__restrict__ hist, unsigned *__restrict__ seg) {
     if (threadIdx.x == 0) {
-        unsigned q = 0;
+        unsigned q = 0, t = 0;
         for (int i = KEY_QUAD0; i < KEY_QUAD0 + QL_MAX; ++i) q += hist[i];
+        for (int i = KEY_MINI0; i < KEY_MINI0 + ML_MAX; ++i) t += hist[i];
         seg[0] = 0, seg[1] = hist[KEY_WARP];
         seg[2] = hist[KEY_WARP], seg[3] = q;
+        seg[4] = hist[KEY_WARP] + q, seg[5] = t;
     }
 }
 

@@ -1,0 +1,318 @@
+// tdb_wfa_thread.cuh -- thread-per-pair tier for the cheapest alignments (sm_100a).
+//
+// Most pairs that reach the wavefront kernels are a read with two or three sequencing errors against
+// its allele: final penalty <= 24, wavefronts a handful of diagonals wide.  The lockstep tier spends
+// a warp instruction on 8 lanes per pair of which 1..5 hold a live diagonal; here ONE THREAD owns a
+// pair and walks its own diagonals, so every lane of a warp instruction is a different alignment.
+//
+// What makes that fit: with the production penalties (x 8, o1+e1 6, e1 2, o2+e2 25) nothing below
+// score 25 can use the second gap piece and only even scores are reachable, so up to score 24 the
+// recurrence is single-piece gap-affine over 12 score steps, diagonals |k| <= (s-4)/2 <= 10.  Per
+// thread: a 5-slot M ring + in-place I1/D1 (147 int16) and 4 provenance bits per computed cell
+// (30 words), all in shared memory interleaved by thread (element e of thread t at e*128 + t: a warp
+// access touches 16 banks at most 2-way).  A pair that is not finished at score 24 is handed to the
+// lockstep tier, which starts it over.
+//
+// Semantics are those of wfa_align_warp (tdb_wfa.cuh) step for step: compute + trim (A.2),
+// wf-adaptive cut-off + equate (A.3), provenance tie-breaks X > D1 > I1 and matches re-extended only
+// in the M component (A.4), flank-clipped score on the fly (src/aligner.rs:320-376).
+#pragma once
+#include "tdb_kernels.cuh"
+
+namespace tdb {
+
+constexpr int TH_NT = 128;                  // threads (= pairs in flight) per CTA
+constexpr int TH_KM = 10;                   // diagonals -TH_KM .. TH_KM
+constexpr int TH_W = 2 * TH_KM + 1;
+constexpr int TH_SMAX = 24;                 // last score this tier computes
+constexpr int TH_MSLOTS = 5;                // M ring: scores s, s-2, .., s-8
+constexpr int TH_HW = TH_MSLOTS * TH_W + 2 * TH_W; // int16 elements per thread
+constexpr int TH_STEPS = TH_SMAX / 2 - 2;   // scores 6, 8, .., 24
+constexpr int TH_PW = 3;                    // provenance words per score step (21 nibbles)
+constexpr size_t th_smem_bytes() { return (size_t)TH_NT * (TH_HW * 2 + TH_STEPS * TH_PW * 4); }
+
+__device__ __forceinline__ int th_extend(const SeqView &P, const SeqView &T, int v, int h) {
+    unsigned long long dummy = 0;
+    return extend_lane(P, T, v, h, dummy);
+}
+
+template <int X, int O1, int E1, int O2, int E2>
+__global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
+    static_assert(X == 8 && O1 + E1 == 6 && E1 == 2 && O2 + E2 > TH_SMAX, "ring geometry is built for 8/4/2/24/1");
+    constexpr int NULLV = OffTraits<int16_t>::NULLV;
+    constexpr int HUGE_D = 1 << 30;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    int16_t *hw = reinterpret_cast<int16_t *>(smem_raw) + threadIdx.x;
+    uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TH_NT * TH_HW * 2) + threadIdx.x;
+#define TH_M(slot, k) hw[((slot) * TH_W + (k) + TH_KM) * TH_NT]
+#define TH_I(k) hw[(TH_MSLOTS * TH_W + (k) + TH_KM) * TH_NT]
+#define TH_D(k) hw[((TH_MSLOTS + 1) * TH_W + (k) + TH_KM) * TH_NT]
+#define TH_P(t, w) pw[((t) * TH_PW + (w)) * TH_NT]
+    const int lane = threadIdx.x & 31;
+    const ItemSrc src = item_src(p);
+    const Penalties pn = {X, O1, E1, O2, E2};
+    const Heur heur = p.heur;
+    unsigned long long tot_cells = 0, tot_ext = 0, tot_cols = 0, tot_done = 0;
+    for (;;) {
+        unsigned b = 0;
+        if (lane == 0) b = atomicAdd(p.work_counter, 32u);
+        b = __shfl_sync(TDB_FULL, b, 0);
+        if (b >= src.total) break;
+        const unsigned it = b + lane;
+        if (it < src.total) {
+            const uint32_t idx = item_at(p, src, it);
+            const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
+            const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
+            const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
+            const SeqView P = {p.packed + (poff >> 4), nullptr, n, (int)(poff & 15)};
+            const SeqView T = {p.packed + (toff >> 4), nullptr, m, (int)(toff & 15)};
+            const int k_end = m - n;
+            unsigned long long ext = 0;
+            unsigned cells = 0;
+            int pen = -1, clipped = 0, cols = 0;
+            // ---- score 0 ---------------------------------------------------------------------------
+            const int m0 = extend_lane(P, T, 0, 0, ext);
+            if (k_end == 0 && m0 >= m) {
+                pen = 0, cols = m;
+            } else {
+                TH_M(0, 0) = (int16_t)m0;
+                // wavefront ranges (lo, span = hi - lo + 1; span 0 = null) of M[s-2], M[s-4], M[s-6], M[s-8], I1/D1[s-2]
+                int ml2 = 1, ms2 = 0, ml4 = 1, ms4 = 0, ml6 = 0, ms6 = 1, ml8 = 1, ms8 = 0;
+                int il = 1, is = 0, dl = 1, ds = 0;
+                int steps_wait = heur.steps;
+                if (heur.kind == 1) --steps_wait;
+                for (int s = 6; s <= TH_SMAX; s += 2) {
+                    const int hh = s >> 1;
+                    const int cur = hh % TH_MSLOTS, s6 = (hh + 2) % TH_MSLOTS, s8 = (hh + 1) % TH_MSLOTS;
+                    int nml = 1, nms = 0, nil = 1, nis = 0, ndl = 1, nds = 0; // ranges of score s
+                    if (ms8 | ms6 | is | ds) {
+                        int lo = INT32_MAX, hi = INT32_MIN;
+                        if (ms8) lo = min(lo, ml8), hi = max(hi, ml8 + ms8 - 1);
+                        if (ms6) lo = min(lo, ml6 - 1), hi = max(hi, ml6 + ms6);
+                        if (is) lo = min(lo, il + 1), hi = max(hi, il + is);
+                        if (ds) lo = min(lo, dl - 1), hi = max(hi, dl + ds - 2);
+                        lo = max(lo, -n - 1);
+                        hi = min(hi, m + 1);
+                        cells += (unsigned)(hi - lo + 1);
+                        const bool has_i1 = ms6 || is, has_d1 = ms6 || ds;
+                        int tl_m = INT32_MAX, th_m = INT32_MIN, tl_i = INT32_MAX, th_i = INT32_MIN, tl_d = INT32_MAX,
+                            th_d = INT32_MIN;
+                        int min_d = HUGE_D;
+                        bool fin = false;
+                        unsigned long long pa = 0;
+                        uint32_t pb = 0, vmask = 0; // vmask: diagonals (bit k + TH_KM) whose M offset lies inside the matrix
+                        // I1 is updated in place: the old I1[k-1] travels in a register
+                        int carry_i = (unsigned)(lo - 1 - il) < (unsigned)is ? (int)TH_I(lo - 1) : NULLV;
+                        for (int k = lo; k <= hi; ++k) {
+                            const int old_i = (unsigned)(k - il) < (unsigned)is ? (int)TH_I(k) : NULLV;
+                            int nib = 0, o, e;
+                            o = (unsigned)(k - 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k - 1) : NULLV;
+                            e = carry_i;
+                            carry_i = old_i;
+                            int ins1;
+                            if (e >= o) ins1 = e, nib |= 4; else ins1 = o;
+                            ins1 += 1;
+                            o = (unsigned)(k + 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k + 1) : NULLV;
+                            e = (unsigned)(k + 1 - dl) < (unsigned)ds ? (int)TH_D(k + 1) : NULLV;
+                            int del1;
+                            if (e >= o) del1 = e, nib |= 8; else del1 = o;
+                            const int mis = ((unsigned)(k - ml8) < (unsigned)ms8 ? (int)TH_M(s8, k) : NULLV) + 1;
+                            int mv = max(max(ins1, del1), max(mis, NULLV + 1));
+                            int sc = 0; // later tests override: priority X > D1 > I1
+                            if (mv == ins1) sc = 1;
+                            if (mv == del1) sc = 2;
+                            if (mv == mis) sc = 3;
+                            nib |= sc;
+                            const int pi = k + TH_KM;
+                            if (pi < 16) pa |= (unsigned long long)nib << (4 * pi);
+                            else pb |= (uint32_t)nib << (4 * (pi - 16));
+                            if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = NULLV;
+                            if (mv >= 0) vmask |= 1u << pi, tl_m = min(tl_m, k), th_m = k;
+                            TH_M(cur, k) = (int16_t)mv;
+                            if (has_i1) {
+                                TH_I(k) = (int16_t)ins1;
+                                if ((unsigned)ins1 <= (unsigned)m && (unsigned)(ins1 - k) <= (unsigned)n) tl_i = min(tl_i, k), th_i = k;
+                            }
+                            if (has_d1) {
+                                TH_D(k) = (int16_t)del1;
+                                if ((unsigned)del1 <= (unsigned)m && (unsigned)(del1 - k) <= (unsigned)n) tl_d = min(tl_d, k), th_d = k;
+                            }
+                        }
+                        // Greedy extension of the live diagonals (trimming never changes offsets, A.1 step 1), as ONE
+                        // loop over 16-base compares: a lane moves on to its next diagonal as soon as the current one
+                        // stops matching, so a warp pays the longest per-lane TOTAL, not the sum of per-diagonal maxima.
+                        {
+                            int k = 0, v = 0, h = 0, room = 0, eq = 0;
+                            bool active = false;
+                            for (;;) {
+                                if (!active) {
+                                    if (!vmask) break;
+                                    const int pi = __ffs(vmask) - 1;
+                                    vmask &= vmask - 1;
+                                    k = pi - TH_KM;
+                                    h = (int)TH_M(cur, k), v = h - k;
+                                    room = min(n - v, m - h), eq = 0;
+                                    active = true;
+                                }
+                                bool stop = eq >= room;
+                                if (!stop) {
+                                    const uint32_t x = get16(P.w, P.sh + v + eq) ^ get16(T.w, T.sh + h + eq);
+                                    if (x) eq += (__ffs(x) - 1) >> 1, stop = true;
+                                    else eq += 16, stop = eq >= room;
+                                }
+                                if (stop) {
+                                    eq = min(eq, room);
+                                    ext += (unsigned)(eq >> 4) + 1u;
+                                    const int mv = h + eq;
+                                    TH_M(cur, k) = (int16_t)mv;
+                                    min_d = min(min_d, max(n - (mv - k), m - mv));
+                                    fin |= (k == k_end) && (mv >= m);
+                                    active = false;
+                                }
+                            }
+                        }
+                        const int t = hh - 3;
+                        TH_P(t, 0) = (uint32_t)pa, TH_P(t, 1) = (uint32_t)(pa >> 32), TH_P(t, 2) = pb;
+                        if (fin) {
+                            pen = s;
+                            break;
+                        }
+                        if (tl_m <= th_m) nml = tl_m, nms = th_m - tl_m + 1;
+                        if (tl_i <= th_i) nil = tl_i, nis = th_i - tl_i + 1;
+                        if (tl_d <= th_d) ndl = tl_d, nds = th_d - tl_d + 1;
+                        // ---- wf-adaptive cut-off + equate (A.3) ------------------------------------------
+                        if (heur.kind == 1 && nms) {
+                            int mlo = nml, mhi = nml + nms - 1;
+                            --steps_wait;
+                            if (steps_wait <= 0 && nms >= heur.min_len) {
+                                const int md = min(max(n, m), min_d);
+                                const int top_limit = min(k_end, mhi);
+                                int new_lo = mlo;
+                                if (top_limit > mlo) {
+                                    int k = mlo;
+                                    for (; k < top_limit; ++k) {
+                                        const int off = (int)TH_M(cur, k);
+                                        const int d = off >= 0 ? max(n - (off - k), m - off) : HUGE_D;
+                                        if (d - md <= heur.max_dist) break;
+                                    }
+                                    new_lo = k; // first diagonal close enough, or top_limit
+                                }
+                                const int bot_limit = max(k_end, new_lo);
+                                int new_hi = mhi;
+                                if (bot_limit < mhi) {
+                                    int k = mhi;
+                                    for (; k > bot_limit; --k) {
+                                        const int off = (int)TH_M(cur, k);
+                                        const int d = off >= 0 ? max(n - (off - k), m - off) : HUGE_D;
+                                        if (d - md <= heur.max_dist) break;
+                                    }
+                                    new_hi = k;
+                                }
+                                mlo = new_lo, mhi = new_hi;
+                                steps_wait = heur.steps;
+                            }
+                            nml = mlo, nms = mhi - mlo + 1;
+                            if (nms > 0) { // equate: the gap wavefronts never reach beyond M
+                                int a = max(nil, mlo), z = min(nil + nis - 1, mhi);
+                                if (nis) nil = a, nis = max(0, z - a + 1);
+                                a = max(ndl, mlo), z = min(ndl + nds - 1, mhi);
+                                if (nds) ndl = a, nds = max(0, z - a + 1);
+                            } else {
+                                nml = 1, nms = 0;
+                            }
+                        }
+                    }
+                    ml8 = ml6, ms8 = ms6, ml6 = ml4, ms6 = ms4, ml4 = ml2, ms4 = ms2, ml2 = nml, ms2 = nms;
+                    il = nil, is = nis, dl = ndl, ds = nds;
+                }
+                // ---- backtrace (A.4) + forward replay with the clipped score --------------------------
+                if (pen > 0) {
+                    unsigned long long ops = 0;
+                    int nops = 0, n_del = 0, comp = 0 /* 0 M, 1 I1, 2 D1 */, cs = pen, k = k_end;
+                    while (!(comp == 0 && cs == 0)) {
+                        const int t = (cs >> 1) - 3, pi = k + TH_KM;
+                        if (t < 0 || (unsigned)pi >= (unsigned)TH_W || nops >= 32) {
+                            pen = -1; // never expected: leave the pair to the next tier
+                            break;
+                        }
+                        const uint32_t wsel = pi < 8 ? TH_P(t, 0) : (pi < 16 ? TH_P(t, 1) : TH_P(t, 2));
+                        const int nib = (int)(wsel >> (4 * (pi & 7))) & 15;
+                        int op;
+                        if (comp == 0) {
+                            const int sc = nib & 3;
+                            if (sc == 3) op = OP_X, cs -= X;
+                            else if (sc == 0) {
+                                pen = -1;
+                                break;
+                            } else op = OP_CLOSE, comp = sc;
+                        } else if (comp == 1) {
+                            op = OP_I;
+                            if (nib & 4) cs -= E1; else cs -= O1 + E1, comp = 0;
+                            k -= 1;
+                        } else {
+                            op = OP_D;
+                            ++n_del;
+                            if (nib & 8) cs -= E1; else cs -= O1 + E1, comp = 0;
+                            k += 1;
+                        }
+                        ops |= (unsigned long long)op << (2 * nops);
+                        ++nops;
+                    }
+                    if (pen > 0) {
+                        ClipAcc acc;
+                        acc.init(m + n_del, p.clip);
+                        int v = 0, h = 0;
+                        bool in_m = true;
+                        for (int i = nops - 1; i >= -1; --i) {
+                            if (in_m) {
+                                const int eq = th_extend(P, T, v, h);
+                                acc.emit('M', eq, pn);
+                                v += eq, h += eq;
+                            }
+                            if (i < 0) break;
+                            const int op = (int)(ops >> (2 * i)) & 3;
+                            if (op == OP_CLOSE) {
+                                in_m = true;
+                                continue;
+                            }
+                            acc.emit(op == OP_X ? 'X' : (op == OP_I ? 'I' : 'D'), 1, pn);
+                            if (op == OP_X) ++v, ++h;
+                            else if (op == OP_I) ++h, in_m = false;
+                            else ++v, in_m = false;
+                        }
+                        clipped = acc.finish(pn);
+                        cols = acc.col;
+                    }
+                }
+            }
+            if (pen >= 0) {
+                p.out_score[idx] = clipped;
+                if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
+                if (p.out_penalty) p.out_penalty[idx] = pen;
+                if (p.work) {
+                    p.work[3 * (size_t)idx] = cells, p.work[3 * (size_t)idx + 1] = (uint32_t)ext;
+                    p.work[3 * (size_t)idx + 2] = (uint32_t)cols;
+                }
+                tot_cells += cells, tot_ext += ext, tot_cols += (unsigned)cols, ++tot_done;
+            } else {
+                const unsigned j = atomicAdd(p.next_count, 1u);
+                p.next_todo[j] = idx;
+            }
+        }
+        __syncwarp();
+    }
+#undef TH_M
+#undef TH_I
+#undef TH_D
+#undef TH_P
+    for (int o = 16; o; o >>= 1) {
+        tot_cells += __shfl_xor_sync(TDB_FULL, tot_cells, o), tot_ext += __shfl_xor_sync(TDB_FULL, tot_ext, o);
+        tot_cols += __shfl_xor_sync(TDB_FULL, tot_cols, o), tot_done += __shfl_xor_sync(TDB_FULL, tot_done, o);
+    }
+    if (lane == 0 && p.counters) {
+        atomicAdd(p.counters + 0, tot_cells), atomicAdd(p.counters + 1, tot_ext);
+        atomicAdd(p.counters + 2, tot_cols), atomicAdd(p.counters + 3, tot_done);
+    }
+}
+
+} // namespace tdb
