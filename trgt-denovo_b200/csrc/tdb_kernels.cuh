@@ -271,6 +271,7 @@ constexpr int KEY_WARP = 0; // sorted first: heaviest pairs of the shared-memory
 constexpr int KEY_QUAD0 = 1;
 constexpr int ML_MAX = 8;       // |n-m| < ML_MAX and both sequences >= ML_MINLEN bases: thread-per-pair tier first
 constexpr int ML_MINLEN = 16;
+constexpr int ML_MAXLEN = 240;  // both sequences are staged in shared memory (TH_MAXLEN, tdb_wfa_thread.cuh)
 constexpr int KEY_MINI0 = KEY_QUAD0 + QL_MAX; // sorted last: the lightest pairs
 constexpr int KEY_NONE = 255;
 static_assert(KEY_MINI0 + ML_MAX <= 32, "histogram size");
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
                         o.glist[q] = j;
                     } else if (!quad_ok || L >= QL_MAX) {
                         key = KEY_WARP;
-                    } else if (mini_ok && L < ML_MAX && n >= ML_MINLEN && m >= ML_MINLEN) {
+                    } else if (mini_ok && L < ML_MAX && n >= ML_MINLEN && m >= ML_MINLEN && n <= ML_MAXLEN && m <= ML_MAXLEN) {
                         key = KEY_MINI0 + (ML_MAX - 1 - L);
                     } else {
                         key = KEY_QUAD0 + (QL_MAX - 1 - L);

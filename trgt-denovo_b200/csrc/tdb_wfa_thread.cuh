@@ -8,10 +8,13 @@
 // What makes that fit: with the production penalties (x 8, o1+e1 6, e1 2, o2+e2 25) nothing below
 // score 25 can use the second gap piece and only even scores are reachable, so up to score 24 the
 // recurrence is single-piece gap-affine over 12 score steps, diagonals |k| <= (s-4)/2 <= 10.  Per
-// thread: a 5-slot M ring + in-place I1/D1 (147 int16) and 4 provenance bits per computed cell
-// (30 words), all in shared memory interleaved by thread (element e of thread t at e*128 + t: a warp
-// access touches 16 banks at most 2-way).  A pair that is not finished at score 24 is handed to the
-// lockstep tier, which starts it over.
+// thread, in shared memory interleaved by thread (element e of thread t at e*128 + t, so a thread's
+// column stays in its own bank): a 5-slot M ring + in-place I1/D1 (147 int16) and BOTH SEQUENCES,
+// staged once with independent loads (2 x 17 words: sequences up to 240 bases) -- the extension
+// compares then never wait for global memory (an ncu capture of the first version, which read the
+// packed stream directly, had a third of its stall samples on those loads).  4 provenance bits per
+// computed cell (30 words) live in thread-local memory: written once per score, read by the backtrace.
+// A pair that is not finished at score 24 is handed to the lockstep tier, which starts it over.
 //
 // Semantics are those of wfa_align_warp (tdb_wfa.cuh) step for step: compute + trim (A.2),
 // wf-adaptive cut-off + equate (A.3), provenance tie-breaks X > D1 > I1 and matches re-extended only
@@ -29,11 +32,29 @@ constexpr int TH_MSLOTS = 5;                // M ring: scores s, s-2, .., s-8
 constexpr int TH_HW = TH_MSLOTS * TH_W + 2 * TH_W; // int16 elements per thread
 constexpr int TH_STEPS = TH_SMAX / 2 - 2;   // scores 6, 8, .., 24
 constexpr int TH_PW = 3;                    // provenance words per score step (21 nibbles)
-constexpr size_t th_smem_bytes() { return (size_t)TH_NT * (TH_HW * 2 + TH_STEPS * TH_PW * 4); }
+constexpr int TH_SEQW = 17;                 // staged 2-bit words per sequence: shift (<= 15) + TH_MAXLEN + 16 bases
+constexpr int TH_MAXLEN = ML_MAXLEN;        // longest sequence this tier takes
+constexpr size_t th_smem_bytes() { return (size_t)TH_NT * (TH_HW * 2 + 2 * TH_SEQW * 4); }
+static_assert(15 + TH_MAXLEN + 16 <= 16 * TH_SEQW, "staging window");
 
-__device__ __forceinline__ int th_extend(const SeqView &P, const SeqView &T, int v, int h) {
-    unsigned long long dummy = 0;
-    return extend_lane(P, T, v, h, dummy);
+// 16 bases from position pos of a sequence staged at words [e0, e0 + TH_SEQW) of this thread's column
+__device__ __forceinline__ uint32_t th_get16(const uint32_t *sw, int e0, int pos) {
+    const int i = e0 + (pos >> 4);
+    return __funnelshift_r(sw[i * TH_NT], sw[(i + 1) * TH_NT], (pos & 15) << 1);
+}
+// greedy match extension from (v, h) on the staged sequences (psh / tsh: base shift inside the first word)
+__device__ __forceinline__ int th_extend(const uint32_t *sw, int psh, int tsh, int n, int m, int v, int h) {
+    const int room = min(n - v, m - h);
+    int eq = 0;
+    while (eq < room) {
+        const uint32_t x = th_get16(sw, 0, psh + v + eq) ^ th_get16(sw, TH_SEQW, tsh + h + eq);
+        if (x) {
+            eq += (__ffs(x) - 1) >> 1;
+            break;
+        }
+        eq += 16;
+    }
+    return min(eq, room);
 }
 
 template <int X, int O1, int E1, int O2, int E2>
@@ -43,11 +64,12 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
     constexpr int HUGE_D = 1 << 30;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     int16_t *hw = reinterpret_cast<int16_t *>(smem_raw) + threadIdx.x;
-    uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TH_NT * TH_HW * 2) + threadIdx.x;
+    uint32_t *sw = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TH_NT * TH_HW * 2) + threadIdx.x;
+    uint32_t prov[TH_STEPS * TH_PW]; // written once per score, read by the backtrace: thread-local memory
 #define TH_M(slot, k) hw[((slot) * TH_W + (k) + TH_KM) * TH_NT]
 #define TH_I(k) hw[(TH_MSLOTS * TH_W + (k) + TH_KM) * TH_NT]
 #define TH_D(k) hw[((TH_MSLOTS + 1) * TH_W + (k) + TH_KM) * TH_NT]
-#define TH_P(t, w) pw[((t) * TH_PW + (w)) * TH_NT]
+#define TH_P(t, w) prov[(t) * TH_PW + (w)]
     const int lane = threadIdx.x & 31;
     const ItemSrc src = item_src(p);
     const Penalties pn = {X, O1, E1, O2, E2};
@@ -64,14 +86,22 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
             const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
             const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
             const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
-            const SeqView P = {p.packed + (poff >> 4), nullptr, n, (int)(poff & 15)};
-            const SeqView T = {p.packed + (toff >> 4), nullptr, m, (int)(toff & 15)};
+            const int psh = (int)(poff & 15), tsh = (int)(toff & 15);
+            { // stage both sequences: the only global loads of the alignment, all independent
+                const uint32_t *gp = p.packed + (poff >> 4), *gt = p.packed + (toff >> 4);
+                const int np = (psh + n + 31) >> 4, nt = (tsh + m + 31) >> 4; // words incl. the funnel-shift neighbour
+#pragma unroll
+                for (int i = 0; i < TH_SEQW; ++i) {
+                    if (i < np) sw[i * TH_NT] = __ldg(gp + i);
+                    if (i < nt) sw[(TH_SEQW + i) * TH_NT] = __ldg(gt + i);
+                }
+            }
             const int k_end = m - n;
-            unsigned long long ext = 0;
-            unsigned cells = 0;
+            unsigned ext = 0, cells = 0;
             int pen = -1, clipped = 0, cols = 0;
             // ---- score 0 ---------------------------------------------------------------------------
-            const int m0 = extend_lane(P, T, 0, 0, ext);
+            const int m0 = th_extend(sw, psh, tsh, n, m, 0, 0);
+            ext += (unsigned)(m0 >> 4) + 1u;
             if (k_end == 0 && m0 >= m) {
                 pen = 0, cols = m;
             } else {
@@ -156,7 +186,7 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                                 }
                                 bool stop = eq >= room;
                                 if (!stop) {
-                                    const uint32_t x = get16(P.w, P.sh + v + eq) ^ get16(T.w, T.sh + h + eq);
+                                    const uint32_t x = th_get16(sw, 0, psh + v + eq) ^ th_get16(sw, TH_SEQW, tsh + h + eq);
                                     if (x) eq += (__ffs(x) - 1) >> 1, stop = true;
                                     else eq += 16, stop = eq >= room;
                                 }
@@ -265,7 +295,7 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                         bool in_m = true;
                         for (int i = nops - 1; i >= -1; --i) {
                             if (in_m) {
-                                const int eq = th_extend(P, T, v, h);
+                                const int eq = th_extend(sw, psh, tsh, n, m, v, h);
                                 acc.emit('M', eq, pn);
                                 v += eq, h += eq;
                             }
@@ -290,7 +320,7 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                 if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
                 if (p.out_penalty) p.out_penalty[idx] = pen;
                 if (p.work) {
-                    p.work[3 * (size_t)idx] = cells, p.work[3 * (size_t)idx + 1] = (uint32_t)ext;
+                    p.work[3 * (size_t)idx] = cells, p.work[3 * (size_t)idx + 1] = ext;
                     p.work[3 * (size_t)idx + 2] = (uint32_t)cols;
                 }
                 tot_cells += cells, tot_ext += ext, tot_cols += (unsigned)cols, ++tot_done;
