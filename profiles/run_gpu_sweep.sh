@@ -5,6 +5,6 @@ TDB_LIB=$PWD/$lib timeout 600 python bench.py --loci 100000 --steps 3 --warmup 2
 import json,sys
 d=json.loads(sys.stdin.read())
 b=d['breakdown_ms_per_step']
-print('$lib','value',round(d['value']),'quad %.2f warp %.2f glob %.2f'%(b['align_quad'],b['align_warp'],b['align_global']),'tiers',d['tier_pairs'])
+print('$lib','value',round(d['value']),'thread %.2f quad %.2f warp %.2f glob %.2f'%(b['align_thread'],b['align_quad'],b['align_warp'],b['align_global']),'thread',d['thread_tier_pairs'],'tiers',d['tier_pairs'])
 "
 done

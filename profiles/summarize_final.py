@@ -27,8 +27,11 @@ for name, what in ((f"launches_{tag}", "first 120 launches of: python bench.py -
             o.write(f"{v/1e6:10.3f} ms {100*v/tot:5.1f}% n={c[k]:3d} {k}\n")
 plain = json.loads([l for l in open(os.path.join(G, f"plain30k_{tag}.log")) if l.startswith("{")][-1])
 traffic = {}
-for kern, ti in (("quad", 0), ("warp", 1)):
+names = {"quad": "k_align_lock<QuadCfg>", "duo": "k_align_lock<DuoCfg>", "thread": "k_align_thread"}
+for kern, ti in (("quad", 0), ("duo", 1), ("thread", -1)):
     rep = os.path.join(G, f"prof_{kern}_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rr[0], rr[1], rr[-1]
@@ -40,8 +43,8 @@ for kern, ti in (("quad", 0), ("warp", 1)):
         x = float(d[name].replace(",", "")); un = u[name].lower()
         return x * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(un, 1)
     b = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-    pairs = plain["tier_pairs"][ti]
-    traffic[{"quad": "k_align_lock<QuadCfg>", "warp": "k_align_warp"}[kern]] = {"dram_bytes_per_launch": b, "pairs_in_launch": pairs, "dram_bytes_per_pair": b / max(1, pairs),
+    pairs = plain["tier_pairs"][ti] if ti >= 0 else plain["thread_tier_pairs"]
+    traffic[names[kern]] = {"dram_bytes_per_launch": b, "pairs_in_launch": pairs, "dram_bytes_per_pair": b / max(1, pairs),
                                   "source": f"ncu --set full, prof_{kern}_{tag}.ncu-rep (30 000-locus step)"}
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))

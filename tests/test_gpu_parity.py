@@ -173,8 +173,8 @@ def test_thread_tier_disabled_gives_same_scores(tdb, monkeypatch):
 
 
 def test_tier1_variants_give_same_scores(tdb, monkeypatch):
-    """Tier 1 has two implementations (one pair per warp -- the default -- and an opt-in two pairs per warp in
-    lockstep): both must agree with the oracle on wide-wavefront pairs."""
+    """Tier 1 has two implementations (two pairs per warp in lockstep -- the default with the production penalties --
+    and one pair per warp): both must agree with the oracle on wide-wavefront pairs."""
     rng = random.Random(36)
     seqs, pp, pt = [], [], []
     for _ in range(200):
@@ -190,9 +190,9 @@ def test_tier1_variants_give_same_scores(tdb, monkeypatch):
     cnt = _check_batch(c, seqs, pp, pt, 50, cigars=False)
     assert cnt.tier_pairs[1] > 100
     c.close()
-    monkeypatch.setenv("TDB_ENABLE_DUO", "1")
+    monkeypatch.setenv("TDB_DISABLE_DUO", "1")
     c = tdb.Context()
-    monkeypatch.delenv("TDB_ENABLE_DUO")
+    monkeypatch.delenv("TDB_DISABLE_DUO")
     cnt2 = _check_batch(c, seqs, pp, pt, 50, cigars=False)
     assert cnt2.tier_pairs[1] > 100
     c.close()

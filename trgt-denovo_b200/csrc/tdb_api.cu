@@ -821,7 +821,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         }
         if (staged) CK(cudaEventRecord(ctx->ev[4], st));
         // tier 1: wavefronts up to 64 diagonals, shared memory, one pair per warp; the quad tier's leftovers (the
-        // heaviest pairs) go first.  (TDB_ENABLE_DUO: two pairs per warp in lockstep, production penalties only.)
+        // heaviest pairs) go first.  Production penalties: two pairs per warp in lockstep (TDB_DISABLE_DUO=1: one per warp).
         {
             p.src1_seg = ck->seg + 0, p.src2 = (const uint32_t *)sl.list_a.p, p.src2_count = &ck->acount;
             p.work_counter = &ck->wc_warp, p.next_todo = (uint32_t *)ctx->list_b.p, p.next_count = &ctrl->gcount;
@@ -1125,9 +1125,9 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         }
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
         c->disable_mini = getenv("TDB_DISABLE_THREAD_TIER") != nullptr;
-        // the two-pairs-per-warp lockstep variant of tier 1 measures the same as one pair per warp (wide wavefronts
-        // already fill the lanes) and overflows a little more often (FIFO arena): opt-in, kept for experiments
-        c->disable_duo = getenv("TDB_ENABLE_DUO") == nullptr;
+        // tier 1 runs two pairs per warp in lockstep (16 lanes each) with the production penalties: 17 % faster than
+        // one pair per warp on the 30x trio (profiles/r01/NOTES.md); TDB_DISABLE_DUO=1 falls back to k_align_warp
+        c->disable_duo = getenv("TDB_DISABLE_DUO") != nullptr;
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
         c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
         c->disable_rle = getenv("TDB_DISABLE_RLE") != nullptr;

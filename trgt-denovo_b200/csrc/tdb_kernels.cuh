@@ -271,7 +271,11 @@ constexpr int KEY_WARP = 0; // sorted first: heaviest pairs of the shared-memory
 constexpr int KEY_QUAD0 = 1;
 constexpr int ML_MAX = 8;       // |n-m| < ML_MAX and both sequences >= ML_MINLEN bases: thread-per-pair tier first
 constexpr int ML_MINLEN = 16;
-constexpr int ML_MAXLEN = 240;  // both sequences are staged in shared memory (TH_MAXLEN, tdb_wfa_thread.cuh)
+#ifndef TDB_TH_SEQW
+#define TDB_TH_SEQW 21
+#endif
+constexpr int TH_SEQW = TDB_TH_SEQW;            // 2-bit words staged per sequence by the thread-per-pair tier
+constexpr int ML_MAXLEN = 16 * TH_SEQW - 32;    // its longest sequence: shift (<= 15) + length + 16 bases fit the window
 constexpr int KEY_MINI0 = KEY_QUAD0 + QL_MAX; // sorted last: the lightest pairs
 constexpr int KEY_NONE = 255;
 static_assert(KEY_MINI0 + ML_MAX <= 32, "histogram size");

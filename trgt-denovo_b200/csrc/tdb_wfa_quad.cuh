@@ -40,7 +40,10 @@ struct LockCfg {
     static constexpr int G = G_, W = W_, MAR = MAR_, SCAP = SCAP_, PROV = PROV_;
 };
 using QuadCfg = LockCfg<8, 32, TDB_Q_MAR, TDB_Q_SCAP, TDB_Q_PROV>; // tier 0: four pairs per warp
-using DuoCfg = LockCfg<16, 64, 1024, 128, 2048>;                    // tier 1: two pairs per warp
+#ifndef TDB_DUO_G
+#define TDB_DUO_G 16
+#endif
+using DuoCfg = LockCfg<TDB_DUO_G, 64, 1024, 128, 2048>;             // tier 1: two pairs per warp
 constexpr int Q_MAXLEN = 8000;
 constexpr int Q_WARPS = TDB_Q_WARPS;
 constexpr int Q_NULL = -16384;

@@ -8,9 +8,9 @@
 // What makes that fit: with the production penalties (x 8, o1+e1 6, e1 2, o2+e2 25) nothing below
 // score 25 can use the second gap piece and only even scores are reachable, so up to score 24 the
 // recurrence is single-piece gap-affine over 12 score steps, diagonals |k| <= (s-4)/2 <= 10.  Per
-// thread, in shared memory interleaved by thread (element e of thread t at e*128 + t, so a thread's
+// thread, in shared memory interleaved by thread (element e of thread t at e*96 + t, so a thread's
 // column stays in its own bank): a 5-slot M ring + in-place I1/D1 (147 int16) and BOTH SEQUENCES,
-// staged once with independent loads (2 x 17 words: sequences up to 240 bases) -- the extension
+// staged once with independent loads (2 x 21 words: sequences up to 304 bases) -- the extension
 // compares then never wait for global memory (an ncu capture of the first version, which read the
 // packed stream directly, had a third of its stall samples on those loads).  4 provenance bits per
 // computed cell (30 words) live in thread-local memory: written once per score, read by the backtrace.
@@ -24,7 +24,10 @@
 
 namespace tdb {
 
-constexpr int TH_NT = 128;                  // threads (= pairs in flight) per CTA
+#ifndef TDB_TH_NT
+#define TDB_TH_NT 96
+#endif
+constexpr int TH_NT = TDB_TH_NT;            // threads (= pairs in flight) per CTA; a multiple of 32
 constexpr int TH_KM = 10;                   // diagonals -TH_KM .. TH_KM
 constexpr int TH_W = 2 * TH_KM + 1;
 constexpr int TH_SMAX = 24;                 // last score this tier computes
@@ -32,7 +35,6 @@ constexpr int TH_MSLOTS = 5;                // M ring: scores s, s-2, .., s-8
 constexpr int TH_HW = TH_MSLOTS * TH_W + 2 * TH_W; // int16 elements per thread
 constexpr int TH_STEPS = TH_SMAX / 2 - 2;   // scores 6, 8, .., 24
 constexpr int TH_PW = 3;                    // provenance words per score step (21 nibbles)
-constexpr int TH_SEQW = 17;                 // staged 2-bit words per sequence: shift (<= 15) + TH_MAXLEN + 16 bases
 constexpr int TH_MAXLEN = ML_MAXLEN;        // longest sequence this tier takes
 constexpr size_t th_smem_bytes() { return (size_t)TH_NT * (TH_HW * 2 + 2 * TH_SEQW * 4); }
 static_assert(15 + TH_MAXLEN + 16 <= 16 * TH_SEQW, "staging window");
