@@ -23,7 +23,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-fil
 echo launches_full rc=$?
 CMD="python bench.py --loci 30000 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain30k_$tag.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k 'regex:LockCfg<8,' -s 3 -c 1 -f -o gpurun_out/prof_quad_$tag $CMD > gpurun_out/ncu_quad_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k 'regex:LockCfg<16,' -s 3 -c 1 -f -o gpurun_out/prof_duo_$tag $CMD > gpurun_out/ncu_duo_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:LockCfgILi8E -s 3 -c 1 -f -o gpurun_out/prof_quad_$tag $CMD > gpurun_out/ncu_quad_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:LockCfgILi16E -s 3 -c 1 -f -o gpurun_out/prof_duo_$tag $CMD > gpurun_out/ncu_duo_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_align_thread -s 3 -c 1 -f -o gpurun_out/prof_thread_$tag $CMD > gpurun_out/ncu_thread_$tag.log 2>&1
 echo full rc=$?
