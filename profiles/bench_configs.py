@@ -34,7 +34,7 @@ def run_loci(name, batch, duo, cpu_loci, reps=3):
     scores = np.zeros(batch.n_pairs, np.int32)
     fn = L.tdb_duo_batch if duo else L.tdb_trio_batch
     def call():
-        r = fn(ctx._h, batch.blob.ctypes.data, batch.blob.size, batch.seq_off.ctypes.data, batch.seq_len.ctypes.data,
+        r = fn(ctx._h, batch.blob.ctypes.data, batch.blob.size, None, batch.seq_len.ctypes.data,  # dense layout
                batch.n_seqs, batch.pair_pattern.ctypes.data, batch.pair_text.ctypes.data, batch.n_pairs, batch.loci_ptr,
                batch.n_loci, 1.0, C.cast(out, C.c_void_p), scores.ctypes.data, mask.ctypes.data)
         assert r == 0, L.tdb_last_error(ctx._h)
@@ -52,7 +52,7 @@ def run_loci(name, batch, duo, cpu_loci, reps=3):
     ok = bool((want == scores[:npc]).all())
     print(json.dumps({"config": name, "loci": batch.n_loci, "pairs": batch.n_pairs, "e2e_loci_per_s": batch.n_loci / dt,
                       "e2e_alignments_per_s": batch.n_pairs / dt, "e2e_ms": dt * 1e3, "gcups": batch.sum_nm / dt / 1e9,
-                      "tier_pairs": [int(x) for x in cnt.tier_pairs], "identical": int(cnt.pairs_identical),
+                      "thread_tier_pairs": int(cnt.thread_pairs), "tier_pairs": [int(x) for x in cnt.tier_pairs], "identical": int(cnt.pairs_identical),
                       "duplicate": int(cnt.pairs_duplicate), "closed_form": int(cnt.pairs_closed_form),
                       "cpu_port": {"threads": threads, "loci": ncpu, "pairs": npc, "loci_per_s": ncpu / cpu_dt,
                                    "alignments_per_s": npc / cpu_dt, "align_only": True},
@@ -74,9 +74,9 @@ if "5" not in args.skip:
             for div in (0.0, 0.01, 0.02, 0.05, 0.10, 0.20):
                 n_pairs = int(max(1000, min(2_000_000, args.micro_cells / (length * length))))
                 b = S.micro(20250005 + length, length, div, n_pairs, threads, pinned=True)
-                c2.align_batch(b.blob, b.seq_off, b.seq_len, b.pair_pattern, b.pair_text)
+                c2.align_batch(b.blob, None, b.seq_len, b.pair_pattern, b.pair_text)
                 t0 = time.perf_counter()
-                got, st = c2.align_batch(b.blob, b.seq_off, b.seq_len, b.pair_pattern, b.pair_text)
+                got, st = c2.align_batch(b.blob, None, b.seq_len, b.pair_pattern, b.pair_text)
                 dt = time.perf_counter() - t0
                 cnt = c2.counters()
                 ncpu = int(max(16, min(n_pairs, 2e9 / (length * length) / (1 + 30 * div))))
@@ -88,7 +88,7 @@ if "5" not in args.skip:
                 nm = float(b.sum_nm)
                 print(json.dumps({"config": "5: microbenchmark", "heuristic": hname, "length": length, "divergence": div,
                                   "pairs": n_pairs, "e2e_gcups": nm / dt / 1e9, "e2e_alignments_per_s": n_pairs / dt,
-                                  "tier_pairs": [int(x) for x in cnt.tier_pairs],
+                                  "thread_tier_pairs": int(cnt.thread_pairs), "tier_pairs": [int(x) for x in cnt.tier_pairs],
                                   "cpu_port_gcups": (nm * ncpu / n_pairs) / cdt / 1e9, "cpu_threads": threads,
                                   "scores_bit_exact_on_cpu_sample": ok}), flush=True)
                 assert ok
