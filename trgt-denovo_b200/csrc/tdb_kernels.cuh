@@ -71,12 +71,13 @@ __device__ __forceinline__ void load16(const uint8_t *__restrict__ blob, uint64_
 }
 // 16 bytes -> one packed word; badm gets one bit per byte outside {A,C,G,T}.  Validity is a round trip: the
 // byte the 2-bit code stands for (one PRMT from the table 'A','C','T','G') must equal the byte itself.
-__device__ __forceinline__ uint32_t pack16(const uint32_t q[4], uint32_t cnt, uint32_t &badm) {
+template <bool FULL>
+__device__ __forceinline__ uint32_t pack16_t(const uint32_t q[4], uint32_t cnt, uint32_t &badm) {
     uint32_t word = 0, anydiff = 0, diff[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int rem = (int)cnt - 4 * t;
-        const uint32_t need = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
+        const uint32_t need = FULL || rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u));
         const uint32_t p8 = pack4(q[t] & need);
         const uint32_t y = (p8 | (p8 << 4)) & 0x0f0fu;
         const uint32_t sel = (y | (y << 2)) & 0x3333u; // the four codes as PRMT selector nibbles
@@ -93,6 +94,10 @@ __device__ __forceinline__ uint32_t pack16(const uint32_t q[4], uint32_t cnt, ui
         }
     }
     return word;
+}
+// whole groups (all but the last of a range) skip the per-byte masks
+__device__ __forceinline__ uint32_t pack16(const uint32_t q[4], uint32_t cnt, uint32_t &badm) {
+    return cnt == 16 ? pack16_t<true>(q, 16, badm) : pack16_t<false>(q, cnt, badm);
 }
 
 // Packs blob bytes [b0, b1) (b0 a multiple of 16).  seq_flag of [s_lo, s_hi) must be zeroed before.
