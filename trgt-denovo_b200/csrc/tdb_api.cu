@@ -758,7 +758,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         uint32_t *svals = dedup ? (uint32_t *)(skeys + (size_t)smask + 1) : nullptr;
         uint32_t *canon = (uint32_t *)sl.canon.p;
         if (dedup && ns) {
-            CK(cudaMemsetAsync(skeys, 0xff, ((size_t)smask + 1) * 12, st));
+            CK(cudaMemsetAsync(skeys, 0xff, ((size_t)smask + 1) * 8, st)); // keys only: a value is written by whoever claims the slot
             k_seq_insert<<<(ns + 255) / 256, 256, 0, st>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p,
                                                            c.s_lo, c.s_hi, skeys, svals, smask);
             CK(cudaGetLastError());
@@ -774,7 +774,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         }
         PairTable tb;
         tb.keys = (unsigned long long *)sl.pair_tab.p, tb.vals = (uint32_t *)(tb.keys + (size_t)pmask + 1), tb.mask = pmask;
-        CK(cudaMemsetAsync(tb.keys, 0xff, ((size_t)pmask + 1) * 12, st));
+        CK(cudaMemsetAsync(tb.keys, 0xff, ((size_t)pmask + 1) * 8, st));
         const unsigned pblocks = (cpairs + 255) / 256;
         k_pair_insert<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, tb, &ctrl->err);
         CK(cudaGetLastError());

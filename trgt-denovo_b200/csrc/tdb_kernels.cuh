@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(256) k_expand_runs(const PairRun *__restrict__
 // allele they come from, so a locus' pair list holds the same (pattern, text) CONTENT many times
 // (synthetic 30x trio: 3.5 pairs per distinct content).  The alignment is a pure function of the two
 // byte strings, so each distinct content is aligned once and its result copied:
-//   1. sequences -> canonical sequence (lowest index with the same bytes): open-addressing table on
+//   1. sequences -> canonical sequence (one index per class of equal bytes): open-addressing table on
 //      the 64-bit content hash, every hit VERIFIED word by word (a hash collision only costs a missed
 //      merge, never a wrong one);
-//   2. pairs -> representative pair (lowest index with the same (canon pattern, canon text)): exact
+//   2. pairs -> representative pair (one index per (canon pattern, canon text) class): exact
 //      64-bit key, no verification needed;
 //   3. representatives are radix-sorted by expected work (|n - m|, the dominant term of the penalty)
 //      so that the four pairs of a warp, and the warps of a wave, run near-identical control flow and
@@ -227,11 +227,11 @@ __global__ void __launch_bounds__(256) k_seq_insert(const uint64_t *__restrict__
     const uint64_t h = seq_hash[i];
     uint32_t slot = (uint32_t)h & mask;
     for (;;) {
+        // the thread that claims the slot names the representative: any member of the class will do, and a plain
+        // store by the winner replaces an atomicMin by everybody (read only after this kernel has finished)
         const unsigned long long old = atomicCAS(keys + slot, (unsigned long long)HT_EMPTY, (unsigned long long)h);
-        if (old == HT_EMPTY || old == h) {
-            atomicMin(vals + slot, i);
-            return;
-        }
+        if (old == HT_EMPTY) vals[slot] = i;
+        if (old == HT_EMPTY || old == h) return;
         slot = (slot + 1) & mask;
     }
 }
@@ -309,10 +309,8 @@ __global__ void __launch_bounds__(256) k_pair_insert(const uint32_t *__restrict_
     uint32_t slot = (uint32_t)mix64(key) & tb.mask;
     for (;;) {
         const unsigned long long old = atomicCAS(tb.keys + slot, (unsigned long long)HT_EMPTY, key);
-        if (old == HT_EMPTY || old == key) {
-            atomicMin(tb.vals + slot, j);
-            return;
-        }
+        if (old == HT_EMPTY) tb.vals[slot] = j; // the winner is the representative pair (see k_seq_insert)
+        if (old == HT_EMPTY || old == key) return;
         slot = (slot + 1) & tb.mask;
     }
 }
