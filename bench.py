@@ -315,7 +315,7 @@ def main():
     host_input_bytes = batch.blob.size + (0 if dense else batch.seq_off.nbytes) + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
         batch.pair_text.nbytes + loci_np.nbytes
     h2d = int(ce.bytes_h2d) + loci_np.nbytes
-    d2h = C.sizeof(h_out) + h_mask.nbytes
+    d2h = int(ce.bytes_d2h)  # rows + the read mask (large calls fetch it as a list of its set positions)
 
     # ---- quick self-check of the step's result against the oracle (outside the timed regions) --------
     check = None

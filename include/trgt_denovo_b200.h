@@ -254,6 +254,9 @@ typedef struct {
     float ms_thread_tier;   /* the thread-per-pair tier that runs in front of tier 0 */
     uint64_t thread_pairs;  /* pairs ALIGNED by the thread-per-pair tier (final penalty <= 24), and the work */
     uint64_t thread_cells, thread_ext16, thread_columns; /* it executed (also included in exec_*) */
+    uint64_t bytes_d2h;     /* result bytes copied device -> host by the fused host-buffer calls (tdb_trio_batch /
+                               tdb_duo_batch): rows, scores if asked for, and the read mask -- as a list of its set
+                               positions for calls of >= 8 Mi pairs, where a few bytes in a million are set */
 } tdb_counters;
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 /* Exact algorithmic work counting (cells / ext16 / columns of tdb_counters: every pair counted as the CPU

@@ -81,6 +81,8 @@ def test_paths_agree_at_scale(env):
     assert (np.concatenate([sa, sb]) == s_fast).all()
     keep = np.array([c < b.loci[i].n_child for i in range(b.n_loci) for c in range(2)])
     assert (np.concatenate([oa, ob])[keep] == o_fast[keep]).all()
+    # the whole batch fetched its mask as a list of set positions (>= 8 Mi pairs), the halves byte per pair
+    assert (np.concatenate([ma, mb]) == m_fast).all()
     # strided oracle sample
     idx = np.arange(0, b.n_pairs, max(1, b.n_pairs // 200000), dtype=np.int64)
     want, st, _ = tdo.align_batch(b.blob, b.seq_off, b.seq_len, b.pair_pattern[idx], b.pair_text[idx], 50,

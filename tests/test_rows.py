@@ -112,3 +112,26 @@ def test_duo_tsv_identical(gpu_ctx, case):
     wtsv, wids = tdo_rows.write_outputs(want, R.DUO_COLUMNS)
     assert R.format_tsv(got, R.DUO_COLUMNS) == wtsv
     assert R.format_read_ids(got) == wids
+
+
+@pytest.mark.gpu
+def test_read_ids_through_the_sparse_mask_path(monkeypatch):
+    """Large host calls fetch the de novo read mask as a list of set positions instead of one byte per pair
+    (forced here for a small batch): the read-id file must not change."""
+    import __graft_entry__ as entry
+    entry.build()
+    import trgt_denovo_b200 as tdb
+    R = _rows_mod()
+    monkeypatch.setenv("TDB_SPARSE_MASK_MIN_PAIRS", "0")
+    ctx = tdb.Context(device_id=0)
+    monkeypatch.delenv("TDB_SPARSE_MASK_MIN_PAIRS")
+    params = R.Params(**CASES[0])
+    rng = random.Random(300)
+    loci, f, m, c = make_family_loci(rng, 150, denovo_rate=0.5)
+    got = R.process_trio_batch(ctx, loci, f, m, c, params)
+    aligner = tdo.Aligner()
+    want = [tdo_rows.process_alleles_trio(loci[i], f[i], m[i], c[i], params, aligner) for i in range(len(loci))]
+    wtsv, wids = tdo_rows.write_outputs(want, R.TRIO_COLUMNS)
+    assert R.format_tsv(got, R.TRIO_COLUMNS) == wtsv
+    assert R.format_read_ids(got) == wids and len(wids) > 0
+    ctx.close()

@@ -56,7 +56,8 @@ class Counters(C.Structure):
                 ("ms_host_plan", C.c_float), ("ms_host_pack_wait", C.c_float), ("ms_host_call", C.c_float),
                 ("ms_host_packed", C.c_float), ("ms_host_enqueued", C.c_float),
                 ("ms_tier", C.c_float * 4), ("ms_thread_tier", C.c_float), ("thread_pairs", C.c_uint64),
-                ("thread_cells", C.c_uint64), ("thread_ext16", C.c_uint64), ("thread_columns", C.c_uint64)]
+                ("thread_cells", C.c_uint64), ("thread_ext16", C.c_uint64), ("thread_columns", C.c_uint64),
+                ("bytes_d2h", C.c_uint64)]
 
 
 # every symbol include/trgt_denovo_b200.h declares (checked by tests/test_abi.py)

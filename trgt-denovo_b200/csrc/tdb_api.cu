@@ -74,7 +74,8 @@ struct tdb_ctx {
     std::vector<cudaEvent_t> up_ev; // one per in-flight chunk upload
     // grow-only device buffers
     DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, pair_p, pair_t, score, status, penalty;
-    DevBuf rep, work, list_b, list_c, scan_tmp;
+    DevBuf rep, work, list_b, list_c, scan_tmp, mask_hits;
+    std::vector<unsigned> h_hits; // host copy of the set mask positions
     // Chunks alternate between two pipeline slots (own stream + own scratch) so that the tail of one chunk's
     // alignment kernels overlaps the next chunk's duplicate elimination and alignment.  (3 and 4 slots, and a
     // warp tier deferred to a call-wide list, were measured and made no difference: profiles/r01/NOTES.md.)
@@ -87,6 +88,7 @@ struct tdb_ctx {
     DevBuf scratch[2];
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0, mini_ctas_per_sm = 0;
     bool disable_mini = false;
+    size_t sparse_mask_min_pairs = (size_t)8 << 20; // host calls at least this large fetch the mask as a list of set positions
     bool disable_quad = false, disable_duo = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
     size_t chunk_pairs = 2u << 20;
     size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
@@ -166,6 +168,7 @@ struct DevBatch {
     const uint64_t *h_seq_off;
     const uint32_t *h_seq_len;
     const uint32_t *h_pp, *h_pt;
+    uint8_t *h_zero; // optional host array of n_pairs bytes the calling thread zeroes chunk by chunk (result mask)
 };
 
 int check_sizes(tdb_ctx *ctx, size_t blob_bytes, size_t n_seqs, size_t n_pairs) {
@@ -589,6 +592,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         }
         const Chunk &c = chunks[k];
         const uint32_t cpairs = (uint32_t)(c.p1 - c.p0);
+        if (b.h_zero) memset(b.h_zero + c.p0, 0, c.p1 - c.p0);
         const uint32_t a = seq_up, e = std::max(seq_up, c.s_hi); // sequences first needed by this chunk: [a, e)
         seq_up = e;
         // blob bytes of the new sequences (device batches: offsets unknown on the host -> everything at once)
@@ -942,13 +946,15 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     return TDB_OK;
 }
 
+constexpr unsigned MASK_HITS_CAP = 1u << 20; // set mask bytes a host call fetches as a list (beyond: the whole mask)
 int run_reduce_device(tdb_ctx *ctx, const tdb_trio_locus *dloci, size_t n_loci, const int32_t *dscores, double q,
-                      int is_duo, tdb_allele_out *dout, uint8_t *dmask) {
+                      int is_duo, tdb_allele_out *dout, uint8_t *dmask, unsigned *hits = nullptr) {
     cudaStream_t s = ctx->stream;
     CK(cudaEventRecord(ctx->ev[8], s));
     if (n_loci) {
         const unsigned threads = 128, blocks = (unsigned)((n_loci + threads - 1) / threads);
-        k_reduce<<<blocks, threads, 0, s>>>(dloci, (uint32_t)n_loci, dscores, q, is_duo, dout, dmask);
+        k_reduce<<<blocks, threads, 0, s>>>(dloci, (uint32_t)n_loci, dscores, q, is_duo, dout, dmask, hits,
+                                            hits ? hits + 1 : nullptr, hits ? MASK_HITS_CAP : 0u);
         CK(cudaGetLastError());
         ctx->counters.kernel_launches += 1;
     }
@@ -1125,6 +1131,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         }
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
         c->disable_mini = getenv("TDB_DISABLE_THREAD_TIER") != nullptr;
+        if (const char *sm = getenv("TDB_SPARSE_MASK_MIN_PAIRS")) c->sparse_mask_min_pairs = (size_t)std::max(0ll, atoll(sm));
         // tier 1 runs two pairs per warp in lockstep (16 lanes each) with the production penalties: 17 % faster than
         // one pair per warp on the 30x trio (profiles/r01/NOTES.md); TDB_DISABLE_DUO=1 falls back to k_align_warp
         c->disable_duo = getenv("TDB_DISABLE_DUO") != nullptr;
@@ -1154,7 +1161,7 @@ void tdb_destroy(tdb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
     DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->pair_p, &c->pair_t,
-                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->scan_tmp, &c->ctrl, &c->loci, &c->runs,
+                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->scan_tmp, &c->mask_hits, &c->ctrl, &c->loci, &c->runs,
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
@@ -1327,17 +1334,53 @@ static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t
     UPLOAD(ctx->loci, loci, n_loci * sizeof(tdb_trio_locus), 0);
     ENSURE(ctx->aout, n_loci * 2 * sizeof(tdb_allele_out) + 16);
     ENSURE(ctx->mask, n_pairs + 16);
+    ENSURE(ctx->mask_hits, ((size_t)MASK_HITS_CAP + 1) * 4);
     CK(cudaMemsetAsync(ctx->aout.p, 0, n_loci * 2 * sizeof(tdb_allele_out), ctx->stream));
     CK(cudaMemsetAsync(ctx->mask.p, 0, n_pairs + 16, ctx->stream));
+    CK(cudaMemsetAsync(ctx->mask_hits.p, 0, 4, ctx->stream));
+    // The mask has a few set bytes in a million: the host copy is zeroed here (chunk by chunk, while the calling
+    // thread waits for the packer threads anyway) and only the list of set positions comes back over PCIe.
+    const bool sparse_mask = denovo_mask && n_pairs >= ctx->sparse_mask_min_pairs;
+    b.h_zero = sparse_mask ? denovo_mask : nullptr;
     r = run_align(ctx, b, false);
     if (r) return r;
+    unsigned *hits = sparse_mask ? (unsigned *)ctx->mask_hits.p : nullptr;
     r = run_reduce_device(ctx, (const tdb_trio_locus *)ctx->loci.p, n_loci, b.score, q, is_duo,
-                          (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p);
+                          (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p, hits);
     if (r) return r;
+    uint64_t d2h = 0;
     if (n_loci) CK(cudaMemcpyAsync(out, ctx->aout.p, n_loci * 2 * sizeof(tdb_allele_out), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_score && n_pairs) CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (denovo_mask && n_pairs) CK(cudaMemcpyAsync(denovo_mask, ctx->mask.p, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    d2h += n_loci * 2 * sizeof(tdb_allele_out);
+    if (out_score && n_pairs) {
+        CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += n_pairs * 4;
+    }
+    if (denovo_mask && n_pairs && !sparse_mask) {
+        CK(cudaMemcpyAsync(denovo_mask, ctx->mask.p, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += n_pairs;
+    }
+    if (sparse_mask) {
+        constexpr unsigned FIRST = 1u << 14; // entries fetched together with the count
+        ctx->h_hits.resize((size_t)MASK_HITS_CAP + 1);
+        unsigned *hh = ctx->h_hits.data();
+        CK(cudaMemcpyAsync(hh, hits, ((size_t)FIRST + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        d2h += ((size_t)FIRST + 1) * 4;
+        CK(cudaStreamSynchronize(ctx->stream));
+        const unsigned cnt = hh[0];
+        if (cnt > MASK_HITS_CAP) { // dense after all: the whole mask
+            CK(cudaMemcpyAsync(denovo_mask, ctx->mask.p, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+            d2h += n_pairs;
+        } else {
+            if (cnt > FIRST) {
+                CK(cudaMemcpyAsync(hh + 1 + FIRST, hits + 1 + FIRST, (size_t)(cnt - FIRST) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                d2h += (size_t)(cnt - FIRST) * 4;
+            }
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (unsigned i = 0; i < cnt; ++i) denovo_mask[hh[1 + i]] = 1;
+        }
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->counters.bytes_d2h = d2h;
     return TDB_OK;
 }
 

@@ -825,7 +825,9 @@ __constant__ int8_t c_combs2[8][2] = {{0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 0}, {3
 
 __global__ void __launch_bounds__(128) k_reduce(const tdb_trio_locus *__restrict__ loci, uint32_t n_loci,
                                                 const int32_t *__restrict__ scores, double q, int is_duo,
-                                                tdb_allele_out *__restrict__ out, uint8_t *__restrict__ mask) {
+                                                tdb_allele_out *__restrict__ out, uint8_t *__restrict__ mask,
+                                                unsigned *__restrict__ hit_count, uint32_t *__restrict__ hit_list,
+                                                unsigned hit_cap) {
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_loci) return;
     const tdb_trio_locus loc = loci[li];
@@ -854,7 +856,15 @@ __global__ void __launch_bounds__(128) k_reduce(const tdb_trio_locus *__restrict
         r.top_mother = top_m, r.top_father = top_f;
         const double thr = is_duo ? top_m : fmax(top_m, top_f);
         if (mask)
-            for (int i = 0; i < nown; ++i) mask[off[4] + i] = ((double)own[i] > thr) ? 1 : 0;
+            for (int i = 0; i < nown; ++i) {
+                const bool hit = (double)own[i] > thr;
+                mask[off[4] + i] = hit ? 1 : 0;
+                // the set bytes are a few in a million: host calls fetch this list instead of the whole mask
+                if (hit && hit_count) {
+                    const unsigned q_ = atomicAdd(hit_count, 1u);
+                    if (q_ < hit_cap) hit_list[q_] = off[4] + (uint32_t)i;
+                }
+            }
         int cm = 0, cf = 0;
         count_diff(top_m, own, nown, cm, r.mean_diff_mother);
         if (!is_duo) count_diff(top_f, own, nown, cf, r.mean_diff_father);
