@@ -268,9 +268,10 @@ __global__ void __launch_bounds__(256) k_seq_canon(const uint64_t *__restrict__ 
 
 // sort keys of representative pairs: 0 quad tier by descending |n-m| ... ; 255 = not in the sorted list
 #ifndef TDB_QL_MAX
-#define TDB_QL_MAX 16
+#define TDB_QL_MAX 14
 #endif
-constexpr int QL_MAX = TDB_QL_MAX; // |n-m| >= QL_MAX: wavefront wider than the quad tier's 32 diagonals
+constexpr int QL_MAX = TDB_QL_MAX; // |n-m| >= QL_MAX: the wavefront outgrows the quad tier's 32 diagonals before the pair ends
+                                    // (swept 10..16 with the thread tier in place: 14 best, profiles/r01/NOTES.md)
 constexpr int WL_MAX = 40;  // |n-m| >= WL_MAX: wider than the warp tier's 64 diagonals
 constexpr int KEY_WARP = 0; // sorted first: heaviest pairs of the shared-memory tiers
 constexpr int KEY_QUAD0 = 1;
