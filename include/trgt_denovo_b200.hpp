@@ -24,6 +24,7 @@
 #include "trgt_denovo_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -188,6 +189,20 @@ inline std::string serialize_with_precision(double v) {
 
 namespace detail {
 
+// -DTDBH_TIMING: per-phase wall times of process_alleles on stderr
+struct PhaseTimer {
+#ifdef TDBH_TIMING
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "  phase %-22s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+#else
+    void lap(const char *) {}
+#endif
+};
+
 struct Batch { // sequence blob + pair list in the reference's visiting order (src/denovo.rs:29-37,48-52)
     std::string blob; // sequences back to back: the ABI's dense layout (seq_off = NULL)
     std::vector<uint32_t> len, pp, pt;
@@ -246,7 +261,9 @@ inline size_t total_reads(const AlleleSet &a) {
 // load_alleles (src/allele.rs:146-191) for many (locus, sample) inputs at once.  With partition_by_alignment
 // every read is aligned against every allele of its own sample in ONE batched GPU call; only the
 // order-dependent tie flip (src/allele.rs:215,238-243) runs on the host.  nullopt in -> nullopt out (Err).
-inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, const std::vector<std::optional<SampleInput>> &samples,
+// The inputs are taken by value: pass std::move(...) for genome-sized batches and the reads are moved, not copied,
+// into the allele sets.
+inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, std::vector<std::optional<SampleInput>> samples,
                                                           const Params &params) {
     std::vector<std::optional<AlleleSet>> out;
     std::vector<int32_t> scores, status;
@@ -275,7 +292,7 @@ inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, co
             out.emplace_back(std::nullopt);
             continue;
         }
-        const SampleInput &s = *samples[si];
+        SampleInput &s = *samples[si];
         const size_t n_all = s.allele_seqs.size();
         AlleleSet set;
         set.karyotype = s.karyotype;
@@ -287,7 +304,7 @@ inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, co
         }
         if (params.partition_by_alignment) {
             size_t index_flip = 0, j = pair_base[si];
-            for (const TrgtRead &r : s.reads) {
+            for (TrgtRead &r : s.reads) {
                 std::vector<std::pair<size_t, int>> max_aligns;
                 bool have = false;
                 int max_score = 0;
@@ -300,18 +317,18 @@ inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, co
                 if (!max_aligns.empty()) {
                     if (max_aligns.size() > 1) index_flip = (index_flip + 1) % max_aligns.size();
                     const auto [ai, al] = max_aligns[index_flip % max_aligns.size()];
-                    set.alleles[ai].read_aligns.push_back({r, al});
+                    set.alleles[ai].read_aligns.emplace_back(std::move(r), al);
                 }
             }
         } else {
-            for (const TrgtRead &r : s.reads) {
+            for (TrgtRead &r : s.reads) {
                 if (!r.classification) throw Error(TDB_E_INVALID, "read without AL tag (src/allele.rs:255 panics)");
-                set.alleles.at((size_t)*r.classification).read_aligns.push_back({r, 0});
+                set.alleles.at((size_t)*r.classification).read_aligns.emplace_back(std::move(r), 0);
             }
         }
         for (size_t i = 0; i < n_all; ++i) {
             Allele &a = set.alleles[i];
-            a.seq = s.allele_seqs[i], a.motif_count = s.motif_counts[i], a.allele_length = s.allele_lengths[i];
+            a.seq = std::move(s.allele_seqs[i]), a.motif_count = std::move(s.motif_counts[i]), a.allele_length = std::move(s.allele_lengths[i]);
             a.genotype = s.genotype_indices[i], a.index = i;
         }
         out.emplace_back(std::move(set));
@@ -428,15 +445,17 @@ inline bool check_field_similarity(const AlleleSet &f, const AlleleSet &m, const
 
 // process_alleles (src/trio/allele.rs:185-349) for many loci: -> rows per locus, in locus order.
 inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner, const std::vector<Locus> &loci,
-                                                              const std::vector<std::optional<SampleInput>> &father,
-                                                              const std::vector<std::optional<SampleInput>> &mother,
-                                                              const std::vector<std::optional<SampleInput>> &child,
+                                                              std::vector<std::optional<SampleInput>> father,
+                                                              std::vector<std::optional<SampleInput>> mother,
+                                                              std::vector<std::optional<SampleInput>> child,
                                                               const Params &params) {
     const size_t n = loci.size();
-    std::vector<std::optional<SampleInput>> all(father);
-    all.insert(all.end(), mother.begin(), mother.end());
-    all.insert(all.end(), child.begin(), child.end());
-    const auto sets = load_alleles(aligner, all, params);
+    std::vector<std::optional<SampleInput>> all(std::move(father));
+    all.insert(all.end(), std::make_move_iterator(mother.begin()), std::make_move_iterator(mother.end()));
+    all.insert(all.end(), std::make_move_iterator(child.begin()), std::make_move_iterator(child.end()));
+    detail::PhaseTimer pt;
+    const auto sets = load_alleles(aligner, std::move(all), params);
+    pt.lap("load_alleles");
     std::vector<AlleleResult> templ;
     std::vector<size_t> todo;
     for (size_t i = 0; i < n; ++i) {
@@ -454,8 +473,19 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
         }
         todo.push_back(i);
     }
+    pt.lap("template rows");
     // one batch for every locus that reaches assess_denovo (src/trio/denovo.rs:83-186)
     detail::Batch b;
+    {
+        size_t bytes = 0, seqs = 0;
+        for (size_t i : todo)
+            for (const auto *set : {&*sets[i], &*sets[n + i], &*sets[2 * n + i]})
+                for (const Allele &a : set->alleles) {
+                    bytes += a.seq.size(), seqs += 1 + a.read_aligns.size();
+                    for (const auto &ra : a.read_aligns) bytes += ra.first.bases.size();
+                }
+        b.blob.reserve(bytes), b.len.reserve(seqs), b.pp.reserve(2 * seqs), b.pt.reserve(2 * seqs);
+    }
     std::vector<tdb_trio_locus> tl(todo.size());
     std::vector<std::pair<uint32_t, uint32_t>> own(2 * todo.size());
     for (size_t li = 0; li < todo.size(); ++li) {
@@ -476,6 +506,7 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
         }
         for (int ci = 0; ci < loc.n_child && ci < 2; ++ci) own[2 * li + ci] = detail::add_lists(b, loc, ci, c.alleles[ci], mr, fr);
     }
+    pt.lap("batch assembly");
     std::vector<tdb_allele_out> out(2 * todo.size());
     std::vector<uint8_t> mask(b.pp.size() + 1);
     if (!todo.empty()) {
@@ -484,6 +515,7 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
                                      b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
                                      params.parent_quantile, out.data(), nullptr, mask.data()));
     }
+    pt.lap("tdb_trio_batch");
     std::vector<std::vector<AlleleResult>> result;
     for (size_t i = 0; i < n; ++i) result.push_back({templ[i]});
     for (size_t li = 0; li < todo.size(); ++li) {
@@ -512,6 +544,7 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
         }
         if (!rows.empty()) result[i] = std::move(rows);
     }
+    pt.lap("rows");
     return result;
 }
 
@@ -562,13 +595,13 @@ inline bool check_field_similarity(const AlleleSet &a, const AlleleSet &b, const
 // duo process_alleles (src/duo/allele.rs:124-246) for many loci.  Row fields reuse AlleleResult: sample A in the
 // child_* / per_allele_reads_child slots, sample B in the mother_* slots, mean_diff_b in mean_diff_mother.
 inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner, const std::vector<Locus> &loci,
-                                                              const std::vector<std::optional<SampleInput>> &sample_a,
-                                                              const std::vector<std::optional<SampleInput>> &sample_b,
+                                                              std::vector<std::optional<SampleInput>> sample_a,
+                                                              std::vector<std::optional<SampleInput>> sample_b,
                                                               const Params &params) {
     const size_t n = loci.size();
-    std::vector<std::optional<SampleInput>> all(sample_a);
-    all.insert(all.end(), sample_b.begin(), sample_b.end());
-    const auto sets = load_alleles(aligner, all, params);
+    std::vector<std::optional<SampleInput>> all(std::move(sample_a));
+    all.insert(all.end(), std::make_move_iterator(sample_b.begin()), std::make_move_iterator(sample_b.end()));
+    const auto sets = load_alleles(aligner, std::move(all), params);
     std::vector<AlleleResult> templ;
     std::vector<size_t> todo;
     for (size_t i = 0; i < n; ++i) {

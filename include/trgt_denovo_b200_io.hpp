@@ -30,6 +30,8 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
+#include <thread>
 #include <unordered_map>
 
 namespace tdbh {
@@ -290,7 +292,9 @@ class SampleFiles {
 
     // get_vcf_data + get_reads for one locus (src/allele.rs:274-426); nullopt where the reference returns Err
     // (TRID absent from the VCF, missing genotype, malformed MC / AL, no reads), with the reason in *why.
-    std::optional<SampleInput> sample_input(const LocusRec &l, std::string *why = nullptr) const {
+    // `take` moves the reads out of this object (a genome-sized shard should not hold its reads twice); a second call
+    // for the same TRID then finds none.
+    std::optional<SampleInput> sample_input(const LocusRec &l, std::string *why = nullptr, bool take = false) {
         auto fail = [&](const std::string &m) {
             if (why) *why = m;
             return std::nullopt;
@@ -316,7 +320,8 @@ class SampleFiles {
         s.motif_counts = rec.mc, s.allele_lengths = rec.al;
         const auto r = reads_.find(id);
         if (r == reads_.end() || r->second.empty()) return fail("No reads found for locus: " + id);
-        s.reads = r->second;
+        if (take) s.reads = std::move(r->second), r->second.clear();
+        else s.reads = r->second;
         return s;
     }
 
@@ -478,20 +483,39 @@ class SampleFiles {
     }
 };
 
+// The samples' files, each pair read on its own thread (they are independent and decompression is the cost).
+inline std::vector<std::unique_ptr<SampleFiles>> open_samples(const std::vector<std::string> &prefixes) {
+    std::vector<std::unique_ptr<SampleFiles>> out(prefixes.size());
+    std::vector<std::string> err(prefixes.size());
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < prefixes.size(); ++i)
+        th.emplace_back([&, i]() {
+            try {
+                out[i].reset(new SampleFiles(SampleFiles::from_prefix(prefixes[i])));
+            } catch (const std::exception &e) {
+                err[i] = e.what();
+            }
+        });
+    for (auto &t : th) t.join();
+    for (const std::string &e : err)
+        if (!e.empty()) throw IoError(e);
+    return out;
+}
+
 // Every locus of the catalog with the inputs of its samples, ready for process_alleles.
 struct FamilyInputs {
     std::vector<Locus> loci;
     std::vector<std::vector<std::optional<SampleInput>>> samples; // [sample][locus]
     std::vector<std::string> messages;                             // per-sample reasons for missing inputs
 };
-inline FamilyInputs gather(const std::vector<LocusRec> &catalog, const std::vector<const SampleFiles *> &files) {
+inline FamilyInputs gather(const std::vector<LocusRec> &catalog, const std::vector<SampleFiles *> &files, bool take = true) {
     FamilyInputs out;
     out.samples.resize(files.size());
     for (const LocusRec &l : catalog) {
         out.loci.push_back(l.locus);
         for (size_t s = 0; s < files.size(); ++s) {
             std::string why;
-            out.samples[s].push_back(files[s]->sample_input(l, &why));
+            out.samples[s].push_back(files[s]->sample_input(l, &why, take));
             if (!why.empty()) out.messages.push_back(l.locus.id + " sample " + std::to_string(s) + ": " + why);
         }
     }

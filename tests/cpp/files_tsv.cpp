@@ -10,6 +10,7 @@
 // the order of the prefixes), followed by "E <message>" lines for catalog errors and missing inputs.
 #include "trgt_denovo_b200_io.hpp"
 
+#include <chrono>
 #include <iostream>
 #include <memory>
 
@@ -22,17 +23,23 @@ int main(int argc, char **argv) {
             return 2;
         }
         const std::string mode = argv[1];
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        const auto t0 = now();
         io::Fasta genome(argv[2]);
         std::vector<std::string> errors;
         const size_t flank = mode == "dump" ? std::stoul(argv[4]) : 50;
         const auto catalog = io::read_catalog(argv[3], genome, flank, &errors);
-        std::vector<std::unique_ptr<io::SampleFiles>> files;
-        std::vector<const io::SampleFiles *> ptrs;
-        for (int i = mode == "dump" ? 6 : 6; i < argc; ++i) {
-            files.emplace_back(new io::SampleFiles(io::SampleFiles::from_prefix(argv[i])));
-            ptrs.push_back(files.back().get());
-        }
-        const io::FamilyInputs fam = io::gather(catalog, ptrs);
+        const auto t1 = now();
+        std::vector<std::string> prefixes(argv + 6, argv + argc);
+        const auto files = io::open_samples(prefixes);
+        std::vector<io::SampleFiles *> ptrs;
+        for (const auto &f : files) ptrs.push_back(f.get());
+        const auto t2 = now();
+        io::FamilyInputs fam = io::gather(catalog, ptrs);
+        const auto t3 = now();
         if (mode == "dump") {
             std::ofstream o(argv[5]);
             o << "P\t50\t1.0\t0\t-\t-\n";
@@ -63,18 +70,23 @@ int main(int argc, char **argv) {
         }
         Params params;
         WFAligner aligner = create_aligner_with_scoring();
+        const auto t4 = now();
         std::string tsv, ids;
         if (mode == "duo") {
             if (fam.samples.size() != 2) throw io::IoError("duo needs two sample prefixes");
-            const auto rows = duo::process_alleles(aligner, fam.loci, fam.samples[0], fam.samples[1], params);
+            const auto rows = duo::process_alleles(aligner, fam.loci, std::move(fam.samples[0]), std::move(fam.samples[1]), params);
             tsv = write_tsv(rows, duo::columns(), duo::row_tsv), ids = write_read_ids(rows);
         } else {
             if (fam.samples.size() != 3) throw io::IoError("trio needs father, mother and child prefixes");
-            const auto rows = trio::process_alleles(aligner, fam.loci, fam.samples[0], fam.samples[1], fam.samples[2], params);
+            const auto rows = trio::process_alleles(aligner, fam.loci, std::move(fam.samples[0]), std::move(fam.samples[1]), std::move(fam.samples[2]), params);
             tsv = write_tsv(rows, trio::columns(), trio::row_tsv), ids = write_read_ids(rows);
         }
+        const auto t5 = now();
         std::ofstream(argv[4]) << tsv;
         std::ofstream(argv[5]) << ids;
+        std::cerr << "timing_ms loci=" << fam.loci.size() << " catalog+flanks=" << ms(t0, t1) << " vcf+bam=" << ms(t1, t2)
+                  << " gather=" << ms(t2, t3) << " context=" << ms(t3, t4) << " process_alleles=" << ms(t4, t5)
+                  << " write=" << ms(t5, now()) << "\n";
         return 0;
     } catch (const Error &e) {
         std::cerr << e.what() << "\n";
