@@ -347,6 +347,38 @@ def test_dense_layout(tdb, ctx):
     assert (got == want).all()
 
 
+def test_two_contexts_from_two_host_threads(tdb):
+    """One ctx per host thread is the threading model (like the reference's thread-local aligner): two contexts on
+    the same GPU, driven concurrently, each give the oracle's scores."""
+    import threading
+    rng = random.Random(39)
+    jobs = []
+    for t in range(2):
+        seqs, pp, pt = make_pairs(rng, n_targets=200, reads_per_target=10, max_units=30, err=0.01)
+        blob, off, ln = to_arrays(seqs)
+        want, _, _ = tdo.align_batch(blob, off, ln, pp, pt, 50, n_threads=4)
+        jobs.append((blob, ln, pp, pt, want))
+    results, errors = [None, None], []
+
+    def work(i):
+        try:
+            c = tdb.Context(device_id=0)
+            for _ in range(5):
+                got, st = c.align_batch(jobs[i][0], None, jobs[i][1], jobs[i][2], jobs[i][3])
+                assert (st == 0).all() and (got == jobs[i][4]).all()
+            results[i] = True
+            c.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors and results == [True, True]
+
+
 def test_bad_layout_and_bad_pair_index_fail(tdb, ctx):
     blob = np.frombuffer(b"ACGTACGTAC" * 4, dtype=np.uint8)
     ln = np.array([10, 10], np.uint32)
