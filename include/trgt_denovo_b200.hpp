@@ -28,11 +28,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <limits>
+#include <mutex>
 #include <optional>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -217,6 +220,75 @@ struct Batch { // sequence blob + pair list in the reference's visiting order (s
     }
 };
 
+// Host threads of the per-locus phases (the reference runs loci on a rayon pool, src/commands/shared.rs:136-146):
+// TDBH_THREADS, default the hardware concurrency (at most 64).
+inline unsigned host_threads() {
+    static const unsigned n = [] {
+        const char *e = getenv("TDBH_THREADS");
+        const unsigned v = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+        return std::max(1u, std::min(v ? v : 1u, 64u));
+    }();
+    return n;
+}
+inline size_t shard_count(size_t n, size_t min_per_shard) {
+    return std::max<size_t>(1, std::min<size_t>(host_threads(), n / std::max<size_t>(1, min_per_shard)));
+}
+// fn(shard, lo, hi) over [0, n) cut into shard_count(n, min_per_shard) contiguous ranges, one thread each; the first
+// exception is rethrown on the calling thread.
+template <class F>
+inline void parallel_ranges(size_t n, size_t min_per_shard, F fn) {
+    const size_t T = shard_count(n, min_per_shard);
+    if (T <= 1) {
+        fn((size_t)0, (size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::exception_ptr err;
+    std::mutex mu;
+    for (size_t t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+            try {
+                fn(t, n * t / T, n * (t + 1) / T);
+            } catch (...) {
+                std::lock_guard<std::mutex> g(mu);
+                if (!err) err = std::current_exception();
+            }
+        });
+    for (auto &x : th) x.join();
+    if (err) std::rethrow_exception(err);
+}
+// Batches assembled shard by shard (same cut as parallel_ranges) -> one batch: sequence and pair indices of shard t are
+// rebased by what the shards before it hold.
+inline Batch merge_shards(std::vector<Batch> &sb, std::vector<tdb_trio_locus> &tl, std::vector<std::pair<uint32_t, uint32_t>> &own) {
+    if (sb.size() == 1) return std::move(sb[0]);
+    Batch b;
+    size_t bytes = 0, seqs = 0, pairs = 0;
+    for (const Batch &x : sb) bytes += x.blob.size(), seqs += x.len.size(), pairs += x.pp.size();
+    b.blob.reserve(bytes), b.len.reserve(seqs), b.pp.resize(pairs), b.pt.resize(pairs);
+    std::vector<uint32_t> seq_base(sb.size()), pair_base(sb.size());
+    size_t at_seq = 0, at_pair = 0;
+    for (size_t t = 0; t < sb.size(); ++t) {
+        seq_base[t] = (uint32_t)at_seq, pair_base[t] = (uint32_t)at_pair;
+        at_seq += sb[t].len.size(), at_pair += sb[t].pp.size();
+        b.blob += sb[t].blob;
+        b.len.insert(b.len.end(), sb[t].len.begin(), sb[t].len.end());
+    }
+    const size_t n = tl.size(), T = sb.size();
+    parallel_ranges(T, 1, [&](size_t, size_t t0, size_t t1) {
+        for (size_t t = t0; t < t1; ++t) {
+            for (size_t k = 0; k < sb[t].pp.size(); ++k)
+                b.pp[pair_base[t] + k] = sb[t].pp[k] + seq_base[t], b.pt[pair_base[t] + k] = sb[t].pt[k] + seq_base[t];
+            for (size_t li = n * t / T; li < n * (t + 1) / T; ++li)
+                for (int c = 0; c < tl[li].n_child && c < 2; ++c) {
+                    for (int j = 0; j < 6; ++j) tl[li].list_off[c][j] += pair_base[t];
+                    own[2 * li + c].first += pair_base[t], own[2 * li + c].second += pair_base[t];
+                }
+            sb[t] = Batch();
+        }
+    });
+    return b;
+}
+
 inline int ploidy(const std::string &kary, const std::string &chrom) { // src/handles.rs:40-62
     const bool xy = chrom == "X" || chrom == "chrX" || chrom == "Y" || chrom == "chrY";
     if (kary == "XX") return (chrom == "Y" || chrom == "chrY") ? 0 : 2;
@@ -287,11 +359,10 @@ inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, st
                                           b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), scores.data(), status.data()));
         }
     }
-    for (size_t si = 0; si < samples.size(); ++si) {
-        if (!samples[si]) {
-            out.emplace_back(std::nullopt);
-            continue;
-        }
+    out.resize(samples.size());
+    detail::parallel_ranges(samples.size(), 128, [&](size_t, size_t s_lo, size_t s_hi) {
+    for (size_t si = s_lo; si < s_hi; ++si) {
+        if (!samples[si]) continue;
         SampleInput &s = *samples[si];
         const size_t n_all = s.allele_seqs.size();
         AlleleSet set;
@@ -331,8 +402,9 @@ inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, st
             a.seq = std::move(s.allele_seqs[i]), a.motif_count = std::move(s.motif_counts[i]), a.allele_length = std::move(s.allele_lengths[i]);
             a.genotype = s.genotype_indices[i], a.index = i;
         }
-        out.emplace_back(std::move(set));
+        out[si] = std::move(set);
     }
+    });
     return out;
 }
 
@@ -454,58 +526,65 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
     all.insert(all.end(), std::make_move_iterator(mother.begin()), std::make_move_iterator(mother.end()));
     all.insert(all.end(), std::make_move_iterator(child.begin()), std::make_move_iterator(child.end()));
     detail::PhaseTimer pt;
-    const auto sets = load_alleles(aligner, std::move(all), params);
+    auto sets = load_alleles(aligner, std::move(all), params);
     pt.lap("load_alleles");
-    std::vector<AlleleResult> templ;
-    std::vector<size_t> todo;
-    for (size_t i = 0; i < n; ++i) {
-        AlleleResult r = detail::template_row(loci[i]);
-        const auto &f = sets[i], &m = sets[n + i], &c = sets[2 * n + i];
-        detail::sample_columns(f, loci[i], r.father_dropout, r.per_allele_reads_father, r.father_MC, r.father_AL, &r.father_dropout_prob);
-        detail::sample_columns(m, loci[i], r.mother_dropout, r.per_allele_reads_mother, r.mother_MC, r.mother_AL, &r.mother_dropout_prob);
-        detail::sample_columns(c, loci[i], r.child_dropout, r.per_allele_reads_child, r.child_MC, r.child_AL, nullptr);
-        templ.push_back(r);
-        if (!f || !m || !c) continue; // missing genotyping: one template row (src/trio/allele.rs:270-286)
-        if (params.quick_mode) {
-            const bool skip = params.quick_mode->is_zero() ? check_field_equivalence(*f, *m, *c, *params.quick_mode)
-                                                           : check_field_similarity(*f, *m, *c, *params.quick_mode);
-            if (skip) continue;
+    std::vector<AlleleResult> templ(n);
+    std::vector<uint8_t> reaches(n, 0);
+    detail::parallel_ranges(n, 256, [&](size_t, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            AlleleResult r = detail::template_row(loci[i]);
+            const auto &f = sets[i], &m = sets[n + i], &c = sets[2 * n + i];
+            detail::sample_columns(f, loci[i], r.father_dropout, r.per_allele_reads_father, r.father_MC, r.father_AL, &r.father_dropout_prob);
+            detail::sample_columns(m, loci[i], r.mother_dropout, r.per_allele_reads_mother, r.mother_MC, r.mother_AL, &r.mother_dropout_prob);
+            detail::sample_columns(c, loci[i], r.child_dropout, r.per_allele_reads_child, r.child_MC, r.child_AL, nullptr);
+            templ[i] = std::move(r);
+            if (!f || !m || !c) continue; // missing genotyping: one template row (src/trio/allele.rs:270-286)
+            if (params.quick_mode) {
+                const bool skip = params.quick_mode->is_zero() ? check_field_equivalence(*f, *m, *c, *params.quick_mode)
+                                                               : check_field_similarity(*f, *m, *c, *params.quick_mode);
+                if (skip) continue;
+            }
+            reaches[i] = 1;
         }
-        todo.push_back(i);
-    }
+    });
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < n; ++i)
+        if (reaches[i]) todo.push_back(i);
     pt.lap("template rows");
-    // one batch for every locus that reaches assess_denovo (src/trio/denovo.rs:83-186)
-    detail::Batch b;
-    {
+    // one batch for every locus that reaches assess_denovo (src/trio/denovo.rs:83-186), assembled shard by shard
+    std::vector<tdb_trio_locus> tl(todo.size());
+    std::vector<std::pair<uint32_t, uint32_t>> own(2 * todo.size());
+    std::vector<detail::Batch> shards(detail::shard_count(todo.size(), 64));
+    detail::parallel_ranges(todo.size(), 64, [&](size_t t, size_t lo, size_t hi) {
+        detail::Batch &b = shards[t];
         size_t bytes = 0, seqs = 0;
-        for (size_t i : todo)
-            for (const auto *set : {&*sets[i], &*sets[n + i], &*sets[2 * n + i]})
+        for (size_t li = lo; li < hi; ++li)
+            for (const auto *set : {&*sets[todo[li]], &*sets[n + todo[li]], &*sets[2 * n + todo[li]]})
                 for (const Allele &a : set->alleles) {
                     bytes += a.seq.size(), seqs += 1 + a.read_aligns.size();
                     for (const auto &ra : a.read_aligns) bytes += ra.first.bases.size();
                 }
         b.blob.reserve(bytes), b.len.reserve(seqs), b.pp.reserve(2 * seqs), b.pt.reserve(2 * seqs);
-    }
-    std::vector<tdb_trio_locus> tl(todo.size());
-    std::vector<std::pair<uint32_t, uint32_t>> own(2 * todo.size());
-    for (size_t li = 0; li < todo.size(); ++li) {
-        const size_t i = todo[li];
-        const AlleleSet &f = *sets[i], &m = *sets[n + i], &c = *sets[2 * n + i];
-        tdb_trio_locus &loc = tl[li];
-        memset(&loc, 0, sizeof(loc));
-        loc.n_child = (int)c.alleles.size(), loc.n_mother = (int)m.alleles.size(), loc.n_father = (int)f.alleles.size();
-        std::vector<std::vector<uint32_t>> mr(m.alleles.size()), fr(f.alleles.size());
-        for (size_t a = 0; a < m.alleles.size(); ++a)
-            for (const auto &ra : m.alleles[a].read_aligns) mr[a].push_back(b.seq(ra.first.bases));
-        for (size_t a = 0; a < f.alleles.size(); ++a)
-            for (const auto &ra : f.alleles[a].read_aligns) fr[a].push_back(b.seq(ra.first.bases));
-        for (int a = 0; a < 2; ++a) {
-            loc.child_len[a] = a < loc.n_child ? (int)c.alleles[a].seq.size() : 0;
-            loc.mother_len[a] = a < loc.n_mother ? (int)m.alleles[a].seq.size() : 0;
-            loc.father_len[a] = a < loc.n_father ? (int)f.alleles[a].seq.size() : 0;
+        for (size_t li = lo; li < hi; ++li) {
+            const size_t i = todo[li];
+            const AlleleSet &f = *sets[i], &m = *sets[n + i], &c = *sets[2 * n + i];
+            tdb_trio_locus &loc = tl[li];
+            memset(&loc, 0, sizeof(loc));
+            loc.n_child = (int)c.alleles.size(), loc.n_mother = (int)m.alleles.size(), loc.n_father = (int)f.alleles.size();
+            std::vector<std::vector<uint32_t>> mr(m.alleles.size()), fr(f.alleles.size());
+            for (size_t a = 0; a < m.alleles.size(); ++a)
+                for (const auto &ra : m.alleles[a].read_aligns) mr[a].push_back(b.seq(ra.first.bases));
+            for (size_t a = 0; a < f.alleles.size(); ++a)
+                for (const auto &ra : f.alleles[a].read_aligns) fr[a].push_back(b.seq(ra.first.bases));
+            for (int a = 0; a < 2; ++a) {
+                loc.child_len[a] = a < loc.n_child ? (int)c.alleles[a].seq.size() : 0;
+                loc.mother_len[a] = a < loc.n_mother ? (int)m.alleles[a].seq.size() : 0;
+                loc.father_len[a] = a < loc.n_father ? (int)f.alleles[a].seq.size() : 0;
+            }
+            for (int ci = 0; ci < loc.n_child && ci < 2; ++ci) own[2 * li + ci] = detail::add_lists(b, loc, ci, c.alleles[ci], mr, fr);
         }
-        for (int ci = 0; ci < loc.n_child && ci < 2; ++ci) own[2 * li + ci] = detail::add_lists(b, loc, ci, c.alleles[ci], mr, fr);
-    }
+    });
+    detail::Batch b = detail::merge_shards(shards, tl, own);
     pt.lap("batch assembly");
     std::vector<tdb_allele_out> out(2 * todo.size());
     std::vector<uint8_t> mask(b.pp.size() + 1);
@@ -516,35 +595,43 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
                                      params.parent_quantile, out.data(), nullptr, mask.data()));
     }
     pt.lap("tdb_trio_batch");
-    std::vector<std::vector<AlleleResult>> result;
-    for (size_t i = 0; i < n; ++i) result.push_back({templ[i]});
-    for (size_t li = 0; li < todo.size(); ++li) {
-        const size_t i = todo[li];
-        const AlleleSet &f = *sets[i], &m = *sets[n + i], &c = *sets[2 * n + i];
-        const size_t child_cov = detail::total_reads(c);
-        std::vector<AlleleResult> rows;
-        for (size_t ci = 0; ci < c.alleles.size() && ci < 2; ++ci) {
-            const tdb_allele_out &o = out[2 * li + ci];
-            if (o.error) throw Error(TDB_E_INVALID, "TRID=" + loci[i].id + ": no parental alignment scores (the reference panics here, src/trio/denovo.rs:333-334)");
-            const Allele &ca = c.alleles[ci];
-            AlleleResult r = templ[i];
-            r.genotype = ca.genotype, r.denovo_coverage = (size_t)o.denovo_coverage, r.allele_coverage = ca.read_aligns.size();
-            r.allele_ratio = r.allele_coverage == 0 ? 0.0 : (double)r.denovo_coverage / (double)r.allele_coverage;
-            r.child_coverage = child_cov, r.child_ratio = detail::fdiv((double)r.denovo_coverage, (double)child_cov);
-            r.mean_diff_father = o.mean_diff_father, r.mean_diff_mother = o.mean_diff_mother;
-            r.allele_origin = allele_origin_str(o.allele_origin), r.denovo_status = denovo_status_str(o.denovo_status);
-            r.index = ca.index;
-            r.father_overlap_coverage = detail::join(std::vector<int>(o.father_overlap, o.father_overlap + f.alleles.size()));
-            r.mother_overlap_coverage = detail::join(std::vector<int>(o.mother_overlap, o.mother_overlap + m.alleles.size()));
-            std::vector<std::string> ids;
-            for (uint32_t k = own[2 * li + ci].first; k < own[2 * li + ci].second; ++k)
-                if (mask[k]) ids.push_back(ca.read_aligns[k - own[2 * li + ci].first].first.name);
-            if (!ids.empty()) r.read_ids = std::move(ids);
-            rows.push_back(std::move(r));
+    std::vector<std::vector<AlleleResult>> result(n);
+    detail::parallel_ranges(n, 256, [&](size_t, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) result[i] = {templ[i]};
+    });
+    detail::parallel_ranges(todo.size(), 64, [&](size_t, size_t lo, size_t hi) {
+        for (size_t li = lo; li < hi; ++li) {
+            const size_t i = todo[li];
+            const AlleleSet &f = *sets[i], &m = *sets[n + i], &c = *sets[2 * n + i];
+            const size_t child_cov = detail::total_reads(c);
+            std::vector<AlleleResult> rows;
+            for (size_t ci = 0; ci < c.alleles.size() && ci < 2; ++ci) {
+                const tdb_allele_out &o = out[2 * li + ci];
+                if (o.error) throw Error(TDB_E_INVALID, "TRID=" + loci[i].id + ": no parental alignment scores (the reference panics here, src/trio/denovo.rs:333-334)");
+                const Allele &ca = c.alleles[ci];
+                AlleleResult r = templ[i];
+                r.genotype = ca.genotype, r.denovo_coverage = (size_t)o.denovo_coverage, r.allele_coverage = ca.read_aligns.size();
+                r.allele_ratio = r.allele_coverage == 0 ? 0.0 : (double)r.denovo_coverage / (double)r.allele_coverage;
+                r.child_coverage = child_cov, r.child_ratio = detail::fdiv((double)r.denovo_coverage, (double)child_cov);
+                r.mean_diff_father = o.mean_diff_father, r.mean_diff_mother = o.mean_diff_mother;
+                r.allele_origin = allele_origin_str(o.allele_origin), r.denovo_status = denovo_status_str(o.denovo_status);
+                r.index = ca.index;
+                r.father_overlap_coverage = detail::join(std::vector<int>(o.father_overlap, o.father_overlap + f.alleles.size()));
+                r.mother_overlap_coverage = detail::join(std::vector<int>(o.mother_overlap, o.mother_overlap + m.alleles.size()));
+                std::vector<std::string> ids;
+                for (uint32_t k = own[2 * li + ci].first; k < own[2 * li + ci].second; ++k)
+                    if (mask[k]) ids.push_back(ca.read_aligns[k - own[2 * li + ci].first].first.name);
+                if (!ids.empty()) r.read_ids = std::move(ids);
+                rows.push_back(std::move(r));
+            }
+            if (!rows.empty()) result[i] = std::move(rows);
         }
-        if (!rows.empty()) result[i] = std::move(rows);
-    }
+    });
     pt.lap("rows");
+    detail::parallel_ranges(sets.size(), 256, [&](size_t, size_t lo, size_t hi) { // millions of small strings to free
+        for (size_t i = lo; i < hi; ++i) sets[i].reset();
+    });
+    pt.lap("teardown");
     return result;
 }
 
@@ -601,41 +688,50 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
     const size_t n = loci.size();
     std::vector<std::optional<SampleInput>> all(std::move(sample_a));
     all.insert(all.end(), std::make_move_iterator(sample_b.begin()), std::make_move_iterator(sample_b.end()));
-    const auto sets = load_alleles(aligner, std::move(all), params);
-    std::vector<AlleleResult> templ;
-    std::vector<size_t> todo;
-    for (size_t i = 0; i < n; ++i) {
-        AlleleResult r = detail::template_row(loci[i]);
-        const auto &a = sets[i], &bb = sets[n + i];
-        detail::sample_columns(a, loci[i], r.child_dropout, r.per_allele_reads_child, r.child_MC, r.child_AL, nullptr);
-        detail::sample_columns(bb, loci[i], r.mother_dropout, r.per_allele_reads_mother, r.mother_MC, r.mother_AL, nullptr);
-        templ.push_back(r);
-        if (!a || !bb) continue;
-        if (params.quick_mode) {
-            const bool skip = params.quick_mode->is_zero() ? check_allele_field_equivalence(*a, *bb, *params.quick_mode)
-                                                           : check_field_similarity(*a, *bb, *params.quick_mode);
-            if (skip) continue;
+    auto sets = load_alleles(aligner, std::move(all), params);
+    std::vector<AlleleResult> templ(n);
+    std::vector<uint8_t> reaches(n, 0);
+    detail::parallel_ranges(n, 256, [&](size_t, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            AlleleResult r = detail::template_row(loci[i]);
+            const auto &a = sets[i], &bb = sets[n + i];
+            detail::sample_columns(a, loci[i], r.child_dropout, r.per_allele_reads_child, r.child_MC, r.child_AL, nullptr);
+            detail::sample_columns(bb, loci[i], r.mother_dropout, r.per_allele_reads_mother, r.mother_MC, r.mother_AL, nullptr);
+            templ[i] = std::move(r);
+            if (!a || !bb) continue;
+            if (params.quick_mode) {
+                const bool skip = params.quick_mode->is_zero() ? check_allele_field_equivalence(*a, *bb, *params.quick_mode)
+                                                               : check_field_similarity(*a, *bb, *params.quick_mode);
+                if (skip) continue;
+            }
+            reaches[i] = 1;
         }
-        todo.push_back(i);
-    }
-    detail::Batch b;
+    });
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < n; ++i)
+        if (reaches[i]) todo.push_back(i);
     std::vector<tdb_trio_locus> tl(todo.size());
     std::vector<std::pair<uint32_t, uint32_t>> own(2 * todo.size());
-    for (size_t li = 0; li < todo.size(); ++li) {
-        const size_t i = todo[li];
-        const AlleleSet &a = *sets[i], &sb = *sets[n + i];
-        tdb_trio_locus &loc = tl[li];
-        memset(&loc, 0, sizeof(loc));
-        loc.n_child = (int)a.alleles.size(), loc.n_mother = (int)sb.alleles.size(), loc.n_father = 0;
-        std::vector<std::vector<uint32_t>> br(sb.alleles.size()), none;
-        for (size_t x = 0; x < sb.alleles.size(); ++x)
-            for (const auto &ra : sb.alleles[x].read_aligns) br[x].push_back(b.seq(ra.first.bases));
-        for (int x = 0; x < 2; ++x) {
-            loc.child_len[x] = x < loc.n_child ? (int)a.alleles[x].seq.size() : 0;
-            loc.mother_len[x] = x < loc.n_mother ? (int)sb.alleles[x].seq.size() : 0;
+    std::vector<detail::Batch> shards(detail::shard_count(todo.size(), 64));
+    detail::parallel_ranges(todo.size(), 64, [&](size_t t, size_t lo, size_t hi) {
+        detail::Batch &b = shards[t];
+        for (size_t li = lo; li < hi; ++li) {
+            const size_t i = todo[li];
+            const AlleleSet &a = *sets[i], &sb = *sets[n + i];
+            tdb_trio_locus &loc = tl[li];
+            memset(&loc, 0, sizeof(loc));
+            loc.n_child = (int)a.alleles.size(), loc.n_mother = (int)sb.alleles.size(), loc.n_father = 0;
+            std::vector<std::vector<uint32_t>> br(sb.alleles.size()), none;
+            for (size_t x = 0; x < sb.alleles.size(); ++x)
+                for (const auto &ra : sb.alleles[x].read_aligns) br[x].push_back(b.seq(ra.first.bases));
+            for (int x = 0; x < 2; ++x) {
+                loc.child_len[x] = x < loc.n_child ? (int)a.alleles[x].seq.size() : 0;
+                loc.mother_len[x] = x < loc.n_mother ? (int)sb.alleles[x].seq.size() : 0;
+            }
+            for (int ci = 0; ci < loc.n_child && ci < 2; ++ci) own[2 * li + ci] = detail::add_lists(b, loc, ci, a.alleles[ci], br, none);
         }
-        for (int ci = 0; ci < loc.n_child && ci < 2; ++ci) own[2 * li + ci] = detail::add_lists(b, loc, ci, a.alleles[ci], br, none);
-    }
+    });
+    detail::Batch b = detail::merge_shards(shards, tl, own);
     std::vector<tdb_allele_out> out(2 * todo.size());
     std::vector<uint8_t> mask(b.pp.size() + 1);
     if (!todo.empty()) {
@@ -644,32 +740,39 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
                                     b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
                                     params.parent_quantile, out.data(), nullptr, mask.data()));
     }
-    std::vector<std::vector<AlleleResult>> result;
-    for (size_t i = 0; i < n; ++i) result.push_back({templ[i]});
-    for (size_t li = 0; li < todo.size(); ++li) {
-        const size_t i = todo[li];
-        const AlleleSet &a = *sets[i], &sb = *sets[n + i];
-        const size_t a_cov = detail::total_reads(a);
-        std::vector<AlleleResult> rows;
-        for (size_t ci = 0; ci < a.alleles.size() && ci < 2; ++ci) {
-            const tdb_allele_out &o = out[2 * li + ci];
-            if (o.error) throw Error(TDB_E_INVALID, "TRID=" + loci[i].id + ": no sample-B alignment scores (the reference panics here, src/duo/denovo.rs:107)");
-            const Allele &ca = a.alleles[ci];
-            AlleleResult r = templ[i];
-            r.genotype = ca.genotype, r.denovo_coverage = (size_t)o.denovo_coverage, r.allele_coverage = ca.read_aligns.size();
-            r.allele_ratio = r.allele_coverage == 0 ? 0.0 : (double)r.denovo_coverage / (double)r.allele_coverage;
-            r.child_coverage = a_cov, r.child_ratio = detail::fdiv((double)r.denovo_coverage, (double)a_cov);
-            r.mean_diff_mother = o.mean_diff_mother;
-            r.denovo_status = denovo_status_str(o.denovo_status), r.index = ca.index;
-            r.mother_overlap_coverage = detail::join(std::vector<int>(o.mother_overlap, o.mother_overlap + sb.alleles.size()));
-            std::vector<std::string> ids;
-            for (uint32_t k = own[2 * li + ci].first; k < own[2 * li + ci].second; ++k)
-                if (mask[k]) ids.push_back(ca.read_aligns[k - own[2 * li + ci].first].first.name);
-            if (!ids.empty()) r.read_ids = std::move(ids);
-            rows.push_back(std::move(r));
+    std::vector<std::vector<AlleleResult>> result(n);
+    detail::parallel_ranges(n, 256, [&](size_t, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) result[i] = {templ[i]};
+    });
+    detail::parallel_ranges(todo.size(), 64, [&](size_t, size_t lo, size_t hi) {
+        for (size_t li = lo; li < hi; ++li) {
+            const size_t i = todo[li];
+            const AlleleSet &a = *sets[i], &sb = *sets[n + i];
+            const size_t a_cov = detail::total_reads(a);
+            std::vector<AlleleResult> rows;
+            for (size_t ci = 0; ci < a.alleles.size() && ci < 2; ++ci) {
+                const tdb_allele_out &o = out[2 * li + ci];
+                if (o.error) throw Error(TDB_E_INVALID, "TRID=" + loci[i].id + ": no sample-B alignment scores (the reference panics here, src/duo/denovo.rs:107)");
+                const Allele &ca = a.alleles[ci];
+                AlleleResult r = templ[i];
+                r.genotype = ca.genotype, r.denovo_coverage = (size_t)o.denovo_coverage, r.allele_coverage = ca.read_aligns.size();
+                r.allele_ratio = r.allele_coverage == 0 ? 0.0 : (double)r.denovo_coverage / (double)r.allele_coverage;
+                r.child_coverage = a_cov, r.child_ratio = detail::fdiv((double)r.denovo_coverage, (double)a_cov);
+                r.mean_diff_mother = o.mean_diff_mother;
+                r.denovo_status = denovo_status_str(o.denovo_status), r.index = ca.index;
+                r.mother_overlap_coverage = detail::join(std::vector<int>(o.mother_overlap, o.mother_overlap + sb.alleles.size()));
+                std::vector<std::string> ids;
+                for (uint32_t k = own[2 * li + ci].first; k < own[2 * li + ci].second; ++k)
+                    if (mask[k]) ids.push_back(ca.read_aligns[k - own[2 * li + ci].first].first.name);
+                if (!ids.empty()) r.read_ids = std::move(ids);
+                rows.push_back(std::move(r));
+            }
+            if (!rows.empty()) result[i] = std::move(rows);
         }
-        if (!rows.empty()) result[i] = std::move(rows);
-    }
+    });
+    detail::parallel_ranges(sets.size(), 256, [&](size_t, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) sets[i].reset();
+    });
     return result;
 }
 

@@ -21,7 +21,7 @@ def exe(tmp_path_factory):
     libdir = os.path.dirname(entry.LIB)
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(entry.ROOT, "include"),
                            os.path.join(HERE, "cpp", "host_tsv.cpp"), "-o", out, "-L", libdir, "-ltrgt_denovo_b200",
-                           "-Wl,-rpath," + libdir])
+                           "-pthread", "-Wl,-rpath," + libdir])
     return out
 
 
