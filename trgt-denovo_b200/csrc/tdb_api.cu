@@ -88,6 +88,7 @@ struct tdb_ctx {
     DevBuf scratch[2];
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0, mini_ctas_per_sm = 0;
     bool disable_mini = false;
+    int global_warps_per_sm = 16; // workers of the first global-scratch tier (TDB_GLOBAL_WARPS_PER_SM)
     size_t sparse_mask_min_pairs = (size_t)8 << 20; // host calls at least this large fetch the mask as a list of set positions
     bool disable_quad = false, disable_duo = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
     size_t chunk_pairs = 2u << 20;
@@ -857,7 +858,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     // ---- global-scratch tiers: pairs too long or too wide for shared memory, once per call ------------
     const uint64_t cap = ctx->cfg.scratch_bytes ? ctx->cfg.scratch_bytes : (48ull << 30);
     const TierCfg gtiers[2] = {
-        {10, 1 << 16, 1 << 17, 8u << 20, ctx->sm_count * 8},   // W=1024, S<65536, 8 MiB provenance
+        {10, 1 << 16, 1 << 17, 8u << 20, ctx->sm_count * ctx->global_warps_per_sm}, // W=1024, S<65536, 8 MiB provenance
         {15, 1 << 18, 1 << 19, 192u << 20, ctx->sm_count * 1}, // W=32768, S<262144, 192 MiB provenance
     };
     Ctrl h;
@@ -1131,6 +1132,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         }
         c->disable_quad = getenv("TDB_DISABLE_QUAD") != nullptr;
         c->disable_mini = getenv("TDB_DISABLE_THREAD_TIER") != nullptr;
+        if (const char *gw = getenv("TDB_GLOBAL_WARPS_PER_SM")) c->global_warps_per_sm = std::max(1, std::min(32, atoi(gw)));
         if (const char *sm = getenv("TDB_SPARSE_MASK_MIN_PAIRS")) c->sparse_mask_min_pairs = (size_t)std::max(0ll, atoll(sm));
         // tier 1 runs two pairs per warp in lockstep (16 lanes each) with the production penalties: 17 % faster than
         // one pair per warp on the 30x trio (profiles/r01/NOTES.md); TDB_DISABLE_DUO=1 falls back to k_align_warp

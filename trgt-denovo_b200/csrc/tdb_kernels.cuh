@@ -686,8 +686,11 @@ __host__ __device__ inline size_t global_tier_stride(int wlog2, int s_cap, int o
            align16((size_t)s_cap * 4) * 2 + align16((size_t)ops_cap) + align16((size_t)prov_cap);
 }
 
+#ifndef TDB_G_MINB
+#define TDB_G_MINB 4
+#endif
 template <bool WANT_CIGAR>
-__global__ void __launch_bounds__(128) k_align_global(const AlignParams p) {
+__global__ void __launch_bounds__(128, TDB_G_MINB) k_align_global(const AlignParams p) {
     const int lane = threadIdx.x & 31;
     const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint8_t *base = p.scratch + gw * p.scratch_stride;
