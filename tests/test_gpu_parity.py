@@ -298,6 +298,18 @@ def test_host_packed_batches(tdb, monkeypatch):
     seqs, pp, pt = make_pairs(rng, n_targets=600, reads_per_target=12, max_units=30, err=0.002, alphabet="ACGT")
     seqs[7] = seqs[7][:30] + b"N" + seqs[7][31:]
     seqs[len(seqs) // 2] = seqs[len(seqs) // 2].lower()
+    # sequences straddling a 256 KB block boundary with their only odd byte on the GPU-packed side: the device flags
+    # them, and their bytes in the neighbouring host-packed block must reach the device too
+    _, off, ln = to_arrays(seqs)
+    n_straddle = 0
+    for bi, B in enumerate(range(262144, int(off[-1]), 262144)):
+        i = int(np.searchsorted(off, B, side="right")) - 1
+        if off[i] < B < off[i] + ln[i] - 1:
+            raw_is_next = bi % 2 == 0  # blocks 1, 3, .. are left to the GPU
+            x = int(B - off[i]) if raw_is_next else int(B - off[i]) - 1
+            seqs[i] = seqs[i][:x] + b"N" + seqs[i][x + 1:]
+            n_straddle += 1
+    assert n_straddle >= 2
     cnt = _check_batch(c2, seqs, pp, pt, 50, cigars=False)
     for v in ("TDB_HOSTPACK_MIN_BYTES", "TDB_CHUNK_PAIRS", "TDB_RAW_EVERY", "TDB_TEST_RAW_BLOCKS"):
         monkeypatch.delenv(v)

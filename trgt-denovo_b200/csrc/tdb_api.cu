@@ -664,12 +664,27 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                         }
                     }
                     cn.ms_host_pack_wait += ms_since(t_wait);
-                    // A chunk with a share left to the GPU ships its ASCII whole: a sequence k_pack flags there may
-                    // reach into a neighbouring host-packed block, and flagged sequences are compared as raw bytes.
-                    const bool chunk_raw = !raw_ranges.empty();
-                    if (chunk_raw) {
-                        CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
-                        cn.bytes_h2d += b1 - b0;
+                    // The share left to the GPU ships as ASCII, widened to whole sequences: a sequence k_pack flags there
+                    // may reach into a neighbouring host-packed block, and flagged sequences are compared as raw bytes.
+                    if (!raw_ranges.empty()) {
+                        std::vector<std::pair<uint64_t, uint64_t>> ext(raw_ranges);
+                        uint64_t pos = off_a;
+                        size_t ri = 0;
+                        for (uint32_t i = a; i < e && ri < raw_ranges.size(); ++i) {
+                            if (!dense) pos = b.h_seq_off[i];
+                            const uint64_t nxt = pos + b.h_seq_len[i];
+                            while (ri < raw_ranges.size() && raw_ranges[ri].second <= pos) ++ri;
+                            for (size_t r = ri; r < raw_ranges.size() && raw_ranges[r].first < nxt; ++r)
+                                if (pos < raw_ranges[r].second) ext[r].first = std::min(ext[r].first, pos), ext[r].second = std::max(ext[r].second, nxt);
+                            pos = nxt;
+                        }
+                        for (const auto &x : ext) {
+                            const uint64_t y0 = std::max<uint64_t>(x.first, b0), y1 = std::min<uint64_t>(x.second, b.blob_bytes);
+                            if (y1 > y0) {
+                                CK(cudaMemcpyAsync((uint8_t *)b.blob + y0, b.h_blob + y0, y1 - y0, cudaMemcpyHostToDevice, cs));
+                                cn.bytes_h2d += y1 - y0;
+                            }
+                        }
                     }
                     // flags found by the host packers (almost always none: one vectorised pass instead of a copy)
                     const bool any_flag = memchr(hf + a, 1, (size_t)(e - a)) != nullptr;
@@ -681,7 +696,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                     }
                     // sequences with bytes outside ACGT are compared as raw bytes on the device: ship those bytes
                     size_t n_flag = 0;
-                    if (any_flag && !chunk_raw)
+                    if (any_flag)
                         for (uint32_t i = a; i < e; ++i) n_flag += hf[i] != 0;
                     const uint64_t *hoff = !n_flag ? nullptr : dense ? dense_off.get() : b.h_seq_off;
                     if (n_flag > 256) {
