@@ -253,6 +253,7 @@ class HostPacker {
             });
     }
     enum : uint8_t { PENDING = 0, PACKED = 1, RAW = 2, BUSY = 3 };
+    size_t n_blocks() const { return n_blocks_; }
     uint8_t peek(size_t i) const { return done_[i].load(std::memory_order_acquire); }
     // The calling thread takes a block no worker has started: it ships as ASCII and the GPU packs it.
     bool try_steal(size_t i) {
@@ -641,11 +642,22 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                         const uint64_t BLK = HostPacker::BLOCK;
                         size_t i = (size_t)(b0 / BLK);
                         const size_t i_end = (size_t)((b1 - 1) / BLK);
-                        // Every steal_div-th chunk is left to the GPU where the workers have not reached it yet: its
-                        // blocks cross PCIe as ASCII in one copy and k_pack packs them.  Pays when the host threads are
-                        // the bottleneck and the link has room (several ranks sharing one host's cores).
-                        if (ctx->allow_steal && K > 1 && k % (size_t)ctx->steal_div == (size_t)ctx->steal_div - 1)
-                            for (size_t q = i; q <= i_end; ++q) packer.try_steal(q);
+                        // Blocks the workers have not reached yet can be left to the GPU: they cross PCIe as ASCII and
+                        // k_pack packs them.  Pays when the host threads are the bottleneck and the link has room (several
+                        // ranks sharing one host's cores).  Automatic mode: whenever the copy stream has drained -- the link
+                        // would idle -- this thread takes about one chunk's worth of blocks AHEAD of the chunk the workers
+                        // are on, so the split between host-packed and GPU-packed bytes follows the two rates.
+                        // TDB_RAW_EVERY=n: every n-th chunk instead (deterministic, used by the tests).
+                        if (ctx->allow_steal && K > 1) {
+                            if (ctx->steal_forced) {
+                                if (k % (size_t)ctx->steal_div == (size_t)ctx->steal_div - 1)
+                                    for (size_t q = i; q <= i_end; ++q) packer.try_steal(q);
+                            } else if (k >= 1 && cudaEventQuery(ctx->up_ev[k - 1]) == cudaSuccess) {
+                                const size_t per_chunk = std::max<size_t>(1, packer.n_blocks() / K);
+                                const size_t from = i_end + 1 + per_chunk;
+                                for (size_t q = from; q < std::min(packer.n_blocks(), from + per_chunk); ++q) packer.try_steal(q);
+                            }
+                        }
                         while (i <= i_end) {
                             const uint8_t st0 = packer.acquire(i);
                             size_t j = i + 1; // extend the run of equal state
