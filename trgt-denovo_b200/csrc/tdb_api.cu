@@ -97,10 +97,10 @@ struct tdb_ctx {
     void *h_packed = nullptr, *h_flag = nullptr, *h_runs = nullptr; // pinned staging of the host packer / planner
     size_t h_packed_cap = 0, h_flag_cap = 0, h_runs_cap = 0;
     DevBuf runs;
-    // host-pack mode: every steal_div-th pipeline chunk ships as ASCII (where the workers have not reached it yet) and
-    // is packed on the GPU.  Automatic: on (every 2nd chunk) when the call has at most 8 packer threads -- several
-    // ranks sharing one host -- where it measured +10 % e2e; off with more threads, where it measured nothing
-    // (profiles/r01/NOTES.md).  TDB_RAW_EVERY=n forces it (n < 2: off).
+    // host-pack mode: blocks the packer threads have not reached can ship as ASCII and be packed on the GPU.  Automatic:
+    // on when the call has at most 8 packer threads -- several ranks sharing one host -- where it measured +10-15 % e2e
+    // (look-ahead rule driven by the copy stream, see run_align); off with more threads, where it measured nothing
+    // (profiles/r01/NOTES.md).  TDB_RAW_EVERY=n forces every n-th chunk instead (n < 2: off).
     bool steal_forced = false, allow_steal = false;
     int steal_div = 2;
     bool count_work = false;
