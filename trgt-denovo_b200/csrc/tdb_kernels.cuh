@@ -273,8 +273,9 @@ __global__ void __launch_bounds__(256) k_seq_canon(const uint64_t *__restrict__ 
 constexpr int QL_MAX = TDB_QL_MAX; // |n-m| >= QL_MAX: the wavefront outgrows the quad tier's 32 diagonals before the pair ends
                                     // (swept 10..16 with the thread tier in place: 14 best, profiles/r01/NOTES.md)
 constexpr int WL_MAX = 40;  // |n-m| >= WL_MAX: wider than the warp tier's 64 diagonals
-constexpr int KEY_WARP = 0; // sorted first: heaviest pairs of the shared-memory tiers
-constexpr int KEY_QUAD0 = 1;
+constexpr int KEY_WARP0 = 0; // sorted first: heaviest pairs of the shared-memory tiers, by descending |n-m| (the two pairs
+                             // of a lockstep warp run to the larger of their penalties: neighbours should be alike)
+constexpr int KEY_QUAD0 = KEY_WARP0 + WL_MAX;
 constexpr int ML_MAX = 8;       // |n-m| < ML_MAX and both sequences >= ML_MINLEN bases: thread-per-pair tier first
 constexpr int ML_MINLEN = 16;
 #ifndef TDB_TH_SEQW
@@ -284,8 +285,8 @@ constexpr int TH_SEQW = TDB_TH_SEQW;            // 2-bit words staged per sequen
 constexpr int ML_MAXLEN = 16 * TH_SEQW - 32;    // its longest sequence: shift (<= 15) + length + 16 bases fit the window
 constexpr int KEY_MINI0 = KEY_QUAD0 + QL_MAX; // sorted last: the lightest pairs
 constexpr int KEY_NONE = 255;
-static_assert(KEY_MINI0 + ML_MAX <= 32, "histogram size");
-constexpr int N_HIST = 32;
+constexpr int N_HIST = 64;
+static_assert(KEY_MINI0 + ML_MAX <= N_HIST, "histogram size");
 
 struct PairTable {
     unsigned long long *keys;
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
                         const unsigned q = atomicAdd(o.gcount, 1u);
                         o.glist[q] = j;
                     } else if (!quad_ok || L >= QL_MAX) {
-                        key = KEY_WARP;
+                        key = KEY_WARP0 + (WL_MAX - 1 - L);
                     } else if (mini_ok && L < ML_MAX && n >= ML_MINLEN && m >= ML_MINLEN && n <= ML_MAXLEN && m <= ML_MAXLEN) {
                         key = KEY_MINI0 + (ML_MAX - 1 - L);
                     } else {
@@ -476,12 +477,13 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
 // seg[2], seg[3] the same for the lockstep (quad) tier; seg[4], seg[5] for the thread-per-pair tier.
 __global__ void k_plan(const unsigned *__restrict__ hist, unsigned *__restrict__ seg) {
     if (threadIdx.x == 0) {
-        unsigned q = 0, t = 0;
+        unsigned w = 0, q = 0, t = 0;
+        for (int i = KEY_WARP0; i < KEY_WARP0 + WL_MAX; ++i) w += hist[i];
         for (int i = KEY_QUAD0; i < KEY_QUAD0 + QL_MAX; ++i) q += hist[i];
         for (int i = KEY_MINI0; i < KEY_MINI0 + ML_MAX; ++i) t += hist[i];
-        seg[0] = 0, seg[1] = hist[KEY_WARP];
-        seg[2] = hist[KEY_WARP], seg[3] = q;
-        seg[4] = hist[KEY_WARP] + q, seg[5] = t;
+        seg[0] = 0, seg[1] = w;
+        seg[2] = w, seg[3] = q;
+        seg[4] = w + q, seg[5] = t;
     }
 }
 
