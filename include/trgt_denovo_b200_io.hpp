@@ -359,7 +359,8 @@ class SampleFiles {
                     std::string tok;
                     for (size_t i = 0; i <= vals[k].size(); ++i) {
                         if (i == vals[k].size() || vals[k][i] == '/' || vals[k][i] == '|') {
-                            rec.gt.push_back(tok.empty() || tok == "." ? -1 : std::stoi(tok));
+                            const bool num = !tok.empty() && tok.size() <= 6 && tok.find_first_not_of("0123456789") == std::string::npos;
+                            rec.gt.push_back(num ? std::stoi(tok) : -1); // "." or anything unreadable: a missing allele
                             tok.clear();
                         } else {
                             tok.push_back(vals[k][i]);
@@ -396,6 +397,7 @@ class SampleFiles {
         in.read_exact(b4, 4, "BAM magic");
         if (memcmp(b4, "BAM\1", 4) != 0) throw IoError(path + ": not a BAM file");
         in.read_exact(b4, 4, "BAM header");
+        if (le32(b4) > (1u << 30)) throw IoError(path + ": implausible BAM header length");
         std::string text(le32(b4), '\0');
         if (!text.empty()) in.read_exact(&text[0], text.size(), "BAM header text");
         trgt_version = pg_field(text, "VN:");
@@ -411,6 +413,7 @@ class SampleFiles {
         in.read_exact(b4, 4, "reference count");
         for (uint32_t i = 0, n = le32(b4); i < n; ++i) {
             in.read_exact(b4, 4, "reference name length");
+            if (le32(b4) > (1u << 16)) throw IoError(path + ": implausible reference name length");
             std::string name(le32(b4), '\0');
             if (!name.empty()) in.read_exact(&name[0], name.size(), "reference name");
             in.read_exact(b4, 4, "reference length");
@@ -420,7 +423,7 @@ class SampleFiles {
         for (;;) {
             if (in.read(b4, 4) != 4) break;
             const uint32_t bs = le32(b4);
-            if (bs < 32) throw IoError(path + ": corrupt BAM record");
+            if (bs < 32 || bs > (1u << 28)) throw IoError(path + ": corrupt BAM record");
             rec.resize(bs);
             in.read_exact(rec.data(), bs, "BAM record");
             const unsigned char *p = rec.data();

@@ -183,3 +183,54 @@ def test_tsv_from_files_identical(exe, tmp_path, mode):
     assert open(out_tsv).read() == wtsv
     assert open(out_ids).read() == wids
     assert wtsv.count("\n") > len(loci) // 2
+
+
+def test_damaged_files_fail_cleanly(exe, tmp_path):
+    """Truncated or bit-flipped BAM / VCF / catalog files: the readers report an error (exit code 1) or read what is
+    still well-formed (0); they never crash."""
+    ref, bed, prefixes, *_ = _family_files(tmp_path, 5, n_loci=12)
+    rng = random.Random(5)
+    targets = [prefixes[0] + ".spanning.sorted.bam", prefixes[0] + ".sorted.vcf.gz", bed]
+    for trial in range(40):
+        path = targets[trial % len(targets)]
+        good = open(path, "rb").read()
+        if trial % 2 == 0:
+            bad = good[: rng.randrange(1, len(good))]
+        else:
+            b = bytearray(good)
+            for _ in range(rng.randint(1, 6)):
+                b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+            bad = bytes(b)
+        with open(path, "wb") as o:
+            o.write(bad)
+        r = subprocess.run([exe, "dump", ref, bed, "50", str(tmp_path / "o.txt")] + prefixes, capture_output=True, text=True)
+        assert r.returncode in (0, 1), (trial, path, r.returncode, r.stderr[-300:])
+        with open(path, "wb") as o:
+            o.write(good)
+    # undamaged again
+    r = subprocess.run([exe, "dump", ref, bed, "50", str(tmp_path / "o.txt")] + prefixes, capture_output=True, text=True)
+    assert r.returncode == 0
+
+
+def test_damaged_bam_payload_fails_cleanly(exe, tmp_path):
+    """Damage INSIDE the decompressed BAM stream (re-compressed, so the gzip layer is intact): record sizes, tag
+    types and lengths that point outside the record."""
+    ref, bed, prefixes, *_ = _family_files(tmp_path, 6, n_loci=10)
+    import zlib
+    path = prefixes[2] + ".spanning.sorted.bam"
+    raw = b""
+    d = zlib.decompressobj(31)
+    data = open(path, "rb").read()
+    while data:
+        raw += d.decompress(data)
+        data = d.unused_data
+        d = zlib.decompressobj(31)
+    rng = random.Random(6)
+    for trial in range(60):
+        b = bytearray(raw)
+        for _ in range(rng.randint(1, 4)):
+            b[rng.randrange(8, len(b))] = rng.randrange(256)
+        with open(path, "wb") as o:
+            o.write(IOF.bgzf_bytes(bytes(b)))
+        r = subprocess.run([exe, "dump", ref, bed, "50", str(tmp_path / "o.txt")] + prefixes, capture_output=True, text=True)
+        assert r.returncode in (0, 1), (trial, r.returncode, r.stderr[-300:])
