@@ -4,7 +4,6 @@
 #include "tdb_wfa_thread.cuh"
 #include "tdb_hostpack.h"
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -57,6 +56,7 @@ struct Ctrl {
         unsigned wc_quad, wc_warp, acount, wc_mini;
         unsigned mcount, pad1[3]; // mcount: pairs the thread-per-pair tier handed on
         unsigned hist[N_HIST];
+        unsigned base[N_HIST], cursor[N_HIST]; // work-list buckets: start and fill level
         unsigned seg[8];
     } ck[2];
 };
@@ -82,7 +82,7 @@ struct tdb_ctx {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf canon, skey_in, skey_out, sval_in, sval_out, cub_tmp, seq_tab, pair_tab, list_a, list_m;
+        DevBuf canon, skey_in, sval_out, seq_tab, pair_tab, list_a, list_m;
     } slot[2];
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
@@ -539,21 +539,15 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     if (!cigar_mode) {
         ENSURE(ctx->rep, (size_t)n_pairs * 4);
         if (want_work) ENSURE(ctx->work, (size_t)n_pairs * 12);
-        size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint8_t *)nullptr, (uint8_t *)nullptr,
-                                           (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_cp, 0, 8, s));
         for (int i = 0; i < n_slot; ++i) {
             tdb_ctx::Slot &sl = ctx->slot[i];
             ENSURE(sl.canon, (size_t)n_seqs * 4);
             ENSURE(sl.skey_in, max_cp);
-            ENSURE(sl.skey_out, max_cp);
-            ENSURE(sl.sval_in, max_cp * 4);
             ENSURE(sl.sval_out, max_cp * 4);
             ENSURE(sl.list_a, max_cp * 4);
             if (mini_ok) ENSURE(sl.list_m, max_cp * 4);
             if (dedup) ENSURE(sl.seq_tab, ((size_t)table_mask(max_cs) + 1) * 12);
             ENSURE(sl.pair_tab, ((size_t)table_mask(max_cp) + 1) * 12);
-            ENSURE(sl.cub_tmp, tmp);
         }
     }
     while (b.h_pp && ctx->up_ev.size() < K) {
@@ -811,19 +805,19 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         k_pair_insert<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, tb, &ctrl->err);
         CK(cudaGetLastError());
         ClassifyOut co;
-        co.rep = (uint32_t *)ctx->rep.p, co.key = (uint8_t *)sl.skey_in.p, co.val = (uint32_t *)sl.sval_in.p;
+        co.rep = (uint32_t *)ctx->rep.p, co.key = (uint8_t *)sl.skey_in.p;
         co.glist = (uint32_t *)ctx->list_b.p, co.gcount = &ctrl->gcount, co.hist = ck->hist, co.n_closed = &ctrl->n_closed;
         co.out_score = b.score, co.out_status = b.status, co.out_penalty = b.penalty, co.work = p.work;
         k_pair_classify<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, b.seq_len,
                                                  (const uint8_t *)ctx->seq_flag.p, b.seq_off, (const uint32_t *)ctx->packed.p,
                                                  tb, quad_ok ? 1 : 0, mini_ok ? 1 : 0, T0_MAXLEN, cf, co);
         CK(cudaGetLastError());
-        size_t tmp = sl.cub_tmp.cap;
-        CK(cub::DeviceRadixSort::SortPairs(sl.cub_tmp.p, tmp, (const uint8_t *)sl.skey_in.p, (uint8_t *)sl.skey_out.p,
-                                           (const uint32_t *)sl.sval_in.p, (uint32_t *)sl.sval_out.p, (int)cpairs, 0, 8, st));
-        k_plan<<<1, 32, 0, st>>>(ck->hist, ck->seg);
+        k_plan<<<1, 32, 0, st>>>(ck->hist, ck->seg, ck->base);
         CK(cudaGetLastError());
-        cn.kernel_launches += 6; // insert, classify, sort (3 kernels), plan
+        k_bucket<<<(cpairs + 256 * BUCKET_PER_THREAD - 1) / (256 * BUCKET_PER_THREAD), 256, 0, st>>>(
+            (const uint8_t *)sl.skey_in.p, (uint32_t)c.p0, cpairs, ck->base, ck->cursor, (uint32_t *)sl.sval_out.p);
+        CK(cudaGetLastError());
+        cn.kernel_launches += 4; // insert, classify, plan, bucket
         if (staged) CK(cudaEventRecord(ctx->ev[3], st));
         p.src1 = (const uint32_t *)sl.sval_out.p;
         // thread-per-pair tier: the lightest pairs (|n-m| < 8), up to penalty 24; the rest moves on to tier 0
@@ -1195,7 +1189,7 @@ void tdb_destroy(tdb_ctx *c) {
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
-        DevBuf *sb[] = {&sl.canon, &sl.skey_in, &sl.skey_out, &sl.sval_in, &sl.sval_out, &sl.cub_tmp, &sl.seq_tab,
+        DevBuf *sb[] = {&sl.canon, &sl.skey_in, &sl.sval_out, &sl.seq_tab,
                         &sl.pair_tab, &sl.list_a, &sl.list_m};
         for (DevBuf *b : sb) b->release();
     }

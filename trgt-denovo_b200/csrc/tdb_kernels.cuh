@@ -392,8 +392,7 @@ __device__ inline bool closed_form(const uint32_t *__restrict__ packed, uint64_t
 
 struct ClassifyOut {
     uint32_t *rep;       // [n_pairs] representative pair of j (itself when unique / identical)
-    uint8_t *key;        // [p1-p0] sort key
-    uint32_t *val;       // [p1-p0] pair index
+    uint8_t *key;        // [p1-p0] work-list bucket of the pair (KEY_NONE: not aligned)
     uint32_t *glist;     // pairs routed straight to the global-scratch tiers
     unsigned *gcount;
     unsigned *hist;      // [N_HIST]
@@ -465,7 +464,6 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
         }
         o.rep[j] = rep;
         o.key[j - p0] = (uint8_t)key;
-        o.val[j - p0] = j;
         if (key != KEY_NONE) atomicAdd(sh_hist + key, 1u);
     }
     __syncthreads();
@@ -473,11 +471,13 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
     if (threadIdx.x == N_HIST && sh_hist[N_HIST]) atomicAdd(o.n_closed, sh_hist[N_HIST]);
 }
 
-// Segment table of the sorted list: seg[0] = begin, seg[1] = count of the warp-tier segment;
-// seg[2], seg[3] the same for the lockstep (quad) tier; seg[4], seg[5] for the thread-per-pair tier.
-__global__ void k_plan(const unsigned *__restrict__ hist, unsigned *__restrict__ seg) {
+// Segment table of the work list: seg[0] = begin, seg[1] = count of the warp-tier segment; seg[2], seg[3] the same for the
+// lockstep (quad) tier; seg[4], seg[5] for the thread-per-pair tier.  base[key] = where bucket `key` starts in the list
+// (buckets in key order: heaviest first inside every tier).
+__global__ void k_plan(const unsigned *__restrict__ hist, unsigned *__restrict__ seg, unsigned *__restrict__ base) {
     if (threadIdx.x == 0) {
-        unsigned w = 0, q = 0, t = 0;
+        unsigned w = 0, q = 0, t = 0, at = 0;
+        for (int i = 0; i < N_HIST; ++i) base[i] = at, at += hist[i];
         for (int i = KEY_WARP0; i < KEY_WARP0 + WL_MAX; ++i) w += hist[i];
         for (int i = KEY_QUAD0; i < KEY_QUAD0 + QL_MAX; ++i) q += hist[i];
         for (int i = KEY_MINI0; i < KEY_MINI0 + ML_MAX; ++i) t += hist[i];
@@ -485,6 +485,34 @@ __global__ void k_plan(const unsigned *__restrict__ hist, unsigned *__restrict__
         seg[2] = w, seg[3] = q;
         seg[4] = w + q, seg[5] = t;
     }
+}
+
+// The work list: every pair that needs an alignment goes to its bucket (a counting sort of the few per cent of pairs
+// that have a key; the histogram came out of k_pair_classify).  A block ranks its pairs per bucket in shared memory and
+// reserves one range per bucket; order inside a bucket follows the pair order up to the block granularity, which keeps
+// the pairs of a locus -- alike in length and penalty -- next to each other.
+constexpr int BUCKET_PER_THREAD = 4;
+__global__ void __launch_bounds__(256) k_bucket(const uint8_t *__restrict__ key, uint32_t p0, uint32_t n,
+                                                const unsigned *__restrict__ base, unsigned *__restrict__ cursor,
+                                                uint32_t *__restrict__ list) {
+    __shared__ unsigned cnt[N_HIST], boff[N_HIST];
+    if (threadIdx.x < N_HIST) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t first = (blockIdx.x * 256u + threadIdx.x) * BUCKET_PER_THREAD;
+    int k[BUCKET_PER_THREAD];
+    unsigned rank[BUCKET_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < BUCKET_PER_THREAD; ++i) {
+        const uint32_t j = first + (uint32_t)i;
+        k[i] = j < n ? (int)key[j] : KEY_NONE;
+        if (k[i] != KEY_NONE) rank[i] = atomicAdd(&cnt[k[i]], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < N_HIST && cnt[threadIdx.x]) boff[threadIdx.x] = base[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < BUCKET_PER_THREAD; ++i)
+        if (k[i] != KEY_NONE) list[boff[k[i]] + rank[i]] = p0 + first + (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restrict__ rep, uint32_t n_pairs,
