@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_expand_runs(const PairRun *__restrict__
 //      merge, never a wrong one);
 //   2. pairs -> representative pair (one index per (canon pattern, canon text) class): exact
 //      64-bit key, no verification needed;
-//   3. representatives are radix-sorted by expected work (|n - m|, the dominant term of the penalty)
+//   3. representatives are bucketed by tier and expected work (|n - m|, the dominant term of the penalty)
 //      so that the four pairs of a warp, and the warps of a wave, run near-identical control flow and
 //      the heaviest pairs start first;
 //   4. after the tiers ran, k_scatter copies score/status/penalty (and the algorithmic work counts)
