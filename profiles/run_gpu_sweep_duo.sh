@@ -1,13 +1,14 @@
 #!/bin/bash
-# warp tier variants: one pair per warp (default), lockstep 2 pairs x 16 lanes, lockstep 4 pairs x 8 lanes (W = 64)
+# tier 1 variants: two pairs per warp in lockstep (default, build with -DTDB_DUO_G=16), one pair per warp
+# (TDB_DISABLE_DUO=1), four pairs x 8 lanes (a build with -DTDB_DUO_G=8 at build/sweep/lib_duoG8.so)
 run() {
-TDB_LIB=$PWD/$1 timeout 600 python bench.py --loci 100000 --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
+TDB_LIB=$1 timeout 600 python bench.py --loci 100000 --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 b=d['breakdown_ms_per_step']
-print('$1 duo=$TDB_ENABLE_DUO','value',round(d['value']),'thread %.2f quad %.2f warp %.2f glob %.2f'%(b['align_thread'],b['align_quad'],b['align_warp'],b['align_global']),'tiers',d['tier_pairs'])
+print('$2','value',round(d['value']),'thread %.2f quad %.2f tier1 %.2f glob %.2f'%(b['align_thread'],b['align_quad'],b['align_warp'],b['align_global']),'tiers',d['tier_pairs'])
 "
 }
-run build/sweep/lib_duoG16.so
-TDB_ENABLE_DUO=1 run build/sweep/lib_duoG16.so
-TDB_ENABLE_DUO=1 run build/sweep/lib_duoG8.so
+run "" "two pairs x 16 lanes (default)"
+TDB_DISABLE_DUO=1 run "" "one pair per warp"
+[ -f build/sweep/lib_duoG8.so ] && run $PWD/build/sweep/lib_duoG8.so "four pairs x 8 lanes"
