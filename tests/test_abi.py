@@ -54,3 +54,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} references oracle/"
+
+
+def test_headers_are_plain_c():
+    """The drop-in boundary is a C ABI: both public headers must compile as C99 on their own (no C++-isms, no
+    torch or CUDA types in any signature)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for h in ("trgt_denovo_b200.h", "tdb_synth.h"):
+        subprocess.check_call(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-I",
+                               os.path.join(root, "include"), os.path.join(root, "include", h)])
+    text = open(os.path.join(root, "include", "trgt_denovo_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)  # declarations only: the comments may name what is absent
+    assert "torch" not in code and "cudaStream" not in code and "at::" not in code and "#include <cuda" not in code
