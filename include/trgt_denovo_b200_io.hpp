@@ -434,9 +434,19 @@ class SampleFiles {
             r.name.assign(reinterpret_cast<const char *>(p + off), l_name ? l_name - 1 : 0);
             off += l_name + 4ull * n_cigar;
             r.bases.resize(l_seq);
-            for (uint32_t i = 0; i < l_seq; ++i) {
-                const unsigned char byte = p[off + i / 2];
-                r.bases[i] = code[(i & 1) ? (byte & 15) : (byte >> 4)];
+            { // two bases per byte through a 256-entry table of character pairs
+                static const auto pairs = [] {
+                    std::vector<uint16_t> t(256);
+                    for (int b = 0; b < 256; ++b) t[(size_t)b] = (uint16_t)((unsigned char)code[b >> 4] | (unsigned char)code[b & 15] << 8);
+                    return t;
+                }();
+                char *dst = &r.bases[0];
+                uint32_t i = 0;
+                for (; i + 2 <= l_seq; i += 2) {
+                    const uint16_t two = pairs[p[off + i / 2]];
+                    dst[i] = (char)(two & 0xff), dst[i + 1] = (char)(two >> 8);
+                }
+                if (i < l_seq) dst[i] = code[p[off + i / 2] >> 4];
             }
             off += (l_seq + 1) / 2 + l_seq;
             std::string tr;
