@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define TDB_ABI_VERSION 3
+#define TDB_ABI_VERSION 4
 
 /* return codes */
 #define TDB_OK 0
@@ -68,6 +68,11 @@ extern "C" {
 #define TDB_STATUS_MAX_STEPS_REACHED (-100)
 #define TDB_STATUS_OOM (-200)
 #define TDB_STATUS_UNATTAINABLE (-300)
+/* out_score of a pair whose status is not 0: there is no score.  The fused calls (tdb_trio_batch, tdb_duo_batch,
+ * tdb_assess_batch_device, *_packed) keep such pairs out of every score list, which is what dropping non-completed
+ * alignments does in the reference (src/denovo.rs:31-35, src/allele.rs:220); tdb_trio_reduce / tdb_duo_reduce skip
+ * entries holding this value for the same reason.  tdb_counters.pairs_failed counts them. */
+#define TDB_SCORE_FAILED (-2147483647 - 1)
 
 /* AlnScoring, src/model.rs:5-23 (match is fixed to 0 as in create_aligner). */
 typedef struct {
@@ -217,6 +222,42 @@ int tdb_assess_batch_device(tdb_ctx *ctx, int32_t is_duo, const uint8_t *seq_blo
                             const tdb_trio_locus *loci, size_t n_loci, double parent_quantile,
                             tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask);
 
+/*
+ * Packed input: the caller packed at load time (north_star: "locus.rs and read.rs pack the reads and alleles ...
+ * into 2-bit/byte-packed device batches"; the reference expands BAM's 4-bit bases to ASCII at src/read.rs:57 and
+ * builds allele targets at src/allele.rs:406-426 -- a host that emits 2-bit codes there never materialises ASCII
+ * and the batch call does no per-base work on the CPU).  The layout is the one tdb_host_pack produces:
+ *   packed    ONE 2-bit stream over all sequences: base at stream position x -> word x / 16, bits 2 (x % 16),
+ *             code (ASCII byte >> 1) & 3  (A 0, C 1, T 2, G 3); tdb_packed_words(n_bases) words (the last two are
+ *             padding and must be readable; their content is ignored)
+ *   seq_off   stream position of base 0 of each sequence, or NULL for the dense layout (back to back)
+ *   seq_len   bases per sequence
+ *   exc_seq   ascending indices of the sequences that hold a byte outside {A,C,G,T} ('N', IUPAC codes, lower
+ *             case): WFA2 compares raw bytes, so those are compared byte-wise from exc_bytes, where their raw
+ *             ASCII is stored back to back in exc_seq order (seq_len[exc_seq[i]] bytes each).  Their 2-bit codes
+ *             in `packed` are still (byte >> 1) & 3 of every byte.  n_exc == 0: all three may be NULL.
+ * Host pointers; pinned memory (tdb_host_alloc) lets the upload of chunk k+1 overlap the alignment of chunk k.
+ * Results are bit-identical to the ASCII entry points on the same sequences.
+ */
+typedef struct {
+    const uint32_t *packed;
+    size_t n_bases;
+    const uint64_t *seq_off;
+    const uint32_t *seq_len;
+    size_t n_seqs;
+    const uint32_t *exc_seq;
+    const uint8_t *exc_bytes;
+    size_t n_exc;
+} tdb_packed_seqs;
+int tdb_align_batch_packed(tdb_ctx *ctx, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
+                           const uint32_t *pair_text, size_t n_pairs, int32_t *out_score, int32_t *out_status);
+int tdb_trio_batch_packed(tdb_ctx *ctx, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
+                          const uint32_t *pair_text, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
+                          double parent_quantile, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask);
+int tdb_duo_batch_packed(tdb_ctx *ctx, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
+                         const uint32_t *pair_text, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
+                         double parent_quantile, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask);
+
 /* Single-pair shim keeping WFAligner's call shape (src/aligner.rs:248-260, :290, :438, :359). */
 int tdb_align_end_to_end(tdb_ctx *ctx, const uint8_t *pattern, int32_t pattern_len, const uint8_t *text,
                          int32_t text_len); /* returns the WFA2 status, or a TDB_E_* (< -1000 never) */
@@ -240,7 +281,8 @@ typedef struct {
                                    exact work counting is on) */
     uint64_t kernel_launches;
     uint64_t chunks;        /* pipeline chunks the call was cut into */
-    uint64_t host_packed;   /* 1: the caller's CPU threads 2-bit packed the sequences before the upload */
+    uint64_t host_packed;   /* 1: the caller's CPU threads 2-bit packed the sequences before the upload;
+                               2: the caller handed over packed sequences (*_packed entry points) */
     uint64_t bytes_h2d;     /* bytes the alignment stage actually copied host -> device (host-buffer calls) */
     uint64_t bytes_raw;     /* ... of which ASCII blocks the calling thread took over from the host packer while the
                                copy engine was idle (packed on the GPU instead) */
@@ -257,6 +299,7 @@ typedef struct {
     uint64_t bytes_d2h;     /* result bytes copied device -> host by the fused host-buffer calls (tdb_trio_batch /
                                tdb_duo_batch): rows, scores if asked for, and the read mask -- as a list of its set
                                positions for calls of >= 8 Mi pairs, where a few bytes in a million are set */
+    uint64_t pairs_failed;  /* pairs no tier could finish (status TDB_STATUS_OOM, score TDB_SCORE_FAILED) */
 } tdb_counters;
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 /* Exact algorithmic work counting (cells / ext16 / columns of tdb_counters: every pair counted as the CPU

@@ -81,6 +81,13 @@ def _check_batch(ctx, seqs, pp, pt, clip, heuristic=tdo.DEFAULT_HEURISTIC, cigar
     got, st = ctx.align_batch(blob, None, ln, pp, pt)
     assert (st == wst).all() and (got == want).all()
     assert ctx.counters().bytes_h2d <= fast.bytes_h2d - 8 * (int(max(pp.max(), pt.max())) if len(pp) else 0)
+    # packed entry point (the caller packed at load time): explicit offsets and dense layout
+    import trgt_denovo_b200 as tdbm
+    for dense in (False, True):
+        pk = tdbm.pack_sequences(blob, off, ln, dense=dense)
+        got, st = ctx.align_batch_packed(pk, pp, pt)
+        assert (st == wst).all() and (got == want).all(), f"packed entry, dense={dense}"
+        assert ctx.counters().host_packed == 2
     # counting mode: every content through the wavefront kernels
     ctx.set_count_work(True)
     got, st = ctx.align_batch(blob, off, ln, pp, pt)
@@ -319,6 +326,84 @@ def test_host_packed_batches(tdb, monkeypatch):
     with pytest.raises(tdb.TdbError):  # layout violations are caught by the host packer too
         c.align_batch(blob, np.array([0, 5], np.uint64), np.array([10, 10], np.uint32), np.array([0], np.uint32),
                       np.array([1], np.uint32))
+    c.close()
+
+
+def test_packed_fused_calls_match_ascii(tdb, monkeypatch):
+    """tdb_trio_batch_packed / tdb_duo_batch_packed == tdb_trio_batch / tdb_duo_batch on the same family data
+    (chunked pipeline, sequences with bytes outside ACGT listed as exceptions), and less H2D traffic."""
+    from importlib import import_module
+    S = import_module("trgt_denovo_b200.synth")
+    monkeypatch.setenv("TDB_CHUNK_PAIRS", "4096")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_CHUNK_PAIRS")
+    for duo in (False, True):
+        b = S.generate(S.config("duo_genome" if duo else "trio_genome"), 1000, 1400, 4)
+        blob = b.blob.copy()
+        for i in (3, 500, b.n_seqs - 1):  # N and lower case: raw byte equality must survive the packed path
+            o = int(b.seq_off[i])
+            blob[o + 5] = ord("N")
+            blob[o + 7] = blob[o + 7] | 0x20
+        out_a, sc_a, mk_a = c.assess_batch(blob, None, b.seq_len, b.pair_pattern, b.pair_text, b.loci, duo=duo)
+        h2d_ascii = c.counters().bytes_h2d
+        pk = tdb.pack_sequences(blob, None, b.seq_len, n_threads=4)
+        assert len(pk.exc_seq) == 3
+        out_p, sc_p, mk_p = c.assess_batch_packed(pk, b.pair_pattern, b.pair_text, b.loci, duo=duo)
+        cnt = c.counters()
+        assert cnt.host_packed == 2 and cnt.chunks > 2 and cnt.pairs_failed == 0
+        assert cnt.bytes_h2d < 0.5 * h2d_ascii
+        assert (sc_a == sc_p).all() and (mk_a == mk_p).all()
+        assert bytes(out_a) == bytes(out_p)
+        want, _, _ = tdo.align_batch(blob, b.seq_off, b.seq_len, b.pair_pattern, b.pair_text, 50, n_threads=8)
+        assert (want == sc_p).all()
+        b.close()
+    c.close()
+
+
+def test_failed_pairs_stay_out_of_the_reductions(tdb, monkeypatch):
+    """A pair no tier can finish has no score (status OOM, TDB_SCORE_FAILED); the fused call drops it from every
+    list as the reference drops non-completed alignments (src/denovo.rs:31-35) instead of counting a perfect 0."""
+    import ctypes as C
+    rng = random.Random(91)
+    lf, rf = rand_seq(rng, 50), rand_seq(rng, 50)
+    target = (lf + "CAG" * 20 + rf).encode()
+    far = rand_seq(rng, 160).encode()           # unrelated read: penalty far above the test cap
+    near = (lf + "CAG" * 19 + rf).encode()      # one unit short
+    seqs = [target, far, near, target, near, far]
+    # lists: mother a0 = {far, near}, father a0 = {near}, child own = {target copy, near, far}
+    pp = np.array([1, 2, 4, 3, 2, 5], np.uint32)
+    pt = np.zeros(6, np.uint32)
+    monkeypatch.setenv("TDB_TEST_MAX_SCORE", "200")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_TEST_MAX_SCORE")
+    blob, off, ln = to_arrays(seqs)
+    got, st = c.align_batch(blob, off, ln, pp, pt)
+    assert c.counters().pairs_failed == 2
+    assert list(st) == [-200, 0, 0, 0, 0, -200]
+    from importlib import import_module
+    assert got[0] == got[5] == import_module("trgt_denovo_b200.binding").SCORE_FAILED
+    loc = tdb.TrioLocus()
+    loc.n_child, loc.n_mother, loc.n_father = 1, 1, 1
+    for j, v in enumerate([0, 2, 2, 3, 3, 6]):
+        loc.list_off[0][j] = v
+    arr = (tdb.TrioLocus * 1)(loc)
+    out, scores, mask = c.assess_batch(blob, off, ln, pp, pt, arr)
+    # the same locus with the failed pairs removed, on the oracle
+    loc2, flat = tdo.make_locus([[[int(got[1])]]], [[[int(got[2])]]], [[int(got[3]), int(got[4])]])
+    want, wmask = tdo.trio_assess(loc2, flat, 1.0)
+    g, w = out[0], want[0]
+    assert (g.denovo_coverage, g.error) == (w.denovo_coverage, w.error)
+    assert g.top_mother == w.top_mother and g.top_father == w.top_father and g.child_median == w.child_median
+    assert list(g.mother_overlap) == list(w.mother_overlap) and list(g.father_overlap) == list(w.father_overlap)
+    assert list(g.mean_col) == list(w.mean_col)
+    assert list(mask[3:6]) == [int(wmask[loc2.list_off[0][4]]), int(wmask[loc2.list_off[0][4] + 1]), 0]
+    # a list made only of failed pairs is an empty list: the reference would panic -> error flag
+    loc.list_off[0][0], loc.list_off[0][1], loc.list_off[0][2] = 0, 1, 1
+    pp2 = np.array([1, 4, 3, 2, 5], np.uint32)
+    loc.list_off[0][3], loc.list_off[0][4], loc.list_off[0][5] = 2, 2, 5
+    arr = (tdb.TrioLocus * 1)(loc)
+    out, _, _ = c.assess_batch(blob, off, ln, pp2, np.zeros(5, np.uint32), arr)
+    assert out[0].error == 1
     c.close()
 
 

@@ -22,6 +22,8 @@ from .binding import (  # noqa: F401
 from .aligner import (  # noqa: F401
     AlignmentStatus,
     Context,
+    PackedInput,
+    pack_sequences,
     WFAligner,
     create_aligner_with_scoring,
 )

@@ -117,6 +117,29 @@ class Context:
         cigs = [cbuf[int(coff[i]):int(coff[i]) + int(clen[i])].tobytes() for i in range(n)]
         return scores, status, pen, cigs
 
+    # ---- packed input (the caller packed at load time; include/trgt_denovo_b200.h tdb_packed_seqs) ----------
+    def align_batch_packed(self, packed: "PackedInput", pair_pattern, pair_text):
+        pp = np.ascontiguousarray(pair_pattern, dtype=np.uint32)
+        pt = np.ascontiguousarray(pair_text, dtype=np.uint32)
+        n = len(pp)
+        scores = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(B.lib().tdb_align_batch_packed(self._h, C.byref(packed.struct), _ptr(pp), _ptr(pt), n,
+                                                   _ptr(scores), _ptr(status)))
+        return scores, status
+
+    def assess_batch_packed(self, packed: "PackedInput", pair_pattern, pair_text, loci, q=1.0, duo=False):
+        pp = np.ascontiguousarray(pair_pattern, dtype=np.uint32)
+        pt = np.ascontiguousarray(pair_text, dtype=np.uint32)
+        n, n_loci = len(pp), len(loci)
+        out = (B.AlleleOut * (2 * max(1, n_loci)))()
+        scores = np.zeros(max(1, n), dtype=np.int32)
+        mask = np.zeros(max(1, n), dtype=np.uint8)
+        fn = B.lib().tdb_duo_batch_packed if duo else B.lib().tdb_trio_batch_packed
+        self._check(fn(self._h, C.byref(packed.struct), _ptr(pp), _ptr(pt), n, C.cast(loci, C.c_void_p), n_loci, q,
+                       C.cast(out, C.c_void_p), _ptr(scores), _ptr(mask)))
+        return out, scores[:n], mask[:n]
+
     # ---- reductions / fused ---------------------------------------------------------------------------
     def reduce(self, loci, scores, q=1.0, duo=False):
         """loci: ctypes array of TrioLocus.  -> (AlleleOut array [2*n_loci], mask uint8[n_scores])."""
@@ -143,6 +166,44 @@ class Context:
                        _ptr(pt), n, C.cast(loci, C.c_void_p), n_loci, q, C.cast(out, C.c_void_p), _ptr(scores),
                        _ptr(mask)))
         return out, scores[:n], mask[:n]
+
+
+class PackedInput:
+    """The arrays behind a tdb_packed_seqs (kept alive with the struct that points at them)."""
+
+    def __init__(self, packed, n_bases, seq_off, seq_len, exc_seq, exc_bytes):
+        self.packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        self.seq_off = None if seq_off is None else np.ascontiguousarray(seq_off, dtype=np.uint64)
+        self.seq_len = np.ascontiguousarray(seq_len, dtype=np.uint32)
+        self.exc_seq = np.ascontiguousarray(exc_seq, dtype=np.uint32)
+        self.exc_bytes = np.ascontiguousarray(exc_bytes, dtype=np.uint8)
+        self.n_bases = int(n_bases)
+        self.struct = B.PackedSeqs(_ptr(self.packed), self.n_bases, _ptr(self.seq_off), _ptr(self.seq_len),
+                                   len(self.seq_len), _ptr(self.exc_seq) if len(self.exc_seq) else None,
+                                   _ptr(self.exc_bytes) if len(self.exc_seq) else None, len(self.exc_seq))
+
+
+def pack_sequences(blob, seq_off, seq_len, n_threads=1, dense=None) -> PackedInput:
+    """ASCII blob -> the packed form of the *_packed entry points, through tdb_host_pack (what a loader that holds
+    ASCII would run once; a loader that holds BAM 4-bit bases emits the same stream directly, tdbh::PackedBatch).
+    dense: hand the library seq_off = NULL (default: when the sequences are back to back)."""
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    seq_len = np.ascontiguousarray(seq_len, dtype=np.uint32)
+    n = len(seq_len)
+    ends = np.cumsum(seq_len, dtype=np.uint64)
+    back_to_back = np.concatenate([[0], ends[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+    off = back_to_back if seq_off is None else np.ascontiguousarray(seq_off, dtype=np.uint64)
+    L = B.lib()
+    packed = np.zeros(L.tdb_packed_words(blob.size), dtype=np.uint32)
+    flag = np.zeros(max(1, n), dtype=np.uint8)
+    r = L.tdb_host_pack(_ptr(blob), blob.size, _ptr(off), _ptr(seq_len), n, _ptr(packed), _ptr(flag), int(n_threads))
+    if r != B.OK:
+        raise B.TdbError(r, "tdb_host_pack: layout contract violated")
+    exc = np.nonzero(flag[:n])[0].astype(np.uint32)
+    raw = b"".join(blob[int(off[i]):int(off[i]) + int(seq_len[i])].tobytes() for i in exc)
+    if dense is None:
+        dense = n == 0 or np.array_equal(off, back_to_back)
+    return PackedInput(packed, blob.size, None if dense else off, seq_len, exc, np.frombuffer(raw, dtype=np.uint8))
 
 
 def _canon(blob, seq_off, seq_len, pp, pt):

@@ -57,7 +57,15 @@ class Counters(C.Structure):
                 ("ms_host_packed", C.c_float), ("ms_host_enqueued", C.c_float),
                 ("ms_tier", C.c_float * 4), ("ms_thread_tier", C.c_float), ("thread_pairs", C.c_uint64),
                 ("thread_cells", C.c_uint64), ("thread_ext16", C.c_uint64), ("thread_columns", C.c_uint64),
-                ("bytes_d2h", C.c_uint64)]
+                ("bytes_d2h", C.c_uint64), ("pairs_failed", C.c_uint64)]
+
+
+class PackedSeqs(C.Structure):
+    _fields_ = [("packed", C.c_void_p), ("n_bases", C.c_size_t), ("seq_off", C.c_void_p), ("seq_len", C.c_void_p),
+                ("n_seqs", C.c_size_t), ("exc_seq", C.c_void_p), ("exc_bytes", C.c_void_p), ("n_exc", C.c_size_t)]
+
+
+SCORE_FAILED = -2147483648
 
 
 # every symbol include/trgt_denovo_b200.h declares (checked by tests/test_abi.py)
@@ -68,6 +76,7 @@ EXPORTS = [
     "tdb_trio_batch", "tdb_duo_batch", "tdb_assess_batch_device", "tdb_align_end_to_end", "tdb_score",
     "tdb_cigar_ops", "tdb_cigar_score_clipped", "tdb_get_counters", "tdb_set_count_work",
     "tdb_host_alloc", "tdb_host_free", "tdb_packed_words", "tdb_host_pack", "tdb_host_pack_isa",
+    "tdb_align_batch_packed", "tdb_trio_batch_packed", "tdb_duo_batch_packed",
 ]
 
 _lib = None
@@ -105,6 +114,10 @@ def lib():
     L.tdb_trio_batch.argtypes = fused
     L.tdb_duo_batch.argtypes = fused
     L.tdb_assess_batch_device.argtypes = [vp, i32] + batch[1:] + [vp, sz, C.c_double, vp, vp, vp]
+    L.tdb_align_batch_packed.argtypes = [vp, C.POINTER(PackedSeqs), vp, vp, sz, vp, vp]
+    pfused = [vp, C.POINTER(PackedSeqs), vp, vp, sz, vp, sz, C.c_double, vp, vp, vp]
+    L.tdb_trio_batch_packed.argtypes = pfused
+    L.tdb_duo_batch_packed.argtypes = pfused
     L.tdb_align_end_to_end.argtypes = [vp, C.c_char_p, i32, C.c_char_p, i32]
     L.tdb_score.restype = i32
     L.tdb_score.argtypes = [vp]

@@ -48,7 +48,8 @@ struct Ctrl {
     unsigned ccount;   // pairs the first global tier could not finish (listC)
     unsigned wc_g[2];  // work counters of the two global tiers
     unsigned n_closed; // pairs resolved in closed form (k_pair_classify)
-    unsigned pad0[2];
+    unsigned n_failed; // pairs the last tier could not finish
+    unsigned pad0[1];
     unsigned long long exec[5][4]; // executed cells, ext16, columns, pairs finished; per tier ([4]: thread-per-pair tier)
     unsigned long long algo[4];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self
     // ---- per chunk (one block per pipeline slot, zeroed before every chunk) ----
@@ -104,6 +105,7 @@ struct tdb_ctx {
     bool steal_forced = false, allow_steal = false;
     int steal_div = 2;
     bool count_work = false;
+    int test_max_score = 0; // TDB_TEST_MAX_SCORE: caps the score range of the global tiers (tests force a last-tier failure)
     tdb_counters counters;
     // single-pair shim state
     std::vector<uint8_t> last_cigar;
@@ -170,6 +172,12 @@ struct DevBatch {
     const uint32_t *h_seq_len;
     const uint32_t *h_pp, *h_pt;
     uint8_t *h_zero; // optional host array of n_pairs bytes the calling thread zeroes chunk by chunk (result mask)
+    // packed host input (tdb_*_batch_packed): the 2-bit stream as tdb_host_pack lays it out, plus the sequences that
+    // hold a byte outside ACGT (ascending indices, raw bytes back to back)
+    const uint32_t *h_packed;
+    const uint32_t *h_exc_seq;
+    const uint8_t *h_exc_bytes;
+    size_t n_exc;
 };
 
 int check_sizes(tdb_ctx *ctx, size_t blob_bytes, size_t n_seqs, size_t n_pairs) {
@@ -454,7 +462,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     // ---- host batches: the caller's CPU threads 2-bit pack the blob (a quarter of the ASCII bytes cross
     // PCIe) while this thread plans and queues chunks; small batches and CIGAR calls ship the ASCII and
     // pack on the device -------------------------------------------------------------------------------
-    const bool host_pack = b.h_pp && !cigar_mode && b.blob_bytes >= ctx->hostpack_min_bytes;
+    const bool prepacked = b.h_pp && b.h_packed != nullptr; // the caller packed at load time: no per-base host work
+    const bool host_pack = b.h_pp && !prepacked && !cigar_mode && b.blob_bytes >= ctx->hostpack_min_bytes;
     const bool dense = b.h_pp && !b.h_seq_off; // host batch without offsets: sequences back to back
     DenseOffsets dense_off; // declared before the packer: its threads may call into it
     dense_off.len = b.h_seq_len, dense_off.n = n_seqs;
@@ -472,6 +481,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         if (r) return r;
         cn.host_packed = 1;
     }
+    if (prepacked) cn.host_packed = 2;
     const bool lazy_scan = b.h_pp && chunks.size() > 1;
     std::vector<Chunk> scan_chunks = chunks; // what the worker threads fill in; `chunks` is the calling thread's copy
     if (b.h_pp && (host_pack || lazy_scan)) {
@@ -572,9 +582,13 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     p.out_score = b.score, p.out_status = b.status, p.out_penalty = b.penalty;
     p.work = want_work ? (uint32_t *)ctx->work.p : nullptr;
     p.cigar_buf = b.cigar_buf, p.cigar_off = b.cigar_off, p.cigar_len = b.cigar_len;
+    p.fail_count = &ctrl->n_failed;
 
     uint32_t seq_up = 0; // sequences [0, seq_up) are uploaded / packed
     uint64_t dense_pos = 0; // dense layout: byte offset of sequence seq_up
+    size_t exc_i = 0;       // packed input: next entry of the exception list, and where its raw bytes start
+    uint64_t exc_pos = 0;
+    std::vector<std::pair<uint64_t, uint32_t>> exc_at; // (blob offset, length) of this chunk's exceptions
     std::vector<std::pair<uint64_t, uint64_t>> raw_ranges; // this chunk's byte ranges shipped as ASCII in host-pack mode
 
     // ---- chunks ---------------------------------------------------------------------------------------
@@ -596,12 +610,19 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         const uint64_t off_a = dense_pos;
         if (b.h_pp && e > a) {
             uint64_t first = 0, end = 0;
+            exc_at.clear();
             if (dense) {
                 uint64_t sum = 0;
-                for (uint32_t i = a; i < e; ++i) sum += b.h_seq_len[i];
+                size_t xi = exc_i;
+                for (uint32_t i = a; i < e; ++i) {
+                    if (xi < b.n_exc && b.h_exc_seq[xi] == i) exc_at.push_back({off_a + sum, b.h_seq_len[i]}), ++xi;
+                    sum += b.h_seq_len[i];
+                }
                 first = off_a, end = off_a + sum;
                 dense_pos = end;
             } else {
+                for (size_t xi = exc_i; xi < b.n_exc && b.h_exc_seq[xi] < e; ++xi)
+                    if (b.h_exc_seq[xi] >= a) exc_at.push_back({b.h_seq_off[b.h_exc_seq[xi]], b.h_seq_len[b.h_exc_seq[xi]]});
                 first = b.h_seq_off[a], end = b.h_seq_off[e - 1] + b.h_seq_len[e - 1];
             }
             b0 = std::min<uint64_t>(first, b.blob_bytes) & ~(uint64_t)15;
@@ -623,7 +644,28 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                     CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
                     cn.bytes_h2d += n_off * 8 + (uint64_t)(e - a) * 4;
                 }
-                if (!host_pack) {
+                if (prepacked) {
+                    // the words of the new sequences, as they are; flags and raw bytes only for the listed exceptions
+                    if (b1 > b0) {
+                        const size_t w0 = (size_t)(b0 >> 4), w1 = (size_t)((b1 + 15) >> 4);
+                        CK(cudaMemcpyAsync((uint32_t *)ctx->packed.p + w0, b.h_packed + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, cs));
+                        cn.bytes_h2d += (uint64_t)(w1 - w0) * 4;
+                    }
+                    CK(cudaMemsetAsync((uint8_t *)ctx->seq_flag.p + a, 0, (size_t)(e - a), cs));
+                    static const uint8_t one = 1;
+                    for (size_t q = 0; q < exc_at.size(); ++q, ++exc_i) {
+                        const uint32_t si = b.h_exc_seq[exc_i];
+                        const uint64_t o = exc_at[q].first;
+                        const uint32_t ln = exc_at[q].second;
+                        CK(cudaMemcpyAsync((uint8_t *)ctx->seq_flag.p + si, &one, 1, cudaMemcpyHostToDevice, cs));
+                        if (ln && o <= b.blob_bytes && ln <= b.blob_bytes - o) {
+                            CK(cudaMemcpyAsync((uint8_t *)b.blob + o, b.h_exc_bytes + exc_pos, ln, cudaMemcpyHostToDevice, cs));
+                            cn.bytes_h2d += ln;
+                        }
+                        exc_pos += ln;
+                        cn.bytes_h2d += 1;
+                    }
+                } else if (!host_pack) {
                     if (b1 > b0) CK(cudaMemcpyAsync((uint8_t *)b.blob + b0, b.h_blob + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
                     cn.bytes_h2d += b1 - b0;
                 } else {
@@ -751,7 +793,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                 CK(cudaGetLastError());
                 cn.kernel_launches += 1;
             }
-            if (!host_pack) {
+            if (!host_pack && !prepacked) {
                 CK(cudaMemsetAsync((uint8_t *)ctx->seq_flag.p + a, 0, (size_t)(e - a), ps));
                 if (b1 > b0) {
                     const unsigned blocks = (unsigned)std::min<uint64_t>(((b1 - b0 + 15) / 16 + 511) / 512, (uint64_t)ctx->sm_count * 32);
@@ -882,6 +924,9 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         {10, 1 << 16, 1 << 17, 8u << 20, ctx->sm_count * ctx->global_warps_per_sm}, // W=1024, S<65536, 8 MiB provenance
         {15, 1 << 18, 1 << 19, 192u << 20, ctx->sm_count * 1}, // W=32768, S<262144, 192 MiB provenance
     };
+    TierCfg gt[2] = {gtiers[0], gtiers[1]};
+    if (ctx->test_max_score > 0)
+        for (auto &t : gt) t.s_cap = std::min(t.s_cap, ctx->test_max_score);
     Ctrl h;
     CK(cudaMemcpyAsync(&h, ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -891,7 +936,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     unsigned pending = cigar_mode ? n_pairs : h.gcount;
     if (staged) CK(cudaEventRecord(ctx->ev[6], s));
     for (int g = 0; g < 2 && pending > 0; ++g) {
-        const TierCfg tc = gtiers[g];
+        const TierCfg tc = gt[g];
         const size_t stride = global_tier_stride(tc.wlog2, tc.s_cap, tc.ops_cap, tc.prov_cap);
         uint64_t workers = std::min<uint64_t>((uint64_t)tc.workers, std::max<uint64_t>(1, (cap / 2) / stride));
         workers = std::min<uint64_t>(workers, pending);
@@ -951,6 +996,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         cn.pairs_closed_form = h.n_closed;
         cn.pairs_identical = h.algo[3] >= aligned + h.n_closed ? h.algo[3] - aligned - h.n_closed : 0;
     }
+    cn.pairs_failed = h.n_failed;
     cn.ms_total_device = elapsed(ctx->ev[0], ctx->ev[1]);
     cn.ms_host_call = ms_since(t_call);
     if (staged) {
@@ -1013,11 +1059,11 @@ int validate_common(tdb_ctx *ctx, const void *blob, const void *off, const void 
 
 int host_align_common(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
                       const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern, const uint32_t *pair_text,
-                      size_t n_pairs, DevBatch &b) {
+                      size_t n_pairs, DevBatch &b, bool need_blob = true) {
     int r = check_sizes(ctx, blob_bytes, n_seqs, n_pairs);
     if (r) return r;
     CK(cudaSetDevice(ctx->dev));
-    ENSURE(ctx->blob, blob_bytes + 64);
+    ENSURE(ctx->blob, (need_blob ? blob_bytes : 0) + 64); // packed input without exceptions never touches raw bytes
     ENSURE(ctx->seq_off, n_seqs * 8 + 8);
     ENSURE(ctx->seq_len, n_seqs * 4 + 4);
     ENSURE(ctx->pair_p, n_pairs * 4 + 4);
@@ -1166,6 +1212,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
             c->allow_steal = atoi(sd) > 1;
             c->steal_div = std::max(2, atoi(sd));
         }
+        if (const char *ms = getenv("TDB_TEST_MAX_SCORE")) c->test_max_score = atoi(ms);
         if (const char *ht = getenv("TDB_HOST_THREADS")) c->host_threads = std::max(0, std::min(256, atoi(ht)));
         if (const char *hp = getenv("TDB_HOSTPACK_MIN_BYTES")) {
             const long long v = atoll(hp); // < 0 disables the host packer
@@ -1342,6 +1389,9 @@ int tdb_duo_reduce(tdb_ctx *ctx, const tdb_trio_locus *loci, size_t n_loci, cons
     return reduce_host(ctx, 1, loci, n_loci, scores, n_scores, parent_quantile, out, denovo_mask);
 }
 
+static int assess_tail(tdb_ctx *ctx, int is_duo, DevBatch &b, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
+                       double q, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask);
+
 static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,
                        const uint32_t *seq_len, size_t n_seqs, const uint32_t *pair_pattern, const uint32_t *pair_text,
                        size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci, double q, tdb_allele_out *out,
@@ -1354,6 +1404,13 @@ static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t
     DevBatch b;
     r = host_align_common(ctx, seq_blob, blob_bytes, seq_off, seq_len, n_seqs, pair_pattern, pair_text, n_pairs, b);
     if (r) return r;
+    return assess_tail(ctx, is_duo, b, n_pairs, loci, n_loci, q, out, out_score, denovo_mask);
+}
+
+// reduction + result download of the fused host-buffer calls (ASCII and packed input alike)
+static int assess_tail(tdb_ctx *ctx, int is_duo, DevBatch &b, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
+                       double q, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
+    int r;
     UPLOAD(ctx->loci, loci, n_loci * sizeof(tdb_trio_locus), 0);
     ENSURE(ctx->aout, n_loci * 2 * sizeof(tdb_allele_out) + 16);
     ENSURE(ctx->mask, n_pairs + 16);
@@ -1405,6 +1462,65 @@ static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->counters.bytes_d2h = d2h;
     return TDB_OK;
+}
+
+// ---- packed input ------------------------------------------------------------------------------------------------
+static int packed_common(tdb_ctx *ctx, const tdb_packed_seqs *sq, const uint32_t *pair_pattern, const uint32_t *pair_text,
+                         size_t n_pairs, const void *out_score, DevBatch &b) {
+    if (!ctx) return TDB_E_INVALID;
+    ctx->err.clear();
+    if (!sq) return fail(ctx, TDB_E_INVALID, "null pointer argument");
+    if ((sq->n_bases && !sq->packed) || (sq->n_exc && (!sq->exc_seq || !sq->exc_bytes)))
+        return fail(ctx, TDB_E_INVALID, "null pointer argument");
+    int r = validate_common(ctx, sq->packed, sq->seq_off, sq->seq_len, pair_pattern, pair_text, sq->n_seqs, n_pairs, out_score);
+    if (r) return r;
+    for (size_t i = 0; i < sq->n_exc; ++i)
+        if (sq->exc_seq[i] >= sq->n_seqs || (i && sq->exc_seq[i] <= sq->exc_seq[i - 1]))
+            return fail(ctx, TDB_E_INVALID, "exc_seq must be ascending sequence indices");
+    r = host_align_common(ctx, nullptr, sq->n_bases, sq->seq_off, sq->seq_len, sq->n_seqs, pair_pattern, pair_text, n_pairs, b,
+                          sq->n_exc != 0);
+    if (r) return r;
+    b.h_packed = sq->packed, b.h_exc_seq = sq->exc_seq, b.h_exc_bytes = sq->exc_bytes, b.n_exc = sq->n_exc;
+    return TDB_OK;
+}
+
+int tdb_align_batch_packed(tdb_ctx *ctx, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
+                           const uint32_t *pair_text, size_t n_pairs, int32_t *out_score, int32_t *out_status) {
+    DevBatch b;
+    int r = packed_common(ctx, seqs, pair_pattern, pair_text, n_pairs, out_score, b);
+    if (r) return r;
+    r = run_align(ctx, b, false);
+    if (r) return r;
+    if (n_pairs) {
+        CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_status) CK(cudaMemcpyAsync(out_status, b.status, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return TDB_OK;
+}
+
+static int assess_packed(tdb_ctx *ctx, int is_duo, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
+                         const uint32_t *pair_text, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci, double q,
+                         tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
+    int32_t dummy = 0;
+    DevBatch b;
+    int r = packed_common(ctx, seqs, pair_pattern, pair_text, n_pairs, &dummy, b);
+    if (r) return r;
+    if (n_loci && (!loci || !out)) return fail(ctx, TDB_E_INVALID, "null pointer argument");
+    if (n_loci >= 0xffffffffull) return fail(ctx, TDB_E_UNSUPPORTED, "too many loci");
+    return assess_tail(ctx, is_duo, b, n_pairs, loci, n_loci, q, out, out_score, denovo_mask);
+}
+int tdb_trio_batch_packed(tdb_ctx *ctx, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
+                          const uint32_t *pair_text, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
+                          double parent_quantile, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
+    return assess_packed(ctx, 0, seqs, pair_pattern, pair_text, n_pairs, loci, n_loci, parent_quantile, out, out_score,
+                         denovo_mask);
+}
+int tdb_duo_batch_packed(tdb_ctx *ctx, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
+                         const uint32_t *pair_text, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
+                         double parent_quantile, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
+    return assess_packed(ctx, 1, seqs, pair_pattern, pair_text, n_pairs, loci, n_loci, parent_quantile, out, out_score,
+                         denovo_mask);
 }
 
 int tdb_trio_batch(tdb_ctx *ctx, const uint8_t *seq_blob, size_t blob_bytes, const uint64_t *seq_off,

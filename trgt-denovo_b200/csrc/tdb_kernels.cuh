@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
         // bad pair index (ERR_PAIR_INDEX, raised by k_pair_insert) or a sequence outside the blob (ERR_LAYOUT,
         // raised by k_pack): the call fails; such pairs never reach an alignment kernel
         if (ip >= n_seqs || jt >= n_seqs || ((seq_flag[ip] | seq_flag[jt]) & 2)) {
-            o.out_score[j] = 0;
+            o.out_score[j] = TDB_SCORE_FAILED;
             if (o.out_status) o.out_status[j] = TDB_STATUS_UNATTAINABLE;
             if (o.out_penalty) o.out_penalty[j] = INT32_MIN;
             if (o.work) o.work[3 * (size_t)j] = o.work[3 * (size_t)j + 1] = o.work[3 * (size_t)j + 2] = 0;
@@ -574,6 +574,7 @@ struct AlignParams {
     const uint64_t *cigar_off;
     uint32_t *cigar_len;
     unsigned long long *counters; // executed cells, ext16, columns, pairs finished by this launch
+    unsigned *fail_count;         // pairs the LAST tier could not finish (score = TDB_SCORE_FAILED, status OOM)
     uint8_t *scratch;             // global tiers: per-warp slices
     size_t scratch_stride;
     int wlog2, s_cap, ops_cap;
@@ -632,9 +633,12 @@ __device__ __forceinline__ void defer_pair(const AlignParams &p, uint32_t idx, i
             const unsigned j = atomicAdd(p.next_count, 1u);
             p.next_todo[j] = idx;
         } else {
-            p.out_score[idx] = 0;
+            // no tier left: the pair has NO score.  The sentinel keeps it out of every reduction (k_reduce skips
+            // it, so the lists shrink exactly as src/denovo.rs:31-35 drops non-completed alignments)
+            p.out_score[idx] = TDB_SCORE_FAILED;
             if (p.out_status) p.out_status[idx] = TDB_STATUS_OOM;
             if (p.out_penalty) p.out_penalty[idx] = INT32_MIN;
+            if (p.fail_count) atomicAdd(p.fail_count, 1u);
             if (p.cigar_len) p.cigar_len[idx] = 0;
             if (p.work) p.work[3 * (size_t)idx] = p.work[3 * (size_t)idx + 1] = p.work[3 * (size_t)idx + 2] = 0;
         }
@@ -778,13 +782,22 @@ __global__ void __launch_bounds__(128, TDB_G_MINB) k_align_global(const AlignPar
 // integer counting plus a handful of IEEE f64 operations that must round exactly as the Rust code
 // does (explicit _rn intrinsics: no FMA contraction).
 // ------------------------------------------------------------------------------------------------
+// Scores equal to TDB_SCORE_FAILED (pairs no tier could finish) are not part of any list: every helper skips
+// them, which is what dropping non-completed alignments does in the reference (src/denovo.rs:31-35).
+__device__ __forceinline__ bool sc_ok(int x) { return x != TDB_SCORE_FAILED; }
+__device__ inline int n_valid(const int32_t *xs, int n) {
+    int c = 0;
+    for (int i = 0; i < n; ++i) c += sc_ok(xs[i]);
+    return c;
+}
 __device__ inline int kth_smallest(const int32_t *xs, int n, int k) {
     for (int i = 0; i < n; ++i) {
         const int x = xs[i];
+        if (!sc_ok(x)) continue;
         int less = 0, eq = 0;
         for (int j = 0; j < n; ++j) {
             const int y = xs[j];
-            less += y < x;
+            less += (y < x) & sc_ok(y);
             eq += y == x;
         }
         if (less <= k && k < less + eq) return x;
@@ -792,15 +805,15 @@ __device__ inline int kth_smallest(const int32_t *xs, int n, int k) {
     return 0;
 }
 
-// math::quantile on one list (src/math.rs:82-98); n > 0.
-__device__ inline double list_quantile(const int32_t *xs, int n, double q) {
-    const double index = __dmul_rn(q, __dsub_rn((double)n, 1.0));
+// math::quantile on one list (src/math.rs:82-98); nv = valid entries > 0.
+__device__ inline double list_quantile(const int32_t *xs, int n, int nv, double q) {
+    const double index = __dmul_rn(q, __dsub_rn((double)nv, 1.0));
     const double fl = floor(index);
     const long long lower = fl <= 0.0 ? 0 : (fl >= 9.0e18 ? (long long)9.0e18 : (long long)fl);
     const long long upper = lower + 1;
-    if (upper >= (long long)n) {
-        int mx = xs[0];
-        for (int i = 1; i < n; ++i) mx = max(mx, xs[i]);
+    if (upper >= (long long)nv) {
+        int mx = INT32_MIN; // the sentinel is the smallest int: the maximum of the list ignores it by itself
+        for (int i = 0; i < n; ++i) mx = max(mx, xs[i]);
         return (double)mx;
     }
     const double fraction = __dsub_rn(index, (double)lower);
@@ -815,8 +828,9 @@ __device__ inline bool top_other(const int32_t *scores, const uint32_t *off, int
     double best = 0.0;
     for (int l = 0; l < n_lists; ++l) {
         const int n = (int)(off[first + l + 1] - off[first + l]);
-        if (n <= 0) continue;
-        const double v = list_quantile(scores + off[first + l], n, q);
+        const int nv = n_valid(scores + off[first + l], n);
+        if (nv <= 0) continue;
+        const double v = list_quantile(scores + off[first + l], n, nv, q);
         if (!have || v >= best) best = v, have = true;
     }
     out = best;
@@ -829,7 +843,7 @@ __device__ inline void count_diff(double top, const int32_t *a, int n, int &coun
     double sum = 0.0;
     for (int i = 0; i < n; ++i) {
         const double x = (double)a[i];
-        if (x > top) ++c, sum = __dadd_rn(sum, x);
+        if (sc_ok(a[i]) && x > top) ++c, sum = __dadd_rn(sum, x);
     }
     count = c;
     mean_diff = c > 0 ? (float)fabs(__dsub_rn(__ddiv_rn(sum, (double)c), top)) : 0.0f;
@@ -837,21 +851,23 @@ __device__ inline void count_diff(double top, const int32_t *a, int n, int &coun
 
 __device__ inline int overlap_cov(double thr, const int32_t *a, int n) {
     int c = 0;
-    for (int i = 0; i < n; ++i) c += ((double)a[i] >= thr);
+    for (int i = 0; i < n; ++i) c += (sc_ok(a[i]) && (double)a[i] >= thr);
     return c;
 }
 
 __device__ inline double list_mean(const int32_t *s, uint32_t b, uint32_t e) {
-    if (e <= b) return -INFINITY;
-    uint32_t sum = 0;
-    for (uint32_t i = b; i < e; ++i) sum += (uint32_t)s[i]; // i32 sum (wrapping)
-    return __ddiv_rn((double)(int32_t)sum, (double)(e - b));
+    uint32_t sum = 0, nv = 0;
+    for (uint32_t i = b; i < e; ++i)
+        if (sc_ok(s[i])) sum += (uint32_t)s[i], ++nv; // i32 sum (wrapping)
+    if (nv == 0) return -INFINITY;
+    return __ddiv_rn((double)(int32_t)sum, (double)nv);
 }
 
-__device__ inline double list_median(const int32_t *a, int n) {
+__device__ inline double list_median(const int32_t *a, int n_raw) {
+    const int n = n_valid(a, n_raw);
     if (n == 0) return 1.7976931348623157e308; // unwrap_or(f64::MAX)
-    if (n & 1) return (double)kth_smallest(a, n, n / 2);
-    const int x = kth_smallest(a, n, n / 2 - 1), y = kth_smallest(a, n, n / 2);
+    if (n & 1) return (double)kth_smallest(a, n_raw, n / 2);
+    const int x = kth_smallest(a, n_raw, n / 2 - 1), y = kth_smallest(a, n_raw, n / 2);
     return __ddiv_rn((double)(int32_t)((uint32_t)x + (uint32_t)y), 2.0);
 }
 
@@ -891,7 +907,7 @@ __global__ void __launch_bounds__(128) k_reduce(const tdb_trio_locus *__restrict
         const double thr = is_duo ? top_m : fmax(top_m, top_f);
         if (mask)
             for (int i = 0; i < nown; ++i) {
-                const bool hit = (double)own[i] > thr;
+                const bool hit = sc_ok(own[i]) && (double)own[i] > thr;
                 mask[off[4] + i] = hit ? 1 : 0;
                 // the set bytes are a few in a million: host calls fetch this list instead of the whole mask
                 if (hit && hit_count) {

@@ -513,9 +513,10 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                         const unsigned j = atomicAdd(p.next_count, 1u);
                         p.next_todo[j] = idx;
                     } else {
-                        p.out_score[idx] = 0;
+                        p.out_score[idx] = TDB_SCORE_FAILED;
                         if (p.out_status) p.out_status[idx] = TDB_STATUS_OOM;
                         if (p.out_penalty) p.out_penalty[idx] = INT32_MIN;
+                        if (p.fail_count) atomicAdd(p.fail_count, 1u);
                     }
                 }
                 if (!overflow) acc_ext += ext;

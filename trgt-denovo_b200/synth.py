@@ -39,8 +39,18 @@ class _Batch(C.Structure):
                 ("n_loci", C.c_size_t), ("sum_nm", C.c_uint64), ("sum_bases", C.c_uint64), ("pinned", C.c_int32)]
 
 
+SYNTH_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtdb_synth.so")
+_lib = None
+
+
 def _L():
-    L = B.lib()
+    """The generator's own library (trgt-denovo_b200/synth_src): loading it maps no product code."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise B.TdbError(B.E_INVALID, f"{SYNTH_LIB_PATH} not built (run __graft_entry__.build())")
+        _lib = C.CDLL(SYNTH_LIB_PATH)
+    L = _lib
     if not getattr(L, "_synth_ready", False):
         L.tdb_synth_default_params.restype = None
         L.tdb_synth_default_params.argtypes = [C.POINTER(SynthParams)]
