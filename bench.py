@@ -3,17 +3,20 @@
 
 A step = one pass of the hot path (2-bit packing, tiered WFA alignment with on-device backtrace and
 clipped scoring, fused per-locus reduction) over the whole synthetic genome-wide trio assigned to
-this rank (configs[1]: 937k-locus catalog at 30x).  Loci are sharded by
-the host with no collective (weak scaling: every rank runs its own 937k-locus shard of an
-N x 937k-locus catalog).
+this rank.  The workload is ONE catalog (configs[1]: 937k loci at 30x); with
+--gpus N it is cut into N contiguous locus ranges balanced on sum(n + m) over the pairs of each locus
+(trgt_denovo_b200.shard.balanced_bounds), one rank / ctx / GPU each, no data-path collective: strong scaling,
+as north_star states it ("loci sharded across 1/2/4/8 B200").
 
   value     loci/s with the inputs already resident in HBM (tdb_assess_batch_device), timed with the
             CUDA events the library records on its launching stream, max over ranks
-  e2e       the same pass through the host-buffer C-ABI call (tdb_trio_batch): pinned host inputs,
-            H2D + kernels + D2H of the per-allele results inside the timed region
-  roofline  the dominant alignment kernel: algorithmic HBM bytes and lane-int-ops of the pairs that
-            launch aligned (ops = 24*C + 8*E + 4*T, counted exactly on the device and
-            checked against the oracle in tests/) over its CUDA-event duration
+  e2e       the same pass through the host-buffer C-ABI call (tdb_trio_batch): pinned host inputs as ASCII
+            (what the reference hands over), H2D + kernels + D2H of the per-allele results inside the timed region
+  e2e_packed  the same through tdb_trio_batch_packed: the host packed to 2 bits at load time (outside the timed
+            region, as a loader that reads BAM 4-bit bases would), so the call does no per-base CPU work
+  roofline  the dominant alignment kernel against the INT32-issue roofline SURVEY.md 8(d) names: lane-int-ops of
+            the pairs that launch aligned (ops = 24*C + 8*E + 4*T, counted exactly on the device and checked
+            against the oracle in tests/) over its CUDA-event duration; the HBM figure is the nested note
   cpu_baseline / --impl reference
             the CPU oracle (scalar C restatement of the reference path, "port": the reference's own
             Rust+WFA2-lib binary cannot be built here) on all host cores, on a bounded sample
@@ -97,12 +100,23 @@ def oracle_pass(tdo, batch, n_loci, clip, q, duo, threads):
     return time.perf_counter() - t0, n_pairs
 
 
+def workload_name(args, world=1, ref_sample=None):
+    kind = "duo" if args.duo else "trio"
+    w = (f"genome-wide synthetic {kind}, ONE catalog of {args.loci} loci at 30x (SURVEY.md 8d config "
+         f"{'3' if args.duo else '2'}, seed 20250002)")
+    if ref_sample is not None:
+        return w + f"; the CPU arm times the first {ref_sample} loci of it per step (a rate: loci/s)"
+    return w + (f", sharded over {world} GPUs in contiguous locus ranges balanced on sum(n+m)" if world > 1 else "") + \
+        ", inputs larger than L2"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port) on all host threads, rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port) on all host threads, rank 0 only.  Maps no product
+    code: the workload generator is its own library (libtdb_synth.so) and build() is told not to load the rest."""
     if rank != 0:
         return 0
     import __graft_entry__ as entry
-    entry.build()
+    entry.build(load=False)
     from importlib import import_module
     from oracle import tdo
     S = import_module("trgt_denovo_b200.synth")
@@ -121,9 +135,9 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "trio_loci_per_sec" if not args.duo else "duo_loci_per_sec", "value": val,
         "unit": "loci/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "loci_per_step": sample,
+        "config": {"workload": workload_name(args, ref_sample=sample), "loci_per_step": sample,
                    "pairs_per_step": n_pairs, "clip_len": args.clip},
         "alignments_per_sec": n_pairs * args.steps / tot,
         "cpu_baseline": {"value": val, "unit": "loci/s", "cores": threads, "kind": "port",
@@ -135,24 +149,21 @@ def run_reference(args, rank, world):
     return 0
 
 
-def workload_name(args):
-    kind = "duo" if args.duo else "trio"
-    return (f"genome-wide synthetic {kind}, {args.loci} loci per GPU at 30x (SURVEY.md 8d config "
-            f"{'3' if args.duo else '2'}, seed 20250002), inputs larger than L2")
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--loci", type=int, default=int(os.environ.get("TDB_BENCH_LOCI", 937000)))
+    ap.add_argument("--loci", type=int, default=int(os.environ.get("TDB_BENCH_LOCI", 937000)),
+                    help="loci of the ONE catalog (sharded over the ranks)")
     ap.add_argument("--duo", action="store_true")
     ap.add_argument("--clip", type=int, default=50)
     ap.add_argument("--quantile", type=float, default=1.0)
     ap.add_argument("--cpu-sample-loci", type=int, default=int(os.environ.get("TDB_BENCH_CPU_LOCI", 150000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-census", action="store_true", help="skip the heuristic-sensitivity census")
+    ap.add_argument("--weak", action="store_true", help="every rank its own --loci catalog (round-1 behaviour)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -177,6 +188,7 @@ def main():
     import trgt_denovo_b200 as tdb
     S = import_module("trgt_denovo_b200.synth")
     B = import_module("trgt_denovo_b200.binding")
+    SH = import_module("trgt_denovo_b200.shard")
     if tdb.device_count() == 0:
         raise SystemExit("no CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -184,22 +196,41 @@ def main():
     L = tdb.lib()
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
 
-    # ---- workload: this rank's shard -----------------------------------------------------------------
+    # ---- workload: ONE catalog, this rank's locus range --------------------------------------------------
     threads = max(1, (os.cpu_count() or 1) // max(1, world))
-    # every rank keeps its shard in pinned host memory for the e2e leg (about 22 KB per locus with the packed
-    # staging and the result buffers): never ask one box for more than 80 % of what it has free
-    try:
+    try:  # about 26 KB of pinned host memory per locus (ASCII + packed + results): stay below 80 % of what is free
         import psutil
-        fit = int(0.8 * psutil.virtual_memory().available / max(1, world) / 22e3)
+        fit = int(0.8 * psutil.virtual_memory().available / 26e3)
         if args.loci > fit:
-            log(f"[rank {rank}] {args.loci} loci per GPU x {world} ranks does not fit the host memory; using {fit}")
-            args.loci = max(1000, fit)
+            log(f"[rank {rank}] a catalog of {args.loci} loci does not fit the host memory; using {fit}")
+            args.loci = max(1000 * world, fit)
     except ImportError:
         pass
     params = S.config("duo_genome" if args.duo else "trio_genome", pinned=1)
     t0 = time.time()
-    batch = S.generate(params, rank * args.loci, (rank + 1) * args.loci, threads)
-    log(f"[rank {rank}] generated {batch.n_loci} loci, {batch.n_pairs} pairs, {batch.blob.size / 1e9:.2f} GB "
+    if args.weak:
+        lo, hi = rank * args.loci, (rank + 1) * args.loci
+        bounds = [r * args.loci for r in range(world + 1)]
+    elif world == 1:
+        lo, hi = 0, args.loci
+        bounds = [0, args.loci]
+    else:
+        # every rank weighs its even slice (sum over the locus' pairs of n + m), the weights are gathered (bookkeeping,
+        # 8 bytes per locus) and every rank derives the same balanced boundaries
+        eb = SH.even_bounds(args.loci, world)
+        probe = S.generate(S.config("duo_genome" if args.duo else "trio_genome"), eb[rank], eb[rank + 1], threads)
+        w_mine = SH.locus_weights_from_meta(probe)
+        probe.close()
+        longest = max(eb[r + 1] - eb[r] for r in range(world))
+        mine = torch.zeros(longest, dtype=torch.int64, device=dev)
+        mine[:len(w_mine)] = torch.from_numpy(w_mine).to(dev)
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        weights = np.concatenate([parts[r][:eb[r + 1] - eb[r]].cpu().numpy() for r in range(world)])
+        bounds = SH.balanced_bounds(weights, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+    batch = S.generate(params, lo, hi, threads)
+    log(f"[rank {rank}] loci [{lo}, {hi}): {batch.n_loci} loci, {batch.n_pairs} pairs, {batch.blob.size / 1e9:.2f} GB "
         f"of reads in {time.time() - t0:.1f}s")
     n_loci, n_pairs, n_seqs = batch.n_loci, batch.n_pairs, batch.n_seqs
     ctx = tdb.Context(device_id=local_rank, clip_len=args.clip)
@@ -256,6 +287,30 @@ def main():
         if rc != 0:
             raise RuntimeError(L.tdb_last_error(h).decode())
 
+    # packed at load time (outside every timed region): the 2-bit stream in pinned memory, exception list
+    n_words = L.tdb_packed_words(batch.blob.size)
+    h_packed_ptr = L.tdb_host_alloc(n_words * 4)
+    if not h_packed_ptr:
+        raise SystemExit("pinned host allocation failed")
+    flag = np.zeros(max(1, n_seqs), dtype=np.uint8)
+    t0 = time.time()
+    rc = L.tdb_host_pack(batch.blob.ctypes.data, batch.blob.size, batch.seq_off.ctypes.data, batch.seq_len.ctypes.data,
+                         n_seqs, h_packed_ptr, flag.ctypes.data, threads)
+    if rc != 0:
+        raise SystemExit("tdb_host_pack failed")
+    load_pack_s = time.time() - t0
+    exc = np.nonzero(flag[:n_seqs])[0].astype(np.uint32)
+    exc_bytes = np.frombuffer(b"".join(batch.seq(int(i)) for i in exc), dtype=np.uint8)
+    pseqs = B.PackedSeqs(h_packed_ptr, batch.blob.size, h_off_ptr, batch.seq_len.ctypes.data, n_seqs,
+                         exc.ctypes.data if len(exc) else None, exc_bytes.ctypes.data if len(exc) else None, len(exc))
+
+    def step_packed():
+        r = L.tdb_trio_batch_packed if not args.duo else L.tdb_duo_batch_packed
+        rc = r(h, C.byref(pseqs), batch.pair_pattern.ctypes.data, batch.pair_text.ctypes.data, n_pairs, batch.loci_ptr,
+               n_loci, args.quantile, C.cast(h_out, C.c_void_p), None, h_mask.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(L.tdb_last_error(h).decode())
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -295,49 +350,102 @@ def main():
     w1 = time.time()
     clocks = sampler.stop(w0, w1)
     wall_ms = 1e3 * (w1 - w0)
+    score_ref = d_score.clone()  # production result of this rank's shard (self-check and census below)
 
-    # ---- end-to-end through the host-buffer C ABI ------------------------------------------------------
-    for _ in range(min(args.warmup, 2)):
-        step_host()
-    barrier()
-    e0 = time.time()
-    for _ in range(args.steps):
-        step_host()
-    barrier()
-    e2e_s = time.time() - e0
-    ce = ctx.counters()
-    e2e_chunks = ce.chunks
-    e2e_host = {"host_packed": int(ce.host_packed), "align_bytes_h2d": int(ce.bytes_h2d), "ascii_bytes_taken_over": int(ce.bytes_raw), "ms_plan": ce.ms_host_plan, "ms_pack_wait": ce.ms_host_pack_wait,
+    # ---- end-to-end through the host-buffer C ABI: ASCII hand-over, then packed hand-over --------------
+    def time_host(fn):
+        for _ in range(min(args.warmup, 3)):
+            fn()
+        barrier()
+        e0 = time.time()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        return time.time() - e0, ctx.counters()
+
+    e2e_s, ce = time_host(step_host)
+    out_ascii = bytes(h_out)
+    e2e_host = {"host_packed": int(ce.host_packed), "align_bytes_h2d": int(ce.bytes_h2d),
+                "ascii_bytes_taken_over": int(ce.bytes_raw), "ms_plan": ce.ms_host_plan, "ms_pack_wait": ce.ms_host_pack_wait,
                 "ms_align_call": ce.ms_host_call, "ms_device_span": ce.ms_total_device,
-                "ms_last_block_packed": ce.ms_host_packed, "ms_last_chunk_queued": ce.ms_host_enqueued}
+                "ms_last_block_packed": ce.ms_host_packed, "ms_last_chunk_queued": ce.ms_host_enqueued,
+                "chunks": int(ce.chunks)}
     # bytes that actually cross PCIe per step: what the library copied for the alignment stage (2-bit packed
     # sequences, tables, run-length encoded pair lists) plus the locus descriptors
-    host_input_bytes = batch.blob.size + (0 if dense else batch.seq_off.nbytes) + batch.seq_len.nbytes + batch.pair_pattern.nbytes + \
-        batch.pair_text.nbytes + loci_np.nbytes
+    host_input_bytes = batch.blob.size + (0 if dense else batch.seq_off.nbytes) + batch.seq_len.nbytes + \
+        batch.pair_pattern.nbytes + batch.pair_text.nbytes + loci_np.nbytes
     h2d = int(ce.bytes_h2d) + loci_np.nbytes
     d2h = int(ce.bytes_d2h)  # rows + the read mask (large calls fetch it as a list of its set positions)
 
-    # ---- quick self-check of the step's result against the oracle (outside the timed regions) --------
+    e2ep_s, cp = time_host(step_packed)
+    if bytes(h_out) != out_ascii:
+        raise SystemExit("bench self-check failed: packed and ASCII entry points disagree")
+    del out_ascii
+    packed_input_bytes = n_words * 4 + (0 if dense else batch.seq_off.nbytes) + batch.seq_len.nbytes + \
+        batch.pair_pattern.nbytes + batch.pair_text.nbytes + loci_np.nbytes
+    e2ep_host = {"host_packed": int(cp.host_packed), "align_bytes_h2d": int(cp.bytes_h2d), "ms_plan": cp.ms_host_plan,
+                 "ms_scan_wait": cp.ms_host_pack_wait, "ms_align_call": cp.ms_host_call,
+                 "ms_device_span": cp.ms_total_device, "ms_last_chunk_queued": cp.ms_host_enqueued,
+                 "chunks": int(cp.chunks), "load_time_pack_s": load_pack_s, "exceptions": int(len(exc))}
+    h2d_p = int(cp.bytes_h2d) + loci_np.nbytes
+    d2h_p = int(cp.bytes_d2h)
+
+    # ---- self-check of the step's result against the oracle (outside the timed regions): a strided sample
+    # of 20 000 pairs over this rank's whole shard ---------------------------------------------------------
     check = None
     if rank == 0:
         from oracle import tdo
-        ncheck = min(n_loci, 300)
-        npc = int(batch.meta[ncheck - 1].pair_end)
-        want, _, _ = tdo.align_batch(batch.blob, batch.seq_off, batch.seq_len, batch.pair_pattern[:npc],
-                                     batch.pair_text[:npc], args.clip, n_threads=threads)
-        got = d_score[:npc].cpu().numpy()
-        check = bool((got == want).all())
+        idx = np.arange(0, n_pairs, max(1, n_pairs // 20000), dtype=np.int64)
+        want, wst, _ = tdo.align_batch(batch.blob, batch.seq_off, batch.seq_len, batch.pair_pattern[idx],
+                                       batch.pair_text[idx], args.clip, n_threads=os.cpu_count() or 1)
+        got = score_ref[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        check = bool((got == want).all() and (wst == 0).all())
         if not check:
             raise SystemExit("bench self-check failed: GPU scores differ from the oracle")
 
+    # ---- heuristic census (rank 0's shard): how many pairs does wf-adaptive touch at all?  For all the others an
+    # independent Gotoh DP pins the penalty and no recollection of WFA2-lib's cut-off is involved --------------
+    census = None
+    if rank == 0 and not args.no_census:
+        def scores_with(heur, clip):
+            ctx.set_heuristic(heur)
+            ctx.set_clip_len(clip)
+            step_device()
+            return d_score.clone()
+        try:
+            on50 = score_ref
+            off50 = scores_with((0, 0, 0, 0), args.clip)
+            off0 = scores_with((0, 0, 0, 0), 0)
+            on0 = scores_with((1, 10, 50, 1), 0)
+            sens_clip = int((on50 != off50).sum().item())
+            sens_pen = int((on0 != off0).sum().item())
+            sens_any = int(((on50 != off50) | (on0 != off0)).sum().item())
+            census = {"pairs": int(n_pairs), "heuristic_sensitive_pairs": sens_any,
+                      "clipped_score_differs": sens_clip, "penalty_differs": sens_pen,
+                      "note": "pairs of rank 0's shard whose clipped score (clip_len) or penalty (= clipped score at "
+                              "clip 0) differs between wf-adaptive(10,50,1) and Heuristic::None"}
+            del off50, off0, on0
+        finally:
+            ctx.set_heuristic((1, 10, 50, 1))
+            ctx.set_clip_len(args.clip)
+
     # ---- reduce over ranks -------------------------------------------------------------------------------
-    vals = torch.tensor([dev_ms, wall_ms, 1e3 * e2e_s], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(n_loci), float(n_pairs)], dtype=torch.float64, device=dev)
+    mine = torch.tensor([dev_ms, wall_ms, 1e3 * e2e_s, 1e3 * e2ep_s, float(n_loci), float(n_pairs),
+                         float(ce.ms_host_pack_wait), float(ce.ms_host_call), float(cp.ms_host_call), float(h2d),
+                         float(d2h), float(h2d_p), float(d2h_p), float(launches), float(host_input_bytes),
+                         float(packed_input_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max, e2e_ms_max = [float(x) for x in vals.tolist()]
-    tot_loci, tot_pairs = [float(x) for x in sums.tolist()]
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        allv = torch.stack(allv).cpu().numpy()
+    else:
+        allv = mine.cpu().numpy()[None, :]
+    dev_ms_max, wall_ms_max, e2e_ms_max, e2ep_ms_max = [float(allv[:, i].max()) for i in range(4)]
+    tot_loci, tot_pairs = float(allv[:, 4].sum()), float(allv[:, 5].sum())
+    per_rank = [{"rank": r, "loci": int(allv[r, 4]), "pairs": int(allv[r, 5]),
+                 "device_ms_per_step": allv[r, 0] / args.steps, "e2e_ms_per_step": allv[r, 2] / args.steps,
+                 "e2e_packed_ms_per_step": allv[r, 3] / args.steps, "last_call_ms_pack_wait": allv[r, 6],
+                 "last_call_ms_e2e": allv[r, 7], "last_call_ms_e2e_packed": allv[r, 8]} for r in range(world)]
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -366,9 +474,8 @@ def main():
         t_cells = [int(x) for x in cnt.tier_cells[:3]] + [int(cnt.thread_cells)]
         t_ext = [int(x) for x in cnt.tier_ext16[:3]] + [int(cnt.thread_ext16)]
         t_cols = [int(x) for x in cnt.tier_columns[:3]] + [int(cnt.thread_columns)]
-        ops = INT_OPS_PER_CELL * t_cells[ti] + INT_OPS_PER_EXT * t_ext[ti] + INT_OPS_PER_COL * t_cols[ti]
-        ops_algo = (INT_OPS_PER_CELL * algo_work["cells"] + INT_OPS_PER_EXT * algo_work["ext16"] +
-                    INT_OPS_PER_COL * algo_work["columns"])
+        t_ops = [INT_OPS_PER_CELL * t_cells[i] + INT_OPS_PER_EXT * t_ext[i] + INT_OPS_PER_COL * t_cols[i] for i in range(4)]
+        ops = t_ops[ti]
         clk = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         int_peak = n_sm * 128 * clk
@@ -377,61 +484,73 @@ def main():
                                         (batch.seq_len[batch.pair_text[:200000]].astype(np.int64) + 3) // 4)) + 16.0
         algo_bytes = mean_pair_bytes * float(t_pairs[ti])
         step_s = dev_ms / args.steps * 1e-3
+        align_ms = sum(stage[t] for t in tiers) / args.steps
         # DRAM traffic of that kernel per launch: bytes per aligned pair from the committed ncu --set full capture
-        # (profiles/r01/traffic.json, written by profiles/summarize_final.py) x the pairs this launch aligned
+        # (profiles/r02/traffic.json, else r01) x the pairs this launch aligned
         traffic, traffic_src = None, None
-        tj = os.path.join(ROOT, "profiles", "r01", "traffic.json")
-        if os.path.exists(tj):
-            tinfo = json.load(open(tj)).get(names[tiers[ti]])
-            if tinfo:
-                traffic = tinfo["dram_bytes_per_pair"] * float(t_pairs[ti])
-                traffic_src = tinfo["source"] + ", per-pair bytes scaled to this launch"
+        for rd in ("r02", "r01"):
+            tj = os.path.join(ROOT, "profiles", rd, "traffic.json")
+            if os.path.exists(tj):
+                tinfo = json.load(open(tj)).get(names[tiers[ti]])
+                if tinfo:
+                    traffic = tinfo["dram_bytes_per_pair"] * float(t_pairs[ti])
+                    traffic_src = tinfo["source"] + ", per-pair bytes scaled to this launch"
+                    break
         roofline = {
-            "bound": "hbm", "kernel": names[tiers[ti]], "achieved": algo_bytes / k_s / 1e9,
-            "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / k_s / 1e9 / hbm_peak, "traffic": traffic,
-            "traffic_source": traffic_src,
-            "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
-            "note": "HBM is not the binding roofline for this integer DP (SURVEY.md 8d); see int_issue",
-            "int_issue": {"bound": "int32_issue", "achieved": ops / k_s, "peak": int_peak, "unit": "lane-int-ops/s",
-                          "frac": ops / k_s / int_peak,
-                          "peak_source": f"{n_sm} SM x 128 lanes x {clk / 1e6:.0f} MHz (clock observed under load)",
-                          "accounting": "24*C + 8*E + 4*T of the pairs this launch aligned (counted exactly on "
-                                        "the device), over its CUDA-event duration",
-                          "pairs_aligned_by_kernel": t_pairs[ti]},
-            "whole_step_algorithmic": {"ops_per_s": ops_algo / step_s, "frac_of_int_peak": ops_algo / step_s / int_peak,
-                                       "note": "every pair counted as the CPU oracle counts it (duplicates "
-                                               "included) over the whole device step"},
-            "kernel_ms": k_ms, "step_share": stage[tiers[ti]] / max(dev_ms, 1e-9),
+            "bound": "int32_issue", "kernel": names[tiers[ti]], "achieved": ops / k_s, "peak": int_peak,
+            "unit": "lane-int-ops/s", "frac": ops / k_s / int_peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": f"{n_sm} SM x 128 lanes x {clk / 1e6:.0f} MHz (clock observed under load)",
+            "accounting": "SURVEY.md 8(d): 24*C + 8*E + 4*T of the pairs this launch aligned (counted exactly on the "
+                          "device, equal to the oracle's count in tests/), over its CUDA-event duration",
+            "pairs_aligned_by_kernel": t_pairs[ti], "kernel_ms": k_ms,
+            "step_share": stage[tiers[ti]] / max(dev_ms, 1e-9),
+            "all_alignment_tiers": {"ops_per_s": sum(t_ops) / max(align_ms * 1e-3, 1e-9),
+                                    "frac": sum(t_ops) / max(align_ms * 1e-3, 1e-9) / int_peak, "ms": align_ms,
+                                    "pairs": sum(t_pairs)},
+            "hbm": {"bound": "hbm", "achieved": algo_bytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": algo_bytes / k_s / 1e9 / hbm_peak, "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs",
+                    "note": "not the binding roofline for this integer DP (SURVEY.md 8d)"},
         }
+        def e2e_obj(ms_max, h2d_col, d2h_col, in_col):
+            return {"value": tot_loci * args.steps / (ms_max * 1e-3), "unit": "loci/s",
+                    "h2d_bytes_per_step": int(allv[:, h2d_col].sum()), "d2h_bytes_per_step": int(allv[:, d2h_col].sum()),
+                    "host_input_bytes_per_step": int(allv[:, in_col].sum()), "ms_per_step": ms_max / args.steps,
+                    "alignments_per_sec": tot_pairs * args.steps / (ms_max * 1e-3)}
+        e2e = e2e_obj(e2e_ms_max, 9, 10, 14)
+        e2e["input"] = "ASCII bytes in pinned host memory (what the reference hands over); the library 2-bit packs them on the caller's CPU threads"
+        e2e_packed = e2e_obj(e2ep_ms_max, 11, 12, 15)
+        e2e_packed["input"] = "2-bit stream packed at load time (tdb_*_batch_packed); no per-base CPU work in the call"
         line = {
             "metric": "trio_loci_per_sec" if not args.duo else "duo_loci_per_sec",
             "value": tot_loci * args.steps / (dev_ms_max * 1e-3), "unit": "loci/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "loci_per_gpu": n_loci, "pairs_per_gpu": n_pairs,
-                       "clip_len": args.clip, "parent_quantile": args.quantile, "sharding": f"loci x{world}, no collective",
+            "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "catalog_loci": int(tot_loci), "catalog_pairs": int(tot_pairs),
+                       "clip_len": args.clip, "parent_quantile": args.quantile,
+                       "sharding": f"one catalog, {world} contiguous locus ranges balanced on sum(n+m), no collective",
+                       "shard_bounds": [int(x) for x in bounds],
                        "layout": "dense (seq_off = NULL)" if dense else "explicit seq_off",
                        "l2": "inputs larger than L2 (no flush needed)"},
             "alignments_per_sec": tot_pairs * args.steps / (dev_ms_max * 1e-3),
             "gcups": batch.sum_nm * args.steps / (dev_ms * 1e-3) / 1e9,
             "wall_ms_per_step": wall_ms_max / args.steps,
-            "e2e": {"value": tot_loci * args.steps / (e2e_ms_max * 1e-3), "unit": "loci/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "host_input_bytes_per_step": int(host_input_bytes),
-                    "ms_per_step": e2e_ms_max / args.steps,
-                    "alignments_per_sec": tot_pairs * args.steps / (e2e_ms_max * 1e-3)},
-            "gpu_launches": int(launches),
+            "e2e": e2e, "e2e_packed": e2e_packed,
+            "gpu_launches": int(allv[:, 13].sum()),
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "per_rank": per_rank,
             "breakdown_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "tier_pairs": [int(x) for x in cnt.tier_pairs], "thread_tier_pairs": int(cnt.thread_pairs),
             "pairs_identical": int(cnt.pairs_identical), "pairs_duplicate": int(cnt.pairs_duplicate),
-            "pairs_closed_form": int(cnt.pairs_closed_form),
+            "pairs_closed_form": int(cnt.pairs_closed_form), "pairs_failed": int(cnt.pairs_failed),
             "work": {"cells": algo_work["cells"], "ext16": algo_work["ext16"], "columns": algo_work["columns"],
                      "exec_cells": int(cnt.exec_cells), "exec_ext16": int(cnt.exec_ext16),
-                     "exec_columns": int(cnt.exec_columns)},
-            "e2e_chunks": int(e2e_chunks), "e2e_host": e2e_host,
+                     "exec_columns": int(cnt.exec_columns), "note": "cells/ext16/columns: every pair of rank 0's shard "
+                     "as the CPU oracle counts it; exec_*: what the kernels executed"},
+            "heuristic_census": census,
+            "e2e_host": e2e_host, "e2e_packed_host": e2ep_host,
             "self_check_vs_oracle": check,
         }
         print(json.dumps(line), flush=True)

@@ -13,7 +13,8 @@
 //   tdbh::load_alleles (incl. assign_reads_by_alignment)  src/allele.rs:146-259
 //   tdbh::trio::process_alleles / duo::process_alleles    src/trio/allele.rs:185-349, src/duo/allele.rs:124-246
 //       for MANY loci per call: every alignment and reduction of those loci runs in one batched GPU call
-//       (tdb_trio_batch / tdb_duo_batch / tdb_align_batch) instead of one FFI call per read x allele
+//       (tdb_trio_batch_packed / tdb_duo_batch_packed / tdb_align_batch_packed: sequences are handed over as the
+//       2-bit stream they were packed into when they were loaded) instead of one FFI call per read x allele
 //   tdbh::serialize_with_precision, write_tsv, write_read_ids   src/allele.rs:32-50, src/commands/shared.rs:161-195
 //
 // Header-only; link with -ltrgt_denovo_b200.  Errors of the C ABI surface as tdbh::Error (the reference
@@ -126,10 +127,84 @@ class WFAligner {
 inline WFAligner create_aligner_with_scoring(int device_id = 0) { return WFAligner(device_id); }
 
 // ---- data carriers ------------------------------------------------------------------------------------
+// A sequence packed AT THE SOURCE (north_star: "locus.rs and read.rs pack the reads and alleles ... into
+// 2-bit/byte-packed device batches"): the reference turns BAM's 4-bit bases into ASCII at src/read.rs:57
+// (`record.seq().as_bytes()`); a loader that builds this instead never materialises ASCII, holds a quarter of the
+// bytes per read, and the batch call does no per-base CPU work (tdb_*_batch_packed).  Codes are (ASCII >> 1) & 3
+// (A 0, C 1, T 2, G 3), base i at word i / 16, bits 2 (i % 16), unused high bits zero.  WFA2 compares raw bytes
+// ('N' == 'N', case matters), so a sequence with any byte outside {A,C,G,T} also keeps its raw ASCII.
+struct PackedBases {
+    std::vector<uint32_t> w;
+    uint32_t len = 0;
+    std::string raw; // non-empty only when a byte outside ACGT occurs (then raw.size() == len)
+
+    bool empty() const { return len == 0; }
+    static PackedBases from_ascii(const char *s, size_t n) {
+        PackedBases p;
+        p.len = (uint32_t)n;
+        p.w.assign((n + 15) / 16, 0u);
+        bool odd = false;
+        for (size_t i = 0; i < n; ++i) {
+            const unsigned char c = (unsigned char)s[i];
+            odd |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+            p.w[i >> 4] |= (uint32_t)((c >> 1) & 3u) << (2 * (i & 15));
+        }
+        if (odd) p.raw.assign(s, n);
+        return p;
+    }
+    static PackedBases from_ascii(const std::string &s) { return from_ascii(s.data(), s.size()); }
+    // BAM SEQ field: two bases per byte, high nibble first, codes "=ACMGRSVTWYHKDBN" (SAM spec 4.2.3).  A C G T are
+    // nibbles 1 2 4 8 -> 2-bit codes 0 1 3 2; eight bytes make one word, ASCII is never written.
+    static PackedBases from_bam(const uint8_t *seq4, size_t l_seq) {
+        struct Tab {
+            uint8_t two[256]; // 4 bits: code(high nibble) | code(low nibble) << 2
+            uint8_t bad[256]; // bit 0: high nibble outside ACGT, bit 1: low nibble
+            Tab() {
+                auto code = [](int nib, bool &ok) { ok = true; switch (nib) { case 1: return 0; case 2: return 1; case 4: return 3; case 8: return 2; default: ok = false; return 0; } };
+                for (int b = 0; b < 256; ++b) {
+                    bool okh, okl;
+                    const int h = code(b >> 4, okh), l = code(b & 15, okl);
+                    two[b] = (uint8_t)(h | l << 2), bad[b] = (uint8_t)((okh ? 0 : 1) | (okl ? 0 : 2));
+                }
+            }
+        };
+        static const Tab T;
+        PackedBases p;
+        p.len = (uint32_t)l_seq;
+        p.w.assign((l_seq + 15) / 16, 0u);
+        const size_t nb = l_seq / 2; // whole bytes
+        unsigned odd = 0;
+        size_t i = 0;
+        for (; i + 8 <= nb; i += 8) { // 16 bases -> one word
+            uint32_t x = 0;
+            for (int k = 0; k < 8; ++k) x |= (uint32_t)T.two[seq4[i + k]] << (4 * k), odd |= T.bad[seq4[i + k]];
+            p.w[i >> 3] = x;
+        }
+        for (; i < nb; ++i) p.w[i >> 3] |= (uint32_t)T.two[seq4[i]] << (4 * (i & 7)), odd |= T.bad[seq4[i]];
+        if (l_seq & 1) p.w[nb >> 3] |= (uint32_t)(T.two[seq4[nb]] & 3u) << (4 * (nb & 7)), odd |= T.bad[seq4[nb]] & 1u;
+        if (odd) { // rare: decode to ASCII as the reference does and keep both forms
+            static const char code[] = "=ACMGRSVTWYHKDBN";
+            std::string a(l_seq, '\0');
+            for (size_t k = 0; k < l_seq; ++k) a[k] = code[(seq4[k >> 1] >> ((~k & 1) << 2)) & 15];
+            return from_ascii(a);
+        }
+        return p;
+    }
+    std::string ascii() const { // `record.seq().as_bytes()` of src/read.rs:57
+        if (!raw.empty()) return raw;
+        std::string a(len, '\0');
+        for (uint32_t i = 0; i < len; ++i) a[i] = "ACTG"[(w[i >> 4] >> (2 * (i & 15))) & 3u];
+        return a;
+    }
+};
+
 struct TrgtRead { // src/read.rs:12-29 (the fields this path uses)
-    std::string name, bases;
+    std::string name, bases;  // bases: ASCII as in the reference; left empty by loaders that fill `packed` instead
+    PackedBases packed;       // the read packed at the source (authoritative when non-empty)
     std::optional<int> classification; // AL tag
     std::optional<int> haplotype;      // HP tag
+    size_t n_bases() const { return packed.empty() ? bases.size() : packed.len; }
+    std::string bases_ascii() const { return packed.empty() ? bases : packed.ascii(); }
 };
 struct Locus { // src/locus.rs:18-29
     std::string chrom;
@@ -206,17 +281,72 @@ struct PhaseTimer {
 #endif
 };
 
-struct Batch { // sequence blob + pair list in the reference's visiting order (src/denovo.rs:29-37,48-52)
-    std::string blob; // sequences back to back: the ABI's dense layout (seq_off = NULL)
-    std::vector<uint32_t> len, pp, pt;
-    uint32_t seq(const std::string &s) {
-        len.push_back((uint32_t)s.size());
-        blob += s;
+// Sequences + pair list in the reference's visiting order (src/denovo.rs:29-37,48-52), in the PACKED form of
+// tdb_packed_seqs: one 2-bit stream, sequences back to back (dense layout), exception list for sequences with
+// bytes outside ACGT.  Reads that were packed at the source are appended with shifts only; ASCII inputs (allele
+// targets = flank + allele + flank, src/allele.rs:406-426, or reads of ASCII loaders) are packed as they are added.
+struct Batch {
+    std::vector<uint32_t> words; // (n_bases + 15) / 16 words while building; finish() adds the ABI's two padding words
+    uint64_t n_bases = 0;
+    std::vector<uint32_t> len, pp, pt, exc_seq;
+    std::string exc_bytes;
+    bool finished = false;
+
+    void append_bits(const uint32_t *src, size_t n) { // n bases, unused high bits of the last source word zero
+        if (!n) return;
+        const unsigned sh = (unsigned)(n_bases & 15) * 2;
+        const size_t nw = (n + 15) / 16;
+        if (sh == 0) {
+            words.insert(words.end(), src, src + nw);
+        } else {
+            for (size_t i = 0; i < nw; ++i) {
+                words.back() |= src[i] << sh;
+                words.push_back(src[i] >> (32 - sh));
+            }
+        }
+        n_bases += n;
+        words.resize((size_t)((n_bases + 15) / 16));
+    }
+    uint32_t seq(const PackedBases &p) {
+        append_bits(p.w.data(), p.len);
+        if (!p.raw.empty()) exc_seq.push_back((uint32_t)len.size()), exc_bytes += p.raw;
+        len.push_back(p.len);
         return (uint32_t)len.size() - 1;
     }
+    uint32_t seq(const std::string &s) { // ASCII in: packed straight onto the stream
+        bool odd = false;
+        words.resize((size_t)((n_bases + s.size() + 15) / 16), 0u);
+        uint64_t x = n_bases;
+        for (const char ch : s) {
+            const unsigned char c = (unsigned char)ch;
+            odd |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+            words[(size_t)(x >> 4)] |= (uint32_t)((c >> 1) & 3u) << (2 * (x & 15));
+            ++x;
+        }
+        n_bases = x;
+        if (odd) exc_seq.push_back((uint32_t)len.size()), exc_bytes += s;
+        len.push_back((uint32_t)s.size());
+        return (uint32_t)len.size() - 1;
+    }
+    uint32_t seq(const TrgtRead &r) { return r.packed.empty() ? seq(r.bases) : seq(r.packed); }
     uint32_t pair(uint32_t p, uint32_t t) {
         pp.push_back(p), pt.push_back(t);
         return (uint32_t)pp.size() - 1;
+    }
+    void append(const Batch &o) { // o's sequences after this batch's (pairs are rebased by the caller)
+        const uint32_t base = (uint32_t)len.size();
+        append_bits(o.words.data(), (size_t)o.n_bases);
+        len.insert(len.end(), o.len.begin(), o.len.end());
+        for (uint32_t e : o.exc_seq) exc_seq.push_back(e + base);
+        exc_bytes += o.exc_bytes;
+    }
+    tdb_packed_seqs view() { // the ABI struct over this batch (valid until the batch changes)
+        if (!finished) words.resize((size_t)tdb_packed_words((size_t)n_bases), 0u), finished = true;
+        tdb_packed_seqs v;
+        v.packed = words.data(), v.n_bases = (size_t)n_bases, v.seq_off = nullptr, v.seq_len = len.data(), v.n_seqs = len.size();
+        v.exc_seq = exc_seq.empty() ? nullptr : exc_seq.data();
+        v.exc_bytes = exc_seq.empty() ? nullptr : (const uint8_t *)exc_bytes.data(), v.n_exc = exc_seq.size();
+        return v;
     }
 };
 
@@ -262,16 +392,15 @@ inline void parallel_ranges(size_t n, size_t min_per_shard, F fn) {
 inline Batch merge_shards(std::vector<Batch> &sb, std::vector<tdb_trio_locus> &tl, std::vector<std::pair<uint32_t, uint32_t>> &own) {
     if (sb.size() == 1) return std::move(sb[0]);
     Batch b;
-    size_t bytes = 0, seqs = 0, pairs = 0;
-    for (const Batch &x : sb) bytes += x.blob.size(), seqs += x.len.size(), pairs += x.pp.size();
-    b.blob.reserve(bytes), b.len.reserve(seqs), b.pp.resize(pairs), b.pt.resize(pairs);
+    size_t bases = 0, seqs = 0, pairs = 0;
+    for (const Batch &x : sb) bases += (size_t)x.n_bases, seqs += x.len.size(), pairs += x.pp.size();
+    b.words.reserve(bases / 16 + 4), b.len.reserve(seqs), b.pp.resize(pairs), b.pt.resize(pairs);
     std::vector<uint32_t> seq_base(sb.size()), pair_base(sb.size());
     size_t at_seq = 0, at_pair = 0;
     for (size_t t = 0; t < sb.size(); ++t) {
         seq_base[t] = (uint32_t)at_seq, pair_base[t] = (uint32_t)at_pair;
         at_seq += sb[t].len.size(), at_pair += sb[t].pp.size();
-        b.blob += sb[t].blob;
-        b.len.insert(b.len.end(), sb[t].len.begin(), sb[t].len.end());
+        b.append(sb[t]);
     }
     const size_t n = tl.size(), T = sb.size();
     parallel_ranges(T, 1, [&](size_t, size_t t0, size_t t1) {
@@ -348,15 +477,15 @@ inline std::vector<std::optional<AlleleSet>> load_alleles(WFAligner &aligner, st
             std::vector<uint32_t> ids;
             for (const std::string &a : s->allele_seqs) ids.push_back(b.seq(a));
             for (const TrgtRead &r : s->reads) {
-                const uint32_t ri = b.seq(r.bases);
+                const uint32_t ri = b.seq(r);
                 for (uint32_t ai : ids) b.pair(ri, ai);
             }
         }
         if (!b.pp.empty()) {
             scores.resize(b.pp.size()), status.resize(b.pp.size());
             aligner.set_clip_len(params.clip_len);
-            aligner.check(tdb_align_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), nullptr, b.len.data(),
-                                          b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), scores.data(), status.data()));
+            const tdb_packed_seqs ps = b.view();
+            aligner.check(tdb_align_batch_packed(aligner.ctx(), &ps, b.pp.data(), b.pt.data(), b.pp.size(), scores.data(), status.data()));
         }
     }
     out.resize(samples.size());
@@ -447,7 +576,7 @@ inline std::pair<uint32_t, uint32_t> add_lists(Batch &b, tdb_trio_locus &loc, in
         for (uint32_t ri : *lists[j]) b.pair(ri, tgt);
     }
     loc.list_off[c][4] = (uint32_t)b.pp.size();
-    for (const auto &ra : ca.read_aligns) b.pair(b.seq(ra.first.bases), tgt);
+    for (const auto &ra : ca.read_aligns) b.pair(b.seq(ra.first), tgt);
     loc.list_off[c][5] = (uint32_t)b.pp.size();
     return {loc.list_off[c][4], loc.list_off[c][5]};
 }
@@ -562,9 +691,9 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
             for (const auto *set : {&*sets[todo[li]], &*sets[n + todo[li]], &*sets[2 * n + todo[li]]})
                 for (const Allele &a : set->alleles) {
                     bytes += a.seq.size(), seqs += 1 + a.read_aligns.size();
-                    for (const auto &ra : a.read_aligns) bytes += ra.first.bases.size();
+                    for (const auto &ra : a.read_aligns) bytes += ra.first.n_bases();
                 }
-        b.blob.reserve(bytes), b.len.reserve(seqs), b.pp.reserve(2 * seqs), b.pt.reserve(2 * seqs);
+        b.words.reserve(bytes / 16 + 4), b.len.reserve(seqs), b.pp.reserve(2 * seqs), b.pt.reserve(2 * seqs);
         for (size_t li = lo; li < hi; ++li) {
             const size_t i = todo[li];
             const AlleleSet &f = *sets[i], &m = *sets[n + i], &c = *sets[2 * n + i];
@@ -573,9 +702,9 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
             loc.n_child = (int)c.alleles.size(), loc.n_mother = (int)m.alleles.size(), loc.n_father = (int)f.alleles.size();
             std::vector<std::vector<uint32_t>> mr(m.alleles.size()), fr(f.alleles.size());
             for (size_t a = 0; a < m.alleles.size(); ++a)
-                for (const auto &ra : m.alleles[a].read_aligns) mr[a].push_back(b.seq(ra.first.bases));
+                for (const auto &ra : m.alleles[a].read_aligns) mr[a].push_back(b.seq(ra.first));
             for (size_t a = 0; a < f.alleles.size(); ++a)
-                for (const auto &ra : f.alleles[a].read_aligns) fr[a].push_back(b.seq(ra.first.bases));
+                for (const auto &ra : f.alleles[a].read_aligns) fr[a].push_back(b.seq(ra.first));
             for (int a = 0; a < 2; ++a) {
                 loc.child_len[a] = a < loc.n_child ? (int)c.alleles[a].seq.size() : 0;
                 loc.mother_len[a] = a < loc.n_mother ? (int)m.alleles[a].seq.size() : 0;
@@ -590,11 +719,11 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
     std::vector<uint8_t> mask(b.pp.size() + 1);
     if (!todo.empty()) {
         aligner.set_clip_len(params.clip_len);
-        aligner.check(tdb_trio_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), nullptr, b.len.data(),
-                                     b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
-                                     params.parent_quantile, out.data(), nullptr, mask.data()));
+        const tdb_packed_seqs ps = b.view();
+        aligner.check(tdb_trio_batch_packed(aligner.ctx(), &ps, b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
+                                            params.parent_quantile, out.data(), nullptr, mask.data()));
     }
-    pt.lap("tdb_trio_batch");
+    pt.lap("tdb_trio_batch_packed");
     std::vector<std::vector<AlleleResult>> result(n);
     detail::parallel_ranges(n, 256, [&](size_t, size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) result[i] = {templ[i]};
@@ -723,7 +852,7 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
             loc.n_child = (int)a.alleles.size(), loc.n_mother = (int)sb.alleles.size(), loc.n_father = 0;
             std::vector<std::vector<uint32_t>> br(sb.alleles.size()), none;
             for (size_t x = 0; x < sb.alleles.size(); ++x)
-                for (const auto &ra : sb.alleles[x].read_aligns) br[x].push_back(b.seq(ra.first.bases));
+                for (const auto &ra : sb.alleles[x].read_aligns) br[x].push_back(b.seq(ra.first));
             for (int x = 0; x < 2; ++x) {
                 loc.child_len[x] = x < loc.n_child ? (int)a.alleles[x].seq.size() : 0;
                 loc.mother_len[x] = x < loc.n_mother ? (int)sb.alleles[x].seq.size() : 0;
@@ -736,9 +865,9 @@ inline std::vector<std::vector<AlleleResult>> process_alleles(WFAligner &aligner
     std::vector<uint8_t> mask(b.pp.size() + 1);
     if (!todo.empty()) {
         aligner.set_clip_len(params.clip_len);
-        aligner.check(tdb_duo_batch(aligner.ctx(), (const uint8_t *)b.blob.data(), b.blob.size(), nullptr, b.len.data(),
-                                    b.len.size(), b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
-                                    params.parent_quantile, out.data(), nullptr, mask.data()));
+        const tdb_packed_seqs ps = b.view();
+        aligner.check(tdb_duo_batch_packed(aligner.ctx(), &ps, b.pp.data(), b.pt.data(), b.pp.size(), tl.data(), tl.size(),
+                                           params.parent_quantile, out.data(), nullptr, mask.data()));
     }
     std::vector<std::vector<AlleleResult>> result(n);
     detail::parallel_ranges(n, 256, [&](size_t, size_t lo, size_t hi) {
@@ -795,6 +924,112 @@ inline std::string row_tsv(const AlleleResult &r) {
 }
 
 } // namespace duo
+
+// ---- several GPUs of one box ------------------------------------------------------------------------------
+// The reference treats the one locus stream as the unit of parallelism (src/commands/shared.rs:107-146: rayon
+// par_bridge at :138, one thread-local aligner per worker, :136-145).  Here: one WFAligner (= one tdb_ctx, one GPU)
+// and one host thread per GPU; the locus list is cut into contiguous ranges balanced on the alignment work proxy
+// sum over pairs of (n + m), every range runs the whole per-locus pipeline on its own GPU, and the
+// rows are concatenated in locus (BED) order -- the order the reference writes with -@1.  No collective: loci are
+// independent.  n_gpus may exceed the visible devices (contexts then share devices round-robin), which keeps the
+// sharding and merging testable on a one-GPU box.
+class MultiGpu {
+  public:
+    explicit MultiGpu(int n_gpus = 0) {
+        const int visible = tdb_device_count();
+        if (visible <= 0) throw Error(TDB_E_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+        const int n = n_gpus > 0 ? n_gpus : visible;
+        for (int i = 0; i < n; ++i) aligners_.emplace_back(i % visible);
+        const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+        for (auto &a : aligners_) a.check(tdb_set_host_threads(a.ctx(), (int32_t)std::max(1u, hc / (unsigned)n)));
+    }
+    size_t size() const { return aligners_.size(); }
+
+    // contiguous ranges whose weight sums are as equal as the prefix sums allow: parts + 1 boundaries
+    static std::vector<size_t> balanced_bounds(const std::vector<uint64_t> &w, size_t parts) {
+        const size_t n = w.size();
+        std::vector<uint64_t> pre(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) pre[i + 1] = pre[i] + w[i];
+        std::vector<size_t> b(1, 0);
+        for (size_t r = 1; r < parts; ++r) {
+            const long double target = (long double)pre[n] * r / parts;
+            size_t i = (size_t)(std::lower_bound(pre.begin(), pre.end(), (uint64_t)target) - pre.begin());
+            if (i > 0 && std::fabs((long double)pre[i - 1] - target) <= std::fabs((long double)pre[std::min(i, n)] - target)) --i;
+            b.push_back(std::min(std::max(i, b.back()), n));
+        }
+        b.push_back(n);
+        return b;
+    }
+    // sum over the locus' pairs of (read length + target length), from the inputs (before any alignment)
+    static uint64_t locus_weight(const std::optional<SampleInput> &parent1, const std::optional<SampleInput> &parent2,
+                                 const std::optional<SampleInput> &child) {
+        if (!child || !parent1) return 1;
+        uint64_t reads = 0, bases = 0, own_reads = child->reads.size(), own_bases = 0, tgt = 0;
+        for (const auto *p : {&parent1, &parent2})
+            if (*p)
+                for (const TrgtRead &r : (**p).reads) ++reads, bases += r.n_bases();
+        for (const TrgtRead &r : child->reads) own_bases += r.n_bases();
+        for (const std::string &a : child->allele_seqs) tgt += a.size();
+        const uint64_t n_t = std::max<uint64_t>(1, child->allele_seqs.size());
+        return 1 + n_t * bases + reads * tgt + own_bases + own_reads * (tgt / n_t);
+    }
+
+    std::vector<std::vector<AlleleResult>> trio_process_alleles(const std::vector<Locus> &loci,
+                                                                std::vector<std::optional<SampleInput>> father,
+                                                                std::vector<std::optional<SampleInput>> mother,
+                                                                std::vector<std::optional<SampleInput>> child, const Params &params) {
+        std::vector<uint64_t> w(loci.size());
+        for (size_t i = 0; i < loci.size(); ++i) w[i] = locus_weight(mother[i], father[i], child[i]);
+        return run(loci, w, [&](WFAligner &a, size_t lo, size_t hi) {
+            return trio::process_alleles(a, slice(loci, lo, hi), take(father, lo, hi), take(mother, lo, hi), take(child, lo, hi), params);
+        });
+    }
+    std::vector<std::vector<AlleleResult>> duo_process_alleles(const std::vector<Locus> &loci,
+                                                               std::vector<std::optional<SampleInput>> sample_a,
+                                                               std::vector<std::optional<SampleInput>> sample_b, const Params &params) {
+        std::vector<uint64_t> w(loci.size());
+        for (size_t i = 0; i < loci.size(); ++i) w[i] = locus_weight(sample_b[i], std::nullopt, sample_a[i]);
+        return run(loci, w, [&](WFAligner &a, size_t lo, size_t hi) {
+            return duo::process_alleles(a, slice(loci, lo, hi), take(sample_a, lo, hi), take(sample_b, lo, hi), params);
+        });
+    }
+    const std::vector<size_t> &last_bounds() const { return bounds_; }
+
+  private:
+    template <class T>
+    static std::vector<T> slice(const std::vector<T> &v, size_t lo, size_t hi) { return std::vector<T>(v.begin() + (long)lo, v.begin() + (long)hi); }
+    template <class T>
+    static std::vector<T> take(std::vector<T> &v, size_t lo, size_t hi) { // moves the range out (the reads are large)
+        return std::vector<T>(std::make_move_iterator(v.begin() + (long)lo), std::make_move_iterator(v.begin() + (long)hi));
+    }
+    template <class F>
+    std::vector<std::vector<AlleleResult>> run(const std::vector<Locus> &loci, const std::vector<uint64_t> &w, F fn) {
+        const size_t G = aligners_.size();
+        bounds_ = balanced_bounds(w, G);
+        std::vector<std::vector<std::vector<AlleleResult>>> part(G);
+        std::vector<std::thread> th;
+        std::exception_ptr err;
+        std::mutex mu;
+        for (size_t g = 0; g < G; ++g)
+            th.emplace_back([&, g]() {
+                try {
+                    if (bounds_[g + 1] > bounds_[g]) part[g] = fn(aligners_[g], bounds_[g], bounds_[g + 1]);
+                } catch (...) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!err) err = std::current_exception();
+                }
+            });
+        for (auto &t : th) t.join();
+        if (err) std::rethrow_exception(err);
+        std::vector<std::vector<AlleleResult>> rows; // BED order: the ranges are contiguous and ascending
+        rows.reserve(loci.size());
+        for (auto &p : part)
+            for (auto &r : p) rows.push_back(std::move(r));
+        return rows;
+    }
+    std::vector<WFAligner> aligners_;
+    std::vector<size_t> bounds_;
+};
 
 // The writer thread of src/commands/shared.rs:161-195 with -@1 ordering: TSV text and the read-id side file.
 template <class RowFn>

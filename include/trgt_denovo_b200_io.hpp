@@ -419,7 +419,6 @@ class SampleFiles {
             in.read_exact(b4, 4, "reference length");
         }
         std::vector<unsigned char> rec;
-        static const char code[] = "=ACMGRSVTWYHKDBN";
         for (;;) {
             if (in.read(b4, 4) != 4) break;
             const uint32_t bs = le32(b4);
@@ -433,21 +432,8 @@ class SampleFiles {
             TrgtRead r;
             r.name.assign(reinterpret_cast<const char *>(p + off), l_name ? l_name - 1 : 0);
             off += l_name + 4ull * n_cigar;
-            r.bases.resize(l_seq);
-            { // two bases per byte through a 256-entry table of character pairs
-                static const auto pairs = [] {
-                    std::vector<uint16_t> t(256);
-                    for (int b = 0; b < 256; ++b) t[(size_t)b] = (uint16_t)((unsigned char)code[b >> 4] | (unsigned char)code[b & 15] << 8);
-                    return t;
-                }();
-                char *dst = &r.bases[0];
-                uint32_t i = 0;
-                for (; i + 2 <= l_seq; i += 2) {
-                    const uint16_t two = pairs[p[off + i / 2]];
-                    dst[i] = (char)(two & 0xff), dst[i + 1] = (char)(two >> 8);
-                }
-                if (i < l_seq) dst[i] = code[p[off + i / 2] >> 4];
-            }
+            // packed at the source: BAM's 4-bit bases go straight to 2-bit codes, ASCII (src/read.rs:57) is never written
+            r.packed = PackedBases::from_bam(p + off, l_seq);
             off += (l_seq + 1) / 2 + l_seq;
             std::string tr;
             bool have_tr = false;

@@ -57,7 +57,7 @@ int main(int argc, char **argv) {
                         o << "A\t" << in->allele_seqs[k] << "\t" << in->motif_counts[k] << "\t" << in->allele_lengths[k] << "\t"
                           << in->genotype_indices[k] << "\n";
                     for (const TrgtRead &r : in->reads)
-                        o << "R\t" << r.name << "\t" << r.bases << "\t" << (r.classification ? *r.classification : -1) << "\t"
+                        o << "R\t" << r.name << "\t" << r.bases_ascii() << "\t" << (r.classification ? *r.classification : -1) << "\t"
                           << (r.haplotype ? *r.haplotype : 0) << "\n";
                 }
             }

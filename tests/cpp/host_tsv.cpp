@@ -2,8 +2,15 @@
 // src/trio/allele.rs / src/duo/allele.rs on a family description and writes the TSV + read-id file, or
 // aligns one pair through the WFAligner shim.  Built and driven by tests/test_cpp_host.py.
 //
-//   host_tsv trio|duo <family.txt> <out.tsv> <out_read_ids.txt>
+//   host_tsv trio|duo <family.txt> <out.tsv> <out_read_ids.txt> [n_gpus]
+//                                                 n_gpus > 0: through tdbh::MultiGpu (one ctx + host thread per GPU,
+//                                                 loci in balanced contiguous ranges, rows merged in locus order)
 //   host_tsv align <pattern> <text> <clip>        -> "status score cigar clipped clipped_cigar"
+//   host_tsv pack <in.txt> <out.txt>              packing at the source, no device needed: lines "A ascii" (ASCII
+//                                                 appended to the batch), "P ascii" (PackedBases::from_ascii),
+//                                                 "N hex l_seq" (PackedBases::from_bam: BAM 4-bit SEQ bytes),
+//                                                 "B" (start a new shard; shards are merged with Batch::append)
+//                                                 -> n_bases / words / lengths / exception indices / exception bytes
 //
 // family.txt (tab separated):
 //   P clip_len parent_quantile partition_by_alignment quick_kind(-|AL|MC) quick_tol(-|float)
@@ -36,6 +43,38 @@ int main(int argc, char **argv) {
             const size_t clip = (size_t)std::stoul(argv[4]);
             std::cout << (int)st << " " << a.score() << " " << a.cigar() << " " << a.cigar_score_clipped(clip) << " "
                       << a.cigar(clip) << "\n";
+            return 0;
+        }
+        if (argc >= 4 && std::string(argv[1]) == "pack") {
+            std::ifstream in(argv[2]);
+            std::vector<detail::Batch> shards(1);
+            std::string line;
+            while (std::getline(in, line)) {
+                const auto f = split(line, '\t');
+                if (f.empty()) continue;
+                detail::Batch &b = shards.back();
+                if (f[0] == "B") shards.emplace_back();
+                else if (f[0] == "A") b.seq(f.size() > 1 ? f[1] : std::string());
+                else if (f[0] == "P") b.seq(PackedBases::from_ascii(f.size() > 1 ? f[1] : std::string()));
+                else if (f[0] == "N") {
+                    std::vector<uint8_t> raw;
+                    for (size_t i = 0; i + 1 < f[1].size(); i += 2) raw.push_back((uint8_t)std::stoul(f[1].substr(i, 2), nullptr, 16));
+                    const PackedBases pb = PackedBases::from_bam(raw.data(), std::stoul(f[2]));
+                    if (PackedBases::from_ascii(pb.ascii()).w != pb.w) throw Error(TDB_E_INVALID, "from_bam / ascii round trip");
+                    b.seq(pb);
+                }
+            }
+            detail::Batch all;
+            for (const auto &sh : shards) all.append(sh);
+            const tdb_packed_seqs v = all.view();
+            std::ofstream o(argv[3]);
+            o << v.n_bases << "\n";
+            for (size_t i = 0; i < tdb_packed_words(v.n_bases); ++i) o << std::hex << v.packed[i] << (i + 1 < tdb_packed_words(v.n_bases) ? " " : "");
+            o << std::dec << "\n";
+            for (size_t i = 0; i < v.n_seqs; ++i) o << v.seq_len[i] << " ";
+            o << "\n";
+            for (size_t i = 0; i < v.n_exc; ++i) o << v.exc_seq[i] << " ";
+            o << "\n" << all.exc_bytes << "\n";
             return 0;
         }
         if (argc < 5) {
@@ -78,14 +117,31 @@ int main(int argc, char **argv) {
                 (*cur)->allele_lengths.push_back(f[3]), (*cur)->genotype_indices.push_back(std::stoul(f[4]));
             } else if (f[0] == "R") {
                 TrgtRead r;
-                r.name = f[1], r.bases = f[2];
+                r.name = f[1];
+                // every other read arrives packed at the source, the rest as ASCII: both forms go through one batch
+                if ((*cur)->reads.size() % 2) r.packed = PackedBases::from_ascii(f[2]);
+                else r.bases = f[2];
                 if (f[3] != "-1") r.classification = std::stoi(f[3]);
                 if (f[4] != "0") r.haplotype = std::stoi(f[4]);
                 (*cur)->reads.push_back(r);
             }
         }
-        WFAligner aligner = create_aligner_with_scoring();
         std::string tsv, ids;
+        const int n_gpus = argc >= 6 ? std::stoi(argv[5]) : 0;
+        if (n_gpus > 0) {
+            MultiGpu mg(n_gpus);
+            const auto rows = is_duo ? mg.duo_process_alleles(loci, fam[0], fam[1], params)
+                                     : mg.trio_process_alleles(loci, fam[0], fam[1], fam[2], params);
+            tsv = is_duo ? write_tsv(rows, duo::columns(), duo::row_tsv) : write_tsv(rows, trio::columns(), trio::row_tsv);
+            ids = write_read_ids(rows);
+            std::ofstream(argv[3]) << tsv;
+            std::ofstream(argv[4]) << ids;
+            std::cout << "bounds";
+            for (size_t b : mg.last_bounds()) std::cout << " " << b;
+            std::cout << "\n";
+            return 0;
+        }
+        WFAligner aligner = create_aligner_with_scoring();
         if (is_duo) {
             const auto rows = duo::process_alleles(aligner, loci, fam[0], fam[1], params);
             tsv = write_tsv(rows, duo::columns(), duo::row_tsv), ids = write_read_ids(rows);

@@ -33,6 +33,47 @@ def test_cpp_host_builds_and_fails_loudly_without_device(exe):
     assert r.returncode == 42 and "no CUDA device" in r.stderr
 
 
+def test_cpp_packing_at_the_source_equals_host_pack(exe, tmp_path):
+    """tdbh::PackedBases (from ASCII, and straight from BAM 4-bit SEQ bytes) + detail::Batch (shift-append of
+    packed reads, ASCII targets packed in place, shards merged) produce the stream, lengths and exception list of
+    tdb_packed_seqs -- word for word what tdb_host_pack makes of the same ASCII blob.  No device needed."""
+    import ctypes as C
+    import numpy as np
+    import trgt_denovo_b200 as tdb
+    rng = random.Random(7)
+    code = "=ACMGRSVTWYHKDBN"
+    seqs, lines = [], []
+    for i in range(400):
+        n = rng.choice([0, 1, 2, 15, 16, 17, 31, 33, rng.randint(1, 400)])
+        alpha = "ACGT" if rng.random() < 0.9 else "ACGTNRYacgt"
+        kind = rng.choice("APN")
+        if kind == "N":
+            alpha = "ACGT" if rng.random() < 0.9 else "ACGTNRYKM="  # what BAM can hold
+        s = "".join(rng.choice(alpha) for _ in range(n))
+        seqs.append(s)
+        if kind == "N":
+            nib = [code.index(c) for c in s] + ([0] if n % 2 else [])
+            hexs = "".join(f"{(nib[k] << 4) | nib[k + 1]:02x}" for k in range(0, len(nib), 2))
+            lines.append(f"N\t{hexs}\t{n}")
+        else:
+            lines.append(f"{kind}\t{s}")
+        if i % 97 == 96:
+            lines.append("B")
+    (tmp_path / "in.txt").write_text("\n".join(lines) + "\n")
+    subprocess.run([exe, "pack", str(tmp_path / "in.txt"), str(tmp_path / "out.txt")], check=True)
+    out = (tmp_path / "out.txt").read_text().split("\n")
+    blob = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+    ln = np.array([len(s) for s in seqs], dtype=np.uint32)
+    pk = tdb.pack_sequences(blob, None, ln)
+    assert int(out[0]) == blob.size
+    words = np.array([int(x, 16) for x in out[1].split()], dtype=np.uint32)
+    nw = (blob.size + 15) // 16
+    assert len(words) == len(pk.packed) and (words[:nw] == pk.packed[:nw]).all() and (words[nw:] == 0).all()
+    assert [int(x) for x in out[2].split()] == list(ln)
+    assert [int(x) for x in out[3].split()] == list(pk.exc_seq) and len(pk.exc_seq) > 5
+    assert out[4].encode() == pk.exc_bytes.tobytes()
+
+
 @pytest.mark.gpu
 def test_cpp_wfaligner_known_answers(exe, golden_dir):
     for x in json.load(open(os.path.join(golden_dir, "aligner_vectors.json"))):
@@ -100,3 +141,52 @@ def test_cpp_process_alleles_tsv_identical(exe, tmp_path, mode, case):
     subprocess.run([exe, mode, fam, out_tsv, out_ids], check=True)
     assert open(out_tsv).read() == wtsv
     assert open(out_ids).read() == wids
+
+
+def _multi_gpu_case(exe, tmp_path, mode, n_gpus):
+    """tdbh::MultiGpu: one ctx + host thread per GPU, loci in balanced contiguous ranges, rows merged in locus order
+    -> the same TSV and read-id text as one GPU (and as the CPU restatement)."""
+    from importlib import import_module
+    import trgt_denovo_b200  # noqa: F401
+    from oracle import tdo, tdo_rows
+    from tests.util import make_family_loci
+    R = import_module("trgt_denovo_b200.rows")
+    params = R.Params(partition_by_alignment=(mode == "duo"))
+    rng = random.Random(900 + n_gpus)
+    loci, f, m, c = make_family_loci(rng, 150, duo=(mode == "duo"), denovo_rate=0.3)
+    fam = str(tmp_path / "family.txt")
+    aligner = tdo.Aligner()
+    if mode == "trio":
+        _write_family(fam, params, loci, (f, m, c), "FMC")
+        want = [tdo_rows.process_alleles_trio(loci[i], f[i], m[i], c[i], params, aligner) for i in range(len(loci))]
+        wtsv, wids = tdo_rows.write_outputs(want, R.TRIO_COLUMNS)
+    else:
+        _write_family(fam, params, loci, (c, m), "AB")
+        want = [tdo_rows.process_alleles_duo(loci[i], c[i], m[i], params, aligner) for i in range(len(loci))]
+        wtsv, wids = tdo_rows.write_outputs(want, R.DUO_COLUMNS)
+    one_tsv, one_ids = str(tmp_path / "one.tsv"), str(tmp_path / "one_ids.txt")
+    subprocess.run([exe, mode, fam, one_tsv, one_ids], check=True)
+    out_tsv, out_ids = str(tmp_path / "multi.tsv"), str(tmp_path / "multi_ids.txt")
+    r = subprocess.run([exe, mode, fam, out_tsv, out_ids, str(n_gpus)], check=True, capture_output=True, text=True)
+    bounds = [int(x) for x in r.stdout.split()[1:]]
+    assert len(bounds) == n_gpus + 1 and bounds[0] == 0 and bounds[-1] == len(loci)
+    assert all(b > a for a, b in zip(bounds, bounds[1:])), bounds  # every GPU got a range
+    assert open(out_tsv).read() == open(one_tsv).read() == wtsv
+    assert open(out_ids).read() == open(one_ids).read() == wids and len(wids) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["trio", "duo"])
+def test_cpp_multi_gpu_driver_shards_and_merges(exe, tmp_path, mode):
+    """Three contexts (sharing the visible devices round-robin when there are fewer): the sharding and the merge in
+    locus order, on any box."""
+    _multi_gpu_case(exe, tmp_path, mode, 3)
+
+
+@pytest.mark.gpu
+def test_cpp_multi_gpu_two_devices(exe, tmp_path):
+    """Two real GPUs (gpurun --gpus 2): the merged TSV equals the one-GPU TSV."""
+    import trgt_denovo_b200 as tdb
+    if tdb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _multi_gpu_case(exe, tmp_path, "trio", 2)

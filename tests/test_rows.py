@@ -135,3 +135,38 @@ def test_read_ids_through_the_sparse_mask_path(monkeypatch):
     assert R.format_tsv(got, R.TRIO_COLUMNS) == wtsv
     assert R.format_read_ids(got) == wids and len(wids) > 0
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_gpus", [2, 3])
+def test_multi_gpu_rows_equal_one_gpu(n_gpus):
+    """shard.MultiGpu (one ctx + host thread per GPU, balanced contiguous locus ranges, rows merged in locus order):
+    TSV and read-id text identical to one context and to the CPU restatement.  With fewer visible devices than
+    contexts they share devices, so the sharding / merging is checked on any box; with gpurun --gpus 2 the two
+    contexts sit on two GPUs."""
+    import __graft_entry__ as entry
+    entry.build()
+    from importlib import import_module
+    import trgt_denovo_b200 as tdb
+    R = _rows_mod()
+    SH = import_module("trgt_denovo_b200.shard")
+    params = R.Params()
+    rng = random.Random(400 + n_gpus)
+    loci, f, m, c = make_family_loci(rng, 200, denovo_rate=0.3)
+    mg = SH.MultiGpu(n_gpus)
+    got = mg.process_trio_batch(loci, f, m, c, params)
+    assert len(mg.bounds) == n_gpus + 1 and all(b > a for a, b in zip(mg.bounds, mg.bounds[1:]))
+    if tdb.device_count() >= n_gpus:
+        assert sorted({x.device_id for x in mg.ctxs}) == list(range(n_gpus))
+    one = tdb.Context(device_id=0)
+    single = R.process_trio_batch(one, loci, f, m, c, params)
+    aligner = tdo.Aligner()
+    want = [tdo_rows.process_alleles_trio(loci[i], f[i], m[i], c[i], params, aligner) for i in range(len(loci))]
+    wtsv, wids = tdo_rows.write_outputs(want, R.TRIO_COLUMNS)
+    assert R.format_tsv(got, R.TRIO_COLUMNS) == R.format_tsv(single, R.TRIO_COLUMNS) == wtsv
+    assert R.format_read_ids(got) == R.format_read_ids(single) == wids and len(wids) > 0
+    got = mg.process_duo_batch(loci, c, m, params)
+    single = R.process_duo_batch(one, loci, c, m, params)
+    assert R.format_tsv(got, R.DUO_COLUMNS) == R.format_tsv(single, R.DUO_COLUMNS)
+    mg.close()
+    one.close()

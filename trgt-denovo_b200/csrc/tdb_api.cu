@@ -51,7 +51,7 @@ struct Ctrl {
     unsigned n_failed; // pairs the last tier could not finish
     unsigned pad0[1];
     unsigned long long exec[5][4]; // executed cells, ext16, columns, pairs finished; per tier ([4]: thread-per-pair tier)
-    unsigned long long algo[4];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self
+    unsigned long long algo[5];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self; failed pairs
     // ---- per chunk (one block per pipeline slot, zeroed before every chunk) ----
     struct Chunk {
         unsigned wc_quad, wc_warp, acount, wc_mini;
@@ -970,7 +970,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     if (!cigar_mode) {
         const unsigned blocks = (unsigned)std::min<size_t>(((size_t)n_pairs + 255) / 256, (size_t)ctx->sm_count * 16);
         k_scatter<<<blocks, 256, 0, s>>>((const uint32_t *)ctx->rep.p, n_pairs, b.score, b.status, b.penalty,
-                                         (const uint32_t *)p.work, ctrl->algo);
+                                         (const uint32_t *)p.work, ctrl->algo, &ctrl->n_failed);
         CK(cudaGetLastError());
         cn.kernel_launches += 1;
     }
@@ -994,9 +994,10 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         cn.cells = h.algo[0], cn.ext16 = h.algo[1], cn.columns = h.algo[2];
         cn.pairs_duplicate = n_pairs - h.algo[3];
         cn.pairs_closed_form = h.n_closed;
-        cn.pairs_identical = h.algo[3] >= aligned + h.n_closed ? h.algo[3] - aligned - h.n_closed : 0;
+        const uint64_t settled = aligned + h.n_closed + h.n_failed; // representatives that are not pattern == text
+        cn.pairs_identical = h.algo[3] >= settled ? h.algo[3] - settled : 0;
     }
-    cn.pairs_failed = h.n_failed;
+    cn.pairs_failed = cigar_mode ? h.n_failed : h.algo[4]; // duplicates of a failed content count too
     cn.ms_total_device = elapsed(ctx->ev[0], ctx->ev[1]);
     cn.ms_host_call = ms_since(t_call);
     if (staged) {

@@ -518,8 +518,10 @@ __global__ void __launch_bounds__(256) k_bucket(const uint8_t *__restrict__ key,
 __global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restrict__ rep, uint32_t n_pairs,
                                                  int32_t *__restrict__ score, int32_t *__restrict__ status,
                                                  int32_t *__restrict__ penalty, const uint32_t *__restrict__ work,
-                                                 unsigned long long *__restrict__ algo) {
-    unsigned long long c = 0, e = 0, t = 0, u = 0;
+                                                 unsigned long long *__restrict__ algo,
+                                                 const unsigned *__restrict__ n_failed_reps) {
+    unsigned long long c = 0, e = 0, t = 0, u = 0, f = 0;
+    const bool any_failed = *n_failed_reps != 0; // rare: only then are the failed pairs (duplicates included) counted
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pairs; j += gridDim.x * blockDim.x) {
         const uint32_t r = rep[j];
         if (r != j) {
@@ -529,15 +531,18 @@ __global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restrict__ re
         } else {
             ++u;
         }
+        if (any_failed && score[r] == TDB_SCORE_FAILED) ++f;
         if (work) c += work[3 * (size_t)r], e += work[3 * (size_t)r + 1], t += work[3 * (size_t)r + 2];
     }
     for (int o = 16; o; o >>= 1) {
         c += __shfl_xor_sync(TDB_FULL, c, o), e += __shfl_xor_sync(TDB_FULL, e, o);
         t += __shfl_xor_sync(TDB_FULL, t, o), u += __shfl_xor_sync(TDB_FULL, u, o);
+        f += __shfl_xor_sync(TDB_FULL, f, o);
     }
     if ((threadIdx.x & 31) == 0) {
         if (work) atomicAdd(algo + 0, c), atomicAdd(algo + 1, e), atomicAdd(algo + 2, t);
         atomicAdd(algo + 3, u);
+        if (f) atomicAdd(algo + 4, f);
     }
 }
 
