@@ -32,6 +32,7 @@
 #include <fstream>
 #include <memory>
 #include <thread>
+#include <tuple>
 #include <unordered_map>
 
 namespace tdbh {
@@ -215,6 +216,25 @@ struct LocusRec { // src/locus.rs:18-29 with the flanks the hot path concatenate
 };
 
 // src/locus.rs:88-140.  Throws IoError with the reference's messages.
+// src/locus.rs:249-260: "name=value"; anything without '=' is an error (the reference's test at :266-277)
+inline std::pair<std::string, std::string> decode_info_field(const std::string &enc) {
+    const size_t eq = enc.find('=');
+    if (eq == std::string::npos) throw IoError("Invalid entry: " + enc);
+    return {enc.substr(0, eq), enc.substr(eq + 1)};
+}
+
+// src/allele.rs:406-426: genotype indices sorted (phased 1|0 == 0|1), every allele = left flank + VCF allele + right
+// flank; a homozygous genotype gives two identical targets (the reference's tests at :529-580)
+inline std::pair<std::vector<std::string>, std::vector<size_t>> build_allele_seqs(const std::vector<std::string> &vcf_allele_seqs,
+                                                                                 std::vector<size_t> genotype_indices,
+                                                                                 const std::string &left_flank,
+                                                                                 const std::string &right_flank) {
+    std::sort(genotype_indices.begin(), genotype_indices.end());
+    std::vector<std::string> alleles;
+    for (size_t g : genotype_indices) alleles.push_back(left_flank + vcf_allele_seqs.at(g) + right_flank);
+    return {alleles, genotype_indices};
+}
+
 inline LocusRec parse_catalog_line(const Fasta &genome, const std::string &line, size_t flank_len) {
     const auto f = split_whitespace(line);
     if (f.size() != 4)
@@ -232,9 +252,7 @@ inline LocusRec parse_catalog_line(const Fasta &genome, const std::string &line,
     bool have_id = false, have_motifs = false;
     std::vector<std::string> seen;
     for (const std::string &enc : split(f[3], ';')) {
-        const size_t eq = enc.find('=');
-        if (eq == std::string::npos) throw IoError("Invalid entry: " + enc);
-        const std::string name = enc.substr(0, eq), value = enc.substr(eq + 1);
+        const auto [name, value] = decode_info_field(enc);
         if (std::find(seen.begin(), seen.end(), name) != seen.end()) throw IoError("Duplicate field: " + name);
         seen.push_back(name);
         if (name == "ID") r.locus.id = value, have_id = true;
@@ -310,13 +328,12 @@ class SampleFiles {
         s.karyotype = karyotype;
         for (int g : rec.gt)
             if (g >= 0) s.genotype_indices.push_back((size_t)g);
-        std::sort(s.genotype_indices.begin(), s.genotype_indices.end()); // src/allele.rs:412
-        const size_t skip = is_trgt_v1 ? 1 : 0;
-        for (size_t g : s.genotype_indices) {
+        const size_t skip = is_trgt_v1 ? 1 : 0; // TRGT >= 1.0 alleles carry a padding base (src/allele.rs:386-390)
+        std::vector<std::string> vcf_alleles;
+        for (const std::string &a : rec.alleles) vcf_alleles.push_back(a.size() > skip ? a.substr(skip) : std::string());
+        for (size_t g : s.genotype_indices)
             if (g >= rec.alleles.size()) return fail("genotype index beyond the alleles of TRID=" + id);
-            const std::string &a = rec.alleles[g];
-            s.allele_seqs.push_back(l.left_flank + (a.size() > skip ? a.substr(skip) : std::string()) + l.right_flank);
-        }
+        std::tie(s.allele_seqs, s.genotype_indices) = build_allele_seqs(vcf_alleles, s.genotype_indices, l.left_flank, l.right_flank);
         s.motif_counts = rec.mc, s.allele_lengths = rec.al;
         const auto r = reads_.find(id);
         if (r == reads_.end() || r->second.empty()) return fail("No reads found for locus: " + id);

@@ -9,7 +9,12 @@ Reads the inline unit tests of
     /root/reference/src/aligner.rs      (tests at :764-1252)
     /root/reference/src/trio/denovo.rs  (tests at :364-612)
     /root/reference/src/math.rs         (tests at :157-201)
-and writes tests/golden/aligner_vectors.json and tests/golden/reduction_vectors.json.
+    /root/reference/src/trio/allele.rs  (quick-mode tests at :351-416)
+    /root/reference/src/duo/allele.rs   (quick-mode tests at :248-364)
+    /root/reference/src/allele.rs       (build_allele_seqs tests at :523-580)
+    /root/reference/src/locus.rs        (decode_info_field tests at :262-277)
+and writes tests/golden/aligner_vectors.json, tests/golden/reduction_vectors.json and
+tests/golden/host_vectors.json.
 Only test *data* (input byte strings, asserted outputs) is extracted; no code is copied.
 """
 import json
@@ -121,6 +126,87 @@ def main():
                      dict(cite="src/math.rs:160-163", data=[], expect=None)]
     json.dump(red, open(os.path.join(HERE, "reduction_vectors.json"), "w"), indent=1)
     print("wrote", len(vec), "aligner vectors and", len(red), "reduction groups")
+    host = host_vectors()
+    json.dump(host, open(os.path.join(HERE, "host_vectors.json"), "w"), indent=1)
+    print("wrote", sum(len(v) for v in host.values()), "host-side vectors")
+
+
+def _vec_strs(s):
+    return re.findall(r'"([^"]*)"', s)
+
+
+def _quick_mode(s):
+    m = re.search(r"QuickMode::(AL|MC)\((None|Some\(([0-9.]+)\))\)", s)
+    return [m.group(1), None if m.group(2) == "None" else float(m.group(3))]
+
+
+def host_vectors():
+    """Quick-mode pre-filter, build_allele_seqs and decode_info_field: the reference's own assertions as data."""
+    out = {}
+    # ---- src/trio/allele.rs:351-416 test_check_minimal_cost_inheritance ----
+    b = fn_body(open(os.path.join(REF, "trio/allele.rs")).read(), "test_check_minimal_cost_inheritance")
+    sets = {}
+    for name, mc, al in re.findall(r"let (\w+) = create_allele_set\(vec!\[(.*?)\], vec!\[(.*?)\]\);", b, re.S):
+        sets[name] = [list(x) for x in zip(_vec_strs(mc), _vec_strs(al))]
+    cases = []
+    for neg, fn, args in re.findall(r"assert!\(\s*(!?)(check_field_equivalence|check_field_similarity)\((.*?)\)\s*\);", b, re.S):
+        parts = []
+        for a in re.split(r",\s*\n", args.strip()):
+            a = a.strip().rstrip(",")
+            if a.startswith("&QuickMode"):
+                continue
+            m = re.match(r"&create_allele_set\(vec!\[(.*?)\], vec!\[(.*?)\]\)", a, re.S)
+            parts.append([list(x) for x in zip(_vec_strs(m.group(1)), _vec_strs(m.group(2)))] if m else sets[a.lstrip("&")])
+        assert len(parts) == 3, args
+        cases.append(dict(cite="src/trio/allele.rs:351-416", fn=fn, quick_mode=_quick_mode(args), father=parts[0],
+                          mother=parts[1], child=parts[2], expect=(neg == "")))
+    assert len(cases) == 5 and [c["expect"] for c in cases] == [True, False, False, True, True]
+    out["trio_quick_mode"] = cases
+    # ---- src/duo/allele.rs:248-364 test_check_allele_field_equivalence ----
+    b = fn_body(open(os.path.join(REF, "duo/allele.rs")).read(), "test_check_allele_field_equivalence")
+    alleles = {}
+    for name, mc, al in re.findall(r'let (allele\d+) = Allele \{.*?motif_count: "(\d+)"\.to_string\(\),\s*allele_length: "(\d+)"\.to_string\(\)', b, re.S):
+        alleles[name] = [mc, al]
+    sets = {}
+    for name, members in re.findall(r"let (allele_set_\w) = AlleleSet \{\s*alleles: vec!\[(.*?)\],", b, re.S):
+        sets[name] = [alleles[re.match(r"(allele\d+)", m.strip()).group(1)] for m in members.split(",") if m.strip()]
+    cases = []
+    for neg, fn, a, bb, qm in re.findall(r"assert!\(\s*(!?)(check_allele_field_equivalence|check_field_similarity)\(\s*&(\w+),\s*&(\w+),\s*&(QuickMode::.*?\))\s*\)\s*\);", b, re.S):
+        cases.append(dict(cite="src/duo/allele.rs:248-364", fn=fn, quick_mode=_quick_mode(qm), a=sets[a], b=sets[bb],
+                          expect=(neg == "")))
+    assert len(cases) == 8 and [c["expect"] for c in cases] == [True, True, False, False, False, False, False, True]
+    out["duo_quick_mode"] = cases
+    # ---- src/allele.rs:523-580 build_allele_seqs ----
+    a = open(os.path.join(REF, "allele.rs")).read()
+    cases = []
+    for test in ("test_build_allele_seqs_sorts_indices", "test_build_allele_seqs_with_homozygous",
+                 "test_build_allele_seqs_with_three_alleles"):
+        b = fn_body(a, test)
+        vcf = re.findall(r'b"(\w+)"\.to_vec\(\)', re.search(r"let vcf_allele_seqs = vec!\[(.*?)\];", b).group(1))
+        lf = re.search(r'let left_flank = b"(\w+)";', b).group(1)
+        rf = re.search(r'let right_flank = b"(\w+)";', b).group(1)
+        for gi in re.findall(r"build_allele_seqs\(&vcf_allele_seqs, vec!\[([\d, ]+)\], left_flank, right_flank\)", b):
+            idx = sorted(int(x) for x in gi.split(","))
+            cases.append(dict(cite="src/allele.rs:523-580 " + test, vcf_allele_seqs=vcf, genotype_indices=[int(x) for x in gi.split(",")],
+                              left_flank=lf, right_flank=rf, expect_indices=idx,
+                              expect_alleles=[lf + vcf[i] + rf for i in idx]))
+    # the literal assertions of the reference, checked against what was just derived
+    b = fn_body(a, "test_build_allele_seqs_sorts_indices")
+    assert 'b"LFREFRF"' in b and 'b"LFALT1RF"' in b and "vec![0, 1]" in b
+    assert cases[0]["expect_alleles"] == ["LFREFRF", "LFALT1RF"] and cases[0]["expect_indices"] == [0, 1]
+    b = fn_body(a, "test_build_allele_seqs_with_homozygous")
+    assert "vec![1, 1]" in b and 'b"LFALT1RF"' in b and cases[2]["expect_alleles"] == ["LFALT1RF", "LFALT1RF"]
+    assert "vec![0, 2]" in fn_body(a, "test_build_allele_seqs_with_three_alleles") and cases[3]["expect_indices"] == [0, 2]
+    out["build_allele_seqs"] = cases
+    # ---- src/locus.rs:262-277 decode_info_field ----
+    l = open(os.path.join(REF, "locus.rs")).read()
+    b = fn_body(l, "can_decode_info_field")
+    enc = re.search(r'decode_info_field\("([^"]+)"\)', b).group(1)
+    name, value = re.findall(r'assert_eq!\("(\w+)", decoded\.\d\)', b)
+    bad = re.search(r'decode_info_field\("([^"]+)"\)', fn_body(l, "panic_invalid_decode_info_field")).group(1)
+    out["decode_info_field"] = [dict(cite="src/locus.rs:266-271", encoding=enc, expect=[name, value]),
+                                dict(cite="src/locus.rs:273-277", encoding=bad, expect=None)]
+    return out
 
 
 if __name__ == "__main__":

@@ -47,7 +47,7 @@ struct Ctrl {
     unsigned gcount;   // pairs queued for the global-scratch tier (listB)
     unsigned ccount;   // pairs the first global tier could not finish (listC)
     unsigned wc_g[2];  // work counters of the two global tiers
-    unsigned n_closed; // pairs resolved in closed form (k_pair_classify)
+    unsigned n_closed; // pairs resolved in closed form (k_dedup_window)
     unsigned n_failed; // pairs the last tier could not finish
     unsigned pad0[1];
     unsigned long long exec[5][4]; // executed cells, ext16, columns, pairs finished; per tier ([4]: thread-per-pair tier)
@@ -83,7 +83,7 @@ struct tdb_ctx {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf canon, skey_in, sval_out, seq_tab, pair_tab, list_a, list_m;
+        DevBuf skey_in, sval_out, list_a, list_m;
     } slot[2];
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
@@ -318,12 +318,6 @@ int ensure_pinned(tdb_ctx *ctx, void *&p, size_t &cap, size_t bytes) {
     return TDB_OK;
 }
 
-uint32_t table_mask(size_t n) {
-    size_t cap = 1024;
-    while (cap < n + n / 2) cap <<= 1; // load factor 0.33 .. 0.67
-    return (uint32_t)(cap - 1);
-}
-
 // Dense layout (seq_off == NULL at the ABI): sequence i starts where sequence i-1 ends, sequence 0 at byte 0.
 // The device derives the offsets with a prefix sum of the lengths; the host needs them only to find the owner
 // of a byte outside ACGT, and builds the table the first time such a byte turns up.
@@ -526,9 +520,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     const size_t K = chunks.size();
     cn.chunks = K;
     const bool staged = K == 1; // per-stage CUDA-event timing only when the call is one chunk
-    size_t max_cp = 0, max_cs = 0;
+    size_t max_cp = 0;
     for (const Chunk &c : chunks) max_cp = std::max(max_cp, c.p1 - c.p0);
-    max_cs = n_seqs; // chunk sequence ranges are only known as the scan proceeds: size for the worst case
 
     // ---- buffers ------------------------------------------------------------------------------------
     const size_t max_words = b.blob_bytes / 16 + 2;
@@ -551,13 +544,10 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         if (want_work) ENSURE(ctx->work, (size_t)n_pairs * 12);
         for (int i = 0; i < n_slot; ++i) {
             tdb_ctx::Slot &sl = ctx->slot[i];
-            ENSURE(sl.canon, (size_t)n_seqs * 4);
             ENSURE(sl.skey_in, max_cp);
             ENSURE(sl.sval_out, max_cp * 4);
             ENSURE(sl.list_a, max_cp * 4);
             if (mini_ok) ENSURE(sl.list_m, max_cp * 4);
-            if (dedup) ENSURE(sl.seq_tab, ((size_t)table_mask(max_cs) + 1) * 12);
-            ENSURE(sl.pair_tab, ((size_t)table_mask(max_cp) + 1) * 12);
         }
     }
     while (b.h_pp && ctx->up_ev.size() < K) {
@@ -820,46 +810,22 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         if (cigar_mode) continue; // CIGAR output lives in the general kernel: no dedup, no shared-memory tiers
         Ctrl::Chunk *ck = &ctrl->ck[si];
         CK(cudaMemsetAsync(ck, 0, sizeof(Ctrl::Chunk), st));
-        const uint32_t ns = c.s_hi - c.s_lo;
-        const uint32_t smask = table_mask(ns), pmask = table_mask(cpairs);
-        unsigned long long *skeys = (unsigned long long *)sl.seq_tab.p;
-        uint32_t *svals = dedup ? (uint32_t *)(skeys + (size_t)smask + 1) : nullptr;
-        uint32_t *canon = (uint32_t *)sl.canon.p;
-        if (dedup && ns) {
-            CK(cudaMemsetAsync(skeys, 0xff, ((size_t)smask + 1) * 8, st)); // keys only: a value is written by whoever claims the slot
-            k_seq_insert<<<(ns + 255) / 256, 256, 0, st>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p,
-                                                           c.s_lo, c.s_hi, skeys, svals, smask);
-            CK(cudaGetLastError());
-            cn.kernel_launches += 1;
-        }
-        if (ns) {
-            const unsigned blocks = (unsigned)(((size_t)ns + 255) / 256);
-            k_seq_canon<<<blocks, 256, 0, st>>>((const uint64_t *)ctx->seq_hash.p, (const uint8_t *)ctx->seq_flag.p, b.seq_off,
-                                                b.seq_len, (const uint32_t *)ctx->packed.p, c.s_lo, c.s_hi, skeys, svals,
-                                                smask, canon, dedup ? 1 : 0);
-            CK(cudaGetLastError());
-            cn.kernel_launches += 1;
-        }
-        PairTable tb;
-        tb.keys = (unsigned long long *)sl.pair_tab.p, tb.vals = (uint32_t *)(tb.keys + (size_t)pmask + 1), tb.mask = pmask;
-        CK(cudaMemsetAsync(tb.keys, 0xff, ((size_t)pmask + 1) * 8, st));
-        const unsigned pblocks = (cpairs + 255) / 256;
-        k_pair_insert<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, tb, &ctrl->err);
-        CK(cudaGetLastError());
+        // duplicate elimination + classification: windows of DW_PAIRS consecutive pairs, tables in shared memory
         ClassifyOut co;
         co.rep = (uint32_t *)ctx->rep.p, co.key = (uint8_t *)sl.skey_in.p;
         co.glist = (uint32_t *)ctx->list_b.p, co.gcount = &ctrl->gcount, co.hist = ck->hist, co.n_closed = &ctrl->n_closed;
         co.out_score = b.score, co.out_status = b.status, co.out_penalty = b.penalty, co.work = p.work;
-        k_pair_classify<<<pblocks, 256, 0, st>>>(b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, canon, b.seq_len,
-                                                 (const uint8_t *)ctx->seq_flag.p, b.seq_off, (const uint32_t *)ctx->packed.p,
-                                                 tb, quad_ok ? 1 : 0, mini_ok ? 1 : 0, T0_MAXLEN, cf, co);
+        k_dedup_window<<<(cpairs + DW_PAIRS - 1) / DW_PAIRS, DW_THREADS, sizeof(DedupSmem), st>>>(
+            b.pp, b.pt, (uint32_t)c.p0, (uint32_t)c.p1, n_seqs, (const uint64_t *)ctx->seq_hash.p, b.seq_len,
+            (const uint8_t *)ctx->seq_flag.p, b.seq_off, (const uint32_t *)ctx->packed.p, dedup ? 1 : 0, quad_ok ? 1 : 0,
+            mini_ok ? 1 : 0, T0_MAXLEN, cf, co, &ctrl->err);
         CK(cudaGetLastError());
         k_plan<<<1, 32, 0, st>>>(ck->hist, ck->seg, ck->base);
         CK(cudaGetLastError());
         k_bucket<<<(cpairs + 256 * BUCKET_PER_THREAD - 1) / (256 * BUCKET_PER_THREAD), 256, 0, st>>>(
             (const uint8_t *)sl.skey_in.p, (uint32_t)c.p0, cpairs, ck->base, ck->cursor, (uint32_t *)sl.sval_out.p);
         CK(cudaGetLastError());
-        cn.kernel_launches += 4; // insert, classify, plan, bucket
+        cn.kernel_launches += 3; // dedup window, plan, bucket
         if (staged) CK(cudaEventRecord(ctx->ev[3], st));
         p.src1 = (const uint32_t *)sl.sval_out.p;
         // thread-per-pair tier: the lightest pairs (|n-m| < 8), up to penalty 24; the rest moves on to tier 0
@@ -1175,7 +1141,8 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
             occ_out = occ2;
             return e2;
         };
-        e = setup(k_align_lock<QuadCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<QuadCfg>(), c->quad_ctas_per_sm);
+        e = cudaFuncSetAttribute(k_dedup_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem));
+        if (e == cudaSuccess) e = setup(k_align_lock<QuadCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<QuadCfg>(), c->quad_ctas_per_sm);
         if (e == cudaSuccess) e = setup(k_align_lock<DuoCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<DuoCfg>(), c->duo_ctas_per_sm);
         if (e != cudaSuccess || c->quad_ctas_per_sm < 1 || c->duo_ctas_per_sm < 1) {
             int code = fail(nullptr, TDB_E_CUDA, "lockstep kernel setup failed: %s (occupancy %d / %d)", cudaGetErrorString(e),
@@ -1237,8 +1204,7 @@ void tdb_destroy(tdb_ctx *c) {
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
-        DevBuf *sb[] = {&sl.canon, &sl.skey_in, &sl.sval_out, &sl.seq_tab,
-                        &sl.pair_tab, &sl.list_a, &sl.list_m};
+        DevBuf *sb[] = {&sl.skey_in, &sl.sval_out, &sl.list_a, &sl.list_m};
         for (DevBuf *b : sb) b->release();
     }
     if (c->slot[1].st) cudaStreamDestroy(c->slot[1].st);

@@ -206,66 +206,22 @@ __global__ void __launch_bounds__(256) k_expand_runs(const PairRun *__restrict__
 // Duplicate elimination.  HiFi reads that span a short repeat are mostly error-free copies of the
 // allele they come from, so a locus' pair list holds the same (pattern, text) CONTENT many times
 // (synthetic 30x trio: 3.5 pairs per distinct content).  The alignment is a pure function of the two
-// byte strings, so each distinct content is aligned once and its result copied:
-//   1. sequences -> canonical sequence (one index per class of equal bytes): open-addressing table on
-//      the 64-bit content hash, every hit VERIFIED word by word (a hash collision only costs a missed
-//      merge, never a wrong one);
-//   2. pairs -> representative pair (one index per (canon pattern, canon text) class): exact
-//      64-bit key, no verification needed;
-//   3. representatives are bucketed by tier and expected work (|n - m|, the dominant term of the penalty)
-//      so that the four pairs of a warp, and the warps of a wave, run near-identical control flow and
-//      the heaviest pairs start first;
-//   4. after the tiers ran, k_scatter copies score/status/penalty (and the algorithmic work counts)
-//      from each representative to its duplicates.
+// byte strings, so each distinct content is aligned once and its result copied.
+//
+// Copies are LOCAL: pairs arrive locus by locus (src/denovo.rs:22-54 visits the reads of one allele set
+// against one target) and a content recurs among the ~100 sequences of its locus, not across the genome.
+// k_dedup_window therefore works on windows of DW_PAIRS consecutive pairs, one CTA each, with both tables
+// in shared memory (round 1 used two global tables larger than L2: 11.5 ms of random probes per 937 k loci):
+//   1. the sequences the window references -- a contiguous index range -- go into a table keyed by their
+//      64-bit content hash; a hit is VERIFIED word by word (a collision only costs a missed merge, never
+//      a wrong one) -> canonical sequence (local index);
+//   2. pairs -> representative pair by the exact key (canon pattern, canon text);
+//   3. every representative is classified on the spot: pattern == text, closed form, or the tier /
+//      work-list bucket it goes to (|n - m|, the dominant term of the penalty, heaviest first);
+//   4. after the tiers ran, k_scatter copies score/status/penalty from each representative to its copies.
+// A copy whose twin sits in another window is aligned twice (a missed merge, not an error); a window whose
+// pairs reference a wider sequence range than the table holds runs without merging.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_seq_insert(const uint64_t *__restrict__ seq_hash,
-                                                    const uint8_t *__restrict__ seq_flag, uint32_t s0, uint32_t s1,
-                                                    unsigned long long *__restrict__ keys,
-                                                    uint32_t *__restrict__ vals, uint32_t mask) {
-    const uint32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s1 || seq_flag[i]) return;
-    const uint64_t h = seq_hash[i];
-    uint32_t slot = (uint32_t)h & mask;
-    for (;;) {
-        // the thread that claims the slot names the representative: any member of the class will do, and a plain
-        // store by the winner replaces an atomicMin by everybody (read only after this kernel has finished)
-        const unsigned long long old = atomicCAS(keys + slot, (unsigned long long)HT_EMPTY, (unsigned long long)h);
-        if (old == HT_EMPTY) vals[slot] = i;
-        if (old == HT_EMPTY || old == h) return;
-        slot = (slot + 1) & mask;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_seq_canon(const uint64_t *__restrict__ seq_hash,
-                                                   const uint8_t *__restrict__ seq_flag,
-                                                   const uint64_t *__restrict__ seq_off,
-                                                   const uint32_t *__restrict__ seq_len,
-                                                   const uint32_t *__restrict__ packed, uint32_t s0, uint32_t s1,
-                                                   const unsigned long long *__restrict__ keys,
-                                                   const uint32_t *__restrict__ vals, uint32_t mask,
-                                                   uint32_t *__restrict__ canon, int dedup) {
-    const uint32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s1) return;
-    uint32_t c = i;
-    if (dedup && !seq_flag[i]) {
-        const uint64_t h = seq_hash[i];
-        uint32_t slot = (uint32_t)h & mask;
-        while (keys[slot] != h) slot = (slot + 1) & mask; // inserted by k_seq_insert: always found
-        c = vals[slot];
-        if (c != i) { // verify the hash hit word by word
-            const uint32_t len = seq_len[i];
-            bool diff = seq_len[c] != len;
-            if (!diff) {
-                const uint64_t oi = seq_off[i], oc = seq_off[c];
-                const uint32_t nw = (len + 15u) / 16u;
-                for (uint32_t j = 0; j < nw && !diff; ++j) diff = seq_word(packed, oi, len, j) != seq_word(packed, oc, len, j);
-            }
-            if (diff) c = i;
-        }
-    }
-    canon[i] = c;
-}
-
 // sort keys of representative pairs: 0 quad tier by descending |n-m| ... ; 255 = not in the sorted list
 #ifndef TDB_QL_MAX
 #define TDB_QL_MAX 14
@@ -287,35 +243,6 @@ constexpr int KEY_MINI0 = KEY_QUAD0 + QL_MAX; // sorted last: the lightest pairs
 constexpr int KEY_NONE = 255;
 constexpr int N_HIST = 64;
 static_assert(KEY_MINI0 + ML_MAX <= N_HIST, "histogram size");
-
-struct PairTable {
-    unsigned long long *keys;
-    uint32_t *vals;
-    uint32_t mask;
-};
-
-__global__ void __launch_bounds__(256) k_pair_insert(const uint32_t *__restrict__ pair_p,
-                                                     const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1,
-                                                     uint32_t n_seqs, const uint32_t *__restrict__ canon,
-                                                     PairTable tb, unsigned *__restrict__ err) {
-    const uint32_t j = p0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p1) return;
-    const uint32_t ip = pair_p[j], jt = pair_t[j];
-    if (ip >= n_seqs || jt >= n_seqs) {
-        atomicOr(err, (unsigned)ERR_PAIR_INDEX);
-        return;
-    }
-    const uint32_t cp = canon[ip], ct = canon[jt];
-    if (cp == ct) return;
-    const unsigned long long key = ((unsigned long long)cp << 32) | ct;
-    uint32_t slot = (uint32_t)mix64(key) & tb.mask;
-    for (;;) {
-        const unsigned long long old = atomicCAS(tb.keys + slot, (unsigned long long)HT_EMPTY, key);
-        if (old == HT_EMPTY) tb.vals[slot] = j; // the winner is the representative pair (see k_seq_insert)
-        if (old == HT_EMPTY || old == key) return;
-        slot = (slot + 1) & tb.mask;
-    }
-}
 
 // Closed form for the commonest non-identical contents (about two thirds of the aligned pairs of the 30x
 // trio, and the heaviest ones): one substitution, or one gap of L <= CF_MAXGAP bases, everything else matching.
@@ -401,33 +328,133 @@ struct ClassifyOut {
     uint32_t *work;      // [3 n_pairs] algorithmic cells, ext16, columns per pair (nullptr: not counted)
 };
 
-__global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restrict__ pair_p,
-                                                       const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1,
-                                                       uint32_t n_seqs, const uint32_t *__restrict__ canon,
-                                                       const uint32_t *__restrict__ seq_len,
-                                                       const uint8_t *__restrict__ seq_flag,
-                                                       const uint64_t *__restrict__ seq_off,
-                                                       const uint32_t *__restrict__ packed, PairTable tb,
-                                                       int quad_ok, int mini_ok, int max_len16, ClosedFormCfg cf, ClassifyOut o) {
-    __shared__ unsigned sh_hist[N_HIST + 1];
-    if (threadIdx.x <= N_HIST) sh_hist[threadIdx.x] = 0;
+constexpr int DW_THREADS = 256;
+constexpr int DW_PAIRS = 2048;   // pairs per window
+constexpr int DW_SEQS = 4096;    // widest sequence index range a window may reference
+constexpr int DW_SSLOTS = 8192;  // sequence table slots
+constexpr int DW_PSLOTS = 4096;  // pair table slots
+struct DedupSmem {
+    unsigned short stab[DW_SSLOTS]; // local sequence index + 1 of the slot's owner, 0 = empty
+    unsigned short canon[DW_SEQS];  // canonical local index of sequence s_lo + i
+    uint32_t pkey[DW_PSLOTS];       // canon pattern << 12 | canon text, ~0 = empty
+    unsigned short pval[DW_PSLOTS]; // local pair index of the slot's owner
+    unsigned short pslot[DW_PAIRS]; // slot of pair jl (DW_PSLOTS: pattern == text, DW_PSLOTS + 1: unusable)
+    unsigned hist[N_HIST + 1];
+    uint32_t s_lo, s_hi;
+    int bad;
+};
+
+__device__ __forceinline__ bool same_content(const uint32_t *__restrict__ packed, uint64_t oa, uint64_t ob, uint32_t len) {
+    const uint32_t nw = (len + 15u) / 16u;
+    for (uint32_t j = 0; j < nw; ++j)
+        if (seq_word(packed, oa, len, j) != seq_word(packed, ob, len, j)) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(DW_THREADS) k_dedup_window(
+    const uint32_t *__restrict__ pair_p, const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1, uint32_t n_seqs,
+    const uint64_t *__restrict__ seq_hash, const uint32_t *__restrict__ seq_len, const uint8_t *__restrict__ seq_flag,
+    const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ packed, int dedup, int quad_ok, int mini_ok,
+    int max_len16, ClosedFormCfg cf, ClassifyOut o, unsigned *__restrict__ err) {
+    extern __shared__ __align__(16) uint8_t dw_raw[];
+    DedupSmem &sm = *reinterpret_cast<DedupSmem *>(dw_raw);
+    const uint32_t w0 = p0 + blockIdx.x * (uint32_t)DW_PAIRS, w1 = min(p1, w0 + (uint32_t)DW_PAIRS);
+    const int tid = threadIdx.x;
+    // ---- the window's sequence range ----
+    if (tid == 0) sm.s_lo = 0xffffffffu, sm.s_hi = 0, sm.bad = 0;
+    for (int i = tid; i <= N_HIST; i += DW_THREADS) sm.hist[i] = 0;
+    for (int i = tid; i < DW_SSLOTS; i += DW_THREADS) sm.stab[i] = 0;
+    for (int i = tid; i < DW_PSLOTS; i += DW_THREADS) sm.pkey[i] = 0xffffffffu;
     __syncthreads();
-    const uint32_t j = p0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < p1) {
+    {
+        uint32_t lo = 0xffffffffu, hi = 0;
+        bool bad = false;
+        for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
+            const uint32_t ip = pair_p[j], jt = pair_t[j];
+            if (ip >= n_seqs || jt >= n_seqs) bad = true;
+            else lo = min(lo, min(ip, jt)), hi = max(hi, max(ip, jt));
+        }
+        lo = __reduce_min_sync(TDB_FULL, lo), hi = __reduce_max_sync(TDB_FULL, hi);
+        const bool any_bad = __any_sync(TDB_FULL, bad);
+        if ((tid & 31) == 0) {
+            atomicMin(&sm.s_lo, lo), atomicMax(&sm.s_hi, hi);
+            if (any_bad) sm.bad = 1;
+        }
+    }
+    __syncthreads();
+    if (sm.bad && tid == 0) atomicOr(err, (unsigned)ERR_PAIR_INDEX);
+    const uint32_t s_lo = sm.s_lo, s_hi = sm.s_hi;
+    const uint32_t n_loc = s_hi >= s_lo ? s_hi - s_lo + 1u : 0u;
+    const bool local = dedup && n_loc <= (uint32_t)DW_SEQS; // else: no merging in this window
+    // ---- sequences -> canonical sequence ----
+    if (local) {
+        for (uint32_t i = tid; i < n_loc; i += DW_THREADS) {
+            const uint32_t g = s_lo + i;
+            uint32_t c = i;
+            if (!seq_flag[g]) { // sequences with bytes outside ACGT (or outside the blob) are never merged
+                const uint64_t h = seq_hash[g];
+                const uint32_t len = seq_len[g];
+                uint32_t slot = (uint32_t)h & (DW_SSLOTS - 1);
+                for (;;) {
+                    const unsigned short old = atomicCAS(&sm.stab[slot], (unsigned short)0, (unsigned short)(i + 1));
+                    if (old == 0) break; // first of its content: canonical
+                    const uint32_t cand = (uint32_t)old - 1u, gc = s_lo + cand;
+                    if (seq_hash[gc] == h && seq_len[gc] == len && same_content(packed, seq_off[g], seq_off[gc], len)) {
+                        c = cand;
+                        break;
+                    }
+                    slot = (slot + 1) & (DW_SSLOTS - 1);
+                }
+            }
+            sm.canon[i] = (unsigned short)c;
+        }
+    }
+    __syncthreads();
+    // ---- pairs -> slot of their (canon pattern, canon text) key ----
+    for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
+        const uint32_t jl = j - w0;
         const uint32_t ip = pair_p[j], jt = pair_t[j];
+        unsigned short ps = (unsigned short)(DW_PSLOTS + 1);
+        if (ip < n_seqs && jt < n_seqs && !((seq_flag[ip] | seq_flag[jt]) & 2)) {
+            if (!local) {
+                ps = ip == jt ? (unsigned short)DW_PSLOTS : (unsigned short)(DW_PSLOTS + 2); // + 2: its own representative
+            } else {
+                const uint32_t cp = sm.canon[ip - s_lo], ct = sm.canon[jt - s_lo];
+                if (cp == ct) {
+                    ps = (unsigned short)DW_PSLOTS;
+                } else {
+                    const uint32_t key = cp << 12 | ct;
+                    uint32_t slot = (key * 0x9e3779b1u) >> 20; // 12 bits
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&sm.pkey[slot], 0xffffffffu, key);
+                        if (old == 0xffffffffu) sm.pval[slot] = (unsigned short)jl; // the winner is the representative
+                        if (old == 0xffffffffu || old == key) break;
+                        slot = (slot + 1) & (DW_PSLOTS - 1);
+                    }
+                    ps = (unsigned short)slot;
+                }
+            }
+        }
+        sm.pslot[jl] = ps;
+    }
+    __syncthreads();
+    // ---- representatives: identical / closed form / tier and bucket ----
+    for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
+        const uint32_t jl = j - w0;
+        const unsigned ps = sm.pslot[jl];
         int key = KEY_NONE;
         uint32_t rep = j;
-        // bad pair index (ERR_PAIR_INDEX, raised by k_pair_insert) or a sequence outside the blob (ERR_LAYOUT,
-        // raised by k_pack): the call fails; such pairs never reach an alignment kernel
-        if (ip >= n_seqs || jt >= n_seqs || ((seq_flag[ip] | seq_flag[jt]) & 2)) {
+        if (ps == (unsigned)DW_PSLOTS + 1u) {
+            // bad pair index (ERR_PAIR_INDEX) or a sequence outside the blob (ERR_LAYOUT, raised by k_hash): the call
+            // fails; such pairs never reach an alignment kernel
             o.out_score[j] = TDB_SCORE_FAILED;
             if (o.out_status) o.out_status[j] = TDB_STATUS_UNATTAINABLE;
             if (o.out_penalty) o.out_penalty[j] = INT32_MIN;
             if (o.work) o.work[3 * (size_t)j] = o.work[3 * (size_t)j + 1] = o.work[3 * (size_t)j + 2] = 0;
         } else {
-            const uint32_t cp = canon[ip], ct = canon[jt];
+            const uint32_t ip = pair_p[j], jt = pair_t[j];
             const int n = (int)seq_len[ip], m = (int)seq_len[jt];
-            if (cp == ct) { // same bytes: penalty 0, every column a match, clipped score 0
+            if (ps == (unsigned)DW_PSLOTS) { // same bytes: penalty 0, every column a match, clipped score 0
                 o.out_score[j] = 0;
                 if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
                 if (o.out_penalty) o.out_penalty[j] = 0;
@@ -436,20 +463,17 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
                     o.work[3 * (size_t)j + 2] = (uint32_t)m;
                 }
             } else {
-                const unsigned long long k64 = ((unsigned long long)cp << 32) | ct;
-                uint32_t slot = (uint32_t)mix64(k64) & tb.mask;
-                while (tb.keys[slot] != k64) slot = (slot + 1) & tb.mask;
-                rep = tb.vals[slot];
+                if (ps < (unsigned)DW_PSLOTS) rep = w0 + sm.pval[ps];
                 if (rep == j) {
                     const int L = abs(m - n);
+                    const unsigned fl = seq_flag[ip] | seq_flag[jt];
                     int pen = 0, clipped = 0;
-                    if (cf.enabled && !(seq_flag[ip] | seq_flag[jt]) &&
-                        closed_form(packed, seq_off[ip], n, seq_off[jt], m, cf.clip, pen, clipped)) {
+                    if (cf.enabled && !fl && closed_form(packed, seq_off[ip], n, seq_off[jt], m, cf.clip, pen, clipped)) {
                         o.out_score[j] = clipped;
                         if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
                         if (o.out_penalty) o.out_penalty[j] = pen;
-                        atomicAdd(sh_hist + N_HIST, 1u);
-                    } else if ((seq_flag[ip] | seq_flag[jt]) || n > max_len16 || m > max_len16 || L >= WL_MAX) {
+                        atomicAdd(sm.hist + N_HIST, 1u);
+                    } else if (fl || n > max_len16 || m > max_len16 || L >= WL_MAX) {
                         const unsigned q = atomicAdd(o.gcount, 1u);
                         o.glist[q] = j;
                     } else if (!quad_ok || L >= QL_MAX) {
@@ -464,11 +488,11 @@ __global__ void __launch_bounds__(256) k_pair_classify(const uint32_t *__restric
         }
         o.rep[j] = rep;
         o.key[j - p0] = (uint8_t)key;
-        if (key != KEY_NONE) atomicAdd(sh_hist + key, 1u);
+        if (key != KEY_NONE) atomicAdd(sm.hist + key, 1u);
     }
     __syncthreads();
-    if (threadIdx.x < N_HIST && sh_hist[threadIdx.x]) atomicAdd(o.hist + threadIdx.x, sh_hist[threadIdx.x]);
-    if (threadIdx.x == N_HIST && sh_hist[N_HIST]) atomicAdd(o.n_closed, sh_hist[N_HIST]);
+    if (tid < N_HIST && sm.hist[tid]) atomicAdd(o.hist + tid, sm.hist[tid]);
+    if (tid == N_HIST && sm.hist[N_HIST]) atomicAdd(o.n_closed, sm.hist[N_HIST]);
 }
 
 // Segment table of the work list: seg[0] = begin, seg[1] = count of the warp-tier segment; seg[2], seg[3] the same for the

@@ -217,6 +217,20 @@ def duo_check_field_similarity(a, b, quick_mode) -> bool:  # src/duo/allele.rs:5
     return True
 
 
+def build_allele_seqs(vcf_allele_seqs, genotype_indices, left_flank: bytes, right_flank: bytes):
+    """src/allele.rs:406-426: sorted genotype indices, allele = left flank + VCF allele + right flank."""
+    idx = sorted(genotype_indices)
+    return [left_flank + vcf_allele_seqs[i] + right_flank for i in idx], idx
+
+
+def decode_info_field(encoding: str):
+    """src/locus.rs:249-260: 'name=value' of a catalog INFO entry; anything else is an error."""
+    name, sep, value = encoding.partition("=")
+    if not sep:
+        raise ValueError(f"Invalid entry: {encoding}")
+    return name, value
+
+
 class _BatchBuilder:
     """Sequence blob + pair list in the reference's visiting order (src/denovo.rs:29-37,48-52)."""
 
