@@ -525,7 +525,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
 
     // ---- buffers ------------------------------------------------------------------------------------
     const size_t max_words = b.blob_bytes / 16 + 2;
-    ENSURE(ctx->packed, max_words * 4);
+    ENSURE(ctx->packed, (max_words + PACK_SLACK) * 4); // the comparison loops read a few words past a sequence
     ENSURE(ctx->seq_flag, (size_t)n_seqs);
     ENSURE(ctx->seq_hash, (size_t)n_seqs * 8);
     ENSURE(ctx->ctrl, sizeof(Ctrl));

@@ -142,6 +142,36 @@ __device__ __forceinline__ uint32_t seq_word(const uint32_t *__restrict__ packed
     return rem >= 16u ? v : (v & ((1u << (2u * rem)) - 1u));
 }
 
+// Streams of 16-base words of two windows of the packed blob, compared four words per round with all ten loads of a
+// round issued before the first use (the loop is latency bound: one thread walks two sequences).  The packed buffer
+// is allocated PACK_SLACK words beyond the stream, so reading up to four words past a sequence is safe; bases past
+// `n` are masked out of the comparison.
+constexpr int PACK_SLACK = 8;
+struct Diff16 { // position of the first differing base among the first n of two windows, or n
+    __device__ static __forceinline__ uint32_t run(const uint32_t *__restrict__ wa, uint32_t sha, const uint32_t *__restrict__ wb,
+                                                   uint32_t shb, uint32_t n) {
+        uint32_t a0 = __ldg(wa), b0 = __ldg(wb);
+        for (uint32_t base = 0; base < n; base += 64, wa += 4, wb += 4) {
+            const uint32_t a1 = __ldg(wa + 1), a2 = __ldg(wa + 2), a3 = __ldg(wa + 3), a4 = __ldg(wa + 4);
+            const uint32_t b1 = __ldg(wb + 1), b2 = __ldg(wb + 2), b3 = __ldg(wb + 3), b4 = __ldg(wb + 4);
+            const uint32_t x0 = __funnelshift_r(a0, a1, sha) ^ __funnelshift_r(b0, b1, shb);
+            const uint32_t x1 = __funnelshift_r(a1, a2, sha) ^ __funnelshift_r(b1, b2, shb);
+            const uint32_t x2 = __funnelshift_r(a2, a3, sha) ^ __funnelshift_r(b2, b3, shb);
+            const uint32_t x3 = __funnelshift_r(a3, a4, sha) ^ __funnelshift_r(b3, b4, shb);
+            if (x0 | x1 | x2 | x3) {
+                const uint32_t w = x0 ? 0u : (x1 ? 1u : (x2 ? 2u : 3u));
+                const uint32_t x = x0 ? x0 : (x1 ? x1 : (x2 ? x2 : x3));
+                return min(n, base + 16u * w + (uint32_t)((__ffs(x) - 1) >> 1));
+            }
+            a0 = a4, b0 = b4;
+        }
+        return n;
+    }
+};
+__device__ __forceinline__ bool same_content(const uint32_t *__restrict__ packed, uint64_t oa, uint64_t ob, uint32_t len) {
+    return Diff16::run(packed + (oa >> 4), (uint32_t)(oa & 15) << 1, packed + (ob >> 4), (uint32_t)(ob & 15) << 1, len) >= len;
+}
+
 // 64-bit content hash per sequence (feeds the duplicate elimination below) + the blob layout contract
 // (sequences in index order, non-overlapping, inside the blob: what makes chunked uploads possible).
 // One thread per sequence: neighbouring threads walk neighbouring stretches of the packed stream, so a
@@ -165,7 +195,9 @@ __global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_o
     const uint32_t nw = (len + 15u) / 16u;
     const uint32_t *w = packed + (off >> 4);
     const uint32_t sh = (uint32_t)(off & 15) << 1;
-    uint64_t hs = 0;
+    // two independent 32-bit multiplicative chains over the words (order dependent), mixed to 64 bits at the end: four
+    // integer instructions per 16 bases instead of two 64-bit multiplies (every table hit is verified anyway)
+    uint32_t h1 = 0x811c9dc5u, h2 = len;
     uint32_t lo = nw ? __ldg(w) : 0u;
     for (uint32_t j = 0; j < nw; ++j) {
         const uint32_t hi = __ldg(w + j + 1);
@@ -173,9 +205,10 @@ __global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_o
         lo = hi;
         const uint32_t rem = len - 16u * j;
         if (rem < 16u) v &= (1u << (2u * rem)) - 1u;
-        hs += mix64(((uint64_t)j << 32) | v);
+        h1 = (h1 ^ v) * 0x01000193u;
+        h2 = (h2 + v) * 0x9e3779b1u + (h2 >> 15);
     }
-    const uint64_t h = mix64(hs ^ ((uint64_t)len * 0x9e3779b97f4a7c15ull));
+    const uint64_t h = mix64((((uint64_t)h1 << 32) | h2) ^ ((uint64_t)len * 0x9e3779b97f4a7c15ull));
     seq_hash[i] = h == HT_EMPTY ? 0 : h;
 }
 
@@ -272,16 +305,7 @@ __device__ inline bool closed_form(const uint32_t *__restrict__ packed, uint64_t
     const uint32_t *pw = packed + (poff >> 4), *tw = packed + (toff >> 4);
     const int psh = (int)(poff & 15), tsh = (int)(toff & 15);
     const int lim = min(n, m);
-    int p = 0;
-    while (p < lim) {
-        const uint32_t x = get16(pw, psh + p) ^ get16(tw, tsh + p);
-        if (x) {
-            p += (__ffs(x) - 1) >> 1;
-            break;
-        }
-        p += 16;
-    }
-    p = min(p, lim);
+    const int p = (int)Diff16::run(pw, (uint32_t)psh << 1, tw, (uint32_t)tsh << 1, (uint32_t)lim); // common prefix
     int v0, h0;
     if (L == 0) {
         if (p >= n) { // same bytes under two canonical ids (duplicate elimination off)
@@ -295,16 +319,11 @@ __device__ inline bool closed_form(const uint32_t *__restrict__ packed, uint64_t
         v0 = p + L, h0 = p;
     }
     const int room = n - v0; // == m - h0
-    int q = 0;
-    while (q < room) {
-        const uint32_t x = get16(pw, psh + v0 + q) ^ get16(tw, tsh + h0 + q);
-        if (x) {
-            q += (__ffs(x) - 1) >> 1;
-            break;
-        }
-        q += 16;
+    if (room > 0) { // everything behind the gap / substitution must match
+        const int pa = psh + v0, ta = tsh + h0;
+        if ((int)Diff16::run(pw + (pa >> 4), (uint32_t)(pa & 15) << 1, tw + (ta >> 4), (uint32_t)(ta & 15) << 1, (uint32_t)room) < room)
+            return false;
     }
-    if (q < room) return false;
     const int cols = max(n, m), wb = clip, we = cols - clip;
     if (L == 0) {
         pen = 8;
@@ -343,13 +362,6 @@ struct DedupSmem {
     uint32_t s_lo, s_hi;
     int bad;
 };
-
-__device__ __forceinline__ bool same_content(const uint32_t *__restrict__ packed, uint64_t oa, uint64_t ob, uint32_t len) {
-    const uint32_t nw = (len + 15u) / 16u;
-    for (uint32_t j = 0; j < nw; ++j)
-        if (seq_word(packed, oa, len, j) != seq_word(packed, ob, len, j)) return false;
-    return true;
-}
 
 __global__ void __launch_bounds__(DW_THREADS) k_dedup_window(
     const uint32_t *__restrict__ pair_p, const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1, uint32_t n_seqs,

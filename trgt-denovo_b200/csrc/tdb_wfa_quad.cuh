@@ -48,20 +48,24 @@ constexpr int Q_MAXLEN = 8000;
 constexpr int Q_WARPS = TDB_Q_WARPS;
 constexpr int Q_NULL = -16384;
 
-struct __align__(8) QMMeta {
-    int16_t lo, hi;  // valid range
-    uint16_t off;    // arena index of diagonal lo (free-running, masked on access)
-    uint16_t pad;
-};
-struct __align__(4) QGMeta {
-    int16_t lo, hi;
-};
+// Metadata of M[s] in one word: valid range lo..hi (int8 each: |k| < 128 for every geometry below) and the arena index
+// of diagonal lo (free-running 16 bits, masked on access) -> one 4-byte shared-memory load per input wavefront.
+// The ranges of the gap wavefronts never leave registers: only the last two (I1, D1) / one (I2, D2) scores are read.
+__device__ __forceinline__ uint32_t qm_pack(int lo, int hi, unsigned off) {
+    return ((uint32_t)lo & 0xffu) | (((uint32_t)hi & 0xffu) << 8) | (off << 16);
+}
+__device__ __forceinline__ int qm_lo(uint32_t w) { return (int)(int8_t)(w & 0xffu); }
+__device__ __forceinline__ int qm_hi(uint32_t w) { return (int)(int8_t)((w >> 8) & 0xffu); }
+__device__ __forceinline__ unsigned qm_off(uint32_t w) { return w >> 16; }
+// a range in one register: lo in the low half, hi in the high half (int16 each); empty when lo > hi
+__device__ __forceinline__ uint32_t qr_pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int qr_lo(uint32_t r) { return (int)(int16_t)(r & 0xffffu); }
+__device__ __forceinline__ int qr_hi(uint32_t r) { return (int)r >> 16; }
 template <class C>
 struct __align__(16) QPairT {
     int16_t marena[C::MAR];       // FIFO arena of M wavefronts; reused as the op stream at backtrace
     int16_t gap[12][C::W];        // I1[4], D1[4], I2[2], D2[2] rings indexed by score
-    QMMeta mmeta[32];             // valid range + arena position of M[s], slot s & 31 (one 8-byte load)
-    QGMeta gmeta[12];             // valid range of the gap wavefronts (one 4-byte load)
+    uint32_t mmeta[32];           // qm_pack(valid range, arena position) of M[s], slot s & 31
     int16_t step_lo[C::SCAP];     // computed lo of score s (provenance row origin)
     uint16_t step_base[C::SCAP];
     uint8_t prov[C::PROV];
@@ -69,25 +73,6 @@ struct __align__(16) QPairT {
 static_assert(sizeof(QPairT<QuadCfg>) % 16 == 0 && sizeof(QPairT<DuoCfg>) % 16 == 0, "pair state keeps 16-byte alignment");
 template <class C>
 constexpr size_t lock_smem_bytes() { return sizeof(QPairT<C>) * (32 / C::G) * Q_WARPS; }
-
-// Bit mask over the (at most W) diagonals of one wavefront; first / last set bit = trimmed range.
-template <int W>
-struct QMask {
-    static_assert(W == 32 || W == 64, "wavefront width");
-    unsigned long long bits = 0; // W == 32 only uses the low word (the compiler drops the rest)
-    __device__ __forceinline__ void add(unsigned group_bits, int shift) {
-        if (W == 32) bits = (unsigned)bits | (group_bits << shift);
-        else bits |= (unsigned long long)group_bits << shift;
-    }
-    __device__ __forceinline__ void range(int lo, int &first, int &last) const {
-        if (W == 32) {
-            const unsigned b = (unsigned)bits;
-            first = b ? lo + __ffs(b) - 1 : INT32_MAX, last = b ? lo + 31 - __clz(b) : INT32_MIN;
-        } else {
-            first = bits ? lo + __ffsll((long long)bits) - 1 : INT32_MAX, last = bits ? lo + 63 - __clzll((long long)bits) : INT32_MIN;
-        }
-    }
-};
 
 struct QIn { // one input wavefront, group-uniform
     const int16_t *p; // element for diagonal k at p[(base + k) & amask]
@@ -131,7 +116,7 @@ __device__ __forceinline__ int extend_groups(const uint32_t *pw, const uint32_t 
 
 template <class C, int X, int O1, int E1, int O2, int E2>
 __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const AlignParams p) {
-    static_assert(X < 32 && O1 + E1 < 32 && O2 + E2 < 32 && E1 < 4 && E2 < 2, "ring sizes");
+    static_assert(X < 32 && O1 + E1 < 32 && O2 + E2 < 32 && E1 == 2 && E2 == 1, "ring sizes; gap ranges are kept for two / one score(s)");
     constexpr int QG = C::G, QW = C::W, Q_MAR = C::MAR, Q_SCAP = C::SCAP, Q_PROV = C::PROV;
     using QPair = QPairT<C>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -182,12 +167,14 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
             bool running = usable && !identical;
             // ---------------- wavefront loop (score s is warp-uniform) ----------------
             if (running && gl == 0) {
-                sm.mmeta[0] = QMMeta{0, 0, 0, 0};
+                sm.mmeta[0] = qm_pack(0, 0, 0u);
                 sm.marena[0] = (int16_t)m0;
                 sm.step_lo[0] = 0, sm.step_base[0] = 0;
                 sm.prov[0] = 0;
             }
             unsigned Mm = 1u, I1m = 0, I2m = 0, D1m = 0, D2m = 0; // bit j <-> score s-j exists
+            // ranges of the gap wavefronts, in registers: I1 / D1 of scores s-1 (a) and s-2 (b), I2 / D2 of score s-1
+            uint32_t rI1a = 0, rI1b = 0, rD1a = 0, rD1b = 0, rI2 = 0, rD2 = 0;
             unsigned mhead = 1, prov_used = 1;
             int steps_wait = p.heur.steps - (p.heur.kind == 1 ? 1 : 0);
             int s = 0;
@@ -201,44 +188,44 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                 Mm <<= 1, I1m <<= 1, I2m <<= 1, D1m <<= 1, D2m <<= 1;
                 bool live = running && ((Mm & ((1u << X) | (1u << (O1 + E1)) | (1u << (O2 + E2)))) |
                                         ((I1m | D1m) & (1u << E1)) | ((I2m | D2m) & (1u << E2))) != 0;
-                if (!__any_sync(TDB_FULL, live)) continue; // null step for every group: registers only
-                // ---- inputs ----
-                QIn mx, mo1, mo2, i1e, i2e, d1e, d2e;
-#define TDB_QM(w, lag)                                                              \
-    w.p = sm.marena, w.base = 0, w.lo = 1, w.span1 = 0;                             \
-    if (live && (Mm & (1u << (lag)))) {                                             \
-        const QMMeta mm_ = sm.mmeta[(s - (lag)) & 31];                              \
-        w.lo = mm_.lo, w.span1 = (unsigned)(mm_.hi - mm_.lo + 1), w.base = (int)mm_.off - mm_.lo; \
+                if (!__any_sync(TDB_FULL, live)) { // null step for every group: registers only
+                    rI1b = rI1a, rD1b = rD1a;
+                    continue;
+                }
+                // ---- inputs: three M wavefronts (arena, metadata in one word each), four gap wavefronts (rings by score,
+                // ranges in registers).  An absent input has span 0: every read of it yields NULL. ----
+                int mx_lo = 1, mx_base = 0, mo1_lo = 1, mo1_base = 0, mo2_lo = 1, mo2_base = 0;
+                unsigned mx_sp = 0, mo1_sp = 0, mo2_sp = 0;
+#define TDB_QM(w, lag)                                                                \
+    if (live && (Mm & (1u << (lag)))) {                                               \
+        const uint32_t mm_ = sm.mmeta[(s - (lag)) & 31];                              \
+        w##_lo = qm_lo(mm_), w##_sp = (unsigned)(qm_hi(mm_) - w##_lo + 1), w##_base = (int)qm_off(mm_) - w##_lo; \
     }
                 TDB_QM(mx, X)
                 TDB_QM(mo1, O1 + E1)
                 TDB_QM(mo2, O2 + E2)
 #undef TDB_QM
-#define TDB_QG(w, msk, lag, row0, rmask)                                            \
-    w.p = sm.gap[0], w.base = 0, w.lo = 1, w.span1 = 0;                             \
-    if (live && (msk & (1u << (lag)))) {                                            \
-        const int r_ = (row0) + ((s - (lag)) & (rmask));                            \
-        const QGMeta gm_ = sm.gmeta[r_];                                            \
-        w.p = sm.gap[r_], w.lo = gm_.lo, w.span1 = (unsigned)(gm_.hi - gm_.lo + 1); \
-    }
-                TDB_QG(i1e, I1m, E1, 0, 3)
-                TDB_QG(d1e, D1m, E1, 4, 3)
-                TDB_QG(i2e, I2m, E2, 8, 1)
-                TDB_QG(d2e, D2m, E2, 10, 1)
-#undef TDB_QG
+                int i1_lo = 1, d1_lo = 1, i2_lo = 1, d2_lo = 1;
+                unsigned i1_sp = 0, d1_sp = 0, i2_sp = 0, d2_sp = 0;
+                if (live && (I1m & (1u << E1))) i1_lo = qr_lo(rI1b), i1_sp = (unsigned)(qr_hi(rI1b) - i1_lo + 1);
+                if (live && (D1m & (1u << E1))) d1_lo = qr_lo(rD1b), d1_sp = (unsigned)(qr_hi(rD1b) - d1_lo + 1);
+                if (live && (I2m & (1u << E2))) i2_lo = qr_lo(rI2), i2_sp = (unsigned)(qr_hi(rI2) - i2_lo + 1);
+                if (live && (D2m & (1u << E2))) d2_lo = qr_lo(rD2), d2_sp = (unsigned)(qr_hi(rD2) - d2_lo + 1);
+                const int16_t *I1r = sm.gap[0 + ((s - E1) & 3)], *D1r = sm.gap[4 + ((s - E1) & 3)]; // warp-uniform rows
+                const int16_t *I2r = sm.gap[8 + ((s - E2) & 1)], *D2r = sm.gap[10 + ((s - E2) & 1)];
                 int lo = INT32_MAX, hi = INT32_MIN;
 #define TDB_LIM(w, dl, dh)                                              \
-    if ((w).span1) {                                                    \
-        lo = min(lo, (w).lo + (dl));                                    \
-        hi = max(hi, (w).lo + (int)(w).span1 - 1 + (dh));               \
+    if (w##_sp) {                                                       \
+        lo = min(lo, w##_lo + (dl));                                    \
+        hi = max(hi, w##_lo + (int)w##_sp - 1 + (dh));                  \
     }
                 TDB_LIM(mx, 0, 0)
                 TDB_LIM(mo1, -1, 1)
                 TDB_LIM(mo2, -1, 1)
-                TDB_LIM(i1e, 1, 1)
-                TDB_LIM(i2e, 1, 1)
-                TDB_LIM(d1e, -1, -1)
-                TDB_LIM(d2e, -1, -1)
+                TDB_LIM(i1, 1, 1)
+                TDB_LIM(i2, 1, 1)
+                TDB_LIM(d1, -1, -1)
+                TDB_LIM(d2, -1, -1)
 #undef TDB_LIM
                 int width = 0;
                 if (live) {
@@ -247,7 +234,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                     // arena room: everything from the oldest live M wavefront up to the new one
                     const unsigned livem = Mm & 0x03fffffeu; // lags 1..25
                     unsigned tail = mhead;
-                    if (livem) tail = sm.mmeta[(s - (31 - __clz(livem))) & 31].off;
+                    if (livem) tail = qm_off(sm.mmeta[(s - (31 - __clz(livem))) & 31]);
                     if (width > QW || prov_used + (unsigned)width > Q_PROV ||
                         ((mhead - tail) & 0xffffu) + (unsigned)width > Q_MAR) {
                         overflow = true, running = false, live = false, width = 0; // this group drops out
@@ -258,9 +245,16 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                 int16_t *I2o = sm.gap[8 + (s & 1)], *D2o = sm.gap[10 + (s & 1)];
                 uint8_t *pv = sm.prov + prov_used;
                 cells += (unsigned)width;
-                // validity masks of this score's wavefronts, bit = diagonal - lo (a wavefront spans at most QW diagonals)
-                QMask<QW> vmask_m, vmask_i1, vmask_i2, vmask_d1, vmask_d2;
-                int lane_min_d = 1 << 30;
+                // Which cells lie inside the DP matrix decides the trimmed range of each output wavefront (A.2).  M: one vote
+                // per iteration, first / last set bit.  Gap components: per lane and component one word of two halfwords,
+                // (0xffff - smallest, 1 + largest) diagonal (relative to lo) that holds a valid offset -- both grow, so one
+                // VIMNMX.U16x2 per component and iteration, and one halfword butterfly over the group per score.  dpk: the
+                // same for the distance to the end over the valid M cells, (max d, 0xffff - min d), for the cut-off below.
+                // The second gap piece (I2, D2) does not exist below score O2 + E2: its reads, stores and bookkeeping are
+                // skipped (warp-uniform) while no group has a source for it.
+                const bool any2 = __any_sync(TDB_FULL, live && ((Mm & (1u << (O2 + E2))) | ((I2m | D2m) & (1u << E2))) != 0);
+                int tl_m = INT32_MAX, th_m = INT32_MIN;
+                uint32_t wI1 = 0u, wI2 = 0u, wD1 = 0u, wD2 = 0u, dpk = 0u;
                 bool fin = false;
                 const int n_iter = __reduce_max_sync(TDB_FULL, (width + QG - 1) / QG);
                 for (int itk = 0; itk < n_iter; ++itk) {
@@ -271,19 +265,24 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                     bool vm = false;
                     int ev = 0, eroom = 0; // extension state of this lane's diagonal
                     if (act) {
-#define TDB_RDM(w, kk) (((unsigned)((kk) - (w).lo) < (w).span1) ? (int)sm.marena[((w).base + (kk)) & (Q_MAR - 1)] : Q_NULL)
-#define TDB_RDG(w, kk) (((unsigned)((kk) - (w).lo) < (w).span1) ? (int)(w).p[(kk) & (QW - 1)] : Q_NULL)
+#define TDB_RDM(w, kk) (((unsigned)((kk) - w##_lo) < w##_sp) ? (int)sm.marena[(w##_base + (kk)) & (Q_MAR - 1)] : Q_NULL)
+#define TDB_RDG(w, row, kk) (((unsigned)((kk) - w##_lo) < w##_sp) ? (int)(row)[(kk) & (QW - 1)] : Q_NULL)
                         int b = 0, o, e;
-                        o = TDB_RDM(mo1, k - 1), e = TDB_RDG(i1e, k - 1);
+                        o = TDB_RDM(mo1, k - 1), e = TDB_RDG(i1, I1r, k - 1);
                         if (e >= o) ins1 = e, b |= PB_I1E; else ins1 = o;
                         ins1 += 1;
-                        o = TDB_RDM(mo2, k - 1), e = TDB_RDG(i2e, k - 1);
-                        if (e >= o) ins2 = e, b |= PB_I2E; else ins2 = o;
-                        ins2 += 1;
-                        o = TDB_RDM(mo1, k + 1), e = TDB_RDG(d1e, k + 1);
+                        o = TDB_RDM(mo1, k + 1), e = TDB_RDG(d1, D1r, k + 1);
                         if (e >= o) del1 = e, b |= PB_D1E; else del1 = o;
-                        o = TDB_RDM(mo2, k + 1), e = TDB_RDG(d2e, k + 1);
-                        if (e >= o) del2 = e, b |= PB_D2E; else del2 = o;
+                        if (any2) {
+                            o = TDB_RDM(mo2, k - 1), e = TDB_RDG(i2, I2r, k - 1);
+                            if (e >= o) ins2 = e, b |= PB_I2E; else ins2 = o;
+                            ins2 += 1;
+                            o = TDB_RDM(mo2, k + 1), e = TDB_RDG(d2, D2r, k + 1);
+                            if (e >= o) del2 = e, b |= PB_D2E; else del2 = o;
+                        } else {
+                            b |= PB_I2E | PB_D2E; // what two absent sources give (NULL >= NULL): the provenance byte is unchanged
+                            ins2 = Q_NULL + 1;
+                        }
                         const int mis = TDB_RDM(mx, k) + 1;
 #undef TDB_RDM
 #undef TDB_RDG
@@ -314,33 +313,49 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                             eq = min(eq, eroom);
                             ext += (unsigned)(eq >> 4) + 1;
                             mv += eq;
-                            lane_min_d = min(lane_min_d, max(n - (mv - k), m - mv));
+                            const unsigned d = (unsigned)max(n - (mv - k), m - mv);
+                            dpk = __vmaxu2(dpk, (d << 16) | (0xffffu - d));
                             fin |= (k == k_end) && (mv >= m);
                         }
                         sm.marena[(mhead + (unsigned)(k - lo)) & (Q_MAR - 1)] = (int16_t)mv;
                         // a component without a source only holds NULL+1 here: never valid, so its range stays empty
                         I1o[k & (QW - 1)] = (int16_t)ins1;
-                        I2o[k & (QW - 1)] = (int16_t)ins2;
                         D1o[k & (QW - 1)] = (int16_t)del1;
-                        D2o[k & (QW - 1)] = (int16_t)del2;
-                    }
-                    // which cells lie inside the DP matrix: collected per score, trimmed once below (A.2)
-                    const int sh = itk * QG;
-                    vmask_m.add(qballot<QG>(gshift, vm), sh);
-#define TDB_VALID(val) (act && (unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n)
-                    vmask_i1.add(qballot<QG>(gshift, TDB_VALID(ins1)), sh);
-                    vmask_i2.add(qballot<QG>(gshift, TDB_VALID(ins2)), sh);
-                    vmask_d1.add(qballot<QG>(gshift, TDB_VALID(del1)), sh);
-                    vmask_d2.add(qballot<QG>(gshift, TDB_VALID(del2)), sh);
+#define TDB_VALID(val) ((unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n)
+                        const uint32_t rel = (uint32_t)(k - lo);                        // 0..QW-1
+                        const uint32_t cand = ((0xffffu - rel) << 16) | (rel + 1u);    // (0xffff - first, last + 1)
+                        wI1 = __vmaxu2(wI1, TDB_VALID(ins1) ? cand : 0u);
+                        wD1 = __vmaxu2(wD1, TDB_VALID(del1) ? cand : 0u);
+                        if (any2) { // (without a source the rows keep stale values; they are never read: the range stays empty)
+                            I2o[k & (QW - 1)] = (int16_t)ins2;
+                            D2o[k & (QW - 1)] = (int16_t)del2;
+                            wI2 = __vmaxu2(wI2, TDB_VALID(ins2) ? cand : 0u);
+                            wD2 = __vmaxu2(wD2, TDB_VALID(del2) ? cand : 0u);
+                        }
 #undef TDB_VALID
+                    }
+                    const unsigned balm = qballot<QG>(gshift, vm);
+                    if (balm) tl_m = min(tl_m, kb + __ffs(balm) - 1), th_m = kb + 31 - __clz(balm);
                 }
-                // trim_ends (A.2): first / last diagonal whose offset lies inside the DP matrix
-                int tl_m, th_m, tl_i1, th_i1, tl_i2, th_i2, tl_d1, th_d1, tl_d2, th_d2;
-                vmask_m.range(lo, tl_m, th_m);
-                vmask_i1.range(lo, tl_i1, th_i1);
-                vmask_i2.range(lo, tl_i2, th_i2);
-                vmask_d1.range(lo, tl_d1, th_d1);
-                vmask_d2.range(lo, tl_d2, th_d2);
+                // trim_ends (A.2): one halfword butterfly over the group gives the first / last valid diagonal of the gap
+                // components; an empty component (word 0) ends up with first = lo + 0xffff > last = lo - 1
+#pragma unroll
+                for (int o = 1; o < QG; o <<= 1) {
+                    wI1 = __vmaxu2(wI1, __shfl_xor_sync(TDB_FULL, wI1, o));
+                    wD1 = __vmaxu2(wD1, __shfl_xor_sync(TDB_FULL, wD1, o));
+                    dpk = __vmaxu2(dpk, __shfl_xor_sync(TDB_FULL, dpk, o));
+                }
+                if (any2) {
+#pragma unroll
+                    for (int o = 1; o < QG; o <<= 1) {
+                        wI2 = __vmaxu2(wI2, __shfl_xor_sync(TDB_FULL, wI2, o));
+                        wD2 = __vmaxu2(wD2, __shfl_xor_sync(TDB_FULL, wD2, o));
+                    }
+                }
+                int tl_i1 = lo + (int)(0xffffu - (wI1 >> 16)), th_i1 = lo + (int)(wI1 & 0xffffu) - 1;
+                int tl_i2 = lo + (int)(0xffffu - (wI2 >> 16)), th_i2 = lo + (int)(wI2 & 0xffffu) - 1;
+                int tl_d1 = lo + (int)(0xffffu - (wD1 >> 16)), th_d1 = lo + (int)(wD1 & 0xffffu) - 1;
+                int tl_d2 = lo + (int)(0xffffu - (wD2 >> 16)), th_d2 = lo + (int)(wD2 & 0xffffu) - 1;
                 if (live && gl == 0) sm.step_lo[s] = (int16_t)lo, sm.step_base[s] = (uint16_t)prov_used;
                 prov_used += (unsigned)width;
                 __syncwarp();
@@ -352,11 +367,12 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                 const bool heur_on = cont && p.heur.kind == 1 && mlo <= mhi;
                 if (heur_on) --steps_wait;
                 const bool cut = heur_on && steps_wait <= 0 && (mhi - mlo + 1) >= p.heur.min_len;
-                if (__any_sync(TDB_FULL, cut)) {
-                    int md = lane_min_d;
-#pragma unroll
-                    for (int o = 1; o < QG; o <<= 1) md = min(md, __shfl_xor_sync(TDB_FULL, md, o));
-                    const int min_d = min(max(n, m), md), thr = p.heur.max_dist;
+                // The scans drop end diagonals whose distance to the end exceeds the smallest one by more than the threshold
+                // and stop at the first that does not; both ends of the trimmed range hold valid offsets, so when no valid
+                // cell is that far behind nothing is cut and the scans are skipped (almost always).
+                const int min_d = min(max(n, m), (int)(0xffffu - (dpk & 0xffffu))), thr = p.heur.max_dist;
+                const bool scan_needed = cut && (int)(dpk >> 16) - min_d > thr;
+                if (__any_sync(TDB_FULL, scan_needed)) {
                     const int abase = (int)mhead - lo;
 #define TDB_DIST_OK(kk, okv)                                                                  \
     {                                                                                         \
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                     int new_lo = mlo;
                     {
                         int first_ok = INT32_MAX;
-                        bool scan = cut && top_limit > mlo;
+                        bool scan = scan_needed && top_limit > mlo;
                         for (int kb = mlo; __any_sync(TDB_FULL, scan); kb += QG) {
                             const int k = kb + gl;
                             bool ok = false;
@@ -377,13 +393,13 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                             if (scan && bal) first_ok = kb + __ffs(bal) - 1;
                             scan = scan && first_ok == INT32_MAX && kb + QG < top_limit;
                         }
-                        if (cut && top_limit > mlo) new_lo = min(first_ok, top_limit);
+                        if (scan_needed && top_limit > mlo) new_lo = min(first_ok, top_limit);
                     }
                     const int bot_limit = max(k_end, new_lo);
                     int new_hi = mhi;
                     {
                         int last_ok = INT32_MIN;
-                        bool scan = cut && bot_limit < mhi;
+                        bool scan = scan_needed && bot_limit < mhi;
                         for (int kt = mhi; __any_sync(TDB_FULL, scan); kt -= QG) {
                             const int k = kt - gl;
                             bool ok = false;
@@ -392,11 +408,12 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                             if (scan && bal) last_ok = kt - (__ffs(bal) - 1);
                             scan = scan && last_ok == INT32_MIN && kt - QG > bot_limit;
                         }
-                        if (cut && bot_limit < mhi) new_hi = max(last_ok, bot_limit);
+                        if (scan_needed && bot_limit < mhi) new_hi = max(last_ok, bot_limit);
                     }
 #undef TDB_DIST_OK
-                    if (cut) mlo = new_lo, mhi = new_hi, steps_wait = p.heur.steps;
+                    if (scan_needed) mlo = new_lo, mhi = new_hi;
                 }
+                if (cut) steps_wait = p.heur.steps;
                 if (heur_on && mlo <= mhi) { // equate
                     tl_i1 = max(tl_i1, mlo), th_i1 = min(th_i1, mhi);
                     tl_i2 = max(tl_i2, mlo), th_i2 = min(th_i2, mhi);
@@ -404,20 +421,19 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                     tl_d2 = max(tl_d2, mlo), th_d2 = min(th_d2, mhi);
                 }
                 // ---- publish metadata of score s ----
+                rI1b = rI1a, rD1b = rD1a;
                 if (cont) {
                     if (mlo <= mhi) Mm |= 1u;
                     if (tl_i1 <= th_i1) I1m |= 1u;
                     if (tl_i2 <= th_i2) I2m |= 1u;
                     if (tl_d1 <= th_d1) D1m |= 1u;
                     if (tl_d2 <= th_d2) D2m |= 1u;
-                    if (gl == 0) {
-                        sm.mmeta[s & 31] = QMMeta{(int16_t)mlo, (int16_t)mhi, (uint16_t)(mhead + (unsigned)(mlo - lo)), 0};
-                        sm.gmeta[0 + (s & 3)] = QGMeta{(int16_t)tl_i1, (int16_t)th_i1};
-                        sm.gmeta[4 + (s & 3)] = QGMeta{(int16_t)tl_d1, (int16_t)th_d1};
-                        sm.gmeta[8 + (s & 1)] = QGMeta{(int16_t)tl_i2, (int16_t)th_i2};
-                        sm.gmeta[10 + (s & 1)] = QGMeta{(int16_t)tl_d2, (int16_t)th_d2};
+                    rI1a = qr_pack(tl_i1, th_i1), rD1a = qr_pack(tl_d1, th_d1);
+                    rI2 = qr_pack(tl_i2, th_i2), rD2 = qr_pack(tl_d2, th_d2);
+                    if (mlo <= mhi) {
+                        if (gl == 0) sm.mmeta[s & 31] = qm_pack(mlo, mhi, (mhead + (unsigned)(mlo - lo)) & 0xffffu);
+                        mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
                     }
-                    if (mlo <= mhi) mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
                 }
                 __syncwarp();
             }
