@@ -301,8 +301,14 @@ def main():
     load_pack_s = time.time() - t0
     exc = np.nonzero(flag[:n_seqs])[0].astype(np.uint32)
     exc_bytes = np.frombuffer(b"".join(batch.seq(int(i)) for i in exc), dtype=np.uint8)
-    pseqs = B.PackedSeqs(h_packed_ptr, batch.blob.size, h_off_ptr, batch.seq_len.ctypes.data, n_seqs,
-                         exc.ctypes.data if len(exc) else None, exc_bytes.ctypes.data if len(exc) else None, len(exc))
+    # sequence lengths as uint16 when every sequence is shorter than 65 536 bases (pinned, like everything handed over)
+    len16_ptr = None
+    if n_seqs and int(batch.seq_len.max()) < 65536:
+        len16_ptr = L.tdb_host_alloc(2 * n_seqs)
+        np.frombuffer((C.c_uint16 * n_seqs).from_address(len16_ptr), dtype=np.uint16)[:] = batch.seq_len
+    pseqs = B.PackedSeqs(h_packed_ptr, batch.blob.size, h_off_ptr, None if len16_ptr else batch.seq_len.ctypes.data, n_seqs,
+                         exc.ctypes.data if len(exc) else None, exc_bytes.ctypes.data if len(exc) else None, len(exc),
+                         len16_ptr)
 
     def step_packed():
         r = L.tdb_trio_batch_packed if not args.duo else L.tdb_duo_batch_packed
@@ -381,7 +387,7 @@ def main():
     if bytes(h_out) != out_ascii:
         raise SystemExit("bench self-check failed: packed and ASCII entry points disagree")
     del out_ascii
-    packed_input_bytes = n_words * 4 + (0 if dense else batch.seq_off.nbytes) + batch.seq_len.nbytes + \
+    packed_input_bytes = n_words * 4 + (0 if dense else batch.seq_off.nbytes) + (2 * n_seqs if len16_ptr else batch.seq_len.nbytes) + \
         batch.pair_pattern.nbytes + batch.pair_text.nbytes + loci_np.nbytes
     e2ep_host = {"host_packed": int(cp.host_packed), "align_bytes_h2d": int(cp.bytes_h2d), "ms_plan": cp.ms_host_plan,
                  "ms_scan_wait": cp.ms_host_pack_wait, "ms_align_call": cp.ms_host_call,

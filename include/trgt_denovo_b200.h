@@ -231,7 +231,7 @@ int tdb_assess_batch_device(tdb_ctx *ctx, int32_t is_duo, const uint8_t *seq_blo
  *             code (ASCII byte >> 1) & 3  (A 0, C 1, T 2, G 3); tdb_packed_words(n_bases) words (the last two are
  *             padding and must be readable; their content is ignored)
  *   seq_off   stream position of base 0 of each sequence, or NULL for the dense layout (back to back)
- *   seq_len   bases per sequence
+ *   seq_len   bases per sequence (or seq_len16, see below)
  *   exc_seq   ascending indices of the sequences that hold a byte outside {A,C,G,T} ('N', IUPAC codes, lower
  *             case): WFA2 compares raw bytes, so those are compared byte-wise from exc_bytes, where their raw
  *             ASCII is stored back to back in exc_seq order (seq_len[exc_seq[i]] bytes each).  Their 2-bit codes
@@ -248,6 +248,8 @@ typedef struct {
     const uint32_t *exc_seq;
     const uint8_t *exc_bytes;
     size_t n_exc;
+    const uint16_t *seq_len16; /* alternative to seq_len (which must then be NULL) when every sequence is shorter than
+                                  65 536 bases: the length table that crosses PCIe is half as large */
 } tdb_packed_seqs;
 int tdb_align_batch_packed(tdb_ctx *ctx, const tdb_packed_seqs *seqs, const uint32_t *pair_pattern,
                            const uint32_t *pair_text, size_t n_pairs, int32_t *out_score, int32_t *out_status);

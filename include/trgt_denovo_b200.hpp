@@ -346,6 +346,7 @@ struct Batch {
         v.packed = words.data(), v.n_bases = (size_t)n_bases, v.seq_off = nullptr, v.seq_len = len.data(), v.n_seqs = len.size();
         v.exc_seq = exc_seq.empty() ? nullptr : exc_seq.data();
         v.exc_bytes = exc_seq.empty() ? nullptr : (const uint8_t *)exc_bytes.data(), v.n_exc = exc_seq.size();
+        v.seq_len16 = nullptr;
         return v;
     }
 };

@@ -3,7 +3,14 @@
 # usage: run_gpu_r02_quick.sh <tag> [loci] [pytest-selector]
 TAG=${1:-x}; LOCI=${2:-937000}; SEL=${3:-tests}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | head -2
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,pcie.link.gen.current,pcie.link.width.current,pcie.link.gen.max --format=csv,noheader | head -2
+python - <<'PY'
+import torch, time
+a = torch.empty(1 << 30, dtype=torch.uint8).pin_memory(); b = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+for _ in range(2):
+    torch.cuda.synchronize(); t = time.time(); b.copy_(a, non_blocking=True); torch.cuda.synchronize(); dt = time.time() - t
+print(f"H2D pinned 1 GiB: {1.0737 / dt:.1f} GB/s")
+PY
 nproc; free -g | head -2
 timeout 1500 python -m pytest $SEL -q -m gpu -x 2>&1 | tail -15
 timeout 900 python bench.py --loci $LOCI --steps 5 --warmup 3 2>gpurun_out/bench_$TAG.err | tee gpurun_out/bench_$TAG.json | python -c "

@@ -84,7 +84,7 @@ def _check_batch(ctx, seqs, pp, pt, clip, heuristic=tdo.DEFAULT_HEURISTIC, cigar
     # packed entry point (the caller packed at load time): explicit offsets and dense layout
     import trgt_denovo_b200 as tdbm
     for dense in (False, True):
-        pk = tdbm.pack_sequences(blob, off, ln, dense=dense)
+        pk = tdbm.pack_sequences(blob, off, ln, dense=dense, len16=dense and (len(ln) == 0 or int(ln.max()) < 65536))
         got, st = ctx.align_batch_packed(pk, pp, pt)
         assert (st == wst).all() and (got == want).all(), f"packed entry, dense={dense}"
         assert ctx.counters().host_packed == 2

@@ -171,19 +171,25 @@ class Context:
 class PackedInput:
     """The arrays behind a tdb_packed_seqs (kept alive with the struct that points at them)."""
 
-    def __init__(self, packed, n_bases, seq_off, seq_len, exc_seq, exc_bytes):
+    def __init__(self, packed, n_bases, seq_off, seq_len, exc_seq, exc_bytes, len16=False):
         self.packed = np.ascontiguousarray(packed, dtype=np.uint32)
         self.seq_off = None if seq_off is None else np.ascontiguousarray(seq_off, dtype=np.uint64)
         self.seq_len = np.ascontiguousarray(seq_len, dtype=np.uint32)
+        # len16: hand the lengths over as uint16 (tdb_packed_seqs.seq_len16), every sequence < 65 536 bases
+        self.seq_len16 = self.seq_len.astype(np.uint16) if len16 else None
+        if len16 and len(self.seq_len) and int(self.seq_len.max()) > 0xffff:
+            raise ValueError("len16 needs every sequence shorter than 65 536 bases")
         self.exc_seq = np.ascontiguousarray(exc_seq, dtype=np.uint32)
         self.exc_bytes = np.ascontiguousarray(exc_bytes, dtype=np.uint8)
         self.n_bases = int(n_bases)
-        self.struct = B.PackedSeqs(_ptr(self.packed), self.n_bases, _ptr(self.seq_off), _ptr(self.seq_len),
+        self.struct = B.PackedSeqs(_ptr(self.packed), self.n_bases, _ptr(self.seq_off),
+                                   None if len16 else _ptr(self.seq_len),
                                    len(self.seq_len), _ptr(self.exc_seq) if len(self.exc_seq) else None,
-                                   _ptr(self.exc_bytes) if len(self.exc_seq) else None, len(self.exc_seq))
+                                   _ptr(self.exc_bytes) if len(self.exc_seq) else None, len(self.exc_seq),
+                                   _ptr(self.seq_len16))
 
 
-def pack_sequences(blob, seq_off, seq_len, n_threads=1, dense=None) -> PackedInput:
+def pack_sequences(blob, seq_off, seq_len, n_threads=1, dense=None, len16=False) -> PackedInput:
     """ASCII blob -> the packed form of the *_packed entry points, through tdb_host_pack (what a loader that holds
     ASCII would run once; a loader that holds BAM 4-bit bases emits the same stream directly, tdbh::PackedBatch).
     dense: hand the library seq_off = NULL (default: when the sequences are back to back)."""
@@ -203,7 +209,7 @@ def pack_sequences(blob, seq_off, seq_len, n_threads=1, dense=None) -> PackedInp
     raw = b"".join(blob[int(off[i]):int(off[i]) + int(seq_len[i])].tobytes() for i in exc)
     if dense is None:
         dense = n == 0 or np.array_equal(off, back_to_back)
-    return PackedInput(packed, blob.size, None if dense else off, seq_len, exc, np.frombuffer(raw, dtype=np.uint8))
+    return PackedInput(packed, blob.size, None if dense else off, seq_len, exc, np.frombuffer(raw, dtype=np.uint8), len16=len16)
 
 
 def _canon(blob, seq_off, seq_len, pp, pt):

@@ -62,7 +62,8 @@ class Counters(C.Structure):
 
 class PackedSeqs(C.Structure):
     _fields_ = [("packed", C.c_void_p), ("n_bases", C.c_size_t), ("seq_off", C.c_void_p), ("seq_len", C.c_void_p),
-                ("n_seqs", C.c_size_t), ("exc_seq", C.c_void_p), ("exc_bytes", C.c_void_p), ("n_exc", C.c_size_t)]
+                ("n_seqs", C.c_size_t), ("exc_seq", C.c_void_p), ("exc_bytes", C.c_void_p), ("n_exc", C.c_size_t),
+                ("seq_len16", C.c_void_p)]
 
 
 SCORE_FAILED = -2147483648

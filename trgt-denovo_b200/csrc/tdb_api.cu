@@ -75,7 +75,7 @@ struct tdb_ctx {
     std::vector<cudaEvent_t> up_ev; // one per in-flight chunk upload
     // grow-only device buffers
     DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, pair_p, pair_t, score, status, penalty;
-    DevBuf rep, work, list_b, list_c, scan_tmp, mask_hits;
+    DevBuf rep, work, list_b, list_c, scan_tmp, mask_hits, len16;
     std::vector<unsigned> h_hits; // host copy of the set mask positions
     // Chunks alternate between two pipeline slots (own stream + own scratch) so that the tail of one chunk's
     // alignment kernels overlaps the next chunk's duplicate elimination and alignment.  (3 and 4 slots, and a
@@ -170,10 +170,16 @@ struct DevBatch {
     const uint8_t *h_blob;
     const uint64_t *h_seq_off;
     const uint32_t *h_seq_len;
+    const uint16_t *h_seq_len16; // packed input: lengths as uint16 instead (h_seq_len == nullptr)
     const uint32_t *h_pp, *h_pt;
     uint8_t *h_zero; // optional host array of n_pairs bytes the calling thread zeroes chunk by chunk (result mask)
     // packed host input (tdb_*_batch_packed): the 2-bit stream as tdb_host_pack lays it out, plus the sequences that
     // hold a byte outside ACGT (ascending indices, raw bytes back to back)
+    // an upload the alignment stage does not need (the locus descriptors of the fused calls): queued on the copy stream
+    // behind the last chunk, so that it does not delay the first one
+    void *late_dst;
+    const void *late_src;
+    size_t late_bytes;
     const uint32_t *h_packed;
     const uint32_t *h_exc_seq;
     const uint8_t *h_exc_bytes;
@@ -419,6 +425,31 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
+template <class T>
+uint64_t sum_lengths(const T *__restrict__ p, size_t n) {
+    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) s0 += p[i], s1 += p[i + 1], s2 += p[i + 2], s3 += p[i + 3];
+    for (; i < n; ++i) s0 += p[i];
+    return s0 + s1 + s2 + s3;
+}
+
+// lengths of sequences [a, a + n) to the device: uint32 as they are, or uint16 widened by a small kernel next to the data
+int upload_lengths(tdb_ctx *ctx, const DevBatch &b, uint32_t a, size_t n, cudaStream_t cs, tdb_counters &cn) {
+    if (b.h_seq_len) {
+        CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, n * 4, cudaMemcpyHostToDevice, cs));
+        cn.bytes_h2d += n * 4;
+    } else {
+        uint16_t *d16 = (uint16_t *)ctx->len16.p + a;
+        CK(cudaMemcpyAsync(d16, b.h_seq_len16 + a, n * 2, cudaMemcpyHostToDevice, cs));
+        k_widen_len<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(d16, (uint32_t *)b.seq_len + a, (uint32_t)n);
+        CK(cudaGetLastError());
+        cn.bytes_h2d += n * 2;
+        cn.kernel_launches += 1;
+    }
+    return TDB_OK;
+}
+
 // Pack + duplicate elimination + alignment tiers + scatter.  Leaves results in b.score/status/penalty.
 int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     DevBatch b = b_in;
@@ -429,6 +460,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     cn.pairs = n_pairs;
     CK(cudaEventRecord(ctx->ev[0], s));
     if (n_pairs == 0 || n_seqs == 0) {
+        if (b.late_bytes) CK(cudaMemcpyAsync(b.late_dst, b.late_src, b.late_bytes, cudaMemcpyHostToDevice, s));
         CK(cudaEventRecord(ctx->ev[1], s));
         CK(cudaStreamSynchronize(s));
         return TDB_OK;
@@ -460,7 +492,8 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     const bool host_pack = b.h_pp && !prepacked && !cigar_mode && b.blob_bytes >= ctx->hostpack_min_bytes;
     const bool dense = b.h_pp && !b.h_seq_off; // host batch without offsets: sequences back to back
     DenseOffsets dense_off; // declared before the packer: its threads may call into it
-    dense_off.len = b.h_seq_len, dense_off.n = n_seqs;
+    dense_off.len = b.h_seq_len, dense_off.n = n_seqs; // (only the ASCII host packer asks for it)
+    auto hlen = [&b](uint32_t i) -> uint32_t { return b.h_seq_len ? b.h_seq_len[i] : (uint32_t)b.h_seq_len16[i]; };
     HostPacker packer;
     std::vector<Chunk> chunks;
     plan_prepare(ctx, b, chunks);
@@ -602,18 +635,30 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             uint64_t first = 0, end = 0;
             exc_at.clear();
             if (dense) {
+                // bytes of the new sequences = sum of their lengths: a tight loop over plain local pointers (this runs on the
+                // calling thread once per chunk, over ~a million lengths: it must not be slower than the chunk's upload),
+                // cut at the listed exceptions, whose offsets it yields on the way
+                const uint32_t *l32 = b.h_seq_len;
+                const uint16_t *l16 = b.h_seq_len16;
+                auto span_sum = [l32, l16](uint32_t i0, uint32_t i1) {
+                    return l32 ? sum_lengths(l32 + i0, i1 - i0) : sum_lengths(l16 + i0, i1 - i0);
+                };
                 uint64_t sum = 0;
-                size_t xi = exc_i;
-                for (uint32_t i = a; i < e; ++i) {
-                    if (xi < b.n_exc && b.h_exc_seq[xi] == i) exc_at.push_back({off_a + sum, b.h_seq_len[i]}), ++xi;
-                    sum += b.h_seq_len[i];
+                uint32_t at = a;
+                for (size_t xi = exc_i; xi < b.n_exc && b.h_exc_seq[xi] < e; ++xi) {
+                    const uint32_t x = b.h_exc_seq[xi];
+                    if (x < at) continue;
+                    sum += span_sum(at, x);
+                    exc_at.push_back({off_a + sum, hlen(x)});
+                    at = x;
                 }
+                sum += span_sum(at, e);
                 first = off_a, end = off_a + sum;
                 dense_pos = end;
             } else {
                 for (size_t xi = exc_i; xi < b.n_exc && b.h_exc_seq[xi] < e; ++xi)
-                    if (b.h_exc_seq[xi] >= a) exc_at.push_back({b.h_seq_off[b.h_exc_seq[xi]], b.h_seq_len[b.h_exc_seq[xi]]});
-                first = b.h_seq_off[a], end = b.h_seq_off[e - 1] + b.h_seq_len[e - 1];
+                    if (b.h_exc_seq[xi] >= a) exc_at.push_back({b.h_seq_off[b.h_exc_seq[xi]], hlen(b.h_exc_seq[xi])});
+                first = b.h_seq_off[a], end = b.h_seq_off[e - 1] + hlen(e - 1);
             }
             b0 = std::min<uint64_t>(first, b.blob_bytes) & ~(uint64_t)15;
             b1 = e == n_seqs ? b.blob_bytes : std::min<uint64_t>(end, b.blob_bytes);
@@ -624,15 +669,14 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                 // one offset beyond the chunk: k_hash checks every sequence against its successor's offset
                 const size_t n_off = (size_t)(e - a) + (e < n_seqs ? 1 : 0);
                 if (dense) { // lengths only (one beyond the chunk feeds the scan's last output); offsets by prefix sum
-                    CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, n_off * 4, cudaMemcpyHostToDevice, cs));
+                    { int r = upload_lengths(ctx, b, a, n_off, cs, cn); if (r) return r; }
                     int r = scan_offsets(ctx, b.seq_len + a, (uint64_t *)b.seq_off + a, n_off, off_a, cs);
                     if (r) return r;
                     cn.kernel_launches += 1;
-                    cn.bytes_h2d += n_off * 4;
                 } else {
                     CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, n_off * 8, cudaMemcpyHostToDevice, cs));
-                    CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, (size_t)(e - a) * 4, cudaMemcpyHostToDevice, cs));
-                    cn.bytes_h2d += n_off * 8 + (uint64_t)(e - a) * 4;
+                    { int r = upload_lengths(ctx, b, a, (size_t)(e - a), cs, cn); if (r) return r; }
+                    cn.bytes_h2d += n_off * 8;
                 }
                 if (prepacked) {
                     // the words of the new sequences, as they are; flags and raw bytes only for the listed exceptions
@@ -874,6 +918,15 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             cn.kernel_launches += 1;
         }
         if (staged) CK(cudaEventRecord(ctx->ev[5], st));
+    }
+    if (b.late_bytes) {
+        if (b.h_pp) {
+            CK(cudaMemcpyAsync(b.late_dst, b.late_src, b.late_bytes, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(ctx->ev[12], cs));
+            CK(cudaStreamWaitEvent(s, ctx->ev[12], 0));
+        } else {
+            CK(cudaMemcpyAsync(b.late_dst, b.late_src, b.late_bytes, cudaMemcpyHostToDevice, s));
+        }
     }
     cn.ms_host_enqueued = ms_since(t_call);
     if (packer.last_pack_ns())
@@ -1199,7 +1252,7 @@ void tdb_destroy(tdb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->dev);
     DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->pair_p, &c->pair_t,
-                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->scan_tmp, &c->mask_hits, &c->ctrl, &c->loci, &c->runs,
+                      &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->scan_tmp, &c->mask_hits, &c->len16, &c->ctrl, &c->loci, &c->runs,
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
@@ -1378,7 +1431,8 @@ static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t
 static int assess_tail(tdb_ctx *ctx, int is_duo, DevBatch &b, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
                        double q, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
     int r;
-    UPLOAD(ctx->loci, loci, n_loci * sizeof(tdb_trio_locus), 0);
+    ENSURE(ctx->loci, n_loci * sizeof(tdb_trio_locus) + 16); // uploaded behind the last chunk (run_align)
+    b.late_dst = ctx->loci.p, b.late_src = loci, b.late_bytes = n_loci * sizeof(tdb_trio_locus);
     ENSURE(ctx->aout, n_loci * 2 * sizeof(tdb_allele_out) + 16);
     ENSURE(ctx->mask, n_pairs + 16);
     ENSURE(ctx->mask_hits, ((size_t)MASK_HITS_CAP + 1) * 4);
@@ -1439,7 +1493,9 @@ static int packed_common(tdb_ctx *ctx, const tdb_packed_seqs *sq, const uint32_t
     if (!sq) return fail(ctx, TDB_E_INVALID, "null pointer argument");
     if ((sq->n_bases && !sq->packed) || (sq->n_exc && (!sq->exc_seq || !sq->exc_bytes)))
         return fail(ctx, TDB_E_INVALID, "null pointer argument");
-    int r = validate_common(ctx, sq->packed, sq->seq_off, sq->seq_len, pair_pattern, pair_text, sq->n_seqs, n_pairs, out_score);
+    if (sq->seq_len && sq->seq_len16) return fail(ctx, TDB_E_INVALID, "give seq_len or seq_len16, not both");
+    const void *any_len = sq->seq_len ? (const void *)sq->seq_len : (const void *)sq->seq_len16;
+    int r = validate_common(ctx, sq->packed, sq->seq_off, any_len, pair_pattern, pair_text, sq->n_seqs, n_pairs, out_score);
     if (r) return r;
     for (size_t i = 0; i < sq->n_exc; ++i)
         if (sq->exc_seq[i] >= sq->n_seqs || (i && sq->exc_seq[i] <= sq->exc_seq[i - 1]))
@@ -1448,6 +1504,8 @@ static int packed_common(tdb_ctx *ctx, const tdb_packed_seqs *sq, const uint32_t
                           sq->n_exc != 0);
     if (r) return r;
     b.h_packed = sq->packed, b.h_exc_seq = sq->exc_seq, b.h_exc_bytes = sq->exc_bytes, b.n_exc = sq->n_exc;
+    b.h_seq_len16 = sq->seq_len16;
+    if (sq->seq_len16) ENSURE(ctx->len16, sq->n_seqs * 2 + 16);
     return TDB_OK;
 }
 

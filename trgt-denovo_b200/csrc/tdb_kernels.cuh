@@ -212,6 +212,12 @@ __global__ void __launch_bounds__(256) k_hash(const uint64_t *__restrict__ seq_o
     seq_hash[i] = h == HT_EMPTY ? 0 : h;
 }
 
+// packed input may hand the sequence lengths over as uint16 (tdb_packed_seqs.seq_len16): widened here, next to the data
+__global__ void __launch_bounds__(256) k_widen_len(const uint16_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
 // Pair lists are runs -- "reads r .. r+c-1 of one allele against target t" is how align_alleleset /
 // align_allele (src/denovo.rs:22-54) visit them -- so a host batch ships them run-length encoded
 // (12 bytes per run instead of 8 bytes per pair) and this kernel expands them next to the data.

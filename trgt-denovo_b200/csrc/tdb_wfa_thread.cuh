@@ -59,16 +59,6 @@ __device__ __forceinline__ int th_extend(const uint32_t *sw, int psh, int tsh, i
     return min(eq, room);
 }
 
-// Lanes are DECOUPLED: every lane walks the score steps of its own pair, and a lane whose pair is finished (or has
-// outgrown this tier) waits until at least TH_REFILL lanes of its warp wait -- then those lanes together rebuild their
-// alignments (backtrace + replay), write the results and fetch new pairs.  A warp therefore never idles 31 lanes behind
-// its slowest pair (the first version ran 32 pairs as one batch: 15 of 32 lanes active, ncu r01p / r02c), and the
-// divergent refill section always runs with a quarter of the warp or more.
-#ifndef TDB_TH_REFILL
-#define TDB_TH_REFILL 8
-#endif
-constexpr int TH_REFILL = TDB_TH_REFILL;
-
 template <int X, int O1, int E1, int O2, int E2>
 __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
     static_assert(X == 8 && O1 + E1 == 6 && E1 == 2 && O2 + E2 > TH_SMAX, "ring geometry is built for 8/4/2/24/1");
@@ -87,22 +77,188 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
     const Penalties pn = {X, O1, E1, O2, E2};
     const Heur heur = p.heur;
     unsigned long long tot_cells = 0, tot_ext = 0, tot_cols = 0, tot_done = 0;
-    // ---- per-lane state of the pair in progress ----
-    enum { ST_NONE = 0, ST_RUN = 1, ST_DONE = 2, ST_FAIL = 3 }; // DONE: penalty found, alignment not rebuilt yet; FAIL: not this tier's
-    int state = ST_NONE;
-    uint32_t idx = 0;
-    int n = 0, m = 0, psh = 0, tsh = 0, k_end = 0, s = 0, pen = -1, steps_wait = 0;
-    unsigned ext = 0, cells = 0;
-    int ml2 = 1, ms2 = 0, ml4 = 1, ms4 = 0, ml6 = 1, ms6 = 0, ml8 = 1, ms8 = 0, il = 1, is = 0, dl = 1, ds = 0;
-    bool exhausted = false; // warp-uniform: the work list has run dry
     for (;;) {
-        const unsigned waiting = __ballot_sync(TDB_FULL, state != ST_RUN);
-        const unsigned n_wait = __popc(waiting);
-        if (n_wait == 32u || (n_wait >= (unsigned)TH_REFILL && (!exhausted || __any_sync(TDB_FULL, state == ST_DONE || state == ST_FAIL)))) {
-            // ================= refill: results of the finished lanes, then new pairs =================
-            if (state == ST_DONE || state == ST_FAIL) {
-                int clipped = 0, cols = 0;
-                if (state == ST_DONE && pen > 0) { // backtrace (A.4) + forward replay with the clipped score
+        unsigned b = 0;
+        if (lane == 0) b = atomicAdd(p.work_counter, 32u);
+        b = __shfl_sync(TDB_FULL, b, 0);
+        if (b >= src.total) break;
+        const unsigned it = b + lane;
+        if (it < src.total) {
+            const uint32_t idx = item_at(p, src, it);
+            const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
+            const int n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
+            const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
+            const int psh = (int)(poff & 15), tsh = (int)(toff & 15);
+            { // stage both sequences: the only global loads of the alignment, all independent
+                const uint32_t *gp = p.packed + (poff >> 4), *gt = p.packed + (toff >> 4);
+                const int np = (psh + n + 31) >> 4, nt = (tsh + m + 31) >> 4; // words incl. the funnel-shift neighbour
+#pragma unroll
+                for (int i = 0; i < TH_SEQW; ++i) {
+                    if (i < np) sw[i * TH_NT] = __ldg(gp + i);
+                    if (i < nt) sw[(TH_SEQW + i) * TH_NT] = __ldg(gt + i);
+                }
+            }
+            const int k_end = m - n;
+            unsigned ext = 0, cells = 0;
+            int pen = -1, clipped = 0, cols = 0;
+            // ---- score 0 ---------------------------------------------------------------------------
+            const int m0 = th_extend(sw, psh, tsh, n, m, 0, 0);
+            ext += (unsigned)(m0 >> 4) + 1u;
+            if (k_end == 0 && m0 >= m) {
+                pen = 0, cols = m;
+            } else {
+                TH_M(0, 0) = (int16_t)m0;
+                // wavefront ranges (lo, span = hi - lo + 1; span 0 = null) of M[s-2], M[s-4], M[s-6], M[s-8], I1/D1[s-2]
+                int ml2 = 1, ms2 = 0, ml4 = 1, ms4 = 0, ml6 = 0, ms6 = 1, ml8 = 1, ms8 = 0;
+                int il = 1, is = 0, dl = 1, ds = 0;
+                int steps_wait = heur.steps;
+                if (heur.kind == 1) --steps_wait;
+                for (int s = 6; s <= TH_SMAX; s += 2) {
+                    const int hh = s >> 1;
+                    const int cur = hh % TH_MSLOTS, s6 = (hh + 2) % TH_MSLOTS, s8 = (hh + 1) % TH_MSLOTS;
+                    int nml = 1, nms = 0, nil = 1, nis = 0, ndl = 1, nds = 0; // ranges of score s
+                    if (ms8 | ms6 | is | ds) {
+                        int lo = INT32_MAX, hi = INT32_MIN;
+                        if (ms8) lo = min(lo, ml8), hi = max(hi, ml8 + ms8 - 1);
+                        if (ms6) lo = min(lo, ml6 - 1), hi = max(hi, ml6 + ms6);
+                        if (is) lo = min(lo, il + 1), hi = max(hi, il + is);
+                        if (ds) lo = min(lo, dl - 1), hi = max(hi, dl + ds - 2);
+                        lo = max(lo, -n - 1);
+                        hi = min(hi, m + 1);
+                        cells += (unsigned)(hi - lo + 1);
+                        const bool has_i1 = ms6 || is, has_d1 = ms6 || ds;
+                        int tl_m = INT32_MAX, th_m = INT32_MIN, tl_i = INT32_MAX, th_i = INT32_MIN, tl_d = INT32_MAX,
+                            th_d = INT32_MIN;
+                        int min_d = HUGE_D;
+                        bool fin = false;
+                        unsigned long long pa = 0;
+                        uint32_t pb = 0, vmask = 0; // vmask: diagonals (bit k + TH_KM) whose M offset lies inside the matrix
+                        // I1 is updated in place: the old I1[k-1] travels in a register
+                        int carry_i = (unsigned)(lo - 1 - il) < (unsigned)is ? (int)TH_I(lo - 1) : NULLV;
+                        for (int k = lo; k <= hi; ++k) {
+                            const int old_i = (unsigned)(k - il) < (unsigned)is ? (int)TH_I(k) : NULLV;
+                            int nib = 0, o, e;
+                            o = (unsigned)(k - 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k - 1) : NULLV;
+                            e = carry_i;
+                            carry_i = old_i;
+                            int ins1;
+                            if (e >= o) ins1 = e, nib |= 4; else ins1 = o;
+                            ins1 += 1;
+                            o = (unsigned)(k + 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k + 1) : NULLV;
+                            e = (unsigned)(k + 1 - dl) < (unsigned)ds ? (int)TH_D(k + 1) : NULLV;
+                            int del1;
+                            if (e >= o) del1 = e, nib |= 8; else del1 = o;
+                            const int mis = ((unsigned)(k - ml8) < (unsigned)ms8 ? (int)TH_M(s8, k) : NULLV) + 1;
+                            int mv = max(max(ins1, del1), max(mis, NULLV + 1));
+                            int sc = 0; // later tests override: priority X > D1 > I1
+                            if (mv == ins1) sc = 1;
+                            if (mv == del1) sc = 2;
+                            if (mv == mis) sc = 3;
+                            nib |= sc;
+                            const int pi = k + TH_KM;
+                            if (pi < 16) pa |= (unsigned long long)nib << (4 * pi);
+                            else pb |= (uint32_t)nib << (4 * (pi - 16));
+                            if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = NULLV;
+                            if (mv >= 0) vmask |= 1u << pi, tl_m = min(tl_m, k), th_m = k;
+                            TH_M(cur, k) = (int16_t)mv;
+                            if (has_i1) {
+                                TH_I(k) = (int16_t)ins1;
+                                if ((unsigned)ins1 <= (unsigned)m && (unsigned)(ins1 - k) <= (unsigned)n) tl_i = min(tl_i, k), th_i = k;
+                            }
+                            if (has_d1) {
+                                TH_D(k) = (int16_t)del1;
+                                if ((unsigned)del1 <= (unsigned)m && (unsigned)(del1 - k) <= (unsigned)n) tl_d = min(tl_d, k), th_d = k;
+                            }
+                        }
+                        // Greedy extension of the live diagonals (trimming never changes offsets, A.1 step 1), as ONE
+                        // loop over 16-base compares: a lane moves on to its next diagonal as soon as the current one
+                        // stops matching, so a warp pays the longest per-lane TOTAL, not the sum of per-diagonal maxima.
+                        {
+                            int k = 0, v = 0, h = 0, room = 0, eq = 0;
+                            bool active = false;
+                            for (;;) {
+                                if (!active) {
+                                    if (!vmask) break;
+                                    const int pi = __ffs(vmask) - 1;
+                                    vmask &= vmask - 1;
+                                    k = pi - TH_KM;
+                                    h = (int)TH_M(cur, k), v = h - k;
+                                    room = min(n - v, m - h), eq = 0;
+                                    active = true;
+                                }
+                                bool stop = eq >= room;
+                                if (!stop) {
+                                    const uint32_t x = th_get16(sw, 0, psh + v + eq) ^ th_get16(sw, TH_SEQW, tsh + h + eq);
+                                    if (x) eq += (__ffs(x) - 1) >> 1, stop = true;
+                                    else eq += 16, stop = eq >= room;
+                                }
+                                if (stop) {
+                                    eq = min(eq, room);
+                                    ext += (unsigned)(eq >> 4) + 1u;
+                                    const int mv = h + eq;
+                                    TH_M(cur, k) = (int16_t)mv;
+                                    min_d = min(min_d, max(n - (mv - k), m - mv));
+                                    fin |= (k == k_end) && (mv >= m);
+                                    active = false;
+                                }
+                            }
+                        }
+                        const int t = hh - 3;
+                        TH_P(t, 0) = (uint32_t)pa, TH_P(t, 1) = (uint32_t)(pa >> 32), TH_P(t, 2) = pb;
+                        if (fin) {
+                            pen = s;
+                            break;
+                        }
+                        if (tl_m <= th_m) nml = tl_m, nms = th_m - tl_m + 1;
+                        if (tl_i <= th_i) nil = tl_i, nis = th_i - tl_i + 1;
+                        if (tl_d <= th_d) ndl = tl_d, nds = th_d - tl_d + 1;
+                        // ---- wf-adaptive cut-off + equate (A.3) ------------------------------------------
+                        if (heur.kind == 1 && nms) {
+                            int mlo = nml, mhi = nml + nms - 1;
+                            --steps_wait;
+                            if (steps_wait <= 0 && nms >= heur.min_len) {
+                                const int md = min(max(n, m), min_d);
+                                const int top_limit = min(k_end, mhi);
+                                int new_lo = mlo;
+                                if (top_limit > mlo) {
+                                    int k = mlo;
+                                    for (; k < top_limit; ++k) {
+                                        const int off = (int)TH_M(cur, k);
+                                        const int d = off >= 0 ? max(n - (off - k), m - off) : HUGE_D;
+                                        if (d - md <= heur.max_dist) break;
+                                    }
+                                    new_lo = k; // first diagonal close enough, or top_limit
+                                }
+                                const int bot_limit = max(k_end, new_lo);
+                                int new_hi = mhi;
+                                if (bot_limit < mhi) {
+                                    int k = mhi;
+                                    for (; k > bot_limit; --k) {
+                                        const int off = (int)TH_M(cur, k);
+                                        const int d = off >= 0 ? max(n - (off - k), m - off) : HUGE_D;
+                                        if (d - md <= heur.max_dist) break;
+                                    }
+                                    new_hi = k;
+                                }
+                                mlo = new_lo, mhi = new_hi;
+                                steps_wait = heur.steps;
+                            }
+                            nml = mlo, nms = mhi - mlo + 1;
+                            if (nms > 0) { // equate: the gap wavefronts never reach beyond M
+                                int a = max(nil, mlo), z = min(nil + nis - 1, mhi);
+                                if (nis) nil = a, nis = max(0, z - a + 1);
+                                a = max(ndl, mlo), z = min(ndl + nds - 1, mhi);
+                                if (nds) ndl = a, nds = max(0, z - a + 1);
+                            } else {
+                                nml = 1, nms = 0;
+                            }
+                        }
+                    }
+                    ml8 = ml6, ms8 = ms6, ml6 = ml4, ms6 = ms4, ml4 = ml2, ms4 = ms2, ml2 = nml, ms2 = nms;
+                    il = nil, is = nis, dl = ndl, ds = nds;
+                }
+                // ---- backtrace (A.4) + forward replay with the clipped score --------------------------
+                if (pen > 0) {
                     unsigned long long ops = 0;
                     int nops = 0, n_del = 0, comp = 0 /* 0 M, 1 I1, 2 D1 */, cs = pen, k = k_end;
                     while (!(comp == 0 && cs == 0)) {
@@ -159,216 +315,23 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                         clipped = acc.finish(pn);
                         cols = acc.col;
                     }
-                } else if (state == ST_DONE) {
-                    cols = m; // identical: penalty 0, every column a match
-                }
-                if (state == ST_DONE && pen >= 0) {
-                    p.out_score[idx] = clipped;
-                    if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
-                    if (p.out_penalty) p.out_penalty[idx] = pen;
-                    if (p.work) {
-                        p.work[3 * (size_t)idx] = cells, p.work[3 * (size_t)idx + 1] = ext;
-                        p.work[3 * (size_t)idx + 2] = (uint32_t)cols;
-                    }
-                    tot_cells += cells, tot_ext += ext, tot_cols += (unsigned)cols, ++tot_done;
-                } else {
-                    const unsigned j = atomicAdd(p.next_count, 1u);
-                    p.next_todo[j] = idx;
-                }
-                state = ST_NONE;
-            }
-            if (!exhausted) { // one atomic for all waiting lanes
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(p.work_counter, n_wait);
-                base = __shfl_sync(TDB_FULL, base, 0);
-                const unsigned it = base + __popc(waiting & ((1u << lane) - 1u));
-                exhausted = base + n_wait >= src.total;
-                if (state == ST_NONE && it < src.total) {
-                    idx = item_at(p, src, it);
-                    const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
-                    n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
-                    const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
-                    psh = (int)(poff & 15), tsh = (int)(toff & 15);
-                    { // stage both sequences: the only global loads of the alignment, all independent
-                        const uint32_t *gp = p.packed + (poff >> 4), *gt = p.packed + (toff >> 4);
-                        const int np = (psh + n + 31) >> 4, nt = (tsh + m + 31) >> 4; // words incl. the funnel-shift neighbour
-#pragma unroll
-                        for (int i = 0; i < TH_SEQW; ++i) {
-                            if (i < np) sw[i * TH_NT] = __ldg(gp + i);
-                            if (i < nt) sw[(TH_SEQW + i) * TH_NT] = __ldg(gt + i);
-                        }
-                    }
-                    k_end = m - n;
-                    cells = 0, pen = -1;
-                    // ---- score 0 ----
-                    const int m0 = th_extend(sw, psh, tsh, n, m, 0, 0);
-                    ext = (unsigned)(m0 >> 4) + 1u;
-                    if (k_end == 0 && m0 >= m) {
-                        pen = 0, state = ST_DONE;
-                    } else {
-                        TH_M(0, 0) = (int16_t)m0;
-                        // wavefront ranges (lo, span = hi - lo + 1; span 0 = null) of M[s-2], M[s-4], M[s-6], M[s-8], I1/D1[s-2]
-                        ml2 = 1, ms2 = 0, ml4 = 1, ms4 = 0, ml6 = 0, ms6 = 1, ml8 = 1, ms8 = 0;
-                        il = 1, is = 0, dl = 1, ds = 0;
-                        steps_wait = heur.steps;
-                        if (heur.kind == 1) --steps_wait;
-                        s = 6;
-                        state = ST_RUN;
-                    }
                 }
             }
-            if (__all_sync(TDB_FULL, state == ST_NONE)) break; // nothing in progress, nothing left to fetch
-            continue;
-        }
-        // ================= one score step of every lane that has a pair in progress =================
-        if (state == ST_RUN) {
-            const int hh = s >> 1;
-            const int cur = hh % TH_MSLOTS, s6 = (hh + 2) % TH_MSLOTS, s8 = (hh + 1) % TH_MSLOTS;
-            int nml = 1, nms = 0, nil = 1, nis = 0, ndl = 1, nds = 0; // ranges of score s
-            bool fin = false;
-            if (ms8 | ms6 | is | ds) {
-                int lo = INT32_MAX, hi = INT32_MIN;
-                if (ms8) lo = min(lo, ml8), hi = max(hi, ml8 + ms8 - 1);
-                if (ms6) lo = min(lo, ml6 - 1), hi = max(hi, ml6 + ms6);
-                if (is) lo = min(lo, il + 1), hi = max(hi, il + is);
-                if (ds) lo = min(lo, dl - 1), hi = max(hi, dl + ds - 2);
-                lo = max(lo, -n - 1);
-                hi = min(hi, m + 1);
-                cells += (unsigned)(hi - lo + 1);
-                const bool has_i1 = ms6 || is, has_d1 = ms6 || ds;
-                int tl_m = INT32_MAX, th_m = INT32_MIN, tl_i = INT32_MAX, th_i = INT32_MIN, tl_d = INT32_MAX,
-                    th_d = INT32_MIN;
-                int min_d = HUGE_D;
-                unsigned long long pa = 0;
-                uint32_t pb = 0, vmask = 0; // vmask: diagonals (bit k + TH_KM) whose M offset lies inside the matrix
-                // I1 is updated in place: the old I1[k-1] travels in a register
-                int carry_i = (unsigned)(lo - 1 - il) < (unsigned)is ? (int)TH_I(lo - 1) : NULLV;
-                for (int k = lo; k <= hi; ++k) {
-                    const int old_i = (unsigned)(k - il) < (unsigned)is ? (int)TH_I(k) : NULLV;
-                    int nib = 0, o, e;
-                    o = (unsigned)(k - 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k - 1) : NULLV;
-                    e = carry_i;
-                    carry_i = old_i;
-                    int ins1;
-                    if (e >= o) ins1 = e, nib |= 4; else ins1 = o;
-                    ins1 += 1;
-                    o = (unsigned)(k + 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k + 1) : NULLV;
-                    e = (unsigned)(k + 1 - dl) < (unsigned)ds ? (int)TH_D(k + 1) : NULLV;
-                    int del1;
-                    if (e >= o) del1 = e, nib |= 8; else del1 = o;
-                    const int mis = ((unsigned)(k - ml8) < (unsigned)ms8 ? (int)TH_M(s8, k) : NULLV) + 1;
-                    int mv = max(max(ins1, del1), max(mis, NULLV + 1));
-                    int sc = 0; // later tests override: priority X > D1 > I1
-                    if (mv == ins1) sc = 1;
-                    if (mv == del1) sc = 2;
-                    if (mv == mis) sc = 3;
-                    nib |= sc;
-                    const int pi = k + TH_KM;
-                    if (pi < 16) pa |= (unsigned long long)nib << (4 * pi);
-                    else pb |= (uint32_t)nib << (4 * (pi - 16));
-                    if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = NULLV;
-                    if (mv >= 0) vmask |= 1u << pi, tl_m = min(tl_m, k), th_m = k;
-                    TH_M(cur, k) = (int16_t)mv;
-                    if (has_i1) {
-                        TH_I(k) = (int16_t)ins1;
-                        if ((unsigned)ins1 <= (unsigned)m && (unsigned)(ins1 - k) <= (unsigned)n) tl_i = min(tl_i, k), th_i = k;
-                    }
-                    if (has_d1) {
-                        TH_D(k) = (int16_t)del1;
-                        if ((unsigned)del1 <= (unsigned)m && (unsigned)(del1 - k) <= (unsigned)n) tl_d = min(tl_d, k), th_d = k;
-                    }
+            if (pen >= 0) {
+                p.out_score[idx] = clipped;
+                if (p.out_status) p.out_status[idx] = TDB_STATUS_ALG_COMPLETED;
+                if (p.out_penalty) p.out_penalty[idx] = pen;
+                if (p.work) {
+                    p.work[3 * (size_t)idx] = cells, p.work[3 * (size_t)idx + 1] = ext;
+                    p.work[3 * (size_t)idx + 2] = (uint32_t)cols;
                 }
-                // Greedy extension of the live diagonals (trimming never changes offsets, A.1 step 1), as ONE
-                // loop over 16-base compares: a lane moves on to its next diagonal as soon as the current one
-                // stops matching, so a warp pays the longest per-lane TOTAL, not the sum of per-diagonal maxima.
-                {
-                    int k = 0, v = 0, h = 0, room = 0, eq = 0;
-                    bool active = false;
-                    for (;;) {
-                        if (!active) {
-                            if (!vmask) break;
-                            const int pi = __ffs(vmask) - 1;
-                            vmask &= vmask - 1;
-                            k = pi - TH_KM;
-                            h = (int)TH_M(cur, k), v = h - k;
-                            room = min(n - v, m - h), eq = 0;
-                            active = true;
-                        }
-                        bool stop = eq >= room;
-                        if (!stop) {
-                            const uint32_t x = th_get16(sw, 0, psh + v + eq) ^ th_get16(sw, TH_SEQW, tsh + h + eq);
-                            if (x) eq += (__ffs(x) - 1) >> 1, stop = true;
-                            else eq += 16, stop = eq >= room;
-                        }
-                        if (stop) {
-                            eq = min(eq, room);
-                            ext += (unsigned)(eq >> 4) + 1u;
-                            const int mv = h + eq;
-                            TH_M(cur, k) = (int16_t)mv;
-                            min_d = min(min_d, max(n - (mv - k), m - mv));
-                            fin |= (k == k_end) && (mv >= m);
-                            active = false;
-                        }
-                    }
-                }
-                const int t = hh - 3;
-                TH_P(t, 0) = (uint32_t)pa, TH_P(t, 1) = (uint32_t)(pa >> 32), TH_P(t, 2) = pb;
-                if (!fin) {
-                    if (tl_m <= th_m) nml = tl_m, nms = th_m - tl_m + 1;
-                    if (tl_i <= th_i) nil = tl_i, nis = th_i - tl_i + 1;
-                    if (tl_d <= th_d) ndl = tl_d, nds = th_d - tl_d + 1;
-                    // ---- wf-adaptive cut-off + equate (A.3) ------------------------------------------
-                    if (heur.kind == 1 && nms) {
-                        int mlo = nml, mhi = nml + nms - 1;
-                        --steps_wait;
-                        if (steps_wait <= 0 && nms >= heur.min_len) {
-                            const int md = min(max(n, m), min_d);
-                            const int top_limit = min(k_end, mhi);
-                            int new_lo = mlo;
-                            if (top_limit > mlo) {
-                                int k = mlo;
-                                for (; k < top_limit; ++k) {
-                                    const int off = (int)TH_M(cur, k);
-                                    const int d = off >= 0 ? max(n - (off - k), m - off) : HUGE_D;
-                                    if (d - md <= heur.max_dist) break;
-                                }
-                                new_lo = k; // first diagonal close enough, or top_limit
-                            }
-                            const int bot_limit = max(k_end, new_lo);
-                            int new_hi = mhi;
-                            if (bot_limit < mhi) {
-                                int k = mhi;
-                                for (; k > bot_limit; --k) {
-                                    const int off = (int)TH_M(cur, k);
-                                    const int d = off >= 0 ? max(n - (off - k), m - off) : HUGE_D;
-                                    if (d - md <= heur.max_dist) break;
-                                }
-                                new_hi = k;
-                            }
-                            mlo = new_lo, mhi = new_hi;
-                            steps_wait = heur.steps;
-                        }
-                        nml = mlo, nms = mhi - mlo + 1;
-                        if (nms > 0) { // equate: the gap wavefronts never reach beyond M
-                            int a = max(nil, mlo), z = min(nil + nis - 1, mhi);
-                            if (nis) nil = a, nis = max(0, z - a + 1);
-                            a = max(ndl, mlo), z = min(ndl + nds - 1, mhi);
-                            if (nds) ndl = a, nds = max(0, z - a + 1);
-                        } else {
-                            nml = 1, nms = 0;
-                        }
-                    }
-                }
-            }
-            if (fin) {
-                pen = s, state = ST_DONE;
+                tot_cells += cells, tot_ext += ext, tot_cols += (unsigned)cols, ++tot_done;
             } else {
-                ml8 = ml6, ms8 = ms6, ml6 = ml4, ms6 = ms4, ml4 = ml2, ms4 = ms2, ml2 = nml, ms2 = nms;
-                il = nil, is = nis, dl = ndl, ds = nds;
-                s += 2;
-                if (s > TH_SMAX) state = ST_FAIL; // penalty beyond this tier: the lockstep tier starts it over
+                const unsigned j = atomicAdd(p.next_count, 1u);
+                p.next_todo[j] = idx;
             }
         }
+        __syncwarp();
     }
 #undef TH_M
 #undef TH_I
