@@ -72,7 +72,8 @@ struct tdb_ctx {
     std::string err;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[16] = {};
-    std::vector<cudaEvent_t> up_ev; // one per in-flight chunk upload
+    std::vector<cudaEvent_t> up_ev, cp_ev; // per chunk: data prepared (preparation stream) / copies done (copy stream)
+    cudaStream_t prep_stream = nullptr; // kernels on freshly uploaded data (see run_align)
     // grow-only device buffers
     DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, pair_p, pair_t, score, status, penalty;
     DevBuf rep, work, list_b, list_c, scan_tmp, mask_hits, len16;
@@ -434,18 +435,15 @@ uint64_t sum_lengths(const T *__restrict__ p, size_t n) {
     return s0 + s1 + s2 + s3;
 }
 
-// lengths of sequences [a, a + n) to the device: uint32 as they are, or uint16 widened by a small kernel next to the data
+// lengths of sequences [a, a + n) to the device: uint32 as they are, or uint16 (widened next to the data by k_widen_len,
+// which the caller launches on the preparation stream)
 int upload_lengths(tdb_ctx *ctx, const DevBatch &b, uint32_t a, size_t n, cudaStream_t cs, tdb_counters &cn) {
     if (b.h_seq_len) {
         CK(cudaMemcpyAsync((uint32_t *)b.seq_len + a, b.h_seq_len + a, n * 4, cudaMemcpyHostToDevice, cs));
         cn.bytes_h2d += n * 4;
     } else {
-        uint16_t *d16 = (uint16_t *)ctx->len16.p + a;
-        CK(cudaMemcpyAsync(d16, b.h_seq_len16 + a, n * 2, cudaMemcpyHostToDevice, cs));
-        k_widen_len<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(d16, (uint32_t *)b.seq_len + a, (uint32_t)n);
-        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync((uint16_t *)ctx->len16.p + a, b.h_seq_len16 + a, n * 2, cudaMemcpyHostToDevice, cs));
         cn.bytes_h2d += n * 2;
-        cn.kernel_launches += 1;
     }
     return TDB_OK;
 }
@@ -587,12 +585,15 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->up_ev.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->cp_ev.push_back(e);
     }
     Ctrl *ctrl = (Ctrl *)ctx->ctrl.p;
     CK(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), s));
     CK(cudaEventRecord(ctx->ev[10], s)); // the other slot's stream and the copy stream start after the reset
     for (int i = 1; i < n_slot; ++i) CK(cudaStreamWaitEvent(ctx->slot[i].st, ctx->ev[10], 0));
     if (b.h_pp) CK(cudaStreamWaitEvent(cs, ctx->ev[10], 0));
+    if (b.h_pp) CK(cudaStreamWaitEvent(ctx->prep_stream, ctx->ev[10], 0));
 
     AlignParams p;
     memset(&p, 0, sizeof(p));
@@ -630,6 +631,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         seq_up = e;
         // blob bytes of the new sequences (device batches: offsets unknown on the host -> everything at once)
         uint64_t b0 = 0, b1 = b.blob_bytes;
+        size_t n_len_up = 0; // lengths uploaded for this chunk (the kernels on them run on the preparation stream)
         const uint64_t off_a = dense_pos;
         if (b.h_pp && e > a) {
             uint64_t first = 0, end = 0;
@@ -670,12 +672,11 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                 const size_t n_off = (size_t)(e - a) + (e < n_seqs ? 1 : 0);
                 if (dense) { // lengths only (one beyond the chunk feeds the scan's last output); offsets by prefix sum
                     { int r = upload_lengths(ctx, b, a, n_off, cs, cn); if (r) return r; }
-                    int r = scan_offsets(ctx, b.seq_len + a, (uint64_t *)b.seq_off + a, n_off, off_a, cs);
-                    if (r) return r;
-                    cn.kernel_launches += 1;
+                    n_len_up = n_off;
                 } else {
                     CK(cudaMemcpyAsync((uint64_t *)b.seq_off + a, b.h_seq_off + a, n_off * 8, cudaMemcpyHostToDevice, cs));
                     { int r = upload_lengths(ctx, b, a, (size_t)(e - a), cs, cn); if (r) return r; }
+                    n_len_up = (size_t)(e - a);
                     cn.bytes_h2d += n_off * 8;
                 }
                 if (prepacked) {
@@ -804,10 +805,6 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                                        (size_t)c.part_runs[pt] * sizeof(PairRun), cudaMemcpyHostToDevice, cs));
                     at += c.part_runs[pt];
                 }
-                k_expand_runs<<<(cpairs + 255) / 256, 256, 0, cs>>>(dr, c.n_runs, (uint32_t)c.p0, cpairs, (uint32_t *)b.pp,
-                                                                     (uint32_t *)b.pt);
-                CK(cudaGetLastError());
-                cn.kernel_launches += 1;
                 cn.bytes_h2d += (uint64_t)c.n_runs * sizeof(PairRun);
             } else {
                 CK(cudaMemcpyAsync((uint32_t *)b.pp + c.p0, b.h_pp + c.p0, (c.p1 - c.p0) * 4, cudaMemcpyHostToDevice, cs));
@@ -815,9 +812,33 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
                 cn.bytes_h2d += (uint64_t)(c.p1 - c.p0) * 8;
             }
         }
-        // 2-bit packing (unless the host did it) and content hashes of the new sequences: on the copy stream for
-        // host batches, so that sequences are ready in order whichever slot needs them
-        cudaStream_t ps = b.h_pp ? cs : s;
+        // Everything that is a KERNEL on this chunk's fresh data -- widening of uint16 lengths, the offsets' prefix sum, the
+        // expansion of the run-length encoded pair list, 2-bit packing (unless the host did it), content hashes -- runs
+        // on a preparation stream behind the chunk's copies, so that the copy stream carries nothing but copies and the
+        // link never waits for a kernel (68 chunks x a few kernels had cost ~8 ms of link time per 937 k loci).  The
+        // preparation stream is in order: sequences become ready in order whichever slot needs them.
+        cudaStream_t ps = b.h_pp ? ctx->prep_stream : s;
+        if (b.h_pp) {
+            CK(cudaEventRecord(ctx->cp_ev[k], cs));
+            CK(cudaStreamWaitEvent(ps, ctx->cp_ev[k], 0));
+            if (n_len_up && !b.h_seq_len) {
+                k_widen_len<<<(unsigned)((n_len_up + 255) / 256), 256, 0, ps>>>((const uint16_t *)ctx->len16.p + a,
+                                                                                (uint32_t *)b.seq_len + a, (uint32_t)n_len_up);
+                CK(cudaGetLastError());
+                cn.kernel_launches += 1;
+            }
+            if (dense && n_len_up) {
+                int r = scan_offsets(ctx, b.seq_len + a, (uint64_t *)b.seq_off + a, n_len_up, off_a, ps);
+                if (r) return r;
+                cn.kernel_launches += 1;
+            }
+            if (c.rle) {
+                k_expand_runs<<<(cpairs + 255) / 256, 256, 0, ps>>>((const PairRun *)ctx->runs.p + c.run0, c.n_runs, (uint32_t)c.p0,
+                                                                     cpairs, (uint32_t *)b.pp, (uint32_t *)b.pt);
+                CK(cudaGetLastError());
+                cn.kernel_launches += 1;
+            }
+        }
         if (e > a) {
             for (const auto &rr : raw_ranges) { // blocks taken over from the host packer: 2-bit pack them here
                 const uint64_t x0 = rr.first & ~(uint64_t)15, x1 = rr.second;
@@ -847,7 +868,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         tdb_ctx::Slot &sl = ctx->slot[si];
         cudaStream_t st = sl.st;
         if (b.h_pp) {
-            CK(cudaEventRecord(ctx->up_ev[k], cs));
+            CK(cudaEventRecord(ctx->up_ev[k], ps));
             CK(cudaStreamWaitEvent(st, ctx->up_ev[k], 0));
         }
         if (staged) CK(cudaEventRecord(ctx->ev[2], st));
@@ -1035,18 +1056,28 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
 }
 
 constexpr unsigned MASK_HITS_CAP = 1u << 20; // set mask bytes a host call fetches as a list (beyond: the whole mask)
+// h_out != nullptr (fused host calls): the rows go to the host as they are produced -- the loci are reduced in slices and
+// the download of a slice (copy stream) runs under the reduction of the next one.
 int run_reduce_device(tdb_ctx *ctx, const tdb_trio_locus *dloci, size_t n_loci, const int32_t *dscores, double q,
-                      int is_duo, tdb_allele_out *dout, uint8_t *dmask, unsigned *hits = nullptr) {
-    cudaStream_t s = ctx->stream;
+                      int is_duo, tdb_allele_out *dout, uint8_t *dmask, unsigned *hits = nullptr, tdb_allele_out *h_out = nullptr) {
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
     CK(cudaEventRecord(ctx->ev[8], s));
-    if (n_loci) {
-        const unsigned threads = 128, blocks = (unsigned)((n_loci + threads - 1) / threads);
-        k_reduce<<<blocks, threads, 0, s>>>(dloci, (uint32_t)n_loci, dscores, q, is_duo, dout, dmask, hits,
+    const size_t n_slices = h_out && n_loci >= (1u << 16) ? 8 : 1;
+    for (size_t k = 0; k < n_slices && n_loci; ++k) {
+        const size_t l0 = n_loci * k / n_slices, l1 = n_loci * (k + 1) / n_slices;
+        const unsigned threads = 128, blocks = (unsigned)((l1 - l0 + threads - 1) / threads);
+        k_reduce<<<blocks, threads, 0, s>>>(dloci + l0, (uint32_t)(l1 - l0), dscores, q, is_duo, dout + 2 * l0, dmask, hits,
                                             hits ? hits + 1 : nullptr, hits ? MASK_HITS_CAP : 0u);
         CK(cudaGetLastError());
         ctx->counters.kernel_launches += 1;
+        if (h_out) {
+            CK(cudaEventRecord(ctx->ev[13], s));
+            CK(cudaStreamWaitEvent(cs, ctx->ev[13], 0));
+            CK(cudaMemcpyAsync(h_out + 2 * l0, dout + 2 * l0, (l1 - l0) * 2 * sizeof(tdb_allele_out), cudaMemcpyDeviceToHost, cs));
+        }
     }
     CK(cudaEventRecord(ctx->ev[9], s));
+    if (h_out) CK(cudaStreamSynchronize(cs));
     CK(cudaStreamSynchronize(s));
     const float ms = elapsed(ctx->ev[8], ctx->ev[9]);
     ctx->counters.ms_reduce = ms;
@@ -1167,6 +1198,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
     memset(&c->counters, 0, sizeof(c->counters));
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking);
     c->slot[0].st = c->stream;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->slot[1].st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[1].done, cudaEventDisableTiming);
@@ -1265,6 +1297,8 @@ void tdb_destroy(tdb_ctx *c) {
     for (int i = 0; i < 16; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->up_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->cp_ev) cudaEventDestroy(e);
+    if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
     if (c->h_packed) cudaFreeHost(c->h_packed);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_runs) cudaFreeHost(c->h_runs);
@@ -1447,11 +1481,9 @@ static int assess_tail(tdb_ctx *ctx, int is_duo, DevBatch &b, size_t n_pairs, co
     if (r) return r;
     unsigned *hits = sparse_mask ? (unsigned *)ctx->mask_hits.p : nullptr;
     r = run_reduce_device(ctx, (const tdb_trio_locus *)ctx->loci.p, n_loci, b.score, q, is_duo,
-                          (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p, hits);
+                          (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p, hits, out);
     if (r) return r;
-    uint64_t d2h = 0;
-    if (n_loci) CK(cudaMemcpyAsync(out, ctx->aout.p, n_loci * 2 * sizeof(tdb_allele_out), cudaMemcpyDeviceToHost, ctx->stream));
-    d2h += n_loci * 2 * sizeof(tdb_allele_out);
+    uint64_t d2h = n_loci * 2 * sizeof(tdb_allele_out); // downloaded slice by slice under the reduction
     if (out_score && n_pairs) {
         CK(cudaMemcpyAsync(out_score, b.score, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
         d2h += n_pairs * 4;

@@ -271,7 +271,7 @@ constexpr int WL_MAX = 40;  // |n-m| >= WL_MAX: wider than the warp tier's 64 di
 constexpr int KEY_WARP0 = 0; // sorted first: heaviest pairs of the shared-memory tiers, by descending |n-m| (the two pairs
                              // of a lockstep warp run to the larger of their penalties: neighbours should be alike)
 constexpr int KEY_QUAD0 = KEY_WARP0 + WL_MAX;
-constexpr int ML_MAX = 8;       // |n-m| < ML_MAX and both sequences >= ML_MINLEN bases: thread-per-pair tier first
+constexpr int ML_MAX = 11;      // |n-m| < ML_MAX and both sequences >= ML_MINLEN bases: thread-per-pair tier first
 constexpr int ML_MINLEN = 16;
 #ifndef TDB_TH_SEQW
 #define TDB_TH_SEQW 21
@@ -280,7 +280,7 @@ constexpr int TH_SEQW = TDB_TH_SEQW;            // 2-bit words staged per sequen
 constexpr int ML_MAXLEN = 16 * TH_SEQW - 32;    // its longest sequence: shift (<= 15) + length + 16 bases fit the window
 constexpr int KEY_MINI0 = KEY_QUAD0 + QL_MAX; // sorted last: the lightest pairs
 constexpr int KEY_NONE = 255;
-constexpr int N_HIST = 64;
+constexpr int N_HIST = 72;
 static_assert(KEY_MINI0 + ML_MAX <= N_HIST, "histogram size");
 
 // Closed form for the commonest non-identical contents (about two thirds of the aligned pairs of the 30x

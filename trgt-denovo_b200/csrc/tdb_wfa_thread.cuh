@@ -14,7 +14,13 @@
 // compares then never wait for global memory (an ncu capture of the first version, which read the
 // packed stream directly, had a third of its stall samples on those loads).  4 provenance bits per
 // computed cell (30 words) live in thread-local memory: written once per score, read by the backtrace.
-// A pair that is not finished at score 24 is handed to the lockstep tier, which starts it over.
+// Scores 25..30: the second gap piece appears (O2 + E2 = 25), but up to score 30 it consists of the two pure chains
+// that open at M[0] -- one insertion cell on diagonal +(s - 24), one deletion cell on diagonal -(s - 24) per score --
+// and the odd scores hold nothing else (their first-piece sources M[s-6], M[s-8], I1/D1[s-2] would have to be odd and
+// older than 25).  Those chains are carried in six registers and computed with the same rules as everything else
+// (open / extend, validity, trimming, cut-off, equate, provenance priority X > D2 > D1 > I2 > I1); an odd-score M
+// wavefront is never read again below score 31, so it is extended, counted and dropped.
+// A pair that is not finished at score TH_SMAX is handed to the lockstep tier, which starts it over.
 //
 // Semantics are those of wfa_align_warp (tdb_wfa.cuh) step for step: compute + trim (A.2),
 // wf-adaptive cut-off + equate (A.3), provenance tie-breaks X > D1 > I1 and matches re-extended only
@@ -28,13 +34,14 @@ namespace tdb {
 #define TDB_TH_NT 96
 #endif
 constexpr int TH_NT = TDB_TH_NT;            // threads (= pairs in flight) per CTA; a multiple of 32
-constexpr int TH_KM = 10;                   // diagonals -TH_KM .. TH_KM
+constexpr int TH_KM = 13;                   // diagonals -TH_KM .. TH_KM
 constexpr int TH_W = 2 * TH_KM + 1;
-constexpr int TH_SMAX = 24;                 // last score this tier computes
+constexpr int TH_SMAX = 30;                 // last score this tier computes
 constexpr int TH_MSLOTS = 5;                // M ring: scores s, s-2, .., s-8
 constexpr int TH_HW = TH_MSLOTS * TH_W + 2 * TH_W; // int16 elements per thread
-constexpr int TH_STEPS = TH_SMAX / 2 - 2;   // scores 6, 8, .., 24
-constexpr int TH_PW = 3;                    // provenance words per score step (21 nibbles)
+constexpr int TH_STEPS = TH_SMAX / 2 - 2;   // scores 6, 8, .., 30
+constexpr int TH_PW = 4;                    // provenance words per score step (27 nibbles)
+static_assert(TH_SMAX <= 30 && (TH_SMAX - 4) / 2 <= TH_KM, "second-piece handling below covers scores 25..30 only");
 constexpr int TH_MAXLEN = ML_MAXLEN;        // longest sequence this tier takes
 constexpr size_t th_smem_bytes() { return (size_t)TH_NT * (TH_HW * 2 + 2 * TH_SEQW * 4); }
 static_assert(15 + TH_MAXLEN + 16 <= 16 * TH_SEQW, "staging window");
@@ -61,7 +68,7 @@ __device__ __forceinline__ int th_extend(const uint32_t *sw, int psh, int tsh, i
 
 template <int X, int O1, int E1, int O2, int E2>
 __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
-    static_assert(X == 8 && O1 + E1 == 6 && E1 == 2 && O2 + E2 > TH_SMAX, "ring geometry is built for 8/4/2/24/1");
+    static_assert(X == 8 && O1 + E1 == 6 && E1 == 2 && O2 + E2 == 25 && E2 == 1, "ring geometry is built for 8/4/2/24/1");
     constexpr int NULLV = OffTraits<int16_t>::NULLV;
     constexpr int HUGE_D = 1 << 30;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -113,16 +120,97 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                 int il = 1, is = 0, dl = 1, ds = 0;
                 int steps_wait = heur.steps;
                 if (heur.kind == 1) --steps_wait;
-                for (int s = 6; s <= TH_SMAX; s += 2) {
+                // second gap piece: the cell of I2 / D2 of the previous score (diagonal, un-extended offset), if any
+                bool i2ok = false, d2ok = false;
+                int i2k = 0, i2v = 0, d2k = 0, d2v = 0;
+                unsigned p2 = 0; // bit 2t: M[6 + 2t] on the I2 chain's diagonal came from I2; bit 2t + 1: same for D2
+                for (int s = 6; s <= TH_SMAX && pen < 0; s += 2) {
+                    if (s >= O2 + E2 + 1) {
+                        // ---- the odd score s - 1: only the two second-piece cells exist ----
+                        const int t = s - 1;
+                        int kI = 0, vI = NULLV, kD = 0, vD = NULLV;
+                        bool hI = false, hD = false;
+                        if (t == O2 + E2) hI = hD = true, kI = 1, vI = m0 + 1, kD = -1, vD = m0; // open from M[0] = {0: m0}
+                        else {
+                            if (i2ok) hI = true, kI = i2k + 1, vI = i2v + 1;
+                            if (d2ok) hD = true, kD = d2k - 1, vD = d2v;
+                        }
+                        i2ok = d2ok = false;
+                        if (hI || hD) {
+                            int lo = t == O2 + E2 ? -1 : (hD ? kD : kI), hi = t == O2 + E2 ? 1 : (hI ? kI : kD);
+                            lo = max(lo, -n - 1), hi = min(hi, m + 1);
+                            cells += (unsigned)(hi - lo + 1);
+                            const bool okI = hI && kI <= hi && (unsigned)vI <= (unsigned)m && (unsigned)(vI - kI) <= (unsigned)n;
+                            const bool okD = hD && kD >= lo && (unsigned)vD <= (unsigned)m && (unsigned)(vD - kD) <= (unsigned)n;
+                            int dI = HUGE_D, dD = HUGE_D;
+                            bool fin_odd = false;
+                            if (okI) {
+                                const int eq = th_extend(sw, psh, tsh, n, m, vI - kI, vI);
+                                ext += (unsigned)(eq >> 4) + 1u;
+                                const int mv = vI + eq;
+                                dI = max(n - (mv - kI), m - mv);
+                                fin_odd |= kI == k_end && mv >= m;
+                            }
+                            if (okD) {
+                                const int eq = th_extend(sw, psh, tsh, n, m, vD - kD, vD);
+                                ext += (unsigned)(eq >> 4) + 1u;
+                                const int mv = vD + eq;
+                                dD = max(n - (mv - kD), m - mv);
+                                fin_odd |= kD == k_end && mv >= m;
+                            }
+                            if (fin_odd) break; // an odd final penalty: not this tier's (never seen: the even family gets there first)
+                            int mlo = okD ? kD : kI, mhi = okI ? kI : kD; // trimmed M range (empty when neither cell is valid)
+                            bool m_any = okI || okD;
+                            if (heur.kind == 1 && m_any) {
+                                --steps_wait;
+                                if (steps_wait <= 0 && mhi - mlo + 1 >= heur.min_len) {
+                                    const int md = min(max(n, m), min(dI, dD));
+#define TH_ODD_D(kk) ((kk) == kI && okI ? dI : ((kk) == kD && okD ? dD : HUGE_D))
+                                    const int top_limit = min(k_end, mhi);
+                                    int new_lo = mlo;
+                                    if (top_limit > mlo) {
+                                        int k = mlo;
+                                        for (; k < top_limit; ++k)
+                                            if (TH_ODD_D(k) - md <= heur.max_dist) break;
+                                        new_lo = k;
+                                    }
+                                    const int bot_limit = max(k_end, new_lo);
+                                    int new_hi = mhi;
+                                    if (bot_limit < mhi) {
+                                        int k = mhi;
+                                        for (; k > bot_limit; --k)
+                                            if (TH_ODD_D(k) - md <= heur.max_dist) break;
+                                        new_hi = k;
+                                    }
+#undef TH_ODD_D
+                                    mlo = new_lo, mhi = new_hi;
+                                    steps_wait = heur.steps;
+                                }
+                                m_any = mhi >= mlo;
+                                // equate: the gap wavefronts never reach beyond M
+                                if (m_any) {
+                                    i2ok = okI && kI >= mlo && kI <= mhi;
+                                    d2ok = okD && kD >= mlo && kD <= mhi;
+                                } else {
+                                    i2ok = okI, d2ok = okD; // (the general code leaves the gap ranges alone when M ends up empty)
+                                }
+                            } else {
+                                i2ok = okI, d2ok = okD;
+                            }
+                            i2k = kI, i2v = vI, d2k = kD, d2v = vD;
+                        }
+                    }
                     const int hh = s >> 1;
                     const int cur = hh % TH_MSLOTS, s6 = (hh + 2) % TH_MSLOTS, s8 = (hh + 1) % TH_MSLOTS;
                     int nml = 1, nms = 0, nil = 1, nis = 0, ndl = 1, nds = 0; // ranges of score s
-                    if (ms8 | ms6 | is | ds) {
+                    if (ms8 | ms6 | is | ds | (int)i2ok | (int)d2ok) {
                         int lo = INT32_MAX, hi = INT32_MIN;
                         if (ms8) lo = min(lo, ml8), hi = max(hi, ml8 + ms8 - 1);
                         if (ms6) lo = min(lo, ml6 - 1), hi = max(hi, ml6 + ms6);
                         if (is) lo = min(lo, il + 1), hi = max(hi, il + is);
                         if (ds) lo = min(lo, dl - 1), hi = max(hi, dl + ds - 2);
+                        if (i2ok) lo = min(lo, i2k + 1), hi = max(hi, i2k + 1);
+                        if (d2ok) lo = min(lo, d2k - 1), hi = max(hi, d2k - 1);
                         lo = max(lo, -n - 1);
                         hi = min(hi, m + 1);
                         cells += (unsigned)(hi - lo + 1);
@@ -131,8 +219,11 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                             th_d = INT32_MIN;
                         int min_d = HUGE_D;
                         bool fin = false;
-                        unsigned long long pa = 0;
-                        uint32_t pb = 0, vmask = 0; // vmask: diagonals (bit k + TH_KM) whose M offset lies inside the matrix
+                        unsigned long long pa = 0, pb = 0;
+                        uint32_t vmask = 0; // vmask: diagonals (bit k + TH_KM) whose M offset lies inside the matrix
+                        // the second piece's cells of this score: extensions of the previous score's (none before score 26)
+                        const int kI = i2k + 1, vI = i2v + 1, kD = d2k - 1, vD = d2v;
+                        const bool hI = i2ok && kI <= hi, hD = d2ok && kD >= lo;
                         // I1 is updated in place: the old I1[k-1] travels in a register
                         int carry_i = (unsigned)(lo - 1 - il) < (unsigned)is ? (int)TH_I(lo - 1) : NULLV;
                         for (int k = lo; k <= hi; ++k) {
@@ -149,15 +240,21 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                             int del1;
                             if (e >= o) del1 = e, nib |= 8; else del1 = o;
                             const int mis = ((unsigned)(k - ml8) < (unsigned)ms8 ? (int)TH_M(s8, k) : NULLV) + 1;
-                            int mv = max(max(ins1, del1), max(mis, NULLV + 1));
-                            int sc = 0; // later tests override: priority X > D1 > I1
+                            const int ins2 = hI && k == kI ? vI : NULLV + 1, del2 = hD && k == kD ? vD : NULLV;
+                            int mv = max(max(ins1, del1), max(mis, max(ins2, del2)));
+                            int sc = 0; // later tests override: priority X > D2 > D1 > I2 > I1
+                            bool f_i2 = false, f_d2 = false;
                             if (mv == ins1) sc = 1;
-                            if (mv == del1) sc = 2;
-                            if (mv == mis) sc = 3;
+                            if (mv == ins2) f_i2 = true;
+                            if (mv == del1) sc = 2, f_i2 = false;
+                            if (mv == del2) f_d2 = true, f_i2 = false;
+                            if (mv == mis) sc = 3, f_i2 = f_d2 = false;
                             nib |= sc;
+                            if (hI && k == kI && f_i2) p2 |= 1u << (2 * (hh - 3));
+                            if (hD && k == kD && f_d2) p2 |= 2u << (2 * (hh - 3));
                             const int pi = k + TH_KM;
                             if (pi < 16) pa |= (unsigned long long)nib << (4 * pi);
-                            else pb |= (uint32_t)nib << (4 * (pi - 16));
+                            else pb |= (unsigned long long)nib << (4 * (pi - 16));
                             if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = NULLV;
                             if (mv >= 0) vmask |= 1u << pi, tl_m = min(tl_m, k), th_m = k;
                             TH_M(cur, k) = (int16_t)mv;
@@ -204,7 +301,10 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                             }
                         }
                         const int t = hh - 3;
-                        TH_P(t, 0) = (uint32_t)pa, TH_P(t, 1) = (uint32_t)(pa >> 32), TH_P(t, 2) = pb;
+                        TH_P(t, 0) = (uint32_t)pa, TH_P(t, 1) = (uint32_t)(pa >> 32), TH_P(t, 2) = (uint32_t)pb, TH_P(t, 3) = (uint32_t)(pb >> 32);
+                        // this score's second-piece cells: inside the matrix? (their trimmed ranges, A.2)
+                        bool nI = hI && (unsigned)vI <= (unsigned)m && (unsigned)(vI - kI) <= (unsigned)n;
+                        bool nD = hD && (unsigned)vD <= (unsigned)m && (unsigned)(vD - kD) <= (unsigned)n;
                         if (fin) {
                             pen = s;
                             break;
@@ -249,10 +349,13 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                                 if (nis) nil = a, nis = max(0, z - a + 1);
                                 a = max(ndl, mlo), z = min(ndl + nds - 1, mhi);
                                 if (nds) ndl = a, nds = max(0, z - a + 1);
+                                nI = nI && kI >= mlo && kI <= mhi;
+                                nD = nD && kD >= mlo && kD <= mhi;
                             } else {
                                 nml = 1, nms = 0;
                             }
                         }
+                        i2ok = nI, i2k = kI, i2v = vI, d2ok = nD, d2k = kD, d2v = vD;
                     }
                     ml8 = ml6, ms8 = ms6, ml6 = ml4, ms6 = ms4, ml4 = ml2, ms4 = ms2, ml2 = nml, ms2 = nms;
                     il = nil, is = nis, dl = ndl, ds = nds;
@@ -267,9 +370,23 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                             pen = -1; // never expected: leave the pair to the next tier
                             break;
                         }
-                        const uint32_t wsel = pi < 8 ? TH_P(t, 0) : (pi < 16 ? TH_P(t, 1) : TH_P(t, 2));
+                        const uint32_t wsel = pi < 8 ? TH_P(t, 0) : (pi < 16 ? TH_P(t, 1) : (pi < 24 ? TH_P(t, 2) : TH_P(t, 3)));
                         const int nib = (int)(wsel >> (4 * (pi & 7))) & 15;
                         int op;
+                        const int j2 = cs - (O2 + E2 - 1); // length of the second-piece chain that ends at score cs
+                        if (comp == 0 && j2 >= 2 && ((k == j2 && ((p2 >> (2 * t)) & 1u)) || (k == -j2 && ((p2 >> (2 * t)) & 2u)))) {
+                            // M came from I2 / D2: the whole chain back to its opening at M[0] (A.4), one gap of j2 bases
+                            const bool is_ins = k > 0;
+                            if (nops + j2 + 1 > 32) {
+                                pen = -1;
+                                break;
+                            }
+                            ops |= (unsigned long long)OP_CLOSE << (2 * nops), ++nops;
+                            for (int q = 0; q < j2; ++q) ops |= (unsigned long long)(is_ins ? OP_I : OP_D) << (2 * nops), ++nops;
+                            if (!is_ins) n_del += j2;
+                            cs = 0, k = 0;
+                            continue;
+                        }
                         if (comp == 0) {
                             const int sc = nib & 3;
                             if (sc == 3) op = OP_X, cs -= X;
