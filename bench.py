@@ -392,6 +392,7 @@ def main():
     e2ep_host = {"host_packed": int(cp.host_packed), "align_bytes_h2d": int(cp.bytes_h2d), "ms_plan": cp.ms_host_plan,
                  "ms_scan_wait": cp.ms_host_pack_wait, "ms_align_call": cp.ms_host_call,
                  "ms_device_span": cp.ms_total_device, "ms_last_chunk_queued": cp.ms_host_enqueued,
+                 "ms_fused_call": cp.ms_fused_call, "ms_fused_tail": cp.ms_fused_tail,
                  "chunks": int(cp.chunks), "load_time_pack_s": load_pack_s, "exceptions": int(len(exc))}
     h2d_p = int(cp.bytes_h2d) + loci_np.nbytes
     d2h_p = int(cp.bytes_d2h)
@@ -437,7 +438,7 @@ def main():
 
     # ---- reduce over ranks -------------------------------------------------------------------------------
     mine = torch.tensor([dev_ms, wall_ms, 1e3 * e2e_s, 1e3 * e2ep_s, float(n_loci), float(n_pairs),
-                         float(ce.ms_host_pack_wait), float(ce.ms_host_call), float(cp.ms_host_call), float(h2d),
+                         float(ce.ms_host_pack_wait), float(ce.ms_host_call), float(cp.ms_fused_call), float(h2d),
                          float(d2h), float(h2d_p), float(d2h_p), float(launches), float(host_input_bytes),
                          float(packed_input_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -451,7 +452,7 @@ def main():
     per_rank = [{"rank": r, "loci": int(allv[r, 4]), "pairs": int(allv[r, 5]),
                  "device_ms_per_step": allv[r, 0] / args.steps, "e2e_ms_per_step": allv[r, 2] / args.steps,
                  "e2e_packed_ms_per_step": allv[r, 3] / args.steps, "last_call_ms_pack_wait": allv[r, 6],
-                 "last_call_ms_e2e": allv[r, 7], "last_call_ms_e2e_packed": allv[r, 8]} for r in range(world)]
+                 "last_call_ms_e2e_align": allv[r, 7], "last_call_ms_e2e_packed_whole": allv[r, 8]} for r in range(world)]
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -302,6 +302,8 @@ typedef struct {
                                tdb_duo_batch): rows, scores if asked for, and the read mask -- as a list of its set
                                positions for calls of >= 8 Mi pairs, where a few bytes in a million are set */
     uint64_t pairs_failed;  /* pairs no tier could finish (status TDB_STATUS_OOM, score TDB_SCORE_FAILED) */
+    float ms_fused_call;    /* host wall clock of the whole fused host-buffer call (tdb_trio_batch[_packed] ...), entry to return */
+    float ms_fused_tail;    /* ... of which after the alignment stage: reduction, row and mask download */
 } tdb_counters;
 int tdb_get_counters(const tdb_ctx *ctx, tdb_counters *out);
 /* Exact algorithmic work counting (cells / ext16 / columns of tdb_counters: every pair counted as the CPU

@@ -4,6 +4,8 @@ TAG=$1; shift
 nvidia-smi --query-gpu=index,name,pcie.link.gen.current,pcie.link.width.current --format=csv,noheader
 nproc; free -g | head -2; lscpu | grep -i "numa\|socket\|model name" | head -6
 for N in "$@"; do
+  if [ "$N" = "1" ]; then python profiles/h2d_probe.py 2>/dev/null | tail -1;
+  else python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 profiles/h2d_probe.py 2>/dev/null | tail -1; fi
   if [ "$N" = "1" ]; then CMD="python bench.py --gpus 1 --steps 5 --warmup 3";
   else CMD="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3"; fi
   timeout 1200 $CMD > gpurun_out/scale_${TAG}_$N.json 2> gpurun_out/scale_${TAG}_$N.err

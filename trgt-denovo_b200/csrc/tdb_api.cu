@@ -1465,6 +1465,7 @@ static int assess_host(tdb_ctx *ctx, int is_duo, const uint8_t *seq_blob, size_t
 static int assess_tail(tdb_ctx *ctx, int is_duo, DevBatch &b, size_t n_pairs, const tdb_trio_locus *loci, size_t n_loci,
                        double q, tdb_allele_out *out, int32_t *out_score, uint8_t *denovo_mask) {
     int r;
+    const auto t_fused = std::chrono::steady_clock::now();
     ENSURE(ctx->loci, n_loci * sizeof(tdb_trio_locus) + 16); // uploaded behind the last chunk (run_align)
     b.late_dst = ctx->loci.p, b.late_src = loci, b.late_bytes = n_loci * sizeof(tdb_trio_locus);
     ENSURE(ctx->aout, n_loci * 2 * sizeof(tdb_allele_out) + 16);
@@ -1479,6 +1480,7 @@ static int assess_tail(tdb_ctx *ctx, int is_duo, DevBatch &b, size_t n_pairs, co
     b.h_zero = sparse_mask ? denovo_mask : nullptr;
     r = run_align(ctx, b, false);
     if (r) return r;
+    const auto t_aligned = std::chrono::steady_clock::now();
     unsigned *hits = sparse_mask ? (unsigned *)ctx->mask_hits.p : nullptr;
     r = run_reduce_device(ctx, (const tdb_trio_locus *)ctx->loci.p, n_loci, b.score, q, is_duo,
                           (tdb_allele_out *)ctx->aout.p, (uint8_t *)ctx->mask.p, hits, out);
@@ -1514,6 +1516,9 @@ static int assess_tail(tdb_ctx *ctx, int is_duo, DevBatch &b, size_t n_pairs, co
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->counters.bytes_d2h = d2h;
+    const auto t_end = std::chrono::steady_clock::now();
+    ctx->counters.ms_fused_call = std::chrono::duration<float, std::milli>(t_end - t_fused).count();
+    ctx->counters.ms_fused_tail = std::chrono::duration<float, std::milli>(t_end - t_aligned).count();
     return TDB_OK;
 }
 
