@@ -1,6 +1,7 @@
 // tdb_api.cu -- C ABI (include/trgt_denovo_b200.h) over the sm_100a kernels.  No CPU compute path:
 // every entry point that does arithmetic launches CUDA kernels or fails.
 #include "tdb_wfa_quad.cuh"
+#include "tdb_wfa_frame.cuh"
 #include "tdb_wfa_thread.cuh"
 #include "tdb_hostpack.h"
 
@@ -92,6 +93,8 @@ struct tdb_ctx {
     bool disable_mini = false;
     int global_warps_per_sm = 16; // workers of the first global-scratch tier (TDB_GLOBAL_WARPS_PER_SM)
     size_t sparse_mask_min_pairs = (size_t)8 << 20; // host calls at least this large fetch the mask as a list of set positions
+    bool old_lock = true; // TDB_FRAME_LOCK=1: k_align_frame instead of k_align_lock (measured 2-10 % slower, profiles/r02/NOTES.md)
+    int fquad_ctas_per_sm = 0, fduo_ctas_per_sm = 0;
     bool disable_quad = false, disable_duo = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
     size_t chunk_pairs = 2u << 20;
     size_t hostpack_min_bytes = 8u << 20; // smaller host batches are packed on the device
@@ -914,7 +917,12 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             const size_t smem = lock_smem_bytes<QuadCfg>();
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->quad_ctas_per_sm,
                                                              ((size_t)cpairs + 31) / 32 + 1);
-            k_align_lock<QuadCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, st>>>(p);
+            if (ctx->old_lock) k_align_lock<QuadCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, st>>>(p);
+            else {
+                const unsigned fgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->fquad_ctas_per_sm,
+                                                                  ((size_t)cpairs + 32 * F_WARPS - 1) / (32 * F_WARPS) + 1);
+                k_align_frame<QuadF, 8, 4, 2, 24, 1><<<fgrid, F_WARPS * 32, frame_smem_bytes<QuadF>(), st>>>(p);
+            }
             CK(cudaGetLastError());
             cn.kernel_launches += 1;
         }
@@ -928,7 +936,12 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             if (default_pen && !ctx->disable_duo) {
                 const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->duo_ctas_per_sm,
                                                                  ((size_t)cpairs + 3) / 4 + 1);
-                k_align_lock<DuoCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, lock_smem_bytes<DuoCfg>(), st>>>(p);
+                if (ctx->old_lock) k_align_lock<DuoCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, lock_smem_bytes<DuoCfg>(), st>>>(p);
+                else {
+                    const unsigned fgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->fduo_ctas_per_sm,
+                                                                      ((size_t)cpairs + 4 * F_WARPS - 1) / (4 * F_WARPS) + 1);
+                    k_align_frame<DuoF, 8, 4, 2, 24, 1><<<fgrid, F_WARPS * 32, frame_smem_bytes<DuoF>(), st>>>(p);
+                }
             } else {
                 const size_t smem = sizeof(T0Smem) * T0_WARPS;
                 const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->t0_ctas_per_sm,
@@ -1065,8 +1078,8 @@ int run_reduce_device(tdb_ctx *ctx, const tdb_trio_locus *dloci, size_t n_loci, 
     const size_t n_slices = h_out && n_loci >= (1u << 16) ? 8 : 1;
     for (size_t k = 0; k < n_slices && n_loci; ++k) {
         const size_t l0 = n_loci * k / n_slices, l1 = n_loci * (k + 1) / n_slices;
-        const unsigned threads = 128, blocks = (unsigned)((l1 - l0 + threads - 1) / threads);
-        k_reduce<<<blocks, threads, 0, s>>>(dloci + l0, (uint32_t)(l1 - l0), dscores, q, is_duo, dout + 2 * l0, dmask, hits,
+        const unsigned threads = RED_THREADS, blocks = (unsigned)((l1 - l0 + threads - 1) / threads);
+        k_reduce<<<blocks, threads, RED_STAGE * sizeof(int32_t), s>>>(dloci + l0, (uint32_t)(l1 - l0), dscores, q, is_duo, dout + 2 * l0, dmask, hits,
                                             hits ? hits + 1 : nullptr, hits ? MASK_HITS_CAP : 0u);
         CK(cudaGetLastError());
         ctx->counters.kernel_launches += 1;
@@ -1227,8 +1240,21 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
             return e2;
         };
         e = cudaFuncSetAttribute(k_dedup_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RED_STAGE * sizeof(int32_t)));
         if (e == cudaSuccess) e = setup(k_align_lock<QuadCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<QuadCfg>(), c->quad_ctas_per_sm);
         if (e == cudaSuccess) e = setup(k_align_lock<DuoCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<DuoCfg>(), c->duo_ctas_per_sm);
+        auto fsetup = [&](auto kern, size_t smem, int &occ_out) {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            int occ2 = 0;
+            if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern, F_WARPS * 32, smem);
+            occ_out = occ2;
+            return e2;
+        };
+        if (e == cudaSuccess) e = fsetup(k_align_frame<QuadF, 8, 4, 2, 24, 1>, frame_smem_bytes<QuadF>(), c->fquad_ctas_per_sm);
+        if (e == cudaSuccess) e = fsetup(k_align_frame<DuoF, 8, 4, 2, 24, 1>, frame_smem_bytes<DuoF>(), c->fduo_ctas_per_sm);
+        if (e == cudaSuccess && (c->fquad_ctas_per_sm < 1 || c->fduo_ctas_per_sm < 1)) c->quad_ctas_per_sm = 0;
+        c->old_lock = getenv("TDB_FRAME_LOCK") == nullptr;
         if (e != cudaSuccess || c->quad_ctas_per_sm < 1 || c->duo_ctas_per_sm < 1) {
             int code = fail(nullptr, TDB_E_CUDA, "lockstep kernel setup failed: %s (occupancy %d / %d)", cudaGetErrorString(e),
                             c->quad_ctas_per_sm, c->duo_ctas_per_sm);
