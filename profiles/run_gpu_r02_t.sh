@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2: all GPU tests, then one device-resident bench line (breakdown) at <loci>
+tag=$1; loci=${2:-300000}
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -8
+python bench.py --loci $loci --steps 3 --warmup 3 --no-cpu-baseline --no-census > gpurun_out/t_$tag.json 2>gpurun_out/t_$tag.err || tail -3 gpurun_out/t_$tag.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/t_$tag.json').read().strip().splitlines()[-1])
+print('$tag', round(d['value']), d['ms_per_step'], d['breakdown_ms_per_step'], d['tier_pairs'], d['thread_tier_pairs'])"

@@ -1078,8 +1078,8 @@ int run_reduce_device(tdb_ctx *ctx, const tdb_trio_locus *dloci, size_t n_loci, 
     const size_t n_slices = h_out && n_loci >= (1u << 16) ? 8 : 1;
     for (size_t k = 0; k < n_slices && n_loci; ++k) {
         const size_t l0 = n_loci * k / n_slices, l1 = n_loci * (k + 1) / n_slices;
-        const unsigned threads = RED_THREADS, blocks = (unsigned)((l1 - l0 + threads - 1) / threads);
-        k_reduce<<<blocks, threads, RED_STAGE * sizeof(int32_t), s>>>(dloci + l0, (uint32_t)(l1 - l0), dscores, q, is_duo, dout + 2 * l0, dmask, hits,
+        const unsigned threads = 128, blocks = (unsigned)((l1 - l0 + threads - 1) / threads);
+        k_reduce<<<blocks, threads, 0, s>>>(dloci + l0, (uint32_t)(l1 - l0), dscores, q, is_duo, dout + 2 * l0, dmask, hits,
                                             hits ? hits + 1 : nullptr, hits ? MASK_HITS_CAP : 0u);
         CK(cudaGetLastError());
         ctx->counters.kernel_launches += 1;
@@ -1240,7 +1240,6 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
             return e2;
         };
         e = cudaFuncSetAttribute(k_dedup_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RED_STAGE * sizeof(int32_t)));
         if (e == cudaSuccess) e = setup(k_align_lock<QuadCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<QuadCfg>(), c->quad_ctas_per_sm);
         if (e == cudaSuccess) e = setup(k_align_lock<DuoCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<DuoCfg>(), c->duo_ctas_per_sm);
         auto fsetup = [&](auto kern, size_t smem, int &occ_out) {

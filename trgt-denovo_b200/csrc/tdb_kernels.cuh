@@ -353,7 +353,10 @@ struct ClassifyOut {
     uint32_t *work;      // [3 n_pairs] algorithmic cells, ext16, columns per pair (nullptr: not counted)
 };
 
-constexpr int DW_THREADS = 256;
+#ifndef TDB_DW_THREADS
+#define TDB_DW_THREADS 512
+#endif
+constexpr int DW_THREADS = TDB_DW_THREADS; // 512 threads x 4 CTAs (52 KB each) = 64 warps per SM: the kernel waits on global loads
 constexpr int DW_PAIRS = 2048;   // pairs per window
 constexpr int DW_SEQS = 4096;    // widest sequence index range a window may reference
 constexpr int DW_SSLOTS = 8192;  // sequence table slots
@@ -369,7 +372,7 @@ struct DedupSmem {
     int bad;
 };
 
-__global__ void __launch_bounds__(DW_THREADS) k_dedup_window(
+__global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
     const uint32_t *__restrict__ pair_p, const uint32_t *__restrict__ pair_t, uint32_t p0, uint32_t p1, uint32_t n_seqs,
     const uint64_t *__restrict__ seq_hash, const uint32_t *__restrict__ seq_len, const uint8_t *__restrict__ seq_flag,
     const uint64_t *__restrict__ seq_off, const uint32_t *__restrict__ packed, int dedup, int quad_ok, int mini_ok,
@@ -920,40 +923,14 @@ __device__ inline double list_median(const int32_t *a, int n_raw) {
 
 __constant__ int8_t c_combs2[8][2] = {{0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 0}, {3, 0}, {2, 1}, {3, 1}};
 
-// The scores of the loci of one CTA are one contiguous stretch of the score array (pairs arrive locus by locus): it is
-// staged in shared memory with coalesced loads, so that the per-locus threads -- each walking its own ~150 scores several
-// times -- do not pull 32 different cache lines per instruction from HBM.  A CTA whose stretch does not fit reads global
-// memory as before (offsets are the caller's: any layout stays correct).
-constexpr int RED_THREADS = 64;
-constexpr unsigned RED_STAGE = 12288; // scores staged per CTA (48 KB)
-__global__ void __launch_bounds__(RED_THREADS) k_reduce(const tdb_trio_locus *__restrict__ loci, uint32_t n_loci,
-                                                const int32_t *__restrict__ scores_g, double q, int is_duo,
+__global__ void __launch_bounds__(128) k_reduce(const tdb_trio_locus *__restrict__ loci, uint32_t n_loci,
+                                                const int32_t *__restrict__ scores, double q, int is_duo,
                                                 tdb_allele_out *__restrict__ out, uint8_t *__restrict__ mask,
                                                 unsigned *__restrict__ hit_count, uint32_t *__restrict__ hit_list,
                                                 unsigned hit_cap) {
-    extern __shared__ int32_t red_stage[];
-    __shared__ unsigned s_lo, s_hi;
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = li < n_loci;
-    if (threadIdx.x == 0) s_lo = 0xffffffffu, s_hi = 0u;
-    __syncthreads();
-    tdb_trio_locus loc;
-    if (in_range) {
-        loc = loci[li];
-        for (int c = 0; c < loc.n_child && c < 2; ++c) {
-            atomicMin(&s_lo, loc.list_off[c][0]);
-            atomicMax(&s_hi, loc.list_off[c][5]);
-        }
-    }
-    __syncthreads();
-    const unsigned st_lo = s_lo, st_hi = s_hi;
-    const int32_t *scores = scores_g;
-    if (st_hi > st_lo && st_hi - st_lo <= RED_STAGE) { // CTA-uniform
-        for (unsigned i = threadIdx.x; i < st_hi - st_lo; i += blockDim.x) red_stage[i] = scores_g[st_lo + i];
-        __syncthreads();
-        scores = red_stage - st_lo;
-    }
-    if (!in_range) return;
+    if (li >= n_loci) return;
+    const tdb_trio_locus loc = loci[li];
     const double F64_MIN = -1.7976931348623157e308;
     double matrix[4][2];
     for (int i = 0; i < 4; ++i) matrix[i][0] = matrix[i][1] = F64_MIN;

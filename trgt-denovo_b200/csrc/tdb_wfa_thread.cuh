@@ -27,6 +27,7 @@
 // in the M component (A.4), flank-clipped score on the fly (src/aligner.rs:320-376).
 #pragma once
 #include "tdb_kernels.cuh"
+#include <type_traits>
 
 namespace tdb {
 
@@ -74,11 +75,11 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     int16_t *hw = reinterpret_cast<int16_t *>(smem_raw) + threadIdx.x;
     uint32_t *sw = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TH_NT * TH_HW * 2) + threadIdx.x;
-    uint32_t prov[TH_STEPS * TH_PW]; // written once per score, read by the backtrace: thread-local memory
+    uint8_t prov[TH_STEPS * TH_W]; // one nibble per computed cell, one byte each: written once, read by the backtrace (thread-local memory)
 #define TH_M(slot, k) hw[((slot) * TH_W + (k) + TH_KM) * TH_NT]
 #define TH_I(k) hw[(TH_MSLOTS * TH_W + (k) + TH_KM) * TH_NT]
 #define TH_D(k) hw[((TH_MSLOTS + 1) * TH_W + (k) + TH_KM) * TH_NT]
-#define TH_P(t, w) prov[(t) * TH_PW + (w)]
+#define TH_P(t, pi) prov[(t) * TH_W + (pi)]
     const int lane = threadIdx.x & 31;
     const ItemSrc src = item_src(p);
     const Penalties pn = {X, O1, E1, O2, E2};
@@ -219,54 +220,71 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                             th_d = INT32_MIN;
                         int min_d = HUGE_D;
                         bool fin = false;
-                        unsigned long long pa = 0, pb = 0;
                         uint32_t vmask = 0; // vmask: diagonals (bit k + TH_KM) whose M offset lies inside the matrix
                         // the second piece's cells of this score: extensions of the previous score's (none before score 26)
                         const int kI = i2k + 1, vI = i2v + 1, kD = d2k - 1, vD = d2v;
                         const bool hI = i2ok && kI <= hi, hD = d2ok && kD >= lo;
-                        // I1 is updated in place: the old I1[k-1] travels in a register
-                        int carry_i = (unsigned)(lo - 1 - il) < (unsigned)is ? (int)TH_I(lo - 1) : NULLV;
-                        for (int k = lo; k <= hi; ++k) {
-                            const int old_i = (unsigned)(k - il) < (unsigned)is ? (int)TH_I(k) : NULLV;
-                            int nib = 0, o, e;
-                            o = (unsigned)(k - 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k - 1) : NULLV;
-                            e = carry_i;
-                            carry_i = old_i;
-                            int ins1;
-                            if (e >= o) ins1 = e, nib |= 4; else ins1 = o;
-                            ins1 += 1;
-                            o = (unsigned)(k + 1 - ml6) < (unsigned)ms6 ? (int)TH_M(s6, k + 1) : NULLV;
-                            e = (unsigned)(k + 1 - dl) < (unsigned)ds ? (int)TH_D(k + 1) : NULLV;
-                            int del1;
-                            if (e >= o) del1 = e, nib |= 8; else del1 = o;
-                            const int mis = ((unsigned)(k - ml8) < (unsigned)ms8 ? (int)TH_M(s8, k) : NULLV) + 1;
-                            const int ins2 = hI && k == kI ? vI : NULLV + 1, del2 = hD && k == kD ? vD : NULLV;
-                            int mv = max(max(ins1, del1), max(mis, max(ins2, del2)));
-                            int sc = 0; // later tests override: priority X > D2 > D1 > I2 > I1
-                            bool f_i2 = false, f_d2 = false;
-                            if (mv == ins1) sc = 1;
-                            if (mv == ins2) f_i2 = true;
-                            if (mv == del1) sc = 2, f_i2 = false;
-                            if (mv == del2) f_d2 = true, f_i2 = false;
-                            if (mv == mis) sc = 3, f_i2 = f_d2 = false;
-                            nib |= sc;
-                            if (hI && k == kI && f_i2) p2 |= 1u << (2 * (hh - 3));
-                            if (hD && k == kD && f_d2) p2 |= 2u << (2 * (hh - 3));
-                            const int pi = k + TH_KM;
-                            if (pi < 16) pa |= (unsigned long long)nib << (4 * pi);
-                            else pb |= (unsigned long long)nib << (4 * (pi - 16));
-                            if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = NULLV;
-                            if (mv >= 0) vmask |= 1u << pi, tl_m = min(tl_m, k), th_m = k;
-                            TH_M(cur, k) = (int16_t)mv;
-                            if (has_i1) {
-                                TH_I(k) = (int16_t)ins1;
-                                if ((unsigned)ins1 <= (unsigned)m && (unsigned)(ins1 - k) <= (unsigned)n) tl_i = min(tl_i, k), th_i = k;
+                        uint8_t *const pv = &TH_P(hh - 3, TH_KM); // provenance row of this score, indexed by diagonal
+                        // One body, compiled twice: the second piece's two cells only exist from score 26 on (TWO), and the
+                        // compares that look for them are a sixth of the loop.  Running pointers into this thread's column:
+                        // q6 / q8 / qc at diagonal k of M[s-6] / M[s-8] / M[s], qg at diagonal k of I1 (D1 is one row further).
+                        auto cell_loop = [&](auto two_tag) {
+                            constexpr bool TWO = decltype(two_tag)::value;
+                            const int16_t *q6 = &TH_M(s6, lo), *q8 = &TH_M(s8, lo);
+                            int16_t *qc = &TH_M(cur, lo), *qg = &TH_I(lo);
+                            constexpr int DROW = TH_W * TH_NT; // TH_D(k) == (&TH_I(k))[DROW]
+                            uint32_t kbit = 1u << (lo + TH_KM);
+                            // I1 is updated in place: the old I1[k-1] travels in a register
+                            int carry_i = (unsigned)(lo - 1 - il) < (unsigned)is ? (int)qg[-TH_NT] : NULLV;
+                            for (int k = lo; k <= hi; ++k, q6 += TH_NT, q8 += TH_NT, qc += TH_NT, qg += TH_NT, kbit <<= 1) {
+                                const int old_i = (unsigned)(k - il) < (unsigned)is ? (int)qg[0] : NULLV;
+                                int nib = 0, o, e;
+                                o = (unsigned)(k - 1 - ml6) < (unsigned)ms6 ? (int)q6[-TH_NT] : NULLV;
+                                e = carry_i;
+                                carry_i = old_i;
+                                int ins1;
+                                if (e >= o) ins1 = e, nib |= 4; else ins1 = o;
+                                ins1 += 1;
+                                o = (unsigned)(k + 1 - ml6) < (unsigned)ms6 ? (int)q6[TH_NT] : NULLV;
+                                e = (unsigned)(k + 1 - dl) < (unsigned)ds ? (int)qg[DROW + TH_NT] : NULLV;
+                                int del1;
+                                if (e >= o) del1 = e, nib |= 8; else del1 = o;
+                                const int mis = ((unsigned)(k - ml8) < (unsigned)ms8 ? (int)q8[0] : NULLV) + 1;
+                                int mv = max(max(ins1, del1), mis);
+                                int sc = 0; // later tests override: priority X > D2 > D1 > I2 > I1
+                                if (TWO) {
+                                    const int ins2 = hI && k == kI ? vI : NULLV + 1, del2 = hD && k == kD ? vD : NULLV;
+                                    mv = max(mv, max(ins2, del2));
+                                    bool f_i2 = false, f_d2 = false;
+                                    if (mv == ins1) sc = 1;
+                                    if (mv == ins2) f_i2 = true;
+                                    if (mv == del1) sc = 2, f_i2 = false;
+                                    if (mv == del2) f_d2 = true, f_i2 = false;
+                                    if (mv == mis) sc = 3, f_i2 = f_d2 = false;
+                                    if (hI && k == kI && f_i2) p2 |= 1u << (2 * (hh - 3));
+                                    if (hD && k == kD && f_d2) p2 |= 2u << (2 * (hh - 3));
+                                } else {
+                                    if (mv == ins1) sc = 1;
+                                    if (mv == del1) sc = 2;
+                                    if (mv == mis) sc = 3;
+                                }
+                                nib |= sc;
+                                pv[k] = (uint8_t)nib;
+                                if ((unsigned)mv > (unsigned)m || (unsigned)(mv - k) > (unsigned)n) mv = NULLV;
+                                if (mv >= 0) vmask |= kbit, tl_m = min(tl_m, k), th_m = k;
+                                qc[0] = (int16_t)mv;
+                                if (has_i1) {
+                                    qg[0] = (int16_t)ins1;
+                                    if ((unsigned)ins1 <= (unsigned)m && (unsigned)(ins1 - k) <= (unsigned)n) tl_i = min(tl_i, k), th_i = k;
+                                }
+                                if (has_d1) {
+                                    qg[DROW] = (int16_t)del1;
+                                    if ((unsigned)del1 <= (unsigned)m && (unsigned)(del1 - k) <= (unsigned)n) tl_d = min(tl_d, k), th_d = k;
+                                }
                             }
-                            if (has_d1) {
-                                TH_D(k) = (int16_t)del1;
-                                if ((unsigned)del1 <= (unsigned)m && (unsigned)(del1 - k) <= (unsigned)n) tl_d = min(tl_d, k), th_d = k;
-                            }
-                        }
+                        };
+                        if (s >= O2 + E2 + 1) cell_loop(std::true_type{}); // (the score is the same in every lane still at work)
+                        else cell_loop(std::false_type{});
                         // Greedy extension of the live diagonals (trimming never changes offsets, A.1 step 1), as ONE
                         // loop over 16-base compares: a lane moves on to its next diagonal as soon as the current one
                         // stops matching, so a warp pays the longest per-lane TOTAL, not the sum of per-diagonal maxima.
@@ -300,8 +318,6 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                                 }
                             }
                         }
-                        const int t = hh - 3;
-                        TH_P(t, 0) = (uint32_t)pa, TH_P(t, 1) = (uint32_t)(pa >> 32), TH_P(t, 2) = (uint32_t)pb, TH_P(t, 3) = (uint32_t)(pb >> 32);
                         // this score's second-piece cells: inside the matrix? (their trimmed ranges, A.2)
                         bool nI = hI && (unsigned)vI <= (unsigned)m && (unsigned)(vI - kI) <= (unsigned)n;
                         bool nD = hD && (unsigned)vD <= (unsigned)m && (unsigned)(vD - kD) <= (unsigned)n;
@@ -370,8 +386,7 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                             pen = -1; // never expected: leave the pair to the next tier
                             break;
                         }
-                        const uint32_t wsel = pi < 8 ? TH_P(t, 0) : (pi < 16 ? TH_P(t, 1) : (pi < 24 ? TH_P(t, 2) : TH_P(t, 3)));
-                        const int nib = (int)(wsel >> (4 * (pi & 7))) & 15;
+                        const int nib = (int)TH_P(t, pi);
                         int op;
                         const int j2 = cs - (O2 + E2 - 1); // length of the second-piece chain that ends at score cs
                         if (comp == 0 && j2 >= 2 && ((k == j2 && ((p2 >> (2 * t)) & 1u)) || (k == -j2 && ((p2 >> (2 * t)) & 2u)))) {
