@@ -146,6 +146,23 @@ def test_quad_tier_disabled_gives_same_scores(tdb, monkeypatch):
     c.close()
 
 
+def test_estimate_order_disabled_gives_same_scores(tdb, monkeypatch):
+    """The thread-per-pair tier is ordered by an upper bound of the penalty (k_estimate) and pairs bounded beyond its last
+    score skip it: only order and tier depend on the estimate, so scores and work counts are those of the |n-m| order."""
+    rng = random.Random(91)
+    seqs, pp, pt = make_pairs(rng, n_targets=200, reads_per_target=12, max_units=25, err=0.006)
+    c = tdb.Context()
+    cnt_on = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    c.close()
+    monkeypatch.setenv("TDB_DISABLE_EST_SORT", "1")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_DISABLE_EST_SORT")
+    cnt_off = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    c.close()
+    assert cnt_on.thread_pairs > 0 and cnt_off.thread_pairs >= cnt_on.thread_pairs  # some pairs go straight to the lockstep tier
+    assert (cnt_on.cells, cnt_on.ext16, cnt_on.columns) == (cnt_off.cells, cnt_off.ext16, cnt_off.columns)
+
+
 def test_frame_kernels_give_same_scores(tdb, monkeypatch):
     """k_align_frame (the lockstep tiers on NULL-filled fixed rows, TDB_FRAME_LOCK=1) against the oracle: scores, status,
     exact C / E / T, with and without the thread-per-pair tier in front of it."""

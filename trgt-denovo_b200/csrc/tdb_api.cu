@@ -60,6 +60,8 @@ struct Ctrl {
         unsigned hist[N_HIST];
         unsigned base[N_HIST], cursor[N_HIST]; // work-list buckets: start and fill level
         unsigned seg[8];
+        unsigned hist2[EST_BUCKETS], base2[EST_BUCKETS], cursor2[EST_BUCKETS]; // thread tier re-sorted by the penalty estimate
+        unsigned seg2[4];
     } ck[2];
 };
 constexpr int N_SLOT = 2;
@@ -85,7 +87,7 @@ struct tdb_ctx {
     struct Slot {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf skey_in, sval_out, list_a, list_m;
+        DevBuf skey_in, sval_out, list_a, list_m, list_t;
     } slot[2];
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
@@ -93,6 +95,7 @@ struct tdb_ctx {
     bool disable_mini = false;
     int global_warps_per_sm = 16; // workers of the first global-scratch tier (TDB_GLOBAL_WARPS_PER_SM)
     size_t sparse_mask_min_pairs = (size_t)8 << 20; // host calls at least this large fetch the mask as a list of set positions
+    bool disable_est = false; // TDB_DISABLE_EST_SORT: thread tier in |n-m| order, no penalty estimate
     bool old_lock = true; // TDB_FRAME_LOCK=1: k_align_frame instead of k_align_lock (measured 2-10 % slower, profiles/r02/NOTES.md)
     int fquad_ctas_per_sm = 0, fduo_ctas_per_sm = 0;
     bool disable_quad = false, disable_duo = false, disable_dedup = false, disable_closed_form = false, disable_rle = false;
@@ -582,6 +585,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             ENSURE(sl.sval_out, max_cp * 4);
             ENSURE(sl.list_a, max_cp * 4);
             if (mini_ok) ENSURE(sl.list_m, max_cp * 4);
+            if (mini_ok && !ctx->disable_est) ENSURE(sl.list_t, max_cp * 4);
         }
     }
     while (b.h_pp && ctx->up_ev.size() < K) {
@@ -899,6 +903,21 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         // thread-per-pair tier: the lightest pairs (|n-m| < 8), up to penalty 24; the rest moves on to tier 0
         if (mini_ok) {
             p.src1_seg = ck->seg + 4, p.src2 = nullptr, p.src2_count = nullptr;
+            if (default_pen && !ctx->disable_est) {
+                // order by an upper bound of the penalty (k_estimate); pairs bounded beyond the tier's last score go straight on
+                const unsigned eg = (unsigned)std::min<size_t>(((size_t)cpairs / 8 + 255) / 256 + 1, (size_t)ctx->sm_count * 8);
+                k_estimate<<<eg, 256, 0, st>>>((const uint32_t *)ctx->packed.p, b.seq_off, b.seq_len, b.pp, b.pt,
+                                               (const uint32_t *)sl.sval_out.p, ck->seg + 4, TH_SMAX, (uint8_t *)sl.skey_in.p, ck->hist2,
+                                               (uint32_t *)sl.list_m.p, &ck->mcount);
+                CK(cudaGetLastError());
+                k_plan2<<<1, 32, 0, st>>>(ck->hist2, ck->base2, ck->seg2);
+                CK(cudaGetLastError());
+                k_bucket_list<<<eg, 256, 0, st>>>((const uint8_t *)sl.skey_in.p, (const uint32_t *)sl.sval_out.p, ck->seg + 4, ck->base2,
+                                                  ck->cursor2, (uint32_t *)sl.list_t.p);
+                CK(cudaGetLastError());
+                cn.kernel_launches += 3;
+                p.src1 = (const uint32_t *)sl.list_t.p, p.src1_seg = ck->seg2;
+            }
             p.work_counter = &ck->wc_mini, p.next_todo = (uint32_t *)sl.list_m.p, p.next_count = &ck->mcount;
             p.counters = ctrl->exec[4];
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->mini_ctas_per_sm,
@@ -910,7 +929,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         if (staged) CK(cudaEventRecord(ctx->ev[11], st));
         // tier 0: four pairs per warp, shared memory (default penalties only)
         if (quad_ok) {
-            p.src1_seg = ck->seg + 2;
+            p.src1 = (const uint32_t *)sl.sval_out.p, p.src1_seg = ck->seg + 2;
             p.src2 = mini_ok ? (const uint32_t *)sl.list_m.p : nullptr, p.src2_count = mini_ok ? &ck->mcount : nullptr;
             p.work_counter = &ck->wc_quad, p.next_todo = (uint32_t *)sl.list_a.p, p.next_count = &ck->acount;
             p.counters = ctrl->exec[0];
@@ -930,6 +949,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         // tier 1: wavefronts up to 64 diagonals, shared memory, one pair per warp; the quad tier's leftovers (the
         // heaviest pairs) go first.  Production penalties: two pairs per warp in lockstep (TDB_DISABLE_DUO=1: one per warp).
         {
+            p.src1 = (const uint32_t *)sl.sval_out.p;
             p.src1_seg = ck->seg + 0, p.src2 = (const uint32_t *)sl.list_a.p, p.src2_count = &ck->acount;
             p.work_counter = &ck->wc_warp, p.next_todo = (uint32_t *)ctx->list_b.p, p.next_count = &ctrl->gcount;
             p.counters = ctrl->exec[1];
@@ -1254,6 +1274,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         if (e == cudaSuccess) e = fsetup(k_align_frame<DuoF, 8, 4, 2, 24, 1>, frame_smem_bytes<DuoF>(), c->fduo_ctas_per_sm);
         if (e == cudaSuccess && (c->fquad_ctas_per_sm < 1 || c->fduo_ctas_per_sm < 1)) c->quad_ctas_per_sm = 0;
         c->old_lock = getenv("TDB_FRAME_LOCK") == nullptr;
+        c->disable_est = getenv("TDB_DISABLE_EST_SORT") != nullptr;
         if (e != cudaSuccess || c->quad_ctas_per_sm < 1 || c->duo_ctas_per_sm < 1) {
             int code = fail(nullptr, TDB_E_CUDA, "lockstep kernel setup failed: %s (occupancy %d / %d)", cudaGetErrorString(e),
                             c->quad_ctas_per_sm, c->duo_ctas_per_sm);
@@ -1314,7 +1335,7 @@ void tdb_destroy(tdb_ctx *c) {
                       &c->scratch[1]};
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
-        DevBuf *sb[] = {&sl.skey_in, &sl.sval_out, &sl.list_a, &sl.list_m};
+        DevBuf *sb[] = {&sl.skey_in, &sl.sval_out, &sl.list_a, &sl.list_m, &sl.list_t};
         for (DevBuf *b : sb) b->release();
     }
     if (c->slot[1].st) cudaStreamDestroy(c->slot[1].st);

@@ -560,6 +560,146 @@ __global__ void __launch_bounds__(256) k_bucket(const uint8_t *__restrict__ key,
         if (k[i] != KEY_NONE) list[boff[k[i]] + rank[i]] = p0 + first + (uint32_t)i;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Work order of the thread-per-pair tier.  Its 32 pairs of a warp run to the largest penalty among them, and
+// at a given |n - m| the penalties still spread (12 .. 30 and beyond: a second or third sequencing error,
+// stutter): sorted by |n - m| alone 58 % of the lane-steps of a warp did useful work (CPU study with the
+// oracle's cell counts, profiles/r02/NOTES.md).  k_estimate gives every pair of that tier an UPPER BOUND of
+// its penalty from a greedy walk -- extend the matches, at a mismatch take the edit (substitution, or a gap of
+// up to |n - m| + 2 bases either way) whose next 16 bases match best, repeat -- which is the cost of a real
+// alignment, so never below the optimum, and equal to it for 86 % of the pairs.  Pairs bounded by the tier's
+// last score are sorted by that bound, heaviest first (90 % useful lane-steps in the same study) and are
+// certain to finish there; the others go straight to the lockstep tier instead of running to score 30 first.
+// The walks are a kernel of their own over the tier's segment of the work list (k_estimate, 0.65 ms per 937 k loci), followed
+// by a second counting sort of that segment; run at the end of k_dedup_window instead (the window's few candidates compacted
+// in shared memory) they stretched every window by a third (+1.8 ms): one walk is a long dependent chain.
+// Only the ORDER and the tier of a pair depend on the estimate: results are those of the wavefront kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int EST_BUCKETS = 16;
+#ifndef TDB_EST_SLACK
+#define TDB_EST_SLACK 8
+#endif
+constexpr int EST_SLACK = TDB_EST_SLACK;
+__device__ __forceinline__ int est_gap_cost(int g) { return min(4 + 2 * g, 24 + g); } // production penalties 8,4,2,24,1
+__device__ inline int greedy_estimate(const uint32_t *__restrict__ pw, int psh, int n, const uint32_t *__restrict__ tw, int tsh,
+                                      int m, int cap) {
+    int v = 0, h = 0, est = 0;
+    const int G = min(abs(m - n), 13) + 2;
+    for (int ev = 0; ev < 10; ++ev) {
+        const int room = min(n - v, m - h);
+        if (room > 0) {
+            const int pa = psh + v, ta = tsh + h;
+            const int e = (int)Diff16::run(pw + (pa >> 4), (uint32_t)(pa & 15) << 1, tw + (ta >> 4), (uint32_t)(ta & 15) << 1, (uint32_t)room);
+            v += e, h += e;
+        }
+        if (v >= n || h >= m) {
+            const int rest = (n - v) + (m - h);
+            return rest ? est + est_gap_cost(rest) : est;
+        }
+        if (est > cap + EST_SLACK) return est; // the bound only grows
+        // the next 32 bases of both sequences in one 64-bit register each: every candidate below is a shift of one of them
+        // against the other, so an edit is scored without further loads (gaps up to 15 bases: 16 bases of look-ahead)
+        uint64_t p64, t64;
+        {
+            const int pa = psh + v, ta = tsh + h;
+            const uint32_t *a = pw + (pa >> 4), *c = tw + (ta >> 4);
+            const uint32_t a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2), c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+            const uint32_t sa = (uint32_t)(pa & 15) << 1, sc = (uint32_t)(ta & 15) << 1;
+            p64 = (uint64_t)__funnelshift_r(a0, a1, sa) | ((uint64_t)__funnelshift_r(a1, a2, sa) << 32);
+            t64 = (uint64_t)__funnelshift_r(c0, c1, sc) | ((uint64_t)__funnelshift_r(c1, c2, sc) << 32);
+        }
+        int best_key = INT32_MIN, bc = 0, bv = v, bh = h;
+#define TDB_EST_CAND(cost_, dv_, dh_)                                                                             \
+    {                                                                                                             \
+        const int v2 = v + (dv_), h2 = h + (dh_);                                                                 \
+        if (v2 <= n && h2 <= m) {                                                                                 \
+            const int room2 = min(n - v2, m - h2);                                                                \
+            const uint32_t x = (uint32_t)(p64 >> (2 * (dv_))) ^ (uint32_t)(t64 >> (2 * (dh_)));                    \
+            const int r = min(x ? (__ffs(x) - 1) >> 1 : 16, room2);                                               \
+            const int key = 4 * r - (cost_) + ((v2 + r >= n && h2 + r >= m) ? 400 : 0);                           \
+            if (key > best_key) best_key = key, bc = (cost_), bv = v2, bh = h2;                                   \
+        }                                                                                                         \
+    }
+        TDB_EST_CAND(8, 1, 1)
+        for (int g = 1; g <= G; ++g) {
+            TDB_EST_CAND(4 + 2 * g, 0, g)
+            TDB_EST_CAND(4 + 2 * g, g, 0)
+        }
+#undef TDB_EST_CAND
+        est += bc, v = bv, h = bh;
+    }
+    return 1 << 20; // too many edits for this tier
+}
+
+__global__ void __launch_bounds__(256) k_estimate(const uint32_t *__restrict__ packed, const uint64_t *__restrict__ seq_off,
+                                                  const uint32_t *__restrict__ seq_len, const uint32_t *__restrict__ pair_p,
+                                                  const uint32_t *__restrict__ pair_t, const uint32_t *__restrict__ list,
+                                                  const unsigned *__restrict__ seg, int smax, uint8_t *__restrict__ ekey,
+                                                  unsigned *__restrict__ hist2, uint32_t *__restrict__ over_list,
+                                                  unsigned *__restrict__ over_count) {
+    __shared__ unsigned sh[EST_BUCKETS];
+    if (threadIdx.x < EST_BUCKETS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned b = seg[0], c = seg[1];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < c; i += gridDim.x * blockDim.x) {
+        const uint32_t idx = list[b + i];
+        const uint32_t ip = pair_p[idx], jt = pair_t[idx];
+        const uint64_t poff = seq_off[ip], toff = seq_off[jt];
+        const int est = greedy_estimate(packed + (poff >> 4), (int)(poff & 15), (int)seq_len[ip], packed + (toff >> 4),
+                                        (int)(toff & 15), (int)seq_len[jt], smax);
+        int key = KEY_NONE;
+        // a bound a little beyond the last score still leaves an even chance that the pair ends below it (the walk pays for
+        // an edit it could have merged): such pairs ride with the heaviest bucket, whose warps run to the last score anyway
+        if (est <= smax + EST_SLACK) {
+            key = min(EST_BUCKETS - 1, max(smax - est, 0) >> 1); // heaviest first
+            atomicAdd(&sh[key], 1u);
+        } else {
+            const unsigned q = atomicAdd(over_count, 1u);
+            over_list[q] = idx;
+        }
+        ekey[i] = (uint8_t)key;
+    }
+    __syncthreads();
+    if (threadIdx.x < EST_BUCKETS && sh[threadIdx.x]) atomicAdd(hist2 + threadIdx.x, sh[threadIdx.x]);
+}
+
+__global__ void k_plan2(const unsigned *__restrict__ hist2, unsigned *__restrict__ base2, unsigned *__restrict__ seg2) {
+    if (threadIdx.x == 0) {
+        unsigned at = 0;
+        for (int i = 0; i < EST_BUCKETS; ++i) base2[i] = at, at += hist2[i];
+        seg2[0] = 0, seg2[1] = at;
+    }
+}
+
+// k_bucket for a list: position i of the segment goes to bucket ekey[i]
+__global__ void __launch_bounds__(256) k_bucket_list(const uint8_t *__restrict__ ekey, const uint32_t *__restrict__ list,
+                                                     const unsigned *__restrict__ seg, const unsigned *__restrict__ base2,
+                                                     unsigned *__restrict__ cursor2, uint32_t *__restrict__ out) {
+    __shared__ unsigned cnt[EST_BUCKETS], boff[EST_BUCKETS];
+    const unsigned b = seg[0], n = seg[1];
+    for (uint32_t blk = blockIdx.x; blk * (256u * BUCKET_PER_THREAD) < n; blk += gridDim.x) { // block-uniform trip count
+        if (threadIdx.x < EST_BUCKETS) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t first = (blk * 256u + threadIdx.x) * BUCKET_PER_THREAD;
+        int k[BUCKET_PER_THREAD];
+        unsigned rank[BUCKET_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < BUCKET_PER_THREAD; ++i) {
+            const uint32_t j = first + (uint32_t)i;
+            k[i] = j < n ? (int)ekey[j] : KEY_NONE;
+            if (k[i] != KEY_NONE) rank[i] = atomicAdd(&cnt[k[i]], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < EST_BUCKETS && cnt[threadIdx.x])
+            boff[threadIdx.x] = base2[threadIdx.x] + atomicAdd(&cursor2[threadIdx.x], cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < BUCKET_PER_THREAD; ++i)
+            if (k[i] != KEY_NONE) out[boff[k[i]] + rank[i]] = list[b + first + (uint32_t)i];
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restrict__ rep, uint32_t n_pairs,
                                                  int32_t *__restrict__ score, int32_t *__restrict__ status,
                                                  int32_t *__restrict__ penalty, const uint32_t *__restrict__ work,
