@@ -91,6 +91,10 @@ struct tdb_ctx {
     } slot[2];
     DevBuf ctrl, loci, aout, mask, scores_in, cigar, cigar_off, cigar_len;
     DevBuf scratch[2];
+    DevBuf lockq_scratch[2]; // the same for tier 0
+    DevBuf lock_scratch[2]; // provenance / step records of the four-pairs-per-warp tier 1 (per pipeline slot)
+    int duo4_ctas_per_sm = 0;
+    bool duo4 = true; // TDB_DUO_G16=1: tier 1 with two pairs per warp (16 lanes each), everything in shared memory
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0, mini_ctas_per_sm = 0;
     bool disable_mini = false;
     int global_warps_per_sm = 16; // workers of the first global-scratch tier (TDB_GLOBAL_WARPS_PER_SM)
@@ -936,7 +940,13 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             const size_t smem = lock_smem_bytes<QuadCfg>();
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->quad_ctas_per_sm,
                                                              ((size_t)cpairs + 31) / 32 + 1);
-            if (ctx->old_lock) k_align_lock<QuadCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, st>>>(p);
+            if (ctx->old_lock) {
+                if (QuadCfg::GP) {
+                    ENSURE(ctx->lockq_scratch[si], (size_t)ctx->sm_count * ctx->quad_ctas_per_sm * Q_WARPS * 4 * lock_gscratch_bytes<QuadCfg>());
+                    p.scratch = (uint8_t *)ctx->lockq_scratch[si].p;
+                }
+                k_align_lock<QuadCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, smem, st>>>(p);
+            }
             else {
                 const unsigned fgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->fquad_ctas_per_sm,
                                                                   ((size_t)cpairs + 32 * F_WARPS - 1) / (32 * F_WARPS) + 1);
@@ -956,7 +966,13 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             if (default_pen && !ctx->disable_duo) {
                 const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->duo_ctas_per_sm,
                                                                  ((size_t)cpairs + 3) / 4 + 1);
-                if (ctx->old_lock) k_align_lock<DuoCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, lock_smem_bytes<DuoCfg>(), st>>>(p);
+                if (ctx->old_lock && ctx->duo4) {
+                    const unsigned g4 = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->duo4_ctas_per_sm,
+                                                                   ((size_t)cpairs + 8 * Q_WARPS - 1) / (8 * Q_WARPS) + 1);
+                    ENSURE(ctx->lock_scratch[si], (size_t)ctx->sm_count * ctx->duo4_ctas_per_sm * Q_WARPS * 4 * lock_gscratch_bytes<Duo4Cfg>());
+                    p.scratch = (uint8_t *)ctx->lock_scratch[si].p;
+                    k_align_lock<Duo4Cfg, 8, 4, 2, 24, 1><<<g4, Q_WARPS * 32, lock_smem_bytes<Duo4Cfg>(), st>>>(p);
+                } else if (ctx->old_lock) k_align_lock<DuoCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, lock_smem_bytes<DuoCfg>(), st>>>(p);
                 else {
                     const unsigned fgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->fduo_ctas_per_sm,
                                                                       ((size_t)cpairs + 4 * F_WARPS - 1) / (4 * F_WARPS) + 1);
@@ -1262,6 +1278,8 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         e = cudaFuncSetAttribute(k_dedup_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem));
         if (e == cudaSuccess) e = setup(k_align_lock<QuadCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<QuadCfg>(), c->quad_ctas_per_sm);
         if (e == cudaSuccess) e = setup(k_align_lock<DuoCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<DuoCfg>(), c->duo_ctas_per_sm);
+        if (e == cudaSuccess) e = setup(k_align_lock<Duo4Cfg, 8, 4, 2, 24, 1>, lock_smem_bytes<Duo4Cfg>(), c->duo4_ctas_per_sm);
+        c->duo4 = getenv("TDB_DUO_G16") == nullptr && c->duo4_ctas_per_sm >= 1;
         auto fsetup = [&](auto kern, size_t smem, int &occ_out) {
             cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1332,7 +1350,7 @@ void tdb_destroy(tdb_ctx *c) {
     DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->pair_p, &c->pair_t,
                       &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->scan_tmp, &c->mask_hits, &c->len16, &c->ctrl, &c->loci, &c->runs,
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
-                      &c->scratch[1]};
+                      &c->scratch[1], &c->lock_scratch[0], &c->lock_scratch[1], &c->lockq_scratch[0], &c->lockq_scratch[1]};
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
         DevBuf *sb[] = {&sl.skey_in, &sl.sval_out, &sl.list_a, &sl.list_m, &sl.list_t};

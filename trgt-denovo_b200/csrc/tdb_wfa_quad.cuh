@@ -35,15 +35,40 @@ namespace tdb {
 #endif
 // Geometry of a lockstep configuration: G lanes per pair (32/G pairs per warp), wavefronts up to W
 // diagonals, M arena of MAR entries (power of two), scores < SCAP, PROV provenance bytes.
-template <int G_, int W_, int MAR_, int SCAP_, int PROV_>
+// GP: the provenance bytes and the per-score step records -- written once, read only by the backtrace -- live in a
+// per-pair slice of global scratch (L2) instead of shared memory, which halves a wide pair's shared-memory state.
+template <int G_, int W_, int MAR_, int SCAP_, int PROV_, bool GP_ = false, int MINB_ = TDB_Q_MINB>
 struct LockCfg {
-    static constexpr int G = G_, W = W_, MAR = MAR_, SCAP = SCAP_, PROV = PROV_;
+    static constexpr int G = G_, W = W_, MAR = MAR_, SCAP = SCAP_, PROV = PROV_, MINB = MINB_;
+    static constexpr bool GP = GP_;
 };
+#ifndef TDB_Q_GP
+#define TDB_Q_GP 0
+#endif
+#ifndef TDB_Q_GPROV
+#define TDB_Q_GPROV 1024
+#endif
+#ifndef TDB_Q_GMINB
+#define TDB_Q_GMINB 10
+#endif
+#if TDB_Q_GP
+// tier 0: four pairs per warp; provenance and step records in global scratch, 1.8 KB of shared memory per pair, and a
+// register cap that lets 20 warps stay resident per SM instead of 16 (the kernel waits on dependent-issue latency)
+using QuadCfg = LockCfg<8, 32, TDB_Q_MAR, TDB_Q_SCAP, TDB_Q_GPROV, true, TDB_Q_GMINB>;
+#else
 using QuadCfg = LockCfg<8, 32, TDB_Q_MAR, TDB_Q_SCAP, TDB_Q_PROV>; // tier 0: four pairs per warp
+#endif
 #ifndef TDB_DUO_G
 #define TDB_DUO_G 16
 #endif
 using DuoCfg = LockCfg<TDB_DUO_G, 64, 1024, 128, 2048>;             // tier 1: two pairs per warp
+// tier 1 with FOUR pairs per warp (8 lanes each): the per-score bookkeeping of the lockstep loop serves twice as many
+// pairs, and 8 lanes fit the ~20 diagonals of these wavefronts better than 16 (3 x 8 instead of 2 x 16 lane slots).  What
+// makes it fit: provenance and step records in global scratch (GP), 3.7 KB of shared memory per pair instead of 6.2.
+#ifndef TDB_DUO4_PROV
+#define TDB_DUO4_PROV 4096
+#endif
+using Duo4Cfg = LockCfg<8, 64, 1024, 128, TDB_DUO4_PROV, true, 16 / TDB_Q_WARPS>; // 16 warps per SM: 128 registers
 constexpr int Q_MAXLEN = 8000;
 constexpr int Q_WARPS = TDB_Q_WARPS;
 constexpr int Q_NULL = -16384;
@@ -64,13 +89,16 @@ __device__ __forceinline__ int qr_hi(uint32_t r) { return (int)r >> 16; }
 template <class C>
 struct __align__(16) QPairT {
     int16_t marena[C::MAR];       // FIFO arena of M wavefronts; reused as the op stream at backtrace
-    int16_t gap[12][C::W];        // I1[4], D1[4], I2[2], D2[2] rings indexed by score
+    int16_t gap[10][C::W];        // I1[3], D1[3] (scores s, s-1, s-2: row s mod 3), I2[2], D2[2] (row s & 1)
     uint32_t mmeta[32];           // qm_pack(valid range, arena position) of M[s], slot s & 31
-    int16_t step_lo[C::SCAP];     // computed lo of score s (provenance row origin)
-    uint16_t step_base[C::SCAP];
-    uint8_t prov[C::PROV];
+    int16_t step_lo[C::GP ? 8 : C::SCAP];     // computed lo of score s (provenance row origin)
+    uint16_t step_base[C::GP ? 8 : C::SCAP];
+    uint8_t prov[C::GP ? 16 : C::PROV];
 };
-static_assert(sizeof(QPairT<QuadCfg>) % 16 == 0 && sizeof(QPairT<DuoCfg>) % 16 == 0, "pair state keeps 16-byte alignment");
+template <class C>
+constexpr size_t lock_gscratch_bytes() { return C::GP ? (((size_t)C::PROV + 15) & ~(size_t)15) + (size_t)C::SCAP * 4 : 0; } // per pair
+static_assert(sizeof(QPairT<QuadCfg>) % 16 == 0 && sizeof(QPairT<DuoCfg>) % 16 == 0 && sizeof(QPairT<Duo4Cfg>) % 16 == 0,
+              "pair state keeps 16-byte alignment");
 template <class C>
 constexpr size_t lock_smem_bytes() { return sizeof(QPairT<C>) * (32 / C::G) * Q_WARPS; }
 
@@ -115,7 +143,7 @@ __device__ __forceinline__ int extend_groups(const uint32_t *pw, const uint32_t 
 }
 
 template <class C, int X, int O1, int E1, int O2, int E2>
-__global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const AlignParams p) {
+__global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const AlignParams p) {
     static_assert(X < 32 && O1 + E1 < 32 && O2 + E2 < 32 && E1 == 2 && E2 == 1, "ring sizes; gap ranges are kept for two / one score(s)");
     constexpr int QG = C::G, QW = C::W, Q_MAR = C::MAR, Q_SCAP = C::SCAP, Q_PROV = C::PROV;
     using QPair = QPairT<C>;
@@ -123,6 +151,16 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gl = lane & (QG - 1), gid = lane / QG, gshift = gid * QG;
     QPair &sm = reinterpret_cast<QPair *>(smem_raw)[wid * (32 / QG) + gid];
+    uint8_t *prov = sm.prov;
+    int16_t *step_lo = sm.step_lo;
+    uint16_t *step_base = sm.step_base;
+    if (C::GP) { // this group's slice of the launch's global scratch
+        constexpr size_t GBYTES = (((size_t)Q_PROV + 15) & ~(size_t)15) + (size_t)Q_SCAP * 4;
+        uint8_t *g = p.scratch + ((size_t)(blockIdx.x * Q_WARPS + wid) * (32 / QG) + gid) * GBYTES;
+        prov = g;
+        step_lo = reinterpret_cast<int16_t *>(g + (((size_t)Q_PROV + 15) & ~(size_t)15));
+        step_base = reinterpret_cast<uint16_t *>(step_lo + Q_SCAP);
+    }
     const Penalties pn = {X, O1, E1, O2, E2};
     const ItemSrc src = item_src(p);
     const unsigned n_items = src.total;
@@ -169,18 +207,19 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
             if (running && gl == 0) {
                 sm.mmeta[0] = qm_pack(0, 0, 0u);
                 sm.marena[0] = (int16_t)m0;
-                sm.step_lo[0] = 0, sm.step_base[0] = 0;
-                sm.prov[0] = 0;
+                step_lo[0] = 0, step_base[0] = 0;
+                prov[0] = 0;
             }
             unsigned Mm = 1u, I1m = 0, I2m = 0, D1m = 0, D2m = 0; // bit j <-> score s-j exists
             // ranges of the gap wavefronts, in registers: I1 / D1 of scores s-1 (a) and s-2 (b), I2 / D2 of score s-1
             uint32_t rI1a = 0, rI1b = 0, rD1a = 0, rD1b = 0, rI2 = 0, rD2 = 0;
             unsigned mhead = 1, prov_used = 1;
             int steps_wait = p.heur.steps - (p.heur.kind == 1 ? 1 : 0);
-            int s = 0;
+            int s = 0, s3 = 0; // s3 = s mod 3
             __syncwarp();
             while (__any_sync(TDB_FULL, running)) {
                 ++s;
+                s3 = s3 == 2 ? 0 : s3 + 1;
                 if (s >= Q_SCAP) { // warp-uniform
                     if (running) overflow = true, running = false;
                     break;
@@ -211,8 +250,9 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                 if (live && (D1m & (1u << E1))) d1_lo = qr_lo(rD1b), d1_sp = (unsigned)(qr_hi(rD1b) - d1_lo + 1);
                 if (live && (I2m & (1u << E2))) i2_lo = qr_lo(rI2), i2_sp = (unsigned)(qr_hi(rI2) - i2_lo + 1);
                 if (live && (D2m & (1u << E2))) d2_lo = qr_lo(rD2), d2_sp = (unsigned)(qr_hi(rD2) - d2_lo + 1);
-                const int16_t *I1r = sm.gap[0 + ((s - E1) & 3)], *D1r = sm.gap[4 + ((s - E1) & 3)]; // warp-uniform rows
-                const int16_t *I2r = sm.gap[8 + ((s - E2) & 1)], *D2r = sm.gap[10 + ((s - E2) & 1)];
+                const int s3r = s3 == 2 ? 0 : s3 + 1; // (s - 2) mod 3
+                const int16_t *I1r = sm.gap[0 + s3r], *D1r = sm.gap[3 + s3r]; // warp-uniform rows
+                const int16_t *I2r = sm.gap[6 + ((s - E2) & 1)], *D2r = sm.gap[8 + ((s - E2) & 1)];
                 int lo = INT32_MAX, hi = INT32_MIN;
 #define TDB_LIM(w, dl, dh)                                              \
     if (w##_sp) {                                                       \
@@ -241,9 +281,9 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                     }
                 }
                 if (!live) lo = 0, hi = -1;
-                int16_t *I1o = sm.gap[0 + (s & 3)], *D1o = sm.gap[4 + (s & 3)];
-                int16_t *I2o = sm.gap[8 + (s & 1)], *D2o = sm.gap[10 + (s & 1)];
-                uint8_t *pv = sm.prov + prov_used;
+                int16_t *I1o = sm.gap[0 + s3], *D1o = sm.gap[3 + s3];
+                int16_t *I2o = sm.gap[6 + (s & 1)], *D2o = sm.gap[8 + (s & 1)];
+                uint8_t *pv = prov + prov_used;
                 cells += (unsigned)width;
                 // Which cells lie inside the DP matrix decides the trimmed range of each output wavefront (A.2).  M: one vote
                 // per iteration, first / last set bit.  Gap components: per lane and component one word of two halfwords,
@@ -356,7 +396,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                 int tl_i2 = lo + (int)(0xffffu - (wI2 >> 16)), th_i2 = lo + (int)(wI2 & 0xffffu) - 1;
                 int tl_d1 = lo + (int)(0xffffu - (wD1 >> 16)), th_d1 = lo + (int)(wD1 & 0xffffu) - 1;
                 int tl_d2 = lo + (int)(0xffffu - (wD2 >> 16)), th_d2 = lo + (int)(wD2 & 0xffffu) - 1;
-                if (live && gl == 0) sm.step_lo[s] = (int16_t)lo, sm.step_base[s] = (uint16_t)prov_used;
+                if (live && gl == 0) step_lo[s] = (int16_t)lo, step_base[s] = (uint16_t)prov_used;
                 prov_used += (unsigned)width;
                 __syncwarp();
                 const bool done_now = qballot<QG>(gshift, fin) != 0; // group-uniform
@@ -446,7 +486,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, TDB_Q_MINB) k_align_lock(const A
                 bool walking = aligned && !(comp < 0 && cs == 0);
                 while (__any_sync(TDB_FULL, walking)) {
                     if (walking) {
-                        const int b = sm.prov[(unsigned)sm.step_base[cs] + (unsigned)(k - (int)sm.step_lo[cs])];
+                        const int b = prov[(unsigned)step_base[cs] + (unsigned)(k - (int)step_lo[cs])];
                         int op;
                         if (comp < 0) {
                             const int srcm = b & 7;
