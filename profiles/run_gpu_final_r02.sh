@@ -20,7 +20,7 @@ timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --
 echo launches_full rc=$?
 timeout 1500 python profiles/bench_configs.py > gpurun_out/configs_$tag.jsonl 2> gpurun_out/configs_$tag.err; echo "configs rc=$?"; tail -2 gpurun_out/configs_$tag.err
 CMD="python bench.py --loci 100000 --steps 1 --warmup 3 --no-cpu-baseline --no-census"
-for k in "k_align_lock.*Li16ELi64" "k_align_lock.*Li8ELi32" k_align_thread k_dedup_window; do
+for k in "k_align_lock.*Li8ELi64" "k_align_lock.*Li8ELi32" k_align_thread k_dedup_window k_estimate; do
   name=$(echo $k | tr -c 'A-Za-z0-9_\n' '_')
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$k -s 3 -c 1 -f \
       -o gpurun_out/prof_${name}_$tag $CMD > gpurun_out/ncu_${name}_$tag.log 2>&1
