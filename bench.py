@@ -473,7 +473,8 @@ def main():
         # (representative pairs only; duplicates are copied, not aligned), SURVEY.md 8(d) accounting.
         tiers = ("align_quad", "align_warp", "align_global", "align_thread")
         names = {"align_quad": "k_align_lock<QuadCfg>", "align_global": "k_align_global", "align_thread": "k_align_thread",
-                 "align_warp": "k_align_warp" if os.environ.get("TDB_DISABLE_DUO") else "k_align_lock<DuoCfg>"}
+                 "align_warp": "k_align_warp" if os.environ.get("TDB_DISABLE_DUO") else
+                               ("k_align_lock<DuoCfg>" if os.environ.get("TDB_DUO_G16") else "k_align_lock<Duo4Cfg>")}
         ti = max(range(4), key=lambda i: stage[tiers[i]])
         k_ms = stage[tiers[ti]] / args.steps
         k_s = max(k_ms, 1e-6) * 1e-3
