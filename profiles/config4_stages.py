@@ -17,7 +17,7 @@ for rep in range(2):
     dt = time.perf_counter() - t0
     c = ctx.counters()
     print("call ms", round(dt*1e3,1), "device", round(c.ms_total_device,1), "pack", round(c.ms_pack,2), "dedup", round(c.ms_dedup,2), "thread", round(c.ms_thread_tier,2),
-          "quad", round(c.ms_tier[0],2), "tier1", round(c.ms_tier[1],2), "global", round(c.ms_tier[2],2), "pairs", c.thread_pairs, list(c.tier_pairs),
+          "quad", round(c.ms_tier[0],2), "tier1", round(c.ms_tier[1],2), "global", round(c.ms_tier[2],2), "long", round(c.ms_long_tier,2), c.long_pairs, "pairs", c.thread_pairs, list(c.tier_pairs),
           "cells", list(c.tier_cells), "ext16", list(c.tier_ext16), "cols", list(c.tier_columns), "chunks", c.chunks)
 ln = b.seq_len
 print("len pct", np.percentile(ln, [50, 90, 99, 100]))

@@ -76,7 +76,7 @@ def _check_batch(ctx, seqs, pp, pt, clip, heuristic=tdo.DEFAULT_HEURISTIC, cigar
     assert (st == wst).all()
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, f"{len(bad)} score mismatches (closed form on), first pair {bad[:5]}: gpu {got[bad[:5]]} oracle {want[bad[:5]]}"
-    assert sum(fast.tier_pairs) + fast.thread_pairs + fast.pairs_identical + fast.pairs_duplicate + fast.pairs_closed_form == len(pp)
+    assert sum(fast.tier_pairs) + fast.long_pairs + fast.thread_pairs + fast.pairs_identical + fast.pairs_duplicate + fast.pairs_closed_form == len(pp)
     # dense layout (seq_off = NULL): to_arrays lays the sequences back to back, the device derives the offsets
     got, st = ctx.align_batch(blob, None, ln, pp, pt)
     assert (st == wst).all() and (got == want).all()
@@ -114,7 +114,7 @@ def test_str_pairs_bit_exact(ctx, clip):
     rng = random.Random(100 + clip)
     seqs, pp, pt = make_pairs(rng, n_targets=300, reads_per_target=12)
     cnt = _check_batch(ctx, seqs, pp, pt, clip)
-    aligned = sum(cnt.tier_pairs) + cnt.thread_pairs
+    aligned = sum(cnt.tier_pairs) + cnt.thread_pairs + cnt.long_pairs
     assert aligned + cnt.pairs_identical + cnt.pairs_duplicate == len(pp)
     assert cnt.thread_pairs + cnt.tier_pairs[0] + cnt.tier_pairs[1] > 0.8 * aligned  # the shared-memory tiers carry the bulk
     assert cnt.thread_pairs > 0 and cnt.tier_pairs[0] > 0 and cnt.tier_pairs[1] > 0
@@ -131,7 +131,7 @@ def test_random_divergent_pairs(ctx):
         pt.append(len(seqs)); seqs.append(t.encode())
         pp.append(len(seqs)); seqs.append(p.encode())
     cnt = _check_batch(ctx, seqs, np.array(pp, np.uint32), np.array(pt, np.uint32), 50)
-    assert cnt.tier_pairs[2] > 0
+    assert cnt.tier_pairs[2] + cnt.long_pairs > 0
 
 
 def test_quad_tier_disabled_gives_same_scores(tdb, monkeypatch):
@@ -564,7 +564,8 @@ def test_empty_and_very_long_sequences(ctx):
     pt = np.array([t for _, t in pairs], np.uint32)
     for clip in (50, 0):
         cnt = _check_batch(ctx, seqs, pp, pt, clip)
-    assert cnt.tier_pairs[2] + cnt.tier_pairs[3] >= 4
+    assert cnt.long_pairs + cnt.tier_pairs[2] + cnt.tier_pairs[3] >= 4
+    assert cnt.long_pairs > 0  # up to 16 000 bases and 256 diagonals: the long tier
 
 
 def test_empty_batch(ctx):
@@ -585,6 +586,42 @@ def test_long_expansion_pairs(ctx):
         for src in (big, big, small):
             pp.append(len(seqs)); pt.append(t); seqs.append(mutate(rng, src, 0.003).encode())
     _check_batch(ctx, seqs, np.array(pp, np.uint32), np.array(pt, np.uint32), 50)
+
+
+def _long_pairs(seed):
+    rng = random.Random(seed)
+    seqs, pp, pt = [], [], []
+    for i in range(10):
+        lf, rf, motif = rand_seq(rng, 50), rand_seq(rng, 50), rand_seq(rng, rng.randint(2, 6))
+        big = lf + motif * rng.randint(400, 1500) + rf
+        small = lf + motif * rng.randint(20, 200) + rf
+        t = len(seqs); seqs.append(big.encode())
+        u = len(seqs); seqs.append(small.encode())
+        for src, tgt in ((big, t), (small, t), (big, u), (small, u)):  # long deletions AND long insertions (both gap pieces)
+            pp.append(len(seqs)); pt.append(tgt); seqs.append(mutate(rng, src, 0.004).encode())
+    # two interrupted repeats: gaps of several hundred columns split by matches (runs of the backtrace start and stop)
+    a = rand_seq(rng, 60) + "CAG" * 300 + "CAA" + "CAG" * 200 + rand_seq(rng, 60)
+    b = rand_seq(rng, 5) + a[5:60] + "CAG" * 40 + "CAA" + "CAG" * 350 + a[-60:]
+    pp.append(len(seqs)); seqs.append(a.encode()); pt.append(len(seqs)); seqs.append(b.encode())
+    pp.append(len(seqs) - 1); pt.append(len(seqs) - 2)
+    return seqs, np.array(pp, np.uint32), np.array(pt, np.uint32)
+
+
+def test_long_tier_and_global_tiers_give_same_scores(tdb, monkeypatch):
+    """Long gaps (hundreds to thousands of columns, insertions and deletions): the long tier (k_align_lock<LongCfg>:
+    shared-memory wavefronts, gap runs of the backtrace walked 32 columns per round) and, with the long tier off, the
+    global-scratch tiers must both reproduce the oracle."""
+    seqs, pp, pt = _long_pairs(2024)
+    c = tdb.Context()
+    cnt = _check_batch(c, seqs, pp, pt, 50)
+    assert cnt.long_pairs > 20 and cnt.tier_pairs[2] + cnt.tier_pairs[3] == 0
+    c.close()
+    monkeypatch.setenv("TDB_DISABLE_LONG", "1")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_DISABLE_LONG")
+    cnt2 = _check_batch(c, seqs, pp, pt, 50)
+    assert cnt2.long_pairs == 0 and cnt2.tier_pairs[2] == cnt.long_pairs
+    c.close()
 
 
 def _random_loci(rng, n_loci, duo=False):

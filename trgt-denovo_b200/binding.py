@@ -58,7 +58,9 @@ class Counters(C.Structure):
                 ("ms_tier", C.c_float * 4), ("ms_thread_tier", C.c_float), ("thread_pairs", C.c_uint64),
                 ("thread_cells", C.c_uint64), ("thread_ext16", C.c_uint64), ("thread_columns", C.c_uint64),
                 ("bytes_d2h", C.c_uint64), ("pairs_failed", C.c_uint64),
-                ("ms_fused_call", C.c_float), ("ms_fused_tail", C.c_float)]
+                ("ms_fused_call", C.c_float), ("ms_fused_tail", C.c_float),
+                ("long_pairs", C.c_uint64), ("long_cells", C.c_uint64), ("long_ext16", C.c_uint64),
+                ("long_columns", C.c_uint64), ("ms_long_tier", C.c_float), ("reserved0", C.c_float)]
 
 
 class PackedSeqs(C.Structure):

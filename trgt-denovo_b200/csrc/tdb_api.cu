@@ -50,8 +50,9 @@ struct Ctrl {
     unsigned wc_g[2];  // work counters of the two global tiers
     unsigned n_closed; // pairs resolved in closed form (k_dedup_window)
     unsigned n_failed; // pairs the last tier could not finish
-    unsigned pad0[1];
-    unsigned long long exec[5][4]; // executed cells, ext16, columns, pairs finished; per tier ([4]: thread-per-pair tier)
+    unsigned dcount;   // pairs the long tier could not finish (listD)
+    unsigned wc_long, pad0[3]; // work counter of the long tier
+    unsigned long long exec[6][4]; // executed cells, ext16, columns, pairs finished; per tier ([4]: thread-per-pair tier, [5]: long tier)
     unsigned long long algo[5];    // algorithmic cells, ext16, columns (all pairs); pairs with rep == self; failed pairs
     // ---- per chunk (one block per pipeline slot, zeroed before every chunk) ----
     struct Chunk {
@@ -79,7 +80,7 @@ struct tdb_ctx {
     cudaStream_t prep_stream = nullptr; // kernels on freshly uploaded data (see run_align)
     // grow-only device buffers
     DevBuf blob, seq_off, seq_len, packed, seq_flag, seq_hash, pair_p, pair_t, score, status, penalty;
-    DevBuf rep, work, list_b, list_c, scan_tmp, mask_hits, len16;
+    DevBuf rep, work, list_b, list_c, list_d, scan_tmp, mask_hits, len16;
     std::vector<unsigned> h_hits; // host copy of the set mask positions
     // Chunks alternate between two pipeline slots (own stream + own scratch) so that the tail of one chunk's
     // alignment kernels overlaps the next chunk's duplicate elimination and alignment.  (3 and 4 slots, and a
@@ -93,7 +94,8 @@ struct tdb_ctx {
     DevBuf scratch[2];
     DevBuf lockq_scratch[2]; // the same for tier 0
     DevBuf lock_scratch[2]; // provenance / step records of the four-pairs-per-warp tier 1 (per pipeline slot)
-    int duo4_ctas_per_sm = 0;
+    int duo4_ctas_per_sm = 0, long_ctas_per_sm = 0;
+    bool disable_long = false; // TDB_DISABLE_LONG: no long tier (k_align_lock<LongCfg>) in front of the global-scratch tiers
     bool duo4 = true; // TDB_DUO_G16=1: tier 1 with two pairs per warp (16 lanes each), everything in shared memory
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0, mini_ctas_per_sm = 0;
     bool disable_mini = false;
@@ -1024,6 +1026,33 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     if (h.err & ERR_PAIR_INDEX) return fail(ctx, TDB_E_INVALID, "pair index out of range");
     unsigned pending = cigar_mode ? n_pairs : h.gcount;
     if (staged) CK(cudaEventRecord(ctx->ev[6], s));
+    // ---- long tier: one pair per warp, wavefronts (up to 256 diagonals) in shared memory, provenance / step records / op
+    // stream in a per-warp slice of global scratch; production penalties, sequences up to 16 000 bases.  What it cannot
+    // hold moves on to the global-scratch tiers.
+    const uint32_t *g_src = cigar_mode ? nullptr : (const uint32_t *)ctx->list_b.p;
+    if (!cigar_mode && default_pen && !ctx->disable_long && pending > 0) {
+        const size_t per_pair = lock_gscratch_bytes<LongCfg>();
+        uint64_t warps = std::min<uint64_t>((uint64_t)ctx->sm_count * ctx->long_ctas_per_sm * Q_WARPS,
+                                            std::max<uint64_t>(Q_WARPS, (cap / 2) / per_pair));
+        warps = std::min<uint64_t>(warps, ((uint64_t)pending + Q_WARPS - 1) / Q_WARPS * Q_WARPS);
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, warps / Q_WARPS);
+        ENSURE(ctx->scratch[0], per_pair * (size_t)grid * Q_WARPS);
+        ENSURE(ctx->list_d, (size_t)pending * 4);
+        p.scratch = (uint8_t *)ctx->scratch[0].p;
+        p.src1 = g_src, p.src1_seg = nullptr, p.src1_count = pending, p.src2 = nullptr, p.src2_count = nullptr;
+        p.next_todo = (uint32_t *)ctx->list_d.p, p.next_count = &ctrl->dcount;
+        p.work_counter = &ctrl->wc_long, p.counters = ctrl->exec[5];
+        k_align_lock<LongCfg, 8, 4, 2, 24, 1><<<grid, Q_WARPS * 32, lock_smem_bytes<LongCfg>(), s>>>(p);
+        CK(cudaGetLastError());
+        cn.kernel_launches += 1;
+        if (staged) CK(cudaEventRecord(ctx->ev[14], s));
+        unsigned next = 0;
+        CK(cudaMemcpyAsync(&next, &ctrl->dcount, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (staged) cn.ms_long_tier = elapsed(ctx->ev[6], ctx->ev[14]);
+        pending = next;
+        g_src = (const uint32_t *)ctx->list_d.p;
+    }
     for (int g = 0; g < 2 && pending > 0; ++g) {
         const TierCfg tc = gt[g];
         const size_t stride = global_tier_stride(tc.wlog2, tc.s_cap, tc.ops_cap, tc.prov_cap);
@@ -1035,7 +1064,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         p.wlog2 = tc.wlog2, p.s_cap = tc.s_cap, p.ops_cap = tc.ops_cap, p.prov_cap = tc.prov_cap;
         p.src1_seg = nullptr, p.src1_count = pending, p.src2 = nullptr, p.src2_count = nullptr;
         if (g == 0) {
-            p.src1 = cigar_mode ? nullptr : (const uint32_t *)ctx->list_b.p;
+            p.src1 = g_src;
             ENSURE(ctx->list_c, (size_t)pending * 4);
             p.next_todo = (uint32_t *)ctx->list_c.p, p.next_count = &ctrl->ccount;
         } else {
@@ -1077,6 +1106,10 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     cn.thread_cells = h.exec[4][0], cn.thread_ext16 = h.exec[4][1], cn.thread_columns = h.exec[4][2];
     cn.thread_pairs = h.exec[4][3];
     aligned += h.exec[4][3];
+    cn.exec_cells += h.exec[5][0], cn.exec_ext16 += h.exec[5][1], cn.exec_columns += h.exec[5][2];
+    cn.long_cells = h.exec[5][0], cn.long_ext16 = h.exec[5][1], cn.long_columns = h.exec[5][2];
+    cn.long_pairs = h.exec[5][3];
+    aligned += h.exec[5][3];
     if (cigar_mode) {
         cn.cells = cn.exec_cells, cn.ext16 = cn.exec_ext16, cn.columns = cn.exec_columns;
     } else {
@@ -1280,6 +1313,8 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         if (e == cudaSuccess) e = setup(k_align_lock<DuoCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<DuoCfg>(), c->duo_ctas_per_sm);
         if (e == cudaSuccess) e = setup(k_align_lock<Duo4Cfg, 8, 4, 2, 24, 1>, lock_smem_bytes<Duo4Cfg>(), c->duo4_ctas_per_sm);
         c->duo4 = getenv("TDB_DUO_G16") == nullptr && c->duo4_ctas_per_sm >= 1;
+        if (e == cudaSuccess) e = setup(k_align_lock<LongCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<LongCfg>(), c->long_ctas_per_sm);
+        c->disable_long = getenv("TDB_DISABLE_LONG") != nullptr || c->long_ctas_per_sm < 1;
         auto fsetup = [&](auto kern, size_t smem, int &occ_out) {
             cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1350,7 +1385,7 @@ void tdb_destroy(tdb_ctx *c) {
     DevBuf *bufs[] = {&c->blob, &c->seq_off, &c->seq_len, &c->packed, &c->seq_flag, &c->seq_hash, &c->pair_p, &c->pair_t,
                       &c->score, &c->status, &c->penalty, &c->rep, &c->work, &c->list_b, &c->list_c, &c->scan_tmp, &c->mask_hits, &c->len16, &c->ctrl, &c->loci, &c->runs,
                       &c->aout, &c->mask, &c->scores_in, &c->cigar, &c->cigar_off, &c->cigar_len, &c->scratch[0],
-                      &c->scratch[1], &c->lock_scratch[0], &c->lock_scratch[1], &c->lockq_scratch[0], &c->lockq_scratch[1]};
+                      &c->list_d, &c->scratch[1], &c->lock_scratch[0], &c->lock_scratch[1], &c->lockq_scratch[0], &c->lockq_scratch[1]};
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
         DevBuf *sb[] = {&sl.skey_in, &sl.sval_out, &sl.list_a, &sl.list_m, &sl.list_t};

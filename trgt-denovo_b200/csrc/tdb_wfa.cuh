@@ -433,44 +433,56 @@ __device__ int wfa_align_warp(const SeqView &P, const SeqView &T, const Penaltie
     }
 
     // ---- backtrace (A.4): provenance chain from (M, s, k_end) back to (M, 0, 0) --------------------
+    // Inside a gap the chain is predictable while it extends (score - e, diagonal -+ 1 per column), and every step of the
+    // chain is a dependent load from the scratch (HBM / L2 for the global tiers: microseconds per column of a long
+    // expansion).  So lane j reads the byte the chain reaches after j further extensions, one vote finds the first cell
+    // that OPENED the gap instead, and up to 32 columns are consumed per round.  Lanes past that cell have read bytes that
+    // are not on the path (any byte inside the provenance area: the index is clamped); they are not looked at.
     out_penalty = s;
     int nops = 0, n_del = 0;
     {
         int comp = -1 /* M */, cs = s, k = k_end;
         while (!(comp < 0 && cs == 0)) {
-            const int b = st.prov[(unsigned)st.step_base[cs] + (unsigned)(k - (int)st.step_lo[cs])];
-            int op;
             if (comp < 0) {
+                const int b = st.prov[(unsigned)st.step_base[cs] + (unsigned)(k - (int)st.step_lo[cs])];
                 const int src = b & 7;
+                int op;
                 if (src == PM_X) op = OP_X, cs -= pn.x;
                 else op = OP_CLOSE, comp = src - 1; // PM_I1..PM_D2 -> CI1..CD2
-            } else if (comp == CI1 || comp == CI2) {
-                op = OP_I;
-                const bool ext = b & (comp == CI1 ? PB_I1E : PB_I2E);
-                const int e = comp == CI1 ? pn.e1 : pn.e2, o = comp == CI1 ? pn.o1 : pn.o2;
-                if (ext) cs -= e; else cs -= o + e, comp = -1;
-                k -= 1;
-            } else {
-                op = OP_D;
-                ++n_del;
-                const bool ext = b & (comp == CD1 ? PB_D1E : PB_D2E);
-                const int e = comp == CD1 ? pn.e1 : pn.e2, o = comp == CD1 ? pn.o1 : pn.o2;
-                if (ext) cs -= e; else cs -= o + e, comp = -1;
-                k += 1;
+                if (nops >= st.ops_cap) return WFA_OVERFLOW;
+                if (lane == 0) st.ops[nops] = (uint8_t)op;
+                ++nops;
+                continue;
             }
-            if (nops >= st.ops_cap) return WFA_OVERFLOW;
-            if (lane == 0) st.ops[nops] = (uint8_t)op;
-            ++nops;
+            const bool is_ins = comp == CI1 || comp == CI2, first = comp == CI1 || comp == CD1;
+            const int e = first ? pn.e1 : pn.e2, o = first ? pn.o1 : pn.o2, dk = is_ins ? -1 : 1;
+            const int bit = comp == CI1 ? PB_I1E : (comp == CI2 ? PB_I2E : (comp == CD1 ? PB_D1E : PB_D2E));
+            const int cj = cs - lane * e, kj = k + lane * dk;
+            bool ext = false;
+            if (cj > 0) {
+                const unsigned at = (unsigned)st.step_base[cj] + (unsigned)(kj - (int)st.step_lo[cj]);
+                ext = (st.prov[min(at, prov_used - 1u)] & bit) != 0;
+            }
+            const unsigned opened = ~__ballot_sync(TDB_FULL, ext);
+            const int cnt = opened ? __ffs(opened) : 32; // columns consumed: cnt - 1 extensions and, if any, the opening one
+            if (nops + cnt > st.ops_cap) return WFA_OVERFLOW;
+            if (lane < cnt) st.ops[nops + lane] = (uint8_t)(is_ins ? OP_I : OP_D);
+            nops += cnt;
+            if (!is_ins) n_del += cnt;
+            k += cnt * dk;
+            if (opened) cs -= (cnt - 1) * e + o + e, comp = -1;
+            else cs -= 32 * e;
         }
     }
     __syncwarp();
     // ---- forward replay: matches re-extended only in the M component; clipped score on the fly ------
+    // (a run of equal gap columns is found by one vote over the next 32 ops and emitted at once)
     ClipAcc acc;
     const int total_cols = m + n_del;
     acc.init(total_cols, clip);
     int v = 0, h = 0;
     bool in_m = true;
-    for (int i = nops - 1; i >= -1; --i) {
+    for (int i = nops - 1;;) {
         if (in_m) {
             const int eq = extend_coop(P, T, v, h, lane);
             if (WANT_CIGAR)
@@ -482,14 +494,25 @@ __device__ int wfa_align_warp(const SeqView &P, const SeqView &T, const Penaltie
         const int op = st.ops[i];
         if (op == OP_CLOSE) {
             in_m = true;
+            --i;
             continue;
         }
-        const int ch = op == OP_X ? 'X' : (op == OP_I ? 'I' : 'D');
-        if (WANT_CIGAR && lane == 0) cigar_out[acc.col] = (uint8_t)ch;
-        acc.emit(ch, 1, pn);
-        if (op == OP_X) ++v, ++h;
-        else if (op == OP_I) ++h, in_m = false;
-        else ++v, in_m = false;
+        if (op == OP_X) {
+            if (WANT_CIGAR && lane == 0) cigar_out[acc.col] = (uint8_t)'X';
+            acc.emit('X', 1, pn);
+            ++v, ++h, --i;
+            continue;
+        }
+        const int j = i - lane;
+        const unsigned differs = ~__ballot_sync(TDB_FULL, j >= 0 && st.ops[j] == op);
+        const int run = differs ? __ffs(differs) - 1 : 32; // >= 1: lane 0 holds ops[i] itself
+        const int ch = op == OP_I ? 'I' : 'D';
+        if (WANT_CIGAR && lane < run) cigar_out[acc.col + lane] = (uint8_t)ch;
+        acc.emit(ch, run, pn);
+        if (op == OP_I) h += run;
+        else v += run;
+        in_m = false;
+        i -= run;
     }
     out_clipped = acc.finish(pn);
     wc.columns += (unsigned)acc.col;

@@ -13,6 +13,7 @@
 //     src/model.rs:13-23); other penalties use the general tiers (wfa_align_warp, tdb_wfa.cuh).
 // Semantics are exactly those of wfa_align_warp: SURVEY.md Appendix A.1-A.4.
 #pragma once
+#include <type_traits>
 #include "tdb_kernels.cuh"
 
 namespace tdb {
@@ -37,10 +38,16 @@ namespace tdb {
 // diagonals, M arena of MAR entries (power of two), scores < SCAP, PROV provenance bytes.
 // GP: the provenance bytes and the per-score step records -- written once, read only by the backtrace -- live in a
 // per-pair slice of global scratch (L2) instead of shared memory, which halves a wide pair's shared-memory state.
-template <int G_, int W_, int MAR_, int SCAP_, int PROV_, bool GP_ = false, int MINB_ = TDB_Q_MINB>
+// WIDE (the long tier): diagonals beyond +-127 and scores beyond 16 bits of provenance -- the metadata of an M wavefront
+// takes two words, the provenance index of a score 32 bits, and the op stream of the backtrace (OPS bytes) lives in the
+// global slice too; sequences up to 16 000 bases (offsets stay int16).
+template <int G_, int W_, int MAR_, int SCAP_, int PROV_, bool GP_ = false, int MINB_ = TDB_Q_MINB, bool WIDE_ = false,
+          int OPS_ = 0>
 struct LockCfg {
-    static constexpr int G = G_, W = W_, MAR = MAR_, SCAP = SCAP_, PROV = PROV_, MINB = MINB_;
-    static constexpr bool GP = GP_;
+    static constexpr int G = G_, W = W_, MAR = MAR_, SCAP = SCAP_, PROV = PROV_, MINB = MINB_, OPS = OPS_;
+    static constexpr bool GP = GP_, WIDE = WIDE_;
+    static_assert(!WIDE_ || GP_, "the long tier keeps provenance, step records and ops in global scratch");
+    using StepBase = typename std::conditional<WIDE_, uint32_t, uint16_t>::type;
 };
 #ifndef TDB_Q_GP
 #define TDB_Q_GP 0
@@ -69,7 +76,15 @@ using DuoCfg = LockCfg<TDB_DUO_G, 64, 1024, 128, 2048>;             // tier 1: t
 #define TDB_DUO4_PROV 4096
 #endif
 using Duo4Cfg = LockCfg<8, 64, 1024, 128, TDB_DUO4_PROV, true, 16 / TDB_Q_WARPS>; // 16 warps per SM: 128 registers
+// the long tier: ONE pair per warp (32 lanes), wavefronts up to 256 diagonals, scores < 32768, sequences up to 16 000
+// bases.  What k_align_global did for the long-expansion stress set from a global-memory ring with run-time penalties
+// (1 600 warp instructions and two round trips to L2 per score step), this does from 13 KB of shared memory per pair.
+#ifndef TDB_LONG_PROV
+#define TDB_LONG_PROV (4 << 20)
+#endif
+using LongCfg = LockCfg<32, 256, 4096, 32768, TDB_LONG_PROV, true, 16 / TDB_Q_WARPS, true, 49152>;
 constexpr int Q_MAXLEN = 8000;
+constexpr int Q_MAXLEN_WIDE = 16000;
 constexpr int Q_WARPS = TDB_Q_WARPS;
 constexpr int Q_NULL = -16384;
 
@@ -90,14 +105,19 @@ template <class C>
 struct __align__(16) QPairT {
     int16_t marena[C::MAR];       // FIFO arena of M wavefronts; reused as the op stream at backtrace
     int16_t gap[10][C::W];        // I1[3], D1[3] (scores s, s-1, s-2: row s mod 3), I2[2], D2[2] (row s & 1)
-    uint32_t mmeta[32];           // qm_pack(valid range, arena position) of M[s], slot s & 31
+    uint32_t mmeta[C::WIDE ? 64 : 32]; // qm_pack(valid range, arena position) of M[s], slot s & 31 (WIDE: qr_pack(range), position)
     int16_t step_lo[C::GP ? 8 : C::SCAP];     // computed lo of score s (provenance row origin)
-    uint16_t step_base[C::GP ? 8 : C::SCAP];
+    typename C::StepBase step_base[C::GP ? 8 : C::SCAP];
     uint8_t prov[C::GP ? 16 : C::PROV];
 };
 template <class C>
-constexpr size_t lock_gscratch_bytes() { return C::GP ? (((size_t)C::PROV + 15) & ~(size_t)15) + (size_t)C::SCAP * 4 : 0; } // per pair
-static_assert(sizeof(QPairT<QuadCfg>) % 16 == 0 && sizeof(QPairT<DuoCfg>) % 16 == 0 && sizeof(QPairT<Duo4Cfg>) % 16 == 0,
+__host__ __device__ constexpr size_t lock_gscratch_bytes() { // per pair: provenance | step_lo | step_base | ops
+    return C::GP ? (((size_t)C::PROV + 15) & ~(size_t)15) + (size_t)C::SCAP * (2 + sizeof(typename C::StepBase)) +
+                       (((size_t)C::OPS + 15) & ~(size_t)15)
+                 : 0;
+}
+static_assert(sizeof(QPairT<QuadCfg>) % 16 == 0 && sizeof(QPairT<DuoCfg>) % 16 == 0 && sizeof(QPairT<Duo4Cfg>) % 16 == 0 &&
+                  sizeof(QPairT<LongCfg>) % 16 == 0 && LongCfg::SCAP % 8 == 0,
               "pair state keeps 16-byte alignment");
 template <class C>
 constexpr size_t lock_smem_bytes() { return sizeof(QPairT<C>) * (32 / C::G) * Q_WARPS; }
@@ -151,15 +171,20 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gl = lane & (QG - 1), gid = lane / QG, gshift = gid * QG;
     QPair &sm = reinterpret_cast<QPair *>(smem_raw)[wid * (32 / QG) + gid];
+    using StepBase = typename C::StepBase;
+    constexpr bool WIDE = C::WIDE;
+    constexpr int MAXLEN = WIDE ? Q_MAXLEN_WIDE : Q_MAXLEN;
     uint8_t *prov = sm.prov;
     int16_t *step_lo = sm.step_lo;
-    uint16_t *step_base = sm.step_base;
+    StepBase *step_base = sm.step_base;
+    uint8_t *ops = reinterpret_cast<uint8_t *>(sm.marena); // the arena is dead by the time of the backtrace
     if (C::GP) { // this group's slice of the launch's global scratch
-        constexpr size_t GBYTES = (((size_t)Q_PROV + 15) & ~(size_t)15) + (size_t)Q_SCAP * 4;
+        constexpr size_t GBYTES = lock_gscratch_bytes<C>();
         uint8_t *g = p.scratch + ((size_t)(blockIdx.x * Q_WARPS + wid) * (32 / QG) + gid) * GBYTES;
         prov = g;
         step_lo = reinterpret_cast<int16_t *>(g + (((size_t)Q_PROV + 15) & ~(size_t)15));
-        step_base = reinterpret_cast<uint16_t *>(step_lo + Q_SCAP);
+        step_base = reinterpret_cast<StepBase *>(step_lo + Q_SCAP);
+        if (WIDE) ops = reinterpret_cast<uint8_t *>(step_base + Q_SCAP);
     }
     const Penalties pn = {X, O1, E1, O2, E2};
     const ItemSrc src = item_src(p);
@@ -168,7 +193,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
     // chunk) only has a few batches per warp -- coarse grabs then leave warps idle behind the heaviest ones
     constexpr int PER_BATCH = 32 / QG, MAX_FETCH = 8 * PER_BATCH;
     const unsigned n_warps = gridDim.x * (blockDim.x >> 5);
-    const unsigned per_fetch =
+    const unsigned per_fetch = WIDE ? 1u : // (the long tier's pairs are few and take milliseconds each)
         (unsigned)PER_BATCH * max(1u, min((unsigned)(MAX_FETCH / PER_BATCH), n_items / (n_warps * 8u * (unsigned)PER_BATCH)));
     unsigned long long acc_cells = 0, acc_cols = 0, acc_ext = 0, acc_done = 0; // acc_* valid on group lane 0
 
@@ -189,7 +214,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                 idx = item_at(p, src, it);
                 const uint32_t ip = p.pair_p[idx], jt = p.pair_t[idx];
                 n = (int)p.seq_len[ip], m = (int)p.seq_len[jt];
-                overflow = (p.seq_flag[ip] | p.seq_flag[jt]) || n > Q_MAXLEN || m > Q_MAXLEN;
+                overflow = (p.seq_flag[ip] | p.seq_flag[jt]) || n > MAXLEN || m > MAXLEN;
                 const uint64_t poff = p.seq_off[ip], toff = p.seq_off[jt];
                 pw = p.packed + (poff >> 4), tw = p.packed + (toff >> 4);
                 psh = (int)(poff & 15), tsh = (int)(toff & 15);
@@ -205,7 +230,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
             bool running = usable && !identical;
             // ---------------- wavefront loop (score s is warp-uniform) ----------------
             if (running && gl == 0) {
-                sm.mmeta[0] = qm_pack(0, 0, 0u);
+                if (WIDE) sm.mmeta[0] = qr_pack(0, 0), sm.mmeta[1] = 0u;
+                else sm.mmeta[0] = qm_pack(0, 0, 0u);
                 sm.marena[0] = (int16_t)m0;
                 step_lo[0] = 0, step_base[0] = 0;
                 prov[0] = 0;
@@ -237,8 +263,13 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                 unsigned mx_sp = 0, mo1_sp = 0, mo2_sp = 0;
 #define TDB_QM(w, lag)                                                                \
     if (live && (Mm & (1u << (lag)))) {                                               \
-        const uint32_t mm_ = sm.mmeta[(s - (lag)) & 31];                              \
-        w##_lo = qm_lo(mm_), w##_sp = (unsigned)(qm_hi(mm_) - w##_lo + 1), w##_base = (int)qm_off(mm_) - w##_lo; \
+        if (WIDE) {                                                                   \
+            const uint2 mm_ = reinterpret_cast<const uint2 *>(sm.mmeta)[(s - (lag)) & 31]; \
+            w##_lo = qr_lo(mm_.x), w##_sp = (unsigned)(qr_hi(mm_.x) - w##_lo + 1), w##_base = (int)mm_.y - w##_lo; \
+        } else {                                                                      \
+            const uint32_t mm_ = sm.mmeta[(s - (lag)) & 31];                          \
+            w##_lo = qm_lo(mm_), w##_sp = (unsigned)(qm_hi(mm_) - w##_lo + 1), w##_base = (int)qm_off(mm_) - w##_lo; \
+        }                                                                             \
     }
                 TDB_QM(mx, X)
                 TDB_QM(mo1, O1 + E1)
@@ -274,7 +305,10 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                     // arena room: everything from the oldest live M wavefront up to the new one
                     const unsigned livem = Mm & 0x03fffffeu; // lags 1..25
                     unsigned tail = mhead;
-                    if (livem) tail = qm_off(sm.mmeta[(s - (31 - __clz(livem))) & 31]);
+                    if (livem) {
+                        const int ts = (s - (31 - __clz(livem))) & 31;
+                        tail = WIDE ? sm.mmeta[2 * ts + 1] : qm_off(sm.mmeta[ts]);
+                    }
                     if (width > QW || prov_used + (unsigned)width > Q_PROV ||
                         ((mhead - tail) & 0xffffu) + (unsigned)width > Q_MAR) {
                         overflow = true, running = false, live = false, width = 0; // this group drops out
@@ -339,11 +373,19 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                         if (vm) ev = mv - k, eroom = min(n - ev, m - mv);
                     }
                     // extend at once (trimming never changes offsets); one warp-uniform loop for all lanes
+                    // (running word pointers, the upper word of a round is the lower word of the next: two loads per round)
                     int eq = 0;
                     bool ebusy = vm && eroom > 0;
+                    const uint32_t *pq = pw + ((psh + ev) >> 4), *tq = tw + ((tsh + mv) >> 4);
+                    const int pqs = ((psh + ev) & 15) << 1, tqs = ((tsh + mv) & 15) << 1;
+                    uint32_t plo = 0, tlo = 0;
+                    if (ebusy) plo = __ldg(pq), tlo = __ldg(tq);
                     while (__any_sync(TDB_FULL, ebusy)) {
                         if (ebusy) {
-                            const uint32_t x = get16(pw, psh + ev + eq) ^ get16(tw, tsh + mv + eq);
+                            ++pq, ++tq;
+                            const uint32_t phi = __ldg(pq), thi = __ldg(tq);
+                            const uint32_t x = __funnelshift_r(plo, phi, pqs) ^ __funnelshift_r(tlo, thi, tqs);
+                            plo = phi, tlo = thi;
                             if (x) eq += (__ffs(x) - 1) >> 1, ebusy = false;
                             else eq += 16, ebusy = eq < eroom;
                         }
@@ -396,7 +438,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                 int tl_i2 = lo + (int)(0xffffu - (wI2 >> 16)), th_i2 = lo + (int)(wI2 & 0xffffu) - 1;
                 int tl_d1 = lo + (int)(0xffffu - (wD1 >> 16)), th_d1 = lo + (int)(wD1 & 0xffffu) - 1;
                 int tl_d2 = lo + (int)(0xffffu - (wD2 >> 16)), th_d2 = lo + (int)(wD2 & 0xffffu) - 1;
-                if (live && gl == 0) step_lo[s] = (int16_t)lo, step_base[s] = (uint16_t)prov_used;
+                if (live && gl == 0) step_lo[s] = (int16_t)lo, step_base[s] = (StepBase)prov_used;
                 prov_used += (unsigned)width;
                 __syncwarp();
                 const bool done_now = qballot<QG>(gshift, fin) != 0; // group-uniform
@@ -471,55 +513,80 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                     rI1a = qr_pack(tl_i1, th_i1), rD1a = qr_pack(tl_d1, th_d1);
                     rI2 = qr_pack(tl_i2, th_i2), rD2 = qr_pack(tl_d2, th_d2);
                     if (mlo <= mhi) {
-                        if (gl == 0) sm.mmeta[s & 31] = qm_pack(mlo, mhi, (mhead + (unsigned)(mlo - lo)) & 0xffffu);
+                        if (gl == 0) {
+                            const unsigned at = (mhead + (unsigned)(mlo - lo)) & 0xffffu;
+                            if (WIDE) reinterpret_cast<uint2 *>(sm.mmeta)[s & 31] = make_uint2(qr_pack(mlo, mhi), at);
+                            else sm.mmeta[s & 31] = qm_pack(mlo, mhi, at);
+                        }
                         mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
                     }
                 }
                 __syncwarp();
             }
             // ---------------- backtrace + forward replay (groups that found an alignment) ----------------
-            const bool aligned = usable && !identical && !overflow;
-            uint8_t *ops = reinterpret_cast<uint8_t *>(sm.marena); // arena is dead now
+            bool aligned = usable && !identical && !overflow;
             int nops = 0, n_del = 0;
             {
+                // Inside a gap the chain is predictable while it extends (score - e, diagonal -+ 1 per column): lane j of the
+                // group reads the byte the chain reaches after j further extensions, one vote finds the first cell that opened
+                // the gap instead, and up to G columns are consumed per round of dependent loads.  Lanes past that cell read
+                // bytes that are not on the path (the index is clamped into the provenance area); they are not looked at.
+                constexpr unsigned GM = (QG == 32) ? 0xffffffffu : ((1u << QG) - 1u);
                 int comp = -1, cs = penalty, k = k_end;
                 bool walking = aligned && !(comp < 0 && cs == 0);
                 while (__any_sync(TDB_FULL, walking)) {
+                    const bool gap = walking && comp >= 0;
+                    const bool is_ins = comp == CI1 || comp == CI2, first = comp == CI1 || comp == CD1;
+                    const int e = first ? E1 : E2, o = first ? O1 : O2, dk = is_ins ? -1 : 1;
+                    const int bit = comp == CI1 ? PB_I1E : (comp == CI2 ? PB_I2E : (comp == CD1 ? PB_D1E : PB_D2E));
+                    const int j = gap ? gl : 0;
+                    const int cj = cs - j * e, kj = k + j * dk;
+                    int b = 0;
+                    if (walking && cj > 0) {
+                        const unsigned at = (unsigned)step_base[cj] + (unsigned)(kj - (int)step_lo[cj]);
+                        b = prov[min(at, prov_used - 1u)];
+                    }
+                    const unsigned opened = ~qballot<QG>(gshift, gap && (b & bit) != 0) & GM;
                     if (walking) {
-                        const int b = prov[(unsigned)step_base[cs] + (unsigned)(k - (int)step_lo[cs])];
-                        int op;
-                        if (comp < 0) {
+                        if (WIDE && nops + QG > C::OPS) { // no room for the op stream: the next tier takes the pair
+                            overflow = true, aligned = false, walking = false;
+                        } else if (!gap) {
                             const int srcm = b & 7;
+                            int op;
                             if (srcm == PM_X) op = OP_X, cs -= X;
                             else op = OP_CLOSE, comp = srcm - 1;
-                        } else if (comp == CI1 || comp == CI2) {
-                            op = OP_I;
-                            const bool ex = b & (comp == CI1 ? PB_I1E : PB_I2E);
-                            const int e = comp == CI1 ? E1 : E2, o = comp == CI1 ? O1 : O2;
-                            if (ex) cs -= e; else cs -= o + e, comp = -1;
-                            k -= 1;
+                            if (gl == 0) ops[nops] = (uint8_t)op;
+                            ++nops;
                         } else {
-                            op = OP_D;
-                            ++n_del;
-                            const bool ex = b & (comp == CD1 ? PB_D1E : PB_D2E);
-                            const int e = comp == CD1 ? E1 : E2, o = comp == CD1 ? O1 : O2;
-                            if (ex) cs -= e; else cs -= o + e, comp = -1;
-                            k += 1;
+                            const int cnt = opened ? __ffs(opened) : QG; // cnt - 1 extensions and, if any, the opening column
+                            if (gl < cnt) ops[nops + gl] = (uint8_t)(is_ins ? OP_I : OP_D);
+                            nops += cnt;
+                            if (!is_ins) n_del += cnt;
+                            k += cnt * dk;
+                            if (opened) cs -= (cnt - 1) * e + o + e, comp = -1;
+                            else cs -= QG * e;
                         }
-                        if (gl == 0) ops[nops] = (uint8_t)op;
-                        ++nops;
-                        walking = !(comp < 0 && cs == 0);
+                        walking = walking && !(comp < 0 && cs == 0);
                     }
                 }
             }
             __syncwarp();
             {
+                constexpr unsigned GM = (QG == 32) ? 0xffffffffu : ((1u << QG) - 1u);
                 ClipAcc acc;
                 acc.init(m + n_del, p.clip);
                 int v = 0, h = 0, i = nops - 1;
                 bool in_m = true, replay = aligned;
                 while (__any_sync(TDB_FULL, replay)) {
                     const int eq = extend_groups<QG>(pw, tw, psh, tsh, n, m, v, h, replay && in_m, gl, gshift, lane);
+                    // a run of equal gap columns is found by one vote over the next G ops and emitted at once
+                    int op = OP_CLOSE;
+                    bool same = false;
+                    if (replay && i >= 0) {
+                        op = ops[i];
+                        same = i - gl >= 0 && ops[i - gl] == op;
+                    }
+                    const unsigned differs = ~qballot<QG>(gshift, same) & GM;
                     if (replay) {
                         if (in_m) {
                             acc.emit('M', eq, pn);
@@ -527,17 +594,19 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                         }
                         if (i < 0) {
                             replay = false;
-                        } else {
-                            const int op = ops[i];
+                        } else if (op == OP_CLOSE) {
+                            in_m = true;
                             --i;
-                            if (op == OP_CLOSE) {
-                                in_m = true;
-                            } else {
-                                acc.emit(op == OP_X ? 'X' : (op == OP_I ? 'I' : 'D'), 1, pn);
-                                if (op == OP_X) ++v, ++h, in_m = true;
-                                else if (op == OP_I) ++h, in_m = false;
-                                else ++v, in_m = false;
-                            }
+                        } else if (op == OP_X) {
+                            acc.emit('X', 1, pn);
+                            ++v, ++h, --i;
+                        } else {
+                            const int run = differs ? __ffs(differs) - 1 : QG; // >= 1: lane 0 holds ops[i] itself
+                            acc.emit(op == OP_I ? 'I' : 'D', run, pn);
+                            if (op == OP_I) h += run;
+                            else v += run;
+                            in_m = false;
+                            i -= run;
                         }
                     }
                 }
