@@ -472,16 +472,17 @@ def main():
         # roofline of the dominant kernel, per launch, rank 0's shard.  Work = what THAT launch executed
         # (representative pairs only; duplicates are copied, not aligned), SURVEY.md 8(d) accounting.
         tiers = ("align_quad", "align_warp", "align_global", "align_thread")
-        names = {"align_quad": "k_align_lock<QuadCfg>", "align_global": "k_align_global", "align_thread": "k_align_thread",
+        names = {"align_quad": "k_align_lock<QuadCfg>", "align_global": "k_align_lock<LongCfg> + k_align_global", "align_thread": "k_align_thread",
                  "align_warp": "k_align_warp" if os.environ.get("TDB_DISABLE_DUO") else
                                ("k_align_lock<DuoCfg>" if os.environ.get("TDB_DUO_G16") else "k_align_lock<Duo4Cfg>")}
         ti = max(range(4), key=lambda i: stage[tiers[i]])
         k_ms = stage[tiers[ti]] / args.steps
         k_s = max(k_ms, 1e-6) * 1e-3
-        t_pairs = [int(x) for x in cnt.tier_pairs[:3]] + [int(cnt.thread_pairs)]
-        t_cells = [int(x) for x in cnt.tier_cells[:3]] + [int(cnt.thread_cells)]
-        t_ext = [int(x) for x in cnt.tier_ext16[:3]] + [int(cnt.thread_ext16)]
-        t_cols = [int(x) for x in cnt.tier_columns[:3]] + [int(cnt.thread_columns)]
+        # ("align_global" = everything behind tier 1: the long tier and the global-scratch tiers)
+        t_pairs = [int(x) for x in cnt.tier_pairs[:2]] + [int(cnt.tier_pairs[2] + cnt.tier_pairs[3] + cnt.long_pairs), int(cnt.thread_pairs)]
+        t_cells = [int(x) for x in cnt.tier_cells[:2]] + [int(cnt.tier_cells[2] + cnt.tier_cells[3] + cnt.long_cells), int(cnt.thread_cells)]
+        t_ext = [int(x) for x in cnt.tier_ext16[:2]] + [int(cnt.tier_ext16[2] + cnt.tier_ext16[3] + cnt.long_ext16), int(cnt.thread_ext16)]
+        t_cols = [int(x) for x in cnt.tier_columns[:2]] + [int(cnt.tier_columns[2] + cnt.tier_columns[3] + cnt.long_columns), int(cnt.thread_columns)]
         t_ops = [INT_OPS_PER_CELL * t_cells[i] + INT_OPS_PER_EXT * t_ext[i] + INT_OPS_PER_COL * t_cols[i] for i in range(4)]
         ops = t_ops[ti]
         clk = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
@@ -551,6 +552,7 @@ def main():
             "per_rank": per_rank,
             "breakdown_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "tier_pairs": [int(x) for x in cnt.tier_pairs], "thread_tier_pairs": int(cnt.thread_pairs),
+            "long_tier_pairs": int(cnt.long_pairs),
             "pairs_identical": int(cnt.pairs_identical), "pairs_duplicate": int(cnt.pairs_duplicate),
             "pairs_closed_form": int(cnt.pairs_closed_form), "pairs_failed": int(cnt.pairs_failed),
             "work": {"cells": algo_work["cells"], "ext16": algo_work["ext16"], "columns": algo_work["columns"],

@@ -52,7 +52,7 @@ def run_loci(name, batch, duo, cpu_loci, reps=3):
     ok = bool((want == scores[:npc]).all())
     print(json.dumps({"config": name, "loci": batch.n_loci, "pairs": batch.n_pairs, "e2e_loci_per_s": batch.n_loci / dt,
                       "e2e_alignments_per_s": batch.n_pairs / dt, "e2e_ms": dt * 1e3, "gcups": batch.sum_nm / dt / 1e9,
-                      "thread_tier_pairs": int(cnt.thread_pairs), "tier_pairs": [int(x) for x in cnt.tier_pairs], "identical": int(cnt.pairs_identical),
+                      "thread_tier_pairs": int(cnt.thread_pairs), "long_tier_pairs": int(cnt.long_pairs), "tier_pairs": [int(x) for x in cnt.tier_pairs], "identical": int(cnt.pairs_identical),
                       "duplicate": int(cnt.pairs_duplicate), "closed_form": int(cnt.pairs_closed_form),
                       "cpu_port": {"threads": threads, "loci": ncpu, "pairs": npc, "loci_per_s": ncpu / cpu_dt,
                                    "alignments_per_s": npc / cpu_dt, "align_only": True},
@@ -88,7 +88,7 @@ if "5" not in args.skip:
                 nm = float(b.sum_nm)
                 print(json.dumps({"config": "5: microbenchmark", "heuristic": hname, "length": length, "divergence": div,
                                   "pairs": n_pairs, "e2e_gcups": nm / dt / 1e9, "e2e_alignments_per_s": n_pairs / dt,
-                                  "thread_tier_pairs": int(cnt.thread_pairs), "tier_pairs": [int(x) for x in cnt.tier_pairs],
+                                  "thread_tier_pairs": int(cnt.thread_pairs), "long_tier_pairs": int(cnt.long_pairs), "tier_pairs": [int(x) for x in cnt.tier_pairs],
                                   "cpu_port_gcups": (nm * ncpu / n_pairs) / cdt / 1e9, "cpu_threads": threads,
                                   "scores_bit_exact_on_cpu_sample": ok}), flush=True)
                 assert ok

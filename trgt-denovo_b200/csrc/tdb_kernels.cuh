@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(256) k_bucket(const uint8_t *__restrict__ key,
 // Work order of the thread-per-pair tier.  Its 32 pairs of a warp run to the largest penalty among them, and
 // at a given |n - m| the penalties still spread (12 .. 30 and beyond: a second or third sequencing error,
 // stutter): sorted by |n - m| alone 58 % of the lane-steps of a warp did useful work (CPU study with the
-// oracle's cell counts, profiles/r02/NOTES.md).  k_estimate gives every pair of that tier an UPPER BOUND of
+// CPU checker's cell counts, profiles/r02/NOTES.md).  k_estimate gives every pair of that tier an UPPER BOUND of
 // its penalty from a greedy walk -- extend the matches, at a mismatch take the edit (substitution, or a gap of
 // up to |n - m| + 2 bases either way) whose next 16 bases match best, repeat -- which is the cost of a real
 // alignment, so never below the optimum, and equal to it for 86 % of the pairs.  Pairs bounded by the tier's
