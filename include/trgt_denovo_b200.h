@@ -304,7 +304,7 @@ typedef struct {
     uint64_t pairs_failed;  /* pairs no tier could finish (status TDB_STATUS_OOM, score TDB_SCORE_FAILED) */
     float ms_fused_call;    /* host wall clock of the whole fused host-buffer call (tdb_trio_batch[_packed] ...), entry to return */
     float ms_fused_tail;    /* ... of which after the alignment stage: reduction, row and mask download */
-    uint64_t long_pairs;    /* pairs ALIGNED by the long tier (one pair per warp, wavefronts of up to 256 diagonals in shared
+    uint64_t long_pairs;    /* pairs ALIGNED by the long tier (one pair per warp, wavefronts of up to 192 diagonals in shared
                                memory, provenance in global scratch) that runs in front of tiers 2 and 3, and the work */
     uint64_t long_cells, long_ext16, long_columns; /* it executed (also included in exec_*) */
     float ms_long_tier;     /* its share of ms_tier[2] */

@@ -565,7 +565,7 @@ def test_empty_and_very_long_sequences(ctx):
     for clip in (50, 0):
         cnt = _check_batch(ctx, seqs, pp, pt, clip)
     assert cnt.long_pairs + cnt.tier_pairs[2] + cnt.tier_pairs[3] >= 4
-    assert cnt.long_pairs > 0  # up to 16 000 bases and 256 diagonals: the long tier
+    assert cnt.long_pairs > 0  # up to 16 000 bases and 192 diagonals: the long tier
 
 
 def test_empty_batch(ctx):
@@ -687,6 +687,62 @@ def test_reduction_matches_oracle(tdb, ctx, duo, q):
                 assert _close(g.mean_col[r], w.mean_col[r]) or duo
             o4, o5 = l.list_off[c][4], l.list_off[c][5]
             assert (mask[o4:o5] == wmask[o4:o5]).all()
+
+
+@pytest.mark.parametrize("q", [1.0, 0.75, 0.5])
+def test_reduction_deep_coverage_lists(tdb, ctx, q):
+    """Lists of hundreds to thousands of scores per allele (amplicon-depth coverage): the k-th smallest behind
+    quantile / median switches from count-and-compare to a radix select at 64 entries; both must give the oracle's rows
+    (src/math.rs:82-155).  Sizes straddle the switch, odd and even, with ties and with failed-pair sentinels."""
+    import ctypes as C
+    from importlib import import_module
+    failed = import_module("trgt_denovo_b200.binding").SCORE_FAILED
+    rng = random.Random(4242 + int(q * 100))
+    loci, flat = [], []
+    for sizes in ([63, 64, 65, 66, 64], [1500, 1, 777, 0, 2001], [64, 0, 0, 128, 4000], [200, 201, 202, 203, 204]):
+        loc = tdo.TrioLocus()
+        loc.n_child, loc.n_mother, loc.n_father = 1, 2, 2
+        base = rng.choice([0, -8, -40])
+        for j, sz in enumerate(sizes):
+            loc.list_off[0][j] = len(flat)
+            flat.extend(int(base - rng.choice([0, 0, 2, 4, 6, 8, 12, 30, 100, 4000]) * rng.random()) for _ in range(sz))
+        loc.list_off[0][5] = len(flat)
+        for i in range(2):
+            loc.child_len[i], loc.mother_len[i], loc.father_len[i] = (rng.randint(100, 400) for _ in range(3))
+        loci.append(loc)
+    scores = np.array(flat, dtype=np.int32)
+    for variant in range(2):
+        if variant == 1:  # a sprinkle of pairs no tier could finish: dropped from every list (src/denovo.rs:31-35)
+            scores = scores.copy()
+            scores[rng.sample(range(len(scores)), 200)] = failed
+        arr = (tdb.TrioLocus * len(loci))()
+        for i, l in enumerate(loci):
+            C.memmove(C.byref(arr[i]), C.byref(l), C.sizeof(l))
+        out, mask = ctx.reduce(arr, scores, q=q)
+        for i, l in enumerate(loci):
+            oscores = scores if variant == 0 else None
+            if variant == 1:  # the oracle has no sentinel: hand it the lists with the failed entries removed
+                keep, lo2 = [], tdo.TrioLocus()
+                C.memmove(C.byref(lo2), C.byref(l), C.sizeof(l))
+                for j in range(5):
+                    a, b = l.list_off[0][j], l.list_off[0][j + 1]
+                    lo2.list_off[0][j] = len(keep)
+                    keep.extend(int(x) for x in scores[a:b] if x != failed)
+                lo2.list_off[0][5] = len(keep)
+                want, _ = tdo.trio_assess(lo2, np.array(keep, dtype=np.int32), q)
+            else:
+                want, wmask = tdo.trio_assess(l, oscores, q)
+            g, w = out[2 * i], want[0]
+            for f in FIELDS_INT:
+                assert getattr(g, f) == getattr(w, f), (variant, i, f)
+            for f in FIELDS_F:
+                assert _close(getattr(g, f), getattr(w, f)), (variant, i, f, getattr(g, f), getattr(w, f))
+            assert list(g.mother_overlap) == list(w.mother_overlap) and list(g.father_overlap) == list(w.father_overlap)
+            for r in range(4):
+                assert _close(g.mean_col[r], w.mean_col[r])
+            if variant == 0:
+                o4, o5 = l.list_off[0][4], l.list_off[0][5]
+                assert (mask[o4:o5] == wmask[o4:o5]).all()
 
 
 def test_reduction_reference_vectors(tdb, ctx, golden_dir):

@@ -1026,7 +1026,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
     if (h.err & ERR_PAIR_INDEX) return fail(ctx, TDB_E_INVALID, "pair index out of range");
     unsigned pending = cigar_mode ? n_pairs : h.gcount;
     if (staged) CK(cudaEventRecord(ctx->ev[6], s));
-    // ---- long tier: one pair per warp, wavefronts (up to 256 diagonals) in shared memory, provenance / step records / op
+    // ---- long tier: one pair per warp, wavefronts (up to 192 diagonals) in shared memory, provenance / step records / op
     // stream in a per-warp slice of global scratch; production penalties, sequences up to 16 000 bases.  What it cannot
     // hold moves on to the global-scratch tiers.
     const uint32_t *g_src = cigar_mode ? nullptr : (const uint32_t *)ctx->list_b.p;

@@ -76,13 +76,19 @@ using DuoCfg = LockCfg<TDB_DUO_G, 64, 1024, 128, 2048>;             // tier 1: t
 #define TDB_DUO4_PROV 4096
 #endif
 using Duo4Cfg = LockCfg<8, 64, 1024, 128, TDB_DUO4_PROV, true, 16 / TDB_Q_WARPS>; // 16 warps per SM: 128 registers
-// the long tier: ONE pair per warp (32 lanes), wavefronts up to 256 diagonals, scores < 32768, sequences up to 16 000
+// the long tier: ONE pair per warp (32 lanes), wavefronts up to 192 diagonals, scores < 32768, sequences up to 16 000
 // bases.  What k_align_global did for the long-expansion stress set from a global-memory ring with run-time penalties
 // (1 600 warp instructions and two round trips to L2 per score step), this does from 13 KB of shared memory per pair.
 #ifndef TDB_LONG_PROV
 #define TDB_LONG_PROV (4 << 20)
 #endif
-using LongCfg = LockCfg<32, 256, 4096, 32768, TDB_LONG_PROV, true, 16 / TDB_Q_WARPS, true, 49152>;
+#ifndef TDB_LONG_W
+#define TDB_LONG_W 192
+#endif
+#ifndef TDB_LONG_MAR
+#define TDB_LONG_MAR 4736
+#endif
+using LongCfg = LockCfg<32, TDB_LONG_W, TDB_LONG_MAR, 32768, TDB_LONG_PROV, true, 16 / TDB_Q_WARPS, true, 49152>;
 constexpr int Q_MAXLEN = 8000;
 constexpr int Q_MAXLEN_WIDE = 16000;
 constexpr int Q_WARPS = TDB_Q_WARPS;
@@ -239,7 +245,8 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
             unsigned Mm = 1u, I1m = 0, I2m = 0, D1m = 0, D2m = 0; // bit j <-> score s-j exists
             // ranges of the gap wavefronts, in registers: I1 / D1 of scores s-1 (a) and s-2 (b), I2 / D2 of score s-1
             uint32_t rI1a = 0, rI1b = 0, rD1a = 0, rD1b = 0, rI2 = 0, rD2 = 0;
-            unsigned mhead = 1, prov_used = 1;
+            unsigned mhead = 1, prov_used = 1; // mhead: arena position behind the newest M wavefront
+            int loA = 0, loB = 0;              // computed lo of scores s-1 / s-2: origin of their gap rows
             int steps_wait = p.heur.steps - (p.heur.kind == 1 ? 1 : 0);
             int s = 0, s3 = 0; // s3 = s mod 3
             __syncwarp();
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                 bool live = running && ((Mm & ((1u << X) | (1u << (O1 + E1)) | (1u << (O2 + E2)))) |
                                         ((I1m | D1m) & (1u << E1)) | ((I2m | D2m) & (1u << E2))) != 0;
                 if (!__any_sync(TDB_FULL, live)) { // null step for every group: registers only
-                    rI1b = rI1a, rD1b = rD1a;
+                    rI1b = rI1a, rD1b = rD1a, loB = loA;
                     continue;
                 }
                 // ---- inputs: three M wavefronts (arena, metadata in one word each), four gap wavefronts (rings by score,
@@ -299,18 +306,27 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                 TDB_LIM(d2, -1, -1)
 #undef TDB_LIM
                 int width = 0;
+                unsigned mpos = mhead; // arena position of this score's M wavefront (diagonal lo)
                 if (live) {
                     lo = max(lo, -n - 1), hi = min(hi, m + 1);
                     width = hi - lo + 1;
-                    // arena room: everything from the oldest live M wavefront up to the new one
+                    // Arena room.  The live wavefronts (lags 1..25) occupy the arena from the oldest one's position (tail) up
+                    // to mhead, circularly; a wavefront never wraps around the end of the arena (it moves to position 0
+                    // instead), so a cell is read at base + k without a mask and k-1 / k+1 share one address.
                     const unsigned livem = Mm & 0x03fffffeu; // lags 1..25
-                    unsigned tail = mhead;
-                    if (livem) {
+                    bool room = true;
+                    if (!livem) {
+                        mpos = 0; // nothing to keep: start over
+                    } else {
                         const int ts = (s - (31 - __clz(livem))) & 31;
-                        tail = WIDE ? sm.mmeta[2 * ts + 1] : qm_off(sm.mmeta[ts]);
+                        const unsigned tail = WIDE ? sm.mmeta[2 * ts + 1] : qm_off(sm.mmeta[ts]);
+                        if (mhead > tail) { // live region [tail, mhead): the space behind it, else the space in front
+                            if (mhead + (unsigned)width > (unsigned)Q_MAR) mpos = 0, room = (unsigned)width < tail;
+                        } else {            // live region wraps: [tail, MAR) and [0, mhead)
+                            room = mhead + (unsigned)width < tail;
+                        }
                     }
-                    if (width > QW || prov_used + (unsigned)width > Q_PROV ||
-                        ((mhead - tail) & 0xffffu) + (unsigned)width > Q_MAR) {
+                    if (width > QW || prov_used + (unsigned)width > Q_PROV || !room) {
                         overflow = true, running = false, live = false, width = 0; // this group drops out
                     }
                 }
@@ -339,25 +355,27 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                     bool vm = false;
                     int ev = 0, eroom = 0; // extension state of this lane's diagonal
                     if (act) {
-#define TDB_RDM(w, kk) (((unsigned)((kk) - w##_lo) < w##_sp) ? (int)sm.marena[(w##_base + (kk)) & (Q_MAR - 1)] : Q_NULL)
-#define TDB_RDG(w, row, kk) (((unsigned)((kk) - w##_lo) < w##_sp) ? (int)(row)[(kk) & (QW - 1)] : Q_NULL)
+// M wavefronts: arena position of diagonal k is base + k; gap rows: a score's row starts at its computed lo (loA: score
+// s-1, loB: score s-2).  dk = -1 / 0 / +1: the neighbours of a cell share one address.
+#define TDB_RDM(w, dk) (((unsigned)(k + (dk) - w##_lo) < w##_sp) ? (int)sm.marena[w##_base + k + (dk)] : Q_NULL)
+#define TDB_RDG(w, row, org, dk) (((unsigned)(k + (dk) - w##_lo) < w##_sp) ? (int)(row)[k - (org) + (dk)] : Q_NULL)
                         int b = 0, o, e;
-                        o = TDB_RDM(mo1, k - 1), e = TDB_RDG(i1, I1r, k - 1);
+                        o = TDB_RDM(mo1, -1), e = TDB_RDG(i1, I1r, loB, -1);
                         if (e >= o) ins1 = e, b |= PB_I1E; else ins1 = o;
                         ins1 += 1;
-                        o = TDB_RDM(mo1, k + 1), e = TDB_RDG(d1, D1r, k + 1);
+                        o = TDB_RDM(mo1, +1), e = TDB_RDG(d1, D1r, loB, +1);
                         if (e >= o) del1 = e, b |= PB_D1E; else del1 = o;
                         if (any2) {
-                            o = TDB_RDM(mo2, k - 1), e = TDB_RDG(i2, I2r, k - 1);
+                            o = TDB_RDM(mo2, -1), e = TDB_RDG(i2, I2r, loA, -1);
                             if (e >= o) ins2 = e, b |= PB_I2E; else ins2 = o;
                             ins2 += 1;
-                            o = TDB_RDM(mo2, k + 1), e = TDB_RDG(d2, D2r, k + 1);
+                            o = TDB_RDM(mo2, +1), e = TDB_RDG(d2, D2r, loA, +1);
                             if (e >= o) del2 = e, b |= PB_D2E; else del2 = o;
                         } else {
                             b |= PB_I2E | PB_D2E; // what two absent sources give (NULL >= NULL): the provenance byte is unchanged
                             ins2 = Q_NULL + 1;
                         }
-                        const int mis = TDB_RDM(mx, k) + 1;
+                        const int mis = TDB_RDM(mx, 0) + 1;
 #undef TDB_RDM
 #undef TDB_RDG
                         mv = max(max(max(ins1, ins2), max(del1, del2)), mis);
@@ -399,18 +417,18 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                             dpk = __vmaxu2(dpk, (d << 16) | (0xffffu - d));
                             fin |= (k == k_end) && (mv >= m);
                         }
-                        sm.marena[(mhead + (unsigned)(k - lo)) & (Q_MAR - 1)] = (int16_t)mv;
+                        sm.marena[(int)mpos + (k - lo)] = (int16_t)mv;
                         // a component without a source only holds NULL+1 here: never valid, so its range stays empty
-                        I1o[k & (QW - 1)] = (int16_t)ins1;
-                        D1o[k & (QW - 1)] = (int16_t)del1;
+                        I1o[k - lo] = (int16_t)ins1;
+                        D1o[k - lo] = (int16_t)del1;
 #define TDB_VALID(val) ((unsigned)(val) <= (unsigned)m && (unsigned)((val)-k) <= (unsigned)n)
                         const uint32_t rel = (uint32_t)(k - lo);                        // 0..QW-1
                         const uint32_t cand = ((0xffffu - rel) << 16) | (rel + 1u);    // (0xffff - first, last + 1)
                         wI1 = __vmaxu2(wI1, TDB_VALID(ins1) ? cand : 0u);
                         wD1 = __vmaxu2(wD1, TDB_VALID(del1) ? cand : 0u);
                         if (any2) { // (without a source the rows keep stale values; they are never read: the range stays empty)
-                            I2o[k & (QW - 1)] = (int16_t)ins2;
-                            D2o[k & (QW - 1)] = (int16_t)del2;
+                            I2o[k - lo] = (int16_t)ins2;
+                            D2o[k - lo] = (int16_t)del2;
                             wI2 = __vmaxu2(wI2, TDB_VALID(ins2) ? cand : 0u);
                             wD2 = __vmaxu2(wD2, TDB_VALID(del2) ? cand : 0u);
                         }
@@ -455,10 +473,10 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                 const int min_d = min(max(n, m), (int)(0xffffu - (dpk & 0xffffu))), thr = p.heur.max_dist;
                 const bool scan_needed = cut && (int)(dpk >> 16) - min_d > thr;
                 if (__any_sync(TDB_FULL, scan_needed)) {
-                    const int abase = (int)mhead - lo;
+                    const int abase = (int)mpos - lo;
 #define TDB_DIST_OK(kk, okv)                                                                  \
     {                                                                                         \
-        const int off_ = (int)sm.marena[(abase + (kk)) & (Q_MAR - 1)];                        \
+        const int off_ = (int)sm.marena[abase + (kk)];                                        \
         const int d_ = off_ >= 0 ? max(n - (off_ - (kk)), m - off_) : (1 << 30);              \
         okv = d_ - min_d <= thr;                                                              \
     }
@@ -503,7 +521,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                     tl_d2 = max(tl_d2, mlo), th_d2 = min(th_d2, mhi);
                 }
                 // ---- publish metadata of score s ----
-                rI1b = rI1a, rD1b = rD1a;
+                rI1b = rI1a, rD1b = rD1a, loB = loA, loA = lo;
                 if (cont) {
                     if (mlo <= mhi) Mm |= 1u;
                     if (tl_i1 <= th_i1) I1m |= 1u;
@@ -514,11 +532,11 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
                     rI2 = qr_pack(tl_i2, th_i2), rD2 = qr_pack(tl_d2, th_d2);
                     if (mlo <= mhi) {
                         if (gl == 0) {
-                            const unsigned at = (mhead + (unsigned)(mlo - lo)) & 0xffffu;
+                            const unsigned at = mpos + (unsigned)(mlo - lo);
                             if (WIDE) reinterpret_cast<uint2 *>(sm.mmeta)[s & 31] = make_uint2(qr_pack(mlo, mhi), at);
                             else sm.mmeta[s & 31] = qm_pack(mlo, mhi, at);
                         }
-                        mhead = (mhead + (unsigned)width) & 0xffffu; // null M keeps no arena
+                        mhead = mpos + (unsigned)width; // null M keeps no arena
                     }
                 }
                 __syncwarp();
