@@ -984,21 +984,22 @@ __device__ inline int n_valid(const int32_t *xs, int n) {
 // n^2 / 2 operations without a single store.  Long lists (deep coverage: hundreds to thousands of reads per allele): a
 // radix select on the order-preserving unsigned image of the scores, one pass per bit -- 32 n instead of n^2.
 constexpr int KTH_RADIX_MIN = 64;
-__device__ inline int kth_smallest(const int32_t *xs, int n, int k) {
-    if (n >= KTH_RADIX_MIN) {
-        uint32_t prefix = 0u, decided = 0u; // bits fixed so far
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t b = 1u << bit;
-            int zeros = 0; // valid entries that match the prefix and have this bit clear
-            for (int j = 0; j < n; ++j) {
-                const uint32_t u = (uint32_t)xs[j] ^ 0x80000000u;
-                zeros += (int)(sc_ok(xs[j]) & ((u & decided) == prefix) & ((u & b) == 0u));
-            }
-            if (k >= zeros) k -= zeros, prefix |= b;
-            decided |= b;
+__device__ __noinline__ int kth_smallest_radix(const int32_t *xs, int n, int k) { // (kept out of line: the 30x path stays lean)
+    uint32_t prefix = 0u, decided = 0u; // bits fixed so far
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t b = 1u << bit;
+        int zeros = 0; // valid entries that match the prefix and have this bit clear
+        for (int j = 0; j < n; ++j) {
+            const uint32_t u = (uint32_t)xs[j] ^ 0x80000000u;
+            zeros += (int)(sc_ok(xs[j]) & ((u & decided) == prefix) & ((u & b) == 0u));
         }
-        return (int)(prefix ^ 0x80000000u);
+        if (k >= zeros) k -= zeros, prefix |= b;
+        decided |= b;
     }
+    return (int)(prefix ^ 0x80000000u);
+}
+__device__ inline int kth_smallest(const int32_t *xs, int n, int k) {
+    if (n >= KTH_RADIX_MIN) return kth_smallest_radix(xs, n, k);
     for (int i = 0; i < n; ++i) {
         const int x = xs[i];
         if (!sc_ok(x)) continue;
