@@ -22,12 +22,13 @@ ap.add_argument("--long-loci", type=int, default=1000)
 ap.add_argument("--duo-loci", type=int, default=300000)
 ap.add_argument("--micro-cells", type=float, default=2e10, help="sum(n*m) per microbenchmark cell (SURVEY: 1e8.. per cell)")
 ap.add_argument("--skip", default="")
+ap.add_argument("--census-long-loci", type=int, default=100, help="loci of config 4 aligned with and without the heuristic")
 args = ap.parse_args()
 threads = os.cpu_count() or 1
 ctx = tdb.Context(device_id=0)
 
 
-def run_loci(name, batch, duo, cpu_loci, reps=3):
+def run_loci(name, batch, duo, cpu_loci, reps=3, census_loci=0):
     L = tdb.lib()
     out = (B.AlleleOut * (2 * batch.n_loci))()
     mask = np.zeros(batch.n_pairs, np.uint8)
@@ -50,7 +51,27 @@ def run_loci(name, batch, duo, cpu_loci, reps=3):
     want, wst, _ = tdo.align_batch(batch.blob, batch.seq_off, batch.seq_len, batch.pair_pattern[:npc], batch.pair_text[:npc], 50, n_threads=threads)
     cpu_dt = time.perf_counter() - t1
     ok = bool((want == scores[:npc]).all())
-    print(json.dumps({"config": name, "loci": batch.n_loci, "pairs": batch.n_pairs, "e2e_loci_per_s": batch.n_loci / dt,
+    census = None
+    if census_loci:
+        # heuristic census on the GPU: pairs of the first `census_loci` loci whose clipped score (clip 50) or penalty (clip 0)
+        # differs between wf-adaptive(10,50,1) and Heuristic::None -- only for those does the result rest on the restated
+        # cut-off; for the others the independent Gotoh DP of the checker pins the penalty
+        nl = min(census_loci, batch.n_loci)
+        nq = int(batch.meta[nl - 1].pair_end)
+        pp, pt = batch.pair_pattern[:nq], batch.pair_text[:nq]
+        res = {}
+        for hname, heur in (("on", (1, 10, 50, 1)), ("off", (0, 0, 0, 0))):
+            c2 = tdb.Context(device_id=0, heuristic=heur)
+            for clip in (50, 0):
+                c2.set_clip_len(clip)
+                sc, st = c2.align_batch(batch.blob, None, batch.seq_len, pp, pt)
+                assert (st == 0).all()
+                res[hname, clip] = sc.copy()
+            c2.close()
+        d50, d0 = res["on", 50] != res["off", 50], res["on", 0] != res["off", 0]
+        census = {"loci": nl, "pairs": nq, "heuristic_sensitive_pairs": int((d50 | d0).sum()),
+                  "clipped_score_differs": int(d50.sum()), "penalty_differs": int(d0.sum())}
+    print(json.dumps({"config": name, "loci": batch.n_loci, "pairs": batch.n_pairs, "heuristic_census": census, "e2e_loci_per_s": batch.n_loci / dt,
                       "e2e_alignments_per_s": batch.n_pairs / dt, "e2e_ms": dt * 1e3, "gcups": batch.sum_nm / dt / 1e9,
                       "thread_tier_pairs": int(cnt.thread_pairs), "long_tier_pairs": int(cnt.long_pairs), "tier_pairs": [int(x) for x in cnt.tier_pairs], "identical": int(cnt.pairs_identical),
                       "duplicate": int(cnt.pairs_duplicate), "closed_form": int(cnt.pairs_closed_form),
@@ -61,12 +82,12 @@ def run_loci(name, batch, duo, cpu_loci, reps=3):
 
 
 if "1" not in args.skip:
-    run_loci("1: 1000-locus trio", S.generate(S.config("trio_1k", pinned=1), 0, 1000, threads), False, 1000, reps=10)
+    run_loci("1: 1000-locus trio", S.generate(S.config("trio_1k", pinned=1), 0, 1000, threads), False, 1000, reps=10, census_loci=1000)
 if "3" not in args.skip:
-    run_loci("3: duo genome-wide (%d loci)" % args.duo_loci, S.generate(S.config("duo_genome", pinned=1), 0, args.duo_loci, threads), True, 50000)
+    run_loci("3: duo genome-wide (%d loci)" % args.duo_loci, S.generate(S.config("duo_genome", pinned=1), 0, args.duo_loci, threads), True, 50000, census_loci=50000)
 if "4" not in args.skip:
     run_loci("4: long-expansion stress 60x (%d loci)" % args.long_loci,
-             S.generate(S.config("long_expansion", pinned=1), 0, args.long_loci, threads), False, 40, reps=1)
+             S.generate(S.config("long_expansion", pinned=1), 0, args.long_loci, threads), False, 40, reps=1, census_loci=args.census_long_loci)
 if "5" not in args.skip:
     for heur, hname in (((1, 10, 50, 1), "wf-adaptive(10,50,1) = reference config"), ((0, 0, 0, 0), "none = optimal")):
         c2 = tdb.Context(device_id=0, heuristic=heur)
