@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define TDB_ABI_VERSION 4
+#define TDB_ABI_VERSION 5 /* 5: tdb_counters grew (long tier) */
 
 /* return codes */
 #define TDB_OK 0

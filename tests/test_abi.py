@@ -33,7 +33,7 @@ def test_binding_matches_header(built):
     from importlib import import_module
     B = import_module("trgt_denovo_b200.binding")
     assert sorted(B.EXPORTS) == _declared_symbols()
-    assert tdb.lib().tdb_abi_version() == 4
+    assert tdb.lib().tdb_abi_version() == 5
     assert ctypes.sizeof(B.AlleleOut) == 96 and ctypes.sizeof(B.TrioLocus) == 84
 
 

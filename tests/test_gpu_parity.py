@@ -182,6 +182,25 @@ def test_frame_kernels_give_same_scores(tdb, monkeypatch):
     c.close()
 
 
+def test_quad8_gives_same_scores(tdb, monkeypatch):
+    """Tier 0 with eight pairs per warp (Quad8Cfg, TDB_QUAD8=1: four lanes per pair, provenance in global scratch) against
+    the oracle: scores, status, exact C / E / T, with and without the thread-per-pair tier in front of it."""
+    rng = random.Random(78)
+    seqs, pp, pt = make_pairs(rng, n_targets=200, reads_per_target=12, max_units=40, err=0.004)
+    monkeypatch.setenv("TDB_QUAD8", "1")
+    c = tdb.Context()
+    cnt = _check_batch(c, seqs, pp, pt, 50)
+    assert cnt.tier_pairs[0] > 0 and cnt.tier_pairs[1] > 0
+    c.close()
+    monkeypatch.setenv("TDB_DISABLE_THREAD_TIER", "1")
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_DISABLE_THREAD_TIER")
+    monkeypatch.delenv("TDB_QUAD8")
+    cnt = _check_batch(c, seqs, pp, pt, 0, cigars=False)
+    assert cnt.thread_pairs == 0 and cnt.tier_pairs[0] > 0
+    c.close()
+
+
 def test_thread_tier_disabled_gives_same_scores(tdb, monkeypatch):
     """The thread-per-pair tier takes the lightest pairs (final penalty <= 24) in front of the lockstep tier: the
     lockstep tier alone must give the same scores and work counts, and with it on most light pairs end there."""

@@ -94,7 +94,8 @@ struct tdb_ctx {
     DevBuf scratch[2];
     DevBuf lockq_scratch[2]; // the same for tier 0
     DevBuf lock_scratch[2]; // provenance / step records of the four-pairs-per-warp tier 1 (per pipeline slot)
-    int duo4_ctas_per_sm = 0, long_ctas_per_sm = 0;
+    int duo4_ctas_per_sm = 0, long_ctas_per_sm = 0, quad8_ctas_per_sm = 0;
+    bool quad8 = false; // TDB_QUAD8=1: tier 0 with eight pairs per warp (Quad8Cfg)
     bool disable_long = false; // TDB_DISABLE_LONG: no long tier (k_align_lock<LongCfg>) in front of the global-scratch tiers
     bool duo4 = true; // TDB_DUO_G16=1: tier 1 with two pairs per warp (16 lanes each), everything in shared memory
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0, mini_ctas_per_sm = 0;
@@ -115,7 +116,7 @@ struct tdb_ctx {
     // on when the call has at most 8 packer threads -- several ranks sharing one host -- where it measured +10-15 % e2e
     // (look-ahead rule driven by the copy stream, see run_align); off with more threads, where it measured nothing
     // (profiles/r01/NOTES.md).  TDB_RAW_EVERY=n forces every n-th chunk instead (n < 2: off).
-    bool steal_forced = false, allow_steal = false;
+    bool steal_forced = false, allow_steal = false, steal_auto_always = false; // TDB_STEAL_AUTO=1: the automatic rule whatever the thread count
     int steal_div = 2;
     bool count_work = false;
     int test_max_score = 0; // TDB_TEST_MAX_SCORE: caps the score range of the global tiers (tests force a last-tier failure)
@@ -525,7 +526,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         // one core stays free for the calling thread, which must react quickly to every finished chunk
         const unsigned hc = std::thread::hardware_concurrency();
         const unsigned hw = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::max(1u, std::min(32u, hc > 2 ? hc - 1 : 1u));
-        if (!ctx->steal_forced) ctx->allow_steal = hw <= 8;
+        if (!ctx->steal_forced) ctx->allow_steal = hw <= 8 || ctx->steal_auto_always;
         const size_t n_zero = host_pack ? 16 : 0;
         PairRun *hruns = nullptr;
         if (lazy_scan && !ctx->disable_rle) { // pair lists travel run-length encoded
@@ -942,7 +943,13 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
             const size_t smem = lock_smem_bytes<QuadCfg>();
             const unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->quad_ctas_per_sm,
                                                              ((size_t)cpairs + 31) / 32 + 1);
-            if (ctx->old_lock) {
+            if (ctx->old_lock && ctx->quad8) {
+                const unsigned g8 = (unsigned)std::min<size_t>((size_t)ctx->sm_count * ctx->quad8_ctas_per_sm,
+                                                               ((size_t)cpairs + 8 * Q_WARPS - 1) / (8 * Q_WARPS) + 1);
+                ENSURE(ctx->lockq_scratch[si], (size_t)ctx->sm_count * ctx->quad8_ctas_per_sm * Q_WARPS * 8 * lock_gscratch_bytes<Quad8Cfg>());
+                p.scratch = (uint8_t *)ctx->lockq_scratch[si].p;
+                k_align_lock<Quad8Cfg, 8, 4, 2, 24, 1><<<g8, Q_WARPS * 32, lock_smem_bytes<Quad8Cfg>(), st>>>(p);
+            } else if (ctx->old_lock) {
                 if (QuadCfg::GP) {
                     ENSURE(ctx->lockq_scratch[si], (size_t)ctx->sm_count * ctx->quad_ctas_per_sm * Q_WARPS * 4 * lock_gscratch_bytes<QuadCfg>());
                     p.scratch = (uint8_t *)ctx->lockq_scratch[si].p;
@@ -1313,6 +1320,8 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         if (e == cudaSuccess) e = setup(k_align_lock<DuoCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<DuoCfg>(), c->duo_ctas_per_sm);
         if (e == cudaSuccess) e = setup(k_align_lock<Duo4Cfg, 8, 4, 2, 24, 1>, lock_smem_bytes<Duo4Cfg>(), c->duo4_ctas_per_sm);
         c->duo4 = getenv("TDB_DUO_G16") == nullptr && c->duo4_ctas_per_sm >= 1;
+        if (e == cudaSuccess) e = setup(k_align_lock<Quad8Cfg, 8, 4, 2, 24, 1>, lock_smem_bytes<Quad8Cfg>(), c->quad8_ctas_per_sm);
+        c->quad8 = getenv("TDB_QUAD8") != nullptr && c->quad8_ctas_per_sm >= 1;
         if (e == cudaSuccess) e = setup(k_align_lock<LongCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<LongCfg>(), c->long_ctas_per_sm);
         c->disable_long = getenv("TDB_DISABLE_LONG") != nullptr || c->long_ctas_per_sm < 1;
         auto fsetup = [&](auto kern, size_t smem, int &occ_out) {
@@ -1359,6 +1368,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->disable_dedup = getenv("TDB_DISABLE_DEDUP") != nullptr;
         c->disable_closed_form = getenv("TDB_DISABLE_CLOSED_FORM") != nullptr;
         c->disable_rle = getenv("TDB_DISABLE_RLE") != nullptr;
+        c->steal_auto_always = getenv("TDB_STEAL_AUTO") != nullptr;
         if (const char *sd = getenv("TDB_RAW_EVERY")) {
             c->steal_forced = true;
             c->allow_steal = atoi(sd) > 1;

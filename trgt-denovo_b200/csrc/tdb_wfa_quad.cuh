@@ -65,6 +65,12 @@ using QuadCfg = LockCfg<8, 32, TDB_Q_MAR, TDB_Q_SCAP, TDB_Q_GPROV, true, TDB_Q_G
 #else
 using QuadCfg = LockCfg<8, 32, TDB_Q_MAR, TDB_Q_SCAP, TDB_Q_PROV>; // tier 0: four pairs per warp
 #endif
+// tier 0 with EIGHT pairs per warp (4 lanes each, TDB_QUAD8=1): the per-score bookkeeping serves twice as many pairs; the
+// provenance bytes and step records in global scratch keep a warp's eight pairs at 14.7 KB of shared memory
+#ifndef TDB_Q8_MINB
+#define TDB_Q8_MINB 7
+#endif
+using Quad8Cfg = LockCfg<4, 32, TDB_Q_MAR, TDB_Q_SCAP, TDB_Q_GPROV, true, TDB_Q8_MINB>;
 #ifndef TDB_DUO_G
 #define TDB_DUO_G 16
 #endif

@@ -288,8 +288,12 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                         // Greedy extension of the live diagonals (trimming never changes offsets, A.1 step 1), as ONE
                         // loop over 16-base compares: a lane moves on to its next diagonal as soon as the current one
                         // stops matching, so a warp pays the longest per-lane TOTAL, not the sum of per-diagonal maxima.
+                        // (running word pointers into the staged sequences; the upper word of a round is the lower word of the
+                        // next: two shared-memory loads per round)
                         {
-                            int k = 0, v = 0, h = 0, room = 0, eq = 0;
+                            int k = 0, h = 0, room = 0, eq = 0, pqs = 0, tqs = 0;
+                            const uint32_t *pq = sw, *tq = sw;
+                            uint32_t plo = 0, tlo = 0;
                             bool active = false;
                             for (;;) {
                                 if (!active) {
@@ -297,13 +301,20 @@ __global__ void __launch_bounds__(TH_NT) k_align_thread(const AlignParams p) {
                                     const int pi = __ffs(vmask) - 1;
                                     vmask &= vmask - 1;
                                     k = pi - TH_KM;
-                                    h = (int)TH_M(cur, k), v = h - k;
+                                    h = (int)TH_M(cur, k);
+                                    const int v = h - k;
                                     room = min(n - v, m - h), eq = 0;
+                                    pq = sw + ((psh + v) >> 4) * TH_NT, tq = sw + (TH_SEQW + ((tsh + h) >> 4)) * TH_NT;
+                                    pqs = ((psh + v) & 15) << 1, tqs = ((tsh + h) & 15) << 1;
+                                    plo = *pq, tlo = *tq;
                                     active = true;
                                 }
                                 bool stop = eq >= room;
                                 if (!stop) {
-                                    const uint32_t x = th_get16(sw, 0, psh + v + eq) ^ th_get16(sw, TH_SEQW, tsh + h + eq);
+                                    pq += TH_NT, tq += TH_NT;
+                                    const uint32_t phi = *pq, thi = *tq;
+                                    const uint32_t x = __funnelshift_r(plo, phi, pqs) ^ __funnelshift_r(tlo, thi, tqs);
+                                    plo = phi, tlo = thi;
                                     if (x) eq += (__ffs(x) - 1) >> 1, stop = true;
                                     else eq += 16, stop = eq >= room;
                                 }
