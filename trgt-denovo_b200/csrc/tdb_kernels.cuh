@@ -370,6 +370,7 @@ struct DedupSmem {
     unsigned hist[N_HIST + 1];
     uint32_t s_lo, s_hi;
     int bad;
+    unsigned n_cand; // representatives left for pass B of the classification
 };
 
 __global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
     const uint32_t w0 = p0 + blockIdx.x * (uint32_t)DW_PAIRS, w1 = min(p1, w0 + (uint32_t)DW_PAIRS);
     const int tid = threadIdx.x;
     // ---- the window's sequence range ----
-    if (tid == 0) sm.s_lo = 0xffffffffu, sm.s_hi = 0, sm.bad = 0;
+    if (tid == 0) sm.s_lo = 0xffffffffu, sm.s_hi = 0, sm.bad = 0, sm.n_cand = 0;
     for (int i = tid; i <= N_HIST; i += DW_THREADS) sm.hist[i] = 0;
     for (int i = tid; i < DW_SSLOTS; i += DW_THREADS) sm.stab[i] = 0;
     for (int i = tid; i < DW_PSLOTS; i += DW_THREADS) sm.pkey[i] = 0xffffffffu;
@@ -460,10 +461,14 @@ __global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
     }
     __syncthreads();
     // ---- representatives: identical / closed form / tier and bucket ----
+    // Two passes.  A: every pair gets its representative; pattern == text is settled on the spot; the representatives
+    // that are left -- one pair in six -- are COMPACTED into a candidate list (it reuses the pair-key table, dead by
+    // now).  B: the threads walk that list, so the closed form's sequence scans run with full warps (done in place,
+    // under the one-in-six predicate, they were half of the kernel's instructions at 1-4 active lanes).
+    unsigned short *cand = reinterpret_cast<unsigned short *>(sm.pkey);
     for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
         const uint32_t jl = j - w0;
         const unsigned ps = sm.pslot[jl];
-        int key = KEY_NONE;
         uint32_t rep = j;
         if (ps == (unsigned)DW_PSLOTS + 1u) {
             // bad pair index (ERR_PAIR_INDEX) or a sequence outside the blob (ERR_LAYOUT, raised by k_hash): the call
@@ -472,44 +477,50 @@ __global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
             if (o.out_status) o.out_status[j] = TDB_STATUS_UNATTAINABLE;
             if (o.out_penalty) o.out_penalty[j] = INT32_MIN;
             if (o.work) o.work[3 * (size_t)j] = o.work[3 * (size_t)j + 1] = o.work[3 * (size_t)j + 2] = 0;
-        } else {
-            const uint32_t ip = pair_p[j], jt = pair_t[j];
-            const int n = (int)seq_len[ip], m = (int)seq_len[jt];
-            if (ps == (unsigned)DW_PSLOTS) { // same bytes: penalty 0, every column a match, clipped score 0
-                o.out_score[j] = 0;
-                if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
-                if (o.out_penalty) o.out_penalty[j] = 0;
-                if (o.work) {
-                    o.work[3 * (size_t)j] = 0, o.work[3 * (size_t)j + 1] = (uint32_t)(m >> 4) + 1u;
-                    o.work[3 * (size_t)j + 2] = (uint32_t)m;
-                }
-            } else {
-                if (ps < (unsigned)DW_PSLOTS) rep = w0 + sm.pval[ps];
-                if (rep == j) {
-                    const int L = abs(m - n);
-                    const unsigned fl = seq_flag[ip] | seq_flag[jt];
-                    int pen = 0, clipped = 0;
-                    if (cf.enabled && !fl && closed_form(packed, seq_off[ip], n, seq_off[jt], m, cf.clip, pen, clipped)) {
-                        o.out_score[j] = clipped;
-                        if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
-                        if (o.out_penalty) o.out_penalty[j] = pen;
-                        atomicAdd(sm.hist + N_HIST, 1u);
-                    } else if (fl || n > max_len16 || m > max_len16 || L >= WL_MAX) {
-                        const unsigned q = atomicAdd(o.gcount, 1u);
-                        o.glist[q] = j;
-                    } else if (!quad_ok || L >= QL_MAX) {
-                        key = KEY_WARP0 + (WL_MAX - 1 - L);
-                    } else if (mini_ok && L < ML_MAX && n >= ML_MINLEN && m >= ML_MINLEN && n <= ML_MAXLEN && m <= ML_MAXLEN) {
-                        key = KEY_MINI0 + (ML_MAX - 1 - L);
-                    } else {
-                        key = KEY_QUAD0 + (QL_MAX - 1 - L);
-                    }
-                }
+        } else if (ps == (unsigned)DW_PSLOTS) { // same bytes: penalty 0, every column a match, clipped score 0
+            o.out_score[j] = 0;
+            if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
+            if (o.out_penalty) o.out_penalty[j] = 0;
+            if (o.work) {
+                const int m = (int)seq_len[pair_t[j]];
+                o.work[3 * (size_t)j] = 0, o.work[3 * (size_t)j + 1] = (uint32_t)(m >> 4) + 1u;
+                o.work[3 * (size_t)j + 2] = (uint32_t)m;
             }
+        } else {
+            if (ps < (unsigned)DW_PSLOTS) rep = w0 + sm.pval[ps];
+            if (rep == j) cand[atomicAdd(&sm.n_cand, 1u)] = (unsigned short)jl;
         }
         o.rep[j] = rep;
-        o.key[j - p0] = (uint8_t)key;
-        if (key != KEY_NONE) atomicAdd(sm.hist + key, 1u);
+        o.key[j - p0] = (uint8_t)KEY_NONE; // pass B gives the candidates that need an alignment their bucket
+    }
+    __syncthreads();
+    const uint32_t n_cand = sm.n_cand;
+    for (uint32_t c = tid; c < n_cand; c += DW_THREADS) {
+        const uint32_t j = w0 + cand[c];
+        const uint32_t ip = pair_p[j], jt = pair_t[j];
+        const int n = (int)seq_len[ip], m = (int)seq_len[jt];
+        const int L = abs(m - n);
+        const unsigned fl = seq_flag[ip] | seq_flag[jt];
+        int key = KEY_NONE, pen = 0, clipped = 0;
+        if (cf.enabled && !fl && closed_form(packed, seq_off[ip], n, seq_off[jt], m, cf.clip, pen, clipped)) {
+            o.out_score[j] = clipped;
+            if (o.out_status) o.out_status[j] = TDB_STATUS_ALG_COMPLETED;
+            if (o.out_penalty) o.out_penalty[j] = pen;
+            atomicAdd(sm.hist + N_HIST, 1u);
+        } else if (fl || n > max_len16 || m > max_len16 || L >= WL_MAX) {
+            const unsigned q = atomicAdd(o.gcount, 1u);
+            o.glist[q] = j;
+        } else if (!quad_ok || L >= QL_MAX) {
+            key = KEY_WARP0 + (WL_MAX - 1 - L);
+        } else if (mini_ok && L < ML_MAX && n >= ML_MINLEN && m >= ML_MINLEN && n <= ML_MAXLEN && m <= ML_MAXLEN) {
+            key = KEY_MINI0 + (ML_MAX - 1 - L);
+        } else {
+            key = KEY_QUAD0 + (QL_MAX - 1 - L);
+        }
+        if (key != KEY_NONE) {
+            o.key[j - p0] = (uint8_t)key;
+            atomicAdd(sm.hist + key, 1u);
+        }
     }
     __syncthreads();
     if (tid < N_HIST && sm.hist[tid]) atomicAdd(o.hist + tid, sm.hist[tid]);
