@@ -988,6 +988,7 @@ __global__ void __launch_bounds__(128, TDB_G_MINB) k_align_global(const AlignPar
 __device__ __forceinline__ bool sc_ok(int x) { return x != TDB_SCORE_FAILED; }
 __device__ inline int n_valid(const int32_t *xs, int n) {
     int c = 0;
+#pragma unroll 4
     for (int i = 0; i < n; ++i) c += sc_ok(xs[i]);
     return c;
 }
@@ -1015,6 +1016,7 @@ __device__ inline int kth_smallest(const int32_t *xs, int n, int k) {
         const int x = xs[i];
         if (!sc_ok(x)) continue;
         int less = 0, eq = 0;
+#pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const int y = xs[j];
             less += (y < x) & sc_ok(y);
@@ -1033,6 +1035,7 @@ __device__ inline double list_quantile(const int32_t *xs, int n, int nv, double 
     const long long upper = lower + 1;
     if (upper >= (long long)nv) {
         int mx = INT32_MIN; // the sentinel is the smallest int: the maximum of the list ignores it by itself
+#pragma unroll 4
         for (int i = 0; i < n; ++i) mx = max(mx, xs[i]);
         return (double)mx;
     }
@@ -1061,6 +1064,7 @@ __device__ inline bool top_other(const int32_t *scores, const uint32_t *off, int
 __device__ inline void count_diff(double top, const int32_t *a, int n, int &count, float &mean_diff) {
     int c = 0;
     double sum = 0.0;
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const double x = (double)a[i];
         if (sc_ok(a[i]) && x > top) ++c, sum = __dadd_rn(sum, x);
@@ -1071,12 +1075,14 @@ __device__ inline void count_diff(double top, const int32_t *a, int n, int &coun
 
 __device__ inline int overlap_cov(double thr, const int32_t *a, int n) {
     int c = 0;
+#pragma unroll 4
     for (int i = 0; i < n; ++i) c += (sc_ok(a[i]) && (double)a[i] >= thr);
     return c;
 }
 
 __device__ inline double list_mean(const int32_t *s, uint32_t b, uint32_t e) {
     uint32_t sum = 0, nv = 0;
+#pragma unroll 4
     for (uint32_t i = b; i < e; ++i)
         if (sc_ok(s[i])) sum += (uint32_t)s[i], ++nv; // i32 sum (wrapping)
     if (nv == 0) return -INFINITY;
