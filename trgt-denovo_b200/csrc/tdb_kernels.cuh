@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
     {
         uint32_t lo = 0xffffffffu, hi = 0;
         bool bad = false;
-        for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
+        _Pragma("unroll 4") for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
             const uint32_t ip = pair_p[j], jt = pair_t[j];
             if (ip >= n_seqs || jt >= n_seqs) bad = true;
             else lo = min(lo, min(ip, jt)), hi = max(hi, max(ip, jt));
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
     }
     __syncthreads();
     // ---- pairs -> slot of their (canon pattern, canon text) key ----
-    for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
+    _Pragma("unroll 4") for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
         const uint32_t jl = j - w0;
         const uint32_t ip = pair_p[j], jt = pair_t[j];
         unsigned short ps = (unsigned short)(DW_PSLOTS + 1);
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2048 / DW_THREADS) k_dedup_window(
     // now).  B: the threads walk that list, so the closed form's sequence scans run with full warps (done in place,
     // under the one-in-six predicate, they were half of the kernel's instructions at 1-4 active lanes).
     unsigned short *cand = reinterpret_cast<unsigned short *>(sm.pkey);
-    for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
+    _Pragma("unroll 4") for (uint32_t j = w0 + tid; j < w1; j += DW_THREADS) {
         const uint32_t jl = j - w0;
         const unsigned ps = sm.pslot[jl];
         uint32_t rep = j;
