@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import tdo
+from tests.util import rand_seq
 
 
 def _vectors(golden_dir):
@@ -95,6 +96,47 @@ def test_random_pairs_optimal_and_self_consistent():
                 assert -a.score() == g
             else:
                 assert -a.score() >= g
+
+
+def test_closed_form_territory_is_heuristic_inert():
+    """The product scores one substitution / one gap of <= 20 bases in closed form (tdb_kernels.cuh: closed_form).  That
+    shortcut must not rest on the restated wf-adaptive cut-off: on such pairs -- gaps inside repeats (where they can slide),
+    in the flanks, at the very ends; insertions and deletions -- the checker gives the SAME CIGAR with the heuristic on and
+    off, its penalty is the optimum of the independent Gotoh DP and equals 8 resp. min(4 + 2L, 24 + L).  (For L = 21 the
+    heuristic changes the penalty -- 46 through the first gap piece instead of 45 -- but not the CIGAR, and only the
+    CIGAR enters the clipped score: that case is left to the wavefront kernels.)"""
+    rng = random.Random(7)
+    on, off = tdo.Aligner(), tdo.Aligner(heuristic=tdo.NO_HEURISTIC)
+    seen = 0
+    while seen < 1200:
+        k = rng.randint(1, 6)
+        motif = rand_seq(rng, k)
+        lf, rf = rand_seq(rng, 50), rand_seq(rng, 50)
+        t = lf + motif * rng.randint(3, 90) + rf
+        L = rng.choice([0, 1, 2, 5, 10, 19, 20])
+        if L == 0:  # one substitution
+            i = rng.randrange(len(t))
+            p = t[:i] + rng.choice([c for c in "ACGT" if c != t[i]]) + t[i + 1:]
+        elif rng.random() < 0.5:  # whole motif units in or out
+            u = max(1, L // k)
+            L = u * k
+            j = len(lf) + k * rng.randint(0, 3)
+            p = t[:j] + motif * u + t[j:] if rng.random() < 0.5 else t[:j] + t[j + L:]
+        else:
+            i = rng.randrange(len(t) + 1)
+            p = t[:i] + rand_seq(rng, L) + t[i:] if rng.random() < 0.5 else t[:i] + t[i + L:]
+        if L > 20 or abs(len(p) - len(t)) != L or p == t or not p:
+            continue
+        pe, te = p.encode(), t.encode()
+        assert on.align_end_to_end(pe, te) == 0 and off.align_end_to_end(pe, te) == 0
+        g = tdo.gotoh2p_penalty(pe, te)
+        if g != (8 if L == 0 else min(4 + 2 * L, 24 + L)):
+            continue  # a random insertion that happens to align cheaper: not a single-event pair
+        seen += 1
+        assert on.cigar_ops() == off.cigar_ops(), (p, t)
+        assert -on.score() == -off.score() == g, (p, t)
+        for clip in (0, 50):
+            assert on.cigar_score_clipped(clip) == off.cigar_score_clipped(clip)
 
 
 def test_edge_cases():
