@@ -34,6 +34,9 @@ namespace tdb {
 #ifndef TDB_Q_MINB
 #define TDB_Q_MINB 1
 #endif
+#ifndef TDB_Q_FETCH
+#define TDB_Q_FETCH 2 // warp batches per grab of the work counter (at most)
+#endif
 // Geometry of a lockstep configuration: G lanes per pair (32/G pairs per warp), wavefronts up to W
 // diagonals, M arena of MAR entries (power of two), scores < SCAP, PROV provenance bytes.
 // GP: the provenance bytes and the per-score step records -- written once, read only by the backtrace -- live in a
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(Q_WARPS * 32, C::MINB) k_align_lock(const Alig
     const unsigned n_items = src.total;
     // pairs per work-counter atomic: 8 batches when there is plenty of work, fewer when a launch (a pipeline
     // chunk) only has a few batches per warp -- coarse grabs then leave warps idle behind the heaviest ones
-    constexpr int PER_BATCH = 32 / QG, MAX_FETCH = 8 * PER_BATCH;
+    constexpr int PER_BATCH = 32 / QG, MAX_FETCH = TDB_Q_FETCH * PER_BATCH;
     const unsigned n_warps = gridDim.x * (blockDim.x >> 5);
     const unsigned per_fetch = WIDE ? 1u : // (the long tier's pairs are few and take milliseconds each)
         (unsigned)PER_BATCH * max(1u, min((unsigned)(MAX_FETCH / PER_BATCH), n_items / (n_warps * 8u * (unsigned)PER_BATCH)));
