@@ -8,9 +8,13 @@
 //   * existence of the last 26 M / gap wavefronts is tracked in register bit-masks, so the null score steps of
 //     the 2-piece-affine recurrence (most steps, penalties 8/6/25) touch no memory;
 //   * the M history lives in a FIFO arena (only non-null wavefronts occupy shared memory), which lets a pair
-//     with width <= 32 fit in 3 KB and keeps 16 warps resident per SM;
+//     with width <= 32 fit in 3 KB and keeps 16 warps resident per SM; a wavefront never wraps around the arena end
+//     and a gap row starts at its score's computed lo, so a cell is read at base + k without a mask and the k-1 / k+1
+//     neighbours share one address;
 //   * penalties are compile-time constants (the reference hard-wires 8,4,2,24,1: src/commands/shared.rs:39-51,
 //     src/model.rs:13-23); other penalties use the general tiers (wfa_align_warp, tdb_wfa.cuh).
+// The same kernel serves tier 0 (QuadCfg), tier 1 (Duo4Cfg: provenance in global scratch) and the long tier (LongCfg: one
+// pair per warp, thousands of score steps, wavefronts up to 192 diagonals).
 // Semantics are exactly those of wfa_align_warp: SURVEY.md Appendix A.1-A.4.
 #pragma once
 #include <type_traits>
