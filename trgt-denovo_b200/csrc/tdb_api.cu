@@ -1045,6 +1045,14 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         const unsigned grid = (unsigned)std::max<uint64_t>(1, warps / Q_WARPS);
         ENSURE(ctx->scratch[0], per_pair * (size_t)grid * Q_WARPS);
         ENSURE(ctx->list_d, (size_t)pending * 4);
+        if ((uint64_t)pending > 8 * warps) { // many pairs per warp: heaviest first (one CTA sorts: ~80 us per 13 k entries, which a
+                                               // short launch does not win back; list_c is free until tier 2 runs)
+            ENSURE(ctx->list_c, (size_t)pending * 4);
+            k_sort_long<<<1, 1024, 0, s>>>(g_src, pending, b.pp, b.pt, b.seq_len, (uint32_t *)ctx->list_c.p);
+            CK(cudaGetLastError());
+            cn.kernel_launches += 1;
+            g_src = (const uint32_t *)ctx->list_c.p;
+        }
         p.scratch = (uint8_t *)ctx->scratch[0].p;
         p.src1 = g_src, p.src1_seg = nullptr, p.src1_count = pending, p.src2 = nullptr, p.src2_count = nullptr;
         p.next_todo = (uint32_t *)ctx->list_d.p, p.next_count = &ctrl->dcount;

@@ -711,6 +711,34 @@ __global__ void __launch_bounds__(256) k_bucket_list(const uint8_t *__restrict__
     }
 }
 
+// The long tier's list, heaviest pairs first.  Its pairs take milliseconds each and arrive in the order the windows and the
+// earlier tiers happened to append them; a warp that draws one of the longest pairs at the very end of the launch keeps
+// the whole launch waiting.  One CTA sorts the (few tens of thousands of) entries by |n - m| / 64 -- the length of the gap
+// is what sets the number of score steps -- with a counting sort in shared memory, descending.
+constexpr int LS_BUCKETS = 256;
+__global__ void __launch_bounds__(1024) k_sort_long(const uint32_t *__restrict__ in, unsigned n, const uint32_t *__restrict__ pair_p,
+                                                    const uint32_t *__restrict__ pair_t, const uint32_t *__restrict__ seq_len,
+                                                    uint32_t *__restrict__ out) {
+    __shared__ unsigned cnt[LS_BUCKETS], base[LS_BUCKETS];
+    for (int i = threadIdx.x; i < LS_BUCKETS; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    auto bucket = [&](uint32_t idx) {
+        const int d = abs((int)seq_len[pair_t[idx]] - (int)seq_len[pair_p[idx]]) >> 6;
+        return LS_BUCKETS - 1 - min(d, LS_BUCKETS - 1); // heaviest first
+    };
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cnt[bucket(in[i])], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned at = 0;
+        for (int b = 0; b < LS_BUCKETS; ++b) base[b] = at, at += cnt[b];
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t idx = in[i];
+        out[atomicAdd(&base[bucket(idx)], 1u)] = idx;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restrict__ rep, uint32_t n_pairs,
                                                  int32_t *__restrict__ score, int32_t *__restrict__ status,
                                                  int32_t *__restrict__ penalty, const uint32_t *__restrict__ work,
