@@ -635,6 +635,12 @@ def test_long_tier_and_global_tiers_give_same_scores(tdb, monkeypatch):
     cnt = _check_batch(c, seqs, pp, pt, 50)
     assert cnt.long_pairs > 20 and cnt.tier_pairs[2] + cnt.tier_pairs[3] == 0
     c.close()
+    monkeypatch.setenv("TDB_LONG_SORT_PER_WARP", "0")  # the list sorted heaviest first (k_sort_long) whatever its length
+    c = tdb.Context()
+    monkeypatch.delenv("TDB_LONG_SORT_PER_WARP")
+    cnt1 = _check_batch(c, seqs, pp, pt, 50, cigars=False)
+    assert cnt1.long_pairs == cnt.long_pairs
+    c.close()
     monkeypatch.setenv("TDB_DISABLE_LONG", "1")
     c = tdb.Context()
     monkeypatch.delenv("TDB_DISABLE_LONG")

@@ -96,6 +96,7 @@ struct tdb_ctx {
     DevBuf lock_scratch[2]; // provenance / step records of the four-pairs-per-warp tier 1 (per pipeline slot)
     int duo4_ctas_per_sm = 0, long_ctas_per_sm = 0, quad8_ctas_per_sm = 0;
     bool quad8 = false; // TDB_QUAD8=1: tier 0 with eight pairs per warp (Quad8Cfg)
+    int long_sort_per_warp = 8; // the long tier's list is sorted heaviest first beyond this many pairs per warp (TDB_LONG_SORT_PER_WARP)
     bool disable_long = false; // TDB_DISABLE_LONG: no long tier (k_align_lock<LongCfg>) in front of the global-scratch tiers
     bool duo4 = true; // TDB_DUO_G16=1: tier 1 with two pairs per warp (16 lanes each), everything in shared memory
     int t0_ctas_per_sm = 0, quad_ctas_per_sm = 0, duo_ctas_per_sm = 0, mini_ctas_per_sm = 0;
@@ -1045,7 +1046,7 @@ int run_align(tdb_ctx *ctx, const DevBatch &b_in, bool cigar_mode) {
         const unsigned grid = (unsigned)std::max<uint64_t>(1, warps / Q_WARPS);
         ENSURE(ctx->scratch[0], per_pair * (size_t)grid * Q_WARPS);
         ENSURE(ctx->list_d, (size_t)pending * 4);
-        if ((uint64_t)pending > 8 * warps) { // many pairs per warp: heaviest first (one CTA sorts: ~80 us per 13 k entries, which a
+        if ((uint64_t)pending > (uint64_t)ctx->long_sort_per_warp * warps) { // many pairs per warp: heaviest first (one CTA sorts: ~80 us per 13 k entries, which a
                                                // short launch does not win back; list_c is free until tier 2 runs)
             ENSURE(ctx->list_c, (size_t)pending * 4);
             k_sort_long<<<1, 1024, 0, s>>>(g_src, pending, b.pp, b.pt, b.seq_len, (uint32_t *)ctx->list_c.p);
@@ -1332,6 +1333,7 @@ int tdb_create(const tdb_config *cfg, tdb_ctx **out) {
         c->quad8 = getenv("TDB_QUAD8") != nullptr && c->quad8_ctas_per_sm >= 1;
         if (e == cudaSuccess) e = setup(k_align_lock<LongCfg, 8, 4, 2, 24, 1>, lock_smem_bytes<LongCfg>(), c->long_ctas_per_sm);
         c->disable_long = getenv("TDB_DISABLE_LONG") != nullptr || c->long_ctas_per_sm < 1;
+        if (const char *ls = getenv("TDB_LONG_SORT_PER_WARP")) c->long_sort_per_warp = std::max(0, atoi(ls));
         auto fsetup = [&](auto kern, size_t smem, int &occ_out) {
             cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
