@@ -263,10 +263,10 @@ __global__ void __launch_bounds__(256) k_expand_runs(const PairRun *__restrict__
 // ------------------------------------------------------------------------------------------------
 // sort keys of representative pairs: 0 quad tier by descending |n-m| ... ; 255 = not in the sorted list
 #ifndef TDB_QL_MAX
-#define TDB_QL_MAX 14
+#define TDB_QL_MAX 12
 #endif
 constexpr int QL_MAX = TDB_QL_MAX; // |n-m| >= QL_MAX: the wavefront outgrows the quad tier's 32 diagonals before the pair ends
-                                    // (swept 10..16 with the thread tier in place: 14 best, profiles/r01/NOTES.md)
+                                    // (swept again at the end of round 2, with tier 1 at four pairs per warp: 10 / 12 / 14 -> quad + tier 1 = 19.8 / 19.1 / 19.3 ms)
 constexpr int WL_MAX = 40;  // |n-m| >= WL_MAX: wider than the warp tier's 64 diagonals
 constexpr int KEY_WARP0 = 0; // sorted first: heaviest pairs of the shared-memory tiers, by descending |n-m| (the two pairs
                              // of a lockstep warp run to the larger of their penalties: neighbours should be alike)
