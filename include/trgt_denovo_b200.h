@@ -270,8 +270,9 @@ int32_t tdb_cigar_score_clipped(const tdb_ctx *ctx, int32_t flank_len);
 /* Counters of the last batch call (for roofline accounting and tier diagnostics). */
 typedef struct {
     uint64_t pairs;         /* pairs in the call */
-    uint64_t tier_pairs[4]; /* pairs ALIGNED by tier 0 (four pairs per warp, shared memory), 1 (one pair per
-                               warp, shared memory), 2 and 3 (one pair per warp, global scratch) */
+    uint64_t tier_pairs[4]; /* pairs ALIGNED by tier 0 (four pairs per warp, up to 32 diagonals, shared memory), 1 (four
+                               pairs per warp, up to 64 diagonals; other penalty sets: one pair per warp), 2 and 3 (one
+                               pair per warp, global scratch).  See long_pairs / thread_pairs for the other two tiers. */
     uint64_t cells;         /* C: sum over computed score steps of wavefront width, ALGORITHMIC: */
     uint64_t ext16;         /* E: 16-base extension compares         every pair counted, duplicates included */
     uint64_t columns;       /* T: CIGAR columns replayed             (= what the CPU oracle counts) */
